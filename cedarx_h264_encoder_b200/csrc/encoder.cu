@@ -1,0 +1,701 @@
+// Host layer of the B200 H.264 encoder: the C ABI of include/cedar_b200.h.
+//
+// Mirrors the reference's driver control flow with kernel launches in place of register writes:
+//   cedar_slashdev_ioctl_config  (kernel/cedar.c:732-866)  -> cedar_b200_open
+//   cedar_buffers_init           (kernel/cedar.c:605-704)  -> alloc_buffers (cudaMalloc / pinned host)
+//   cedar_slashdev_ioctl_encode  (kernel/cedar.c:1032-1209) -> cedar_b200_encode_frame / clip_encode
+//   cedar_slashdev_release       (kernel/cedar.c:706-730)  -> cedar_b200_close
+// There is no CPU fallback: without a CUDA device open() fails with -ENODEV.
+#include "../../include/cedar_b200.h"
+#include "cedar_headers.h"
+#include "kernels.cuh"
+
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <errno.h>
+#include <vector>
+
+using namespace cedar;
+
+#define ALIGN_UP(x, a) (((x) + ((a)-1)) & ~((size_t)(a)-1))
+
+namespace {
+
+enum KernelId {
+    K_INGEST, K_ME, K_INTER, K_MVP, K_INTRA, K_DEBLOCK, K_SSE, K_ESIZE, K_ESCAN, K_EZERO, K_EWRITE,
+    K_CABAC, K_EPBCOUNT, K_EPBSCAN, K_PACKSCAN, K_EPBWRITE, K_COUNT
+};
+const char *kKernelNames[K_COUNT] = {
+    "ingest_kernel", "me_kernel", "inter_kernel", "mvp_skip_kernel", "intra_kernel", "deblock_kernel",
+    "sse_kernel", "entropy_size_kernel", "entropy_scan_kernel", "rbsp_zero_kernel", "entropy_write_kernel",
+    "cabac_encode_kernel", "epb_count_kernel", "epb_scan_kernel", "pack_scan_kernel", "epb_write_kernel"};
+
+const uint8_t kChromaQp[52] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17,
+                               18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32, 32, 33,
+                               34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39};
+
+struct ProfEntry {
+    int id;
+    cudaEvent_t a, b;
+};
+
+} // namespace
+
+__global__ void rbsp_zero_kernel(Step s, uint8_t *rbsp, unsigned rbsp_cap, const uint32_t *rbsp_len)
+{
+    int f = lane_frame(s, blockIdx.y);
+    if (f < 0)
+        return;
+    size_t words = ((size_t)rbsp_len[f] + 8 + 3) / 4;
+    uint32_t *p = (uint32_t *)(rbsp + (size_t)f * rbsp_cap);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = 0;
+}
+
+struct cedar_b200_handle {
+    cedar_b200_config cfg;
+    Geom g;
+    int K;                 // keyframe_interval
+    int F;                 // clip capacity in frames (>= 1)
+    int L;                 // lanes (GOPs in flight)
+    size_t raw_frame_bytes;
+    cudaStream_t stream;
+
+    // cedar.c:118-119 counters and the ping-pong reference (frame mode, lane 0)
+    int frame_p_count, frame_count;
+
+    // pinned host
+    uint8_t *h_in_luma, *h_in_chroma, *h_bytestream;
+    int in_luma_size, in_chroma_size, bytestream_size;
+    uint8_t *h_clip_in, *h_clip_out;
+    size_t out_cap;
+    int *h_frame_bytes;
+    unsigned long long *h_total;
+    unsigned long long *h_sse;
+    int *h_error;
+
+    // device
+    uint8_t *d_raw, *d_src, *d_unf, *d_rec[2];
+    MbInfo *d_mbi;
+    uint8_t *d_nnz;
+    int16_t *d_coef;
+    int *d_flags; // [3][L][mbh]
+    unsigned long long *d_sse;
+    EntropyBufs eb;
+    uint32_t *d_hdr_bits;
+    int *d_hdr_nbits;
+    uint32_t *d_chunk_cnt, *d_nal_bytes;
+    unsigned chunks_per_frame;
+    unsigned long long *d_nal_off, *d_total;
+    int *d_frame_bytes;
+    uint8_t *d_out;
+    uint8_t prefix[64];
+    int prefix_len;
+
+    int last_nframes, last_cur;
+    long long launches;
+    bool prof;
+    std::vector<ProfEntry> prof_pending;
+    std::vector<cudaEvent_t> ev_pool;
+    float prof_ms[K_COUNT];
+    int prof_n[K_COUNT];
+    std::chrono::steady_clock::time_point t_open;
+    double busy_ns;
+};
+
+namespace {
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            fprintf(stderr, "cedar_b200: %s failed: %s (%s:%d)\n", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return -EIO;                                                                               \
+        }                                                                                              \
+    } while (0)
+
+cudaEvent_t get_event(cedar_b200_handle *h)
+{
+    if (!h->ev_pool.empty()) {
+        cudaEvent_t e = h->ev_pool.back();
+        h->ev_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct LaunchScope {
+    cedar_b200_handle *h;
+    ProfEntry pe;
+    LaunchScope(cedar_b200_handle *hh, int id) : h(hh)
+    {
+        pe.id = id;
+        h->launches++;
+        if (h->prof) {
+            pe.a = get_event(h);
+            pe.b = get_event(h);
+            cudaEventRecord(pe.a, h->stream);
+        }
+    }
+    ~LaunchScope()
+    {
+        if (h->prof) {
+            cudaEventRecord(pe.b, h->stream);
+            h->prof_pending.push_back(pe);
+        }
+    }
+};
+
+#define LAUNCH(id, kern, grid, block, smem, ...)              \
+    do {                                                      \
+        LaunchScope ls_(h, id);                               \
+        kern<<<grid, block, smem, h->stream>>>(__VA_ARGS__);  \
+    } while (0)
+
+void prof_collect(cedar_b200_handle *h)
+{
+    cudaStreamSynchronize(h->stream);
+    for (auto &pe : h->prof_pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pe.a, pe.b);
+        h->prof_ms[pe.id] += ms;
+        h->prof_n[pe.id]++;
+        h->ev_pool.push_back(pe.a);
+        h->ev_pool.push_back(pe.b);
+    }
+    h->prof_pending.clear();
+}
+
+int validate(const cedar_b200_config *c) // kernel/cedar.c:744-789, same order, same -EINVAL
+{
+    if ((c->src_width & 0x01) || (c->src_height & 0x01)) {
+        fprintf(stderr, "cedar_b200: src width %d, height %d not aligned.\n", c->src_width, c->src_height);
+        return -EINVAL;
+    }
+    if ((c->dst_width & 0x0F) || (c->dst_height & 0x0F)) {
+        fprintf(stderr, "cedar_b200: dst width %d, height %d not aligned.\n", c->dst_width, c->dst_height);
+        return -EINVAL;
+    }
+    if ((c->src_width > c->dst_width) || (c->src_height > c->dst_height)) {
+        fprintf(stderr, "cedar_b200: src (%d,%d) > dst (%d, %d)\n", c->src_width, c->src_height, c->dst_width,
+                c->dst_height);
+        return -EINVAL;
+    }
+    if ((c->qp <= 0) || (c->qp > 47)) {
+        fprintf(stderr, "cedar_b200: invalid QP %d\n", c->qp);
+        return -EINVAL;
+    }
+    if ((c->src_format != CEDAR_B200_FORMAT_NV12) && (c->src_format != CEDAR_B200_FORMAT_NV16)) {
+        fprintf(stderr, "cedar_b200: invalid color format.\n");
+        return -EINVAL;
+    }
+    if ((c->keyframe_interval <= 0) || (c->keyframe_interval >= 32 && !c->relax_gop)) {
+        fprintf(stderr, "cedar_b200: invalid keyframe interval %d\n", c->keyframe_interval);
+        return -EINVAL;
+    }
+    if (c->src_width <= 0 || c->src_height <= 0 || c->me_range < 0 || c->me_range > 64 || c->max_clip_frames < 0 ||
+        c->gops_in_flight < 0) {
+        fprintf(stderr, "cedar_b200: invalid extension field.\n");
+        return -EINVAL;
+    }
+    return 0;
+}
+
+template <class T> int dmalloc(T **p, size_t n)
+{
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) {
+        fprintf(stderr, "cedar_b200: cudaMalloc(%zu) failed: %s\n", n * sizeof(T), cudaGetErrorString(e));
+        return -ENOMEM;
+    }
+    return 0;
+}
+template <class T> int hmalloc(T **p, size_t n)
+{
+    cudaError_t e = cudaHostAlloc((void **)p, n * sizeof(T), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "cedar_b200: cudaHostAlloc(%zu) failed: %s\n", n * sizeof(T), cudaGetErrorString(e));
+        return -ENOMEM;
+    }
+    return 0;
+}
+
+int alloc_buffers(cedar_b200_handle *h)
+{
+    const Geom &g = h->g;
+    const int F = h->F, L = h->L;
+    int r = 0;
+    // frame-mode I/O, sized like cedar_buffers_init (cedar.c:610-624) but in pinned host memory
+    h->in_luma_size = (int)ALIGN_UP((size_t)g.src_w * g.src_h, 4096);
+    size_t chroma_bytes = (size_t)g.src_w * g.src_h / (g.src_format == CEDAR_B200_FORMAT_NV16 ? 1 : 2);
+    h->in_chroma_size = (int)ALIGN_UP(chroma_bytes, 4096);
+    h->bytestream_size = (int)ALIGN_UP((size_t)g.nmb * 1536 + 4096, 4096);
+    r |= hmalloc(&h->h_in_luma, h->in_luma_size);
+    r |= hmalloc(&h->h_in_chroma, h->in_chroma_size);
+    r |= hmalloc(&h->h_bytestream, h->bytestream_size);
+    r |= hmalloc(&h->h_frame_bytes, F);
+    r |= hmalloc(&h->h_total, 1);
+    r |= hmalloc(&h->h_sse, F);
+    r |= hmalloc(&h->h_error, 1);
+    if (r)
+        return r;
+
+    h->eb.rbsp_cap = (unsigned)ALIGN_UP((size_t)g.nmb * (F > 1 ? (g.qp < 20 ? 1024 : 400) : 1024) + 4096, 256);
+    size_t per_frame_out = F > 1 ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) + 4096 : (size_t)h->bytestream_size;
+    h->out_cap = per_frame_out * F;
+    size_t bins_per_mb = F > 1 ? (g.qp < 12 ? 8192 : (g.qp < 20 ? 2048 : 640)) : 16384;
+    if (const char *e = getenv("CEDAR_B200_BINS_PER_MB"))
+        bins_per_mb = (size_t)atoll(e);
+    h->eb.bins_cap = g.cabac ? (unsigned long long)bins_per_mb * g.nmb * F + 64 : 0;
+
+    if (F > 1) {
+        r |= hmalloc(&h->h_clip_in, h->raw_frame_bytes * F);
+        r |= hmalloc(&h->h_clip_out, h->out_cap);
+    }
+    r |= dmalloc(&h->d_raw, h->raw_frame_bytes * F + 64);
+    r |= dmalloc(&h->d_src, g.frame_bytes * L);
+    r |= dmalloc(&h->d_unf, g.frame_bytes * L);
+    r |= dmalloc(&h->d_rec[0], g.frame_bytes * L);
+    r |= dmalloc(&h->d_rec[1], g.frame_bytes * L);
+    r |= dmalloc(&h->d_mbi, (size_t)g.nmb * L);
+    r |= dmalloc(&h->d_nnz, (size_t)g.nmb * L * NNZ_STRIDE);
+    r |= dmalloc(&h->d_coef, (size_t)g.nmb * L * COEF_STRIDE);
+    r |= dmalloc(&h->d_flags, (size_t)3 * L * g.mbh);
+    r |= dmalloc(&h->d_sse, F);
+    r |= dmalloc(&h->eb.mb_size, (size_t)L * (g.nmb + 1));
+    r |= dmalloc(&h->eb.mb_off, (size_t)L * (g.nmb + 1));
+    r |= dmalloc(&h->d_hdr_bits, F);
+    r |= dmalloc(&h->d_hdr_nbits, F);
+    r |= dmalloc(&h->eb.rbsp, (size_t)h->eb.rbsp_cap * F);
+    r |= dmalloc(&h->eb.rbsp_len, F);
+    if (g.cabac)
+        r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap);
+    r |= dmalloc(&h->eb.bins_cursor, 1);
+    r |= dmalloc(&h->eb.bins_off, F);
+    r |= dmalloc(&h->eb.bins_len, F);
+    r |= dmalloc(&h->eb.error, 1);
+    h->chunks_per_frame = (h->eb.rbsp_cap + EPB_CHUNK - 1) / EPB_CHUNK;
+    r |= dmalloc(&h->d_chunk_cnt, (size_t)h->chunks_per_frame * F);
+    r |= dmalloc(&h->d_nal_bytes, F);
+    r |= dmalloc(&h->d_nal_off, F);
+    r |= dmalloc(&h->d_total, 1);
+    r |= dmalloc(&h->d_frame_bytes, F);
+    r |= dmalloc(&h->d_out, h->out_cap + 64);
+    if (r)
+        return r;
+    h->eb.hdr_bits = h->d_hdr_bits;
+    h->eb.hdr_nbits = h->d_hdr_nbits;
+    CK(cudaMemset(h->eb.error, 0, sizeof(int)));
+    CK(cudaMemset(h->d_mbi, 0, sizeof(MbInfo) * g.nmb * L));
+    CK(cudaMemset(h->d_rec[0], 0, g.frame_bytes * L));
+    CK(cudaMemset(h->d_rec[1], 0, g.frame_bytes * L));
+    return 0;
+}
+
+void free_buffers(cedar_b200_handle *h)
+{
+    void *dev[] = {h->d_raw, h->d_src, h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi, h->d_nnz, h->d_coef, h->d_flags,
+                   h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp, h->eb.rbsp_len,
+                   h->eb.bins, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
+                   h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes, h->d_out};
+    for (void *p : dev)
+        if (p)
+            cudaFree(p);
+    void *host[] = {h->h_in_luma, h->h_in_chroma, h->h_bytestream, h->h_frame_bytes, h->h_total, h->h_sse,
+                    h->h_error, h->h_clip_in, h->h_clip_out};
+    for (void *p : host)
+        if (p)
+            cudaFreeHost(p);
+}
+
+// One lock-step pass over `nl` lanes: the macroblock pipeline of one frame per lane plus the
+// parallel part of entropy coding.  t = position inside the GOP (0 => IDR).
+int encode_step(cedar_b200_handle *h, const Step &s, int t)
+{
+    const Geom &g = h->g;
+    const int nl = s.nlanes, cur = t & 1, frame_i = t == 0;
+    const size_t flag_n = (size_t)h->L * g.mbh;
+    int *fl_intra = h->d_flags, *fl_y = h->d_flags + flag_n, *fl_c = h->d_flags + 2 * flag_n;
+    uint8_t *rec = h->d_rec[cur], *ref = h->d_rec[cur ^ 1];
+
+    LAUNCH(K_INGEST, ingest_kernel, dim3((unsigned)((g.frame_bytes / 4 + 255) / 256), nl), 256, 0, g, s, h->d_raw,
+           h->raw_frame_bytes, h->d_src);
+    CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 3 * flag_n, h->stream));
+    if (frame_i) {
+        LAUNCH(K_INTRA, intra_kernel, dim3(g.mbh, nl), 32, 0, g, s, h->d_src, h->d_unf, h->d_mbi, h->d_nnz, h->d_coef,
+               fl_intra);
+    } else {
+        LAUNCH(K_ME, me_kernel, dim3(g.nmb, nl), ME_THREADS, me_smem_bytes(g.R), g, s, h->d_src, ref, h->d_mbi);
+        LAUNCH(K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, h->d_src, ref, h->d_unf, h->d_mbi,
+               h->d_nnz, h->d_coef);
+        LAUNCH(K_MVP, mvp_skip_kernel, dim3((g.nmb + 127) / 128, nl), 128, 0, g, s, h->d_mbi);
+    }
+    LAUNCH(K_DEBLOCK, deblock_kernel, dim3(g.mbh, nl), 64, 0, g, s, h->d_unf, rec, h->d_mbi, h->d_nnz, fl_y, fl_c);
+    LAUNCH(K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, h->d_src, rec, h->d_sse);
+
+    dim3 egrid((g.nmb + 1 + 127) / 128, nl);
+    LAUNCH(K_ESIZE, entropy_size_kernel, egrid, 128, 0, g, s, frame_i, h->d_mbi, h->d_nnz, h->d_coef, h->eb);
+    LAUNCH(K_ESCAN, entropy_scan_kernel, dim3(1, nl), 1024, 0, g, s, h->eb);
+    if (!g.cabac)
+        LAUNCH(K_EZERO, rbsp_zero_kernel, dim3(8, nl), 256, 0, s, h->eb.rbsp, h->eb.rbsp_cap, h->eb.rbsp_len);
+    LAUNCH(K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, h->d_mbi, h->d_nnz, h->d_coef, h->eb);
+    h->last_cur = cur;
+    return 0;
+}
+
+// Serial CABAC stage (all frames at once), emulation prevention and packing of `nframes` frames.
+int finish_stream(cedar_b200_handle *h, int nframes, int gop_pos0, bool with_param_sets)
+{
+    const Geom &g = h->g;
+    if (g.cabac)
+        LAUNCH(K_CABAC, cabac_encode_kernel, nframes, 32, 0, g, 0, nframes, h->K, gop_pos0, h->eb);
+    unsigned cpf = h->chunks_per_frame;
+    LAUNCH(K_EPBCOUNT, epb_count_kernel, dim3((cpf + 255) / 256, nframes), 256, 0, nframes, h->eb.rbsp, h->eb.rbsp_cap,
+           h->eb.rbsp_len, h->d_chunk_cnt, cpf);
+    LAUNCH(K_EPBSCAN, epb_scan_kernel, nframes, 1024, 0, nframes, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_bytes);
+    unsigned prefix = with_param_sets ? (unsigned)h->prefix_len : 0;
+    LAUNCH(K_PACKSCAN, pack_scan_kernel, 1, 1024, 0, nframes, h->d_nal_bytes, prefix, h->d_nal_off, h->d_frame_bytes,
+           h->d_total, (unsigned long long)h->out_cap, h->eb.error);
+    LAUNCH(K_EPBWRITE, epb_write_kernel, dim3((cpf + 255) / 256, nframes), 256, 0, nframes, h->K, gop_pos0, h->eb.rbsp,
+           h->eb.rbsp_cap, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_off, h->d_total, h->d_out);
+    if (prefix)
+        CK(cudaMemcpyAsync(h->d_out, h->prefix, prefix, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int upload_headers(cedar_b200_handle *h, int nframes, int gop_pos0)
+{
+    std::vector<uint32_t> bits(nframes);
+    std::vector<int> nbits(nframes);
+    for (int f = 0; f < nframes; f++) {
+        int p = (gop_pos0 + f) % h->K;
+        int r = cedar_hdr_slice(p == 0, p, h->g.cabac, &bits[f], &nbits[f]);
+        if (r)
+            return r;
+    }
+    CK(cudaMemcpyAsync(h->d_hdr_bits, bits.data(), sizeof(uint32_t) * nframes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_hdr_nbits, nbits.data(), sizeof(int) * nframes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream)); // the vectors go out of scope
+    return 0;
+}
+
+int begin_stream(cedar_b200_handle *h, int nframes)
+{
+    CK(cudaMemsetAsync(h->eb.bins_cursor, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->d_sse, 0, sizeof(unsigned long long) * nframes, h->stream));
+    CK(cudaMemsetAsync(h->eb.rbsp_len, 0, sizeof(uint32_t) * nframes, h->stream));
+    CK(cudaMemsetAsync(h->eb.bins_len, 0, sizeof(uint32_t) * nframes, h->stream));
+    return 0;
+}
+
+int check_error(cedar_b200_handle *h)
+{
+    if (*h->h_error) {
+        fprintf(stderr, "cedar_b200: device buffer overflow (code %d): bitstream larger than the configured bound.\n",
+                *h->h_error);
+        cudaMemset(h->eb.error, 0, sizeof(int));
+        return -ENOMEM;
+    }
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *cedar_b200_version(void) { return "cedar_b200 0.1 (sm_100a)"; }
+
+int cedar_b200_write_sps(const struct cedar_b200_config *cfg, uint8_t *out, int cap)
+{
+    return cedar_hdr_sps(cfg->profile, cfg->level, (int)ALIGN_UP(cfg->dst_width, 16) >> 4,
+                         (int)ALIGN_UP(cfg->dst_height, 16) >> 4, out, cap);
+}
+int cedar_b200_write_pps(const struct cedar_b200_config *cfg, uint8_t *out, int cap)
+{
+    return cedar_hdr_pps(cfg->qp, cfg->entropy_coding_mode == CEDAR_B200_ENTROPY_CABAC, out, cap);
+}
+int cedar_b200_slice_header(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits)
+{
+    return cedar_hdr_slice(frame_i, frame_p_count, cabac, bits, nbits);
+}
+
+int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *io, cedar_b200_handle **out)
+{
+    if (!cfg || !io || !out)
+        return -EINVAL;
+    int r = validate(cfg);
+    if (r)
+        return r;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev) {
+        fprintf(stderr, "cedar_b200: no usable CUDA device (this encoder has no CPU fallback).\n");
+        return -ENODEV;
+    }
+    if (cudaSetDevice(cfg->device) != cudaSuccess)
+        return -ENODEV;
+    cedar_b200_handle *h = new cedar_b200_handle();
+    memset((void *)&h->cfg, 0, sizeof(h->cfg));
+    h->cfg = *cfg;
+    h->t_open = std::chrono::steady_clock::now();
+    Geom &g = h->g;
+    g.W = cfg->dst_width;
+    g.H = cfg->dst_height;
+    g.CW = g.W / 2;
+    g.CH = g.H / 2;
+    g.mbw = g.W >> 4;
+    g.mbh = g.H >> 4;
+    g.nmb = g.mbw * g.mbh;
+    g.src_w = cfg->src_width;
+    g.src_h = cfg->src_height;
+    g.src_format = cfg->src_format;
+    g.qp = cfg->qp;
+    int qpi = cfg->qp + 4; // chroma_qp_index_offset = 4 (cedar.c:969-971, PARA1 cedar.c:1165-1168)
+    g.qpc = kChromaQp[qpi < 0 ? 0 : (qpi > 51 ? 51 : qpi)];
+    g.R = cfg->me_range ? cfg->me_range : 16;
+    int lq = (cfg->qp - 12) / 6;
+    g.lambda = 1 << (lq < 0 ? 0 : (lq > 5 ? 5 : lq));
+    g.cabac = cfg->entropy_coding_mode == CEDAR_B200_ENTROPY_CABAC;
+    g.frame_bytes = (unsigned long long)g.W * g.H * 3 / 2;
+    h->K = cfg->keyframe_interval;
+    h->F = cfg->max_clip_frames > 0 ? cfg->max_clip_frames : 1;
+    int gops = (h->F + h->K - 1) / h->K;
+    int lanes = cfg->gops_in_flight > 0 ? cfg->gops_in_flight : 16;
+    if (lanes > gops)
+        lanes = gops;
+    while (lanes > 1 && (long)lanes * g.mbh > 148L * 16) // keep every wavefront CTA resident
+        lanes--;
+    h->L = lanes;
+    h->raw_frame_bytes = (size_t)g.src_w * g.src_h * (g.src_format == CEDAR_B200_FORMAT_NV16 ? 2 : 3) /
+                         (g.src_format == CEDAR_B200_FORMAT_NV16 ? 1 : 2);
+    h->prof = false;
+    memset(h->prof_ms, 0, sizeof(h->prof_ms));
+    memset(h->prof_n, 0, sizeof(h->prof_n));
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return -ENODEV;
+    }
+    if (me_smem_bytes(g.R) > 48 * 1024)
+        cudaFuncSetAttribute(me_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)me_smem_bytes(g.R));
+    r = alloc_buffers(h);
+    if (r) {
+        free_buffers(h);
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return r;
+    }
+    // SPS + PPS, emitted once before the first frame (cedar.c:1058-1061)
+    int n1 = cedar_b200_write_sps(cfg, h->prefix, 32);
+    int n2 = cedar_b200_write_pps(cfg, h->prefix + n1, 32);
+    h->prefix_len = n1 + n2;
+    io->input_luma = h->h_in_luma;
+    io->input_luma_size = h->in_luma_size;
+    io->input_chroma = h->h_in_chroma;
+    io->input_chroma_size = h->in_chroma_size;
+    io->bytestream = h->h_bytestream;
+    io->bytestream_size = h->bytestream_size;
+    *out = h;
+    return 0;
+}
+
+int cedar_b200_encode_frame(cedar_b200_handle *h)
+{
+    if (!h)
+        return -EINVAL; // cedar.c:1039-1043: not configured
+    auto t0 = std::chrono::steady_clock::now();
+    const Geom &g = h->g;
+    size_t luma_bytes = (size_t)g.src_w * g.src_h;
+    CK(cudaMemcpyAsync(h->d_raw, h->h_in_luma, luma_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_raw + luma_bytes, h->h_in_chroma, h->raw_frame_bytes - luma_bytes, cudaMemcpyHostToDevice,
+                       h->stream));
+    int r;
+    if ((r = upload_headers(h, 1, h->frame_p_count)))
+        return r;
+    if ((r = begin_stream(h, 1)))
+        return r;
+    Step s = {1, 0, 1, 1};
+    if ((r = encode_step(h, s, h->frame_p_count)))
+        return r;
+    if ((r = finish_stream(h, 1, h->frame_p_count, h->frame_count == 0)))
+        return r;
+    CK(cudaMemcpyAsync(h->h_total, h->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_error, h->eb.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_sse, h->d_sse, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if ((r = check_error(h)))
+        return r;
+    size_t total = (size_t)*h->h_total;
+    if (total == 0 || total > (size_t)h->bytestream_size)
+        return -ENOMEM;
+    CK(cudaMemcpyAsync(h->h_bytestream, h->d_out, total, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->last_nframes = 1;
+    // cedar.c:1193-1196 (the reference swap of :1198-1201 is the `t & 1` buffer choice in encode_step)
+    h->frame_p_count++;
+    if (h->frame_p_count == h->K)
+        h->frame_p_count = 0;
+    h->frame_count++;
+    h->busy_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+    return (int)total;
+}
+
+void *cedar_b200_clip_input(cedar_b200_handle *h, size_t *frame_bytes)
+{
+    if (!h)
+        return nullptr;
+    if (frame_bytes)
+        *frame_bytes = h->raw_frame_bytes;
+    return h->h_clip_in;
+}
+
+int cedar_b200_clip_upload(cedar_b200_handle *h, int nframes)
+{
+    if (!h || !h->h_clip_in || nframes <= 0 || nframes > h->F)
+        return -EINVAL;
+    CK(cudaMemcpyAsync(h->d_raw, h->h_clip_in, h->raw_frame_bytes * nframes, cudaMemcpyHostToDevice, h->stream));
+    return 0;
+}
+
+int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_index)
+{
+    if (!h || nframes <= 0 || nframes > h->F || first_frame_index < 0 || (first_frame_index % h->K) != 0)
+        return -EINVAL;
+    auto t0 = std::chrono::steady_clock::now();
+    int r;
+    if ((r = upload_headers(h, nframes, 0)))
+        return r;
+    if ((r = begin_stream(h, nframes)))
+        return r;
+    const int K = h->K, gops = (nframes + K - 1) / K;
+    for (int gop0 = 0; gop0 < gops; gop0 += h->L) {
+        int nl = gops - gop0 < h->L ? gops - gop0 : h->L;
+        for (int t = 0; t < K; t++) {
+            Step s = {nl, gop0 * K + t, K, nframes};
+            if (s.frame0 >= nframes)
+                break;
+            if ((r = encode_step(h, s, t)))
+                return r;
+        }
+    }
+    if ((r = finish_stream(h, nframes, 0, first_frame_index == 0)))
+        return r;
+    h->last_nframes = nframes;
+    h->busy_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+long long cedar_b200_clip_download(cedar_b200_handle *h, const uint8_t **out, int *frame_bytes)
+{
+    if (!h || !h->h_clip_out || h->last_nframes <= 0)
+        return -EINVAL;
+    int n = h->last_nframes;
+    CK(cudaMemcpyAsync(h->h_total, h->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_error, h->eb.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_frame_bytes, h->d_frame_bytes, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(h->h_sse, h->d_sse, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int r = check_error(h);
+    if (r)
+        return r;
+    size_t total = (size_t)*h->h_total;
+    if (total == 0 || total > h->out_cap)
+        return -ENOMEM;
+    CK(cudaMemcpyAsync(h->h_clip_out, h->d_out, total, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (out)
+        *out = h->h_clip_out;
+    if (frame_bytes)
+        memcpy(frame_bytes, h->h_frame_bytes, sizeof(int) * n);
+    return (long long)total;
+}
+
+int cedar_b200_stats(cedar_b200_handle *h, double *sse_y, int nframes)
+{
+    if (!h || !sse_y || nframes > h->last_nframes)
+        return -EINVAL;
+    for (int i = 0; i < nframes; i++)
+        sse_y[i] = (double)h->h_sse[i];
+    return 0;
+}
+
+int cedar_b200_profile_enable(cedar_b200_handle *h, int enable)
+{
+    if (!h)
+        return -EINVAL;
+    if (!enable && h->prof)
+        prof_collect(h);
+    h->prof = enable != 0;
+    return 0;
+}
+
+int cedar_b200_profile_read(cedar_b200_handle *h, const char **names, float *ms, int *launches, int cap, int reset)
+{
+    if (!h)
+        return -EINVAL;
+    prof_collect(h);
+    int n = 0;
+    for (int i = 0; i < K_COUNT && n < cap; i++) {
+        if (!h->prof_n[i])
+            continue;
+        if (names)
+            names[n] = kKernelNames[i];
+        if (ms)
+            ms[n] = h->prof_ms[i];
+        if (launches)
+            launches[n] = h->prof_n[i];
+        n++;
+    }
+    if (reset) {
+        memset(h->prof_ms, 0, sizeof(h->prof_ms));
+        memset(h->prof_n, 0, sizeof(h->prof_n));
+    }
+    return n;
+}
+
+long long cedar_b200_launch_count(cedar_b200_handle *h) { return h ? h->launches : 0; }
+
+long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_t cap)
+{
+    if (!h || !dst)
+        return -EINVAL;
+    const Geom &g = h->g;
+    const void *src = nullptr;
+    size_t n = 0;
+    switch (what) {
+    case 0: src = h->d_src, n = g.frame_bytes; break;
+    case 1: src = h->d_unf, n = g.frame_bytes; break;
+    case 2: src = h->d_rec[h->last_cur], n = g.frame_bytes; break;
+    case 3: src = h->d_mbi, n = sizeof(MbInfo) * g.nmb; break;
+    case 4: src = h->d_nnz, n = (size_t)NNZ_STRIDE * g.nmb; break;
+    case 5: src = h->d_coef, n = sizeof(int16_t) * COEF_STRIDE * g.nmb; break;
+    default: return -EINVAL;
+    }
+    if (n > cap)
+        return -ENOMEM;
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost));
+    return (long long)n;
+}
+
+void cedar_b200_close(cedar_b200_handle *h)
+{
+    if (!h)
+        return;
+    cudaStreamSynchronize(h->stream);
+    prof_collect(h);
+    double total_ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - h->t_open).count();
+    // cedar.c:715-719 prints "Time spent: <waiting>/<total>ns" at release
+    fprintf(stderr, "cedar_b200: Time spent: %.0f/%.0fns\n", h->busy_ns, total_ns);
+    for (cudaEvent_t e : h->ev_pool)
+        cudaEventDestroy(e);
+    free_buffers(h);
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+} // extern "C"

@@ -1,0 +1,624 @@
+// Entropy coding of one macroblock: CAVLC bit strings and CABAC binarisation, plus the serial
+// CABAC arithmetic coder.  Written once, compiled as device code (kernels.cuh) and as host code
+// (host_harness.cpp, CPU unit tests only).  Replaces the entropy stage of the Cedar VE that the
+// reference selects with PARA0 bit 8 (kernel/cedar.c:1155-1158) and never shows in source.
+//
+// Every function takes a "sink": a counting sink (pass 1: sizes, then a prefix sum gives each
+// macroblock its offset) or a writing sink (pass 2: scatter at that offset).  One code path for
+// both passes keeps sizes and contents consistent by construction.
+#pragma once
+#include "h264_core.cuh"
+
+namespace cedar {
+
+struct FrameSyntax {
+    const MbInfo *mbi;
+    const uint8_t *nnz;   // [nmb][NNZ_STRIDE]
+    const int16_t *coef;  // [nmb][COEF_STRIDE]
+    int mbw, mbh;
+};
+
+// total_coeff of the 4x4 block left of / above block `blk`; -1 when outside the picture.
+// kind 0: luma (blk = luma4x4BlkIdx), 1: Cb AC, 2: Cr AC (blk 0..3 raster)
+HD int nnz_left(const FrameSyntax &fs, int mbx, int mby, int kind, int blk)
+{
+    const uint8_t *cur = fs.nnz + (size_t)(mby * fs.mbw + mbx) * NNZ_STRIDE;
+    if (kind == 0) {
+        int bx = blk_x(blk), by = blk_y(blk);
+        if (bx > 0)
+            return cur[xy2blk(bx - 1, by)];
+        if (mbx == 0)
+            return -1;
+        return (cur - NNZ_STRIDE)[xy2blk(3, by)];
+    }
+    int base = kind == 1 ? NNZ_CB : NNZ_CR, bx = blk & 1, by = blk >> 1;
+    if (bx > 0)
+        return cur[base + by * 2];
+    if (mbx == 0)
+        return -1;
+    return (cur - NNZ_STRIDE)[base + by * 2 + 1];
+}
+
+HD int nnz_top(const FrameSyntax &fs, int mbx, int mby, int kind, int blk)
+{
+    const uint8_t *cur = fs.nnz + (size_t)(mby * fs.mbw + mbx) * NNZ_STRIDE;
+    if (kind == 0) {
+        int bx = blk_x(blk), by = blk_y(blk);
+        if (by > 0)
+            return cur[xy2blk(bx, by - 1)];
+        if (mby == 0)
+            return -1;
+        return (cur - (size_t)fs.mbw * NNZ_STRIDE)[xy2blk(bx, 3)];
+    }
+    int base = kind == 1 ? NNZ_CB : NNZ_CR, bx = blk & 1, by = blk >> 1;
+    if (by > 0)
+        return cur[base + bx];
+    if (mby == 0)
+        return -1;
+    return (cur - (size_t)fs.mbw * NNZ_STRIDE)[base + 2 + bx];
+}
+
+// =============================================================================================
+// CAVLC
+// =============================================================================================
+struct BitCount {
+    unsigned n = 0;
+    HD void put(uint32_t, int len) { n += (unsigned)len; }
+};
+
+HD uint32_t bswap32_(uint32_t v)
+{
+#ifdef __CUDACC__
+    return __byte_perm(v, 0, 0x0123);
+#else
+    return __builtin_bswap32(v);
+#endif
+}
+
+// Writes MSB-first bits into a zero-initialised byte stream held as 32-bit words.  Words that may
+// be shared with the neighbouring macroblock (first and last) are OR-ed atomically.
+struct BitScatter {
+    uint32_t *buf;
+    unsigned long long acc = 0; // bits are left aligned in acc
+    unsigned word;              // index of the 32-bit word acc's top bits belong to
+    int n;                      // valid bits in acc
+    bool first = true;
+    HD BitScatter(uint32_t *b, unsigned long long bitpos) : buf(b), word((unsigned)(bitpos >> 5)), n((int)(bitpos & 31)) {}
+    HD void store(uint32_t w, bool atomic)
+    {
+        if (!w && atomic)
+            return;
+        uint32_t v = bswap32_(w);
+#ifdef __CUDACC__
+        if (atomic)
+            atomicOr(buf + word, v);
+        else
+            buf[word] = v;
+#else
+        if (atomic)
+            buf[word] |= v;
+        else
+            buf[word] = v;
+#endif
+    }
+    HD void put(uint32_t v, int len) // len <= 32
+    {
+        if (!len)
+            return;
+        acc |= (unsigned long long)v << (64 - n - len);
+        n += len;
+        if (n >= 32) {
+            store((uint32_t)(acc >> 32), first);
+            first = false;
+            word++;
+            acc <<= 32;
+            n -= 32;
+        }
+    }
+    HD void flush()
+    {
+        if (n > 0)
+            store((uint32_t)(acc >> 32), true);
+    }
+};
+
+template <class S> HD void put_ue(S &s, unsigned v)
+{
+    v++;
+    s.put(v, (32 - (31 - ilog2_(v))) * 2 - 1);
+}
+template <class S> HD void put_se(S &s, int v)
+{
+    v = 2 * v - 1;
+    v ^= (v >> 31);
+    put_ue(s, (unsigned)v);
+}
+
+HD int cavlc_nc(const FrameSyntax &fs, int mbx, int mby, int kind, int blk)
+{
+    int a = nnz_left(fs, mbx, mby, kind, blk), b = nnz_top(fs, mbx, mby, kind, blk);
+    if (a >= 0 && b >= 0)
+        return (a + b + 1) >> 1;
+    if (a >= 0)
+        return a;
+    if (b >= 0)
+        return b;
+    return 0;
+}
+
+// residual_block_cavlc of lev[0 .. max_coeff-1] (zig-zag order); nC < 0 selects the chroma DC tables
+template <class S> HD void cavlc_block(S &s, const int16_t *lev, int max_coeff, int nC)
+{
+    int total = 0, last = -1, t1 = 0;
+    bool t1_open = true;
+    for (int i = max_coeff - 1; i >= 0; i--) {
+        int v = lev[i];
+        if (v) {
+            if (last < 0)
+                last = i;
+            if (t1_open && t1 < 3 && (v == 1 || v == -1))
+                t1++;
+            else
+                t1_open = false;
+            total++;
+        }
+    }
+    if (nC < 0)
+        s.put(h264_chroma_dc_coeff_token_bits[4 * total + t1], h264_chroma_dc_coeff_token_len[4 * total + t1]);
+    else {
+        int tab = nC < 2 ? 0 : (nC < 4 ? 1 : (nC < 8 ? 2 : 3));
+        s.put(h264_coeff_token_bits[tab][4 * total + t1], h264_coeff_token_len[tab][4 * total + t1]);
+    }
+    if (!total)
+        return;
+    // levels, highest frequency first
+    int k = 0, suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
+    for (int i = last; i >= 0; i--) {
+        int level = lev[i];
+        if (!level)
+            continue;
+        if (k < t1) {
+            s.put(level < 0, 1);
+            k++;
+            continue;
+        }
+        int code = level > 0 ? 2 * level - 2 : -2 * level - 1;
+        if (k == t1 && t1 < 3)
+            code -= 2;
+        int thresh = suffix_len == 0 ? 14 : (15 << suffix_len);
+        if (code < thresh) {
+            s.put(1, (code >> suffix_len) + 1);
+            if (suffix_len)
+                s.put((uint32_t)code & ((1u << suffix_len) - 1), suffix_len);
+        } else if (suffix_len == 0 && code < 30) {
+            s.put(1, 15);
+            s.put((uint32_t)(code - 14), 4);
+        } else {
+            int c = code - (suffix_len == 0 ? 30 : (15 << suffix_len)), prefix = 15;
+            while (c >= (1 << (prefix - 3))) {
+                c -= 1 << (prefix - 3);
+                prefix++;
+            }
+            s.put(1, prefix + 1);
+            s.put((uint32_t)c, prefix - 3);
+        }
+        if (suffix_len == 0)
+            suffix_len = 1;
+        if (iabs_(level) > (3 << (suffix_len - 1)) && suffix_len < 6)
+            suffix_len++;
+        k++;
+    }
+    int zeros = last + 1 - total;
+    if (total < max_coeff) {
+        if (nC < 0)
+            s.put(h264_chroma_dc_total_zeros_bits[total - 1][zeros], h264_chroma_dc_total_zeros_len[total - 1][zeros]);
+        else
+            s.put(h264_total_zeros_bits[total - 1][zeros], h264_total_zeros_len[total - 1][zeros]);
+    }
+    // run_before for every coefficient but the lowest-frequency one
+    int zeros_left = zeros, i = last, done = 0;
+    while (zeros_left > 0 && done < total - 1) {
+        int run = 0, j = i - 1;
+        while (j >= 0 && !lev[j]) {
+            run++;
+            j--;
+        }
+        int zl = imin_(zeros_left, 7) - 1;
+        s.put(h264_run_before_bits[zl][run], h264_run_before_len[zl][run]);
+        zeros_left -= run;
+        i = j;
+        done++;
+    }
+}
+
+// One macroblock of slice data.  `skip_run` = number of P_Skip macroblocks directly before it.
+// mb_index == nmb is the virtual terminal element: trailing skip run + rbsp_slice_trailing_bits
+// stop bit (alignment zeros come for free from the zero-initialised buffer).
+template <class S> HD void cavlc_mb(S &s, const FrameSyntax &fs, int mb_index, int frame_i, int skip_run)
+{
+    int nmb = fs.mbw * fs.mbh;
+    if (mb_index == nmb) {
+        if (skip_run)
+            put_ue(s, (unsigned)skip_run);
+        s.put(1, 1);
+        return;
+    }
+    const MbInfo &mb = fs.mbi[mb_index];
+    if (mb.type == MB_PSKIP)
+        return;
+    int mbx = mb_index % fs.mbw, mby = mb_index / fs.mbw;
+    const int16_t *coef = fs.coef + (size_t)mb_index * COEF_STRIDE;
+    int cbpl = mb.cbp & 15, cbpc = mb.cbp >> 4;
+    if (!frame_i)
+        put_ue(s, (unsigned)skip_run);
+    if (mb.type == MB_I16x16) {
+        int t = 1 + mb.i16_mode + 4 * cbpc + (cbpl ? 12 : 0);
+        put_ue(s, (unsigned)(t + (frame_i ? 0 : 5)));
+        put_ue(s, mb.chroma_mode);
+        put_se(s, 0); // mb_qp_delta
+        cavlc_block(s, coef + 16 * 16, 16, cavlc_nc(fs, mbx, mby, 0, 0));
+        if (cbpl)
+            for (int b = 0; b < 16; b++)
+                cavlc_block(s, coef + b * 16 + 1, 15, cavlc_nc(fs, mbx, mby, 0, b));
+    } else {
+        put_ue(s, 0); // P_L0_16x16
+        put_se(s, mb.mvd[0]);
+        put_se(s, mb.mvd[1]);
+        put_ue(s, h264_cbp_to_codenum_inter[mb.cbp]);
+        if (mb.cbp)
+            put_se(s, 0); // mb_qp_delta
+        for (int b = 0; b < 16; b++)
+            if (cbpl & (1 << (b >> 2)))
+                cavlc_block(s, coef + b * 16, 16, cavlc_nc(fs, mbx, mby, 0, b));
+    }
+    if (cbpc) {
+        cavlc_block(s, coef + 17 * 16, 4, -1);
+        cavlc_block(s, coef + 17 * 16 + 4, 4, -1);
+    }
+    if (cbpc == 2)
+        for (int c = 0; c < 2; c++)
+            for (int b = 0; b < 4; b++)
+                cavlc_block(s, coef + (18 + c * 4 + b) * 16 + 1, 15, cavlc_nc(fs, mbx, mby, 1 + c, b));
+}
+
+// =============================================================================================
+// CABAC binarisation.  A bin is 16 bits: ctxIdx (0..459) in bits 0..9, BIN_BYPASS / BIN_TERM flags,
+// value in bit 15.  The serial coder below consumes the stream.
+// =============================================================================================
+enum { BIN_BYPASS = 1 << 10, BIN_TERM = 1 << 11, BIN_VAL = 1 << 15 };
+
+struct BinCount {
+    unsigned n = 0;
+    HD void bin(int, int) { n++; }
+    HD void bypass(int) { n++; }
+    HD void term(int) { n++; }
+};
+
+struct BinWrite {
+    uint16_t *p;
+    HD explicit BinWrite(uint16_t *q) : p(q) {}
+    HD void bin(int ctx, int v) { *p++ = (uint16_t)(ctx | (v ? BIN_VAL : 0)); }
+    HD void bypass(int v) { *p++ = (uint16_t)(BIN_BYPASS | (v ? BIN_VAL : 0)); }
+    HD void term(int v) { *p++ = (uint16_t)(BIN_TERM | (v ? BIN_VAL : 0)); }
+};
+
+template <class S> HD void cabac_ueg_bypass(S &s, int k, int v)
+{
+    while (v >= (1 << k)) {
+        s.bypass(1);
+        v -= 1 << k;
+        k++;
+    }
+    s.bypass(0);
+    while (k--)
+        s.bypass((v >> k) & 1);
+}
+
+// coded_block_flag of the neighbour (left / top) for ctxIdxInc
+HD int cbf_neighbour(const FrameSyntax &fs, int mbx, int mby, int cat, int comp, int blk, int left, int intra)
+{
+    int navail = left ? mbx > 0 : mby > 0;
+    int nidx = mby * fs.mbw + mbx - (left ? 1 : fs.mbw);
+    if (cat == 0) {
+        if (!navail)
+            return intra;
+        return fs.mbi[nidx].type == MB_I16x16 ? fs.nnz[(size_t)nidx * NNZ_STRIDE + NNZ_DC16] != 0 : 0;
+    }
+    if (cat == 3) {
+        if (!navail)
+            return intra;
+        return fs.nnz[(size_t)nidx * NNZ_STRIDE + NNZ_CBDC + comp] != 0;
+    }
+    int kind = cat == 4 ? 1 + comp : 0;
+    int v = left ? nnz_left(fs, mbx, mby, kind, blk) : nnz_top(fs, mbx, mby, kind, blk);
+    if (v < 0)
+        return intra;
+    return v != 0;
+}
+
+template <class S> HD void cabac_block(S &s, const int16_t *lev, int n, int cat, int cbf_inc)
+{
+    const int cbf_off[5] = {0, 4, 8, 12, 16}, sig_off[5] = {0, 15, 29, 44, 47}, abs_off[5] = {0, 10, 20, 30, 39};
+    int last = -1;
+    for (int i = 0; i < n; i++)
+        if (lev[i])
+            last = i;
+    s.bin(85 + cbf_off[cat] + cbf_inc, last >= 0);
+    if (last < 0)
+        return;
+    for (int i = 0; i < n - 1; i++) {
+        int inc = cat == 3 ? imin_(i, 2) : i;
+        if (lev[i]) {
+            s.bin(105 + sig_off[cat] + inc, 1);
+            s.bin(166 + sig_off[cat] + inc, i == last);
+            if (i == last)
+                break;
+        } else
+            s.bin(105 + sig_off[cat] + inc, 0);
+    }
+    int eq1 = 0, gt1 = 0;
+    for (int i = last; i >= 0; i--) {
+        int v = lev[i];
+        if (!v)
+            continue;
+        int a = iabs_(v) - 1;
+        int ctx = 227 + abs_off[cat] + (gt1 ? 0 : imin_(4, 1 + eq1));
+        if (a == 0) {
+            s.bin(ctx, 0);
+            eq1++;
+        } else {
+            s.bin(ctx, 1);
+            ctx = 227 + abs_off[cat] + 5 + imin_(4 - (cat == 3), gt1);
+            int pre = imin_(a, 14);
+            for (int j = 1; j < pre; j++)
+                s.bin(ctx, 1);
+            if (a < 14)
+                s.bin(ctx, 0);
+            else
+                cabac_ueg_bypass(s, 0, a - 14);
+            gt1++;
+        }
+        s.bypass(v < 0);
+    }
+}
+
+template <class S> HD void cabac_mvd(S &s, int base, int mvd, int sum_abs)
+{
+    int inc = sum_abs < 3 ? 0 : (sum_abs > 32 ? 2 : 1);
+    int a = iabs_(mvd);
+    if (a == 0) {
+        s.bin(base + inc, 0);
+        return;
+    }
+    s.bin(base + inc, 1);
+    int pre = imin_(a, 9);
+    for (int i = 1; i < pre; i++)
+        s.bin(base + imin_(2 + i, 6), 1);
+    if (a < 9)
+        s.bin(base + imin_(2 + pre, 6), 0);
+    else
+        cabac_ueg_bypass(s, 3, a - 9);
+    s.bypass(mvd < 0);
+}
+
+// All bins of one macroblock including its end_of_slice_flag.
+template <class S> HD void cabac_mb(S &s, const FrameSyntax &fs, int mb_index, int frame_i)
+{
+    int nmb = fs.mbw * fs.mbh;
+    int mbx = mb_index % fs.mbw, mby = mb_index / fs.mbw;
+    const MbInfo &mb = fs.mbi[mb_index];
+    const MbInfo *A = mbx > 0 ? &mb - 1 : nullptr, *B = mby > 0 ? &mb - fs.mbw : nullptr;
+    const int16_t *coef = fs.coef + (size_t)mb_index * COEF_STRIDE;
+    int intra = is_intra(mb.type);
+    int end = mb_index == nmb - 1;
+    if (!frame_i) {
+        int inc = (A && A->type != MB_PSKIP) + (B && B->type != MB_PSKIP);
+        s.bin(11 + inc, mb.type == MB_PSKIP);
+        if (mb.type == MB_PSKIP) {
+            s.term(end);
+            return;
+        }
+    }
+    int cbpl = mb.cbp & 15, cbpc = mb.cbp >> 4;
+    if (mb.type == MB_I16x16) {
+        int c0, c1, c2, c3, c4, c5;
+        if (frame_i) {
+            int inc = (A && A->type != MB_I4x4) + (B && B->type != MB_I4x4);
+            c0 = 3 + inc, c1 = 3 + 3, c2 = 3 + 4, c3 = 3 + 5, c4 = 3 + 6, c5 = 3 + 7;
+        } else {
+            s.bin(14, 1);
+            c0 = 17, c1 = 17 + 1, c2 = 17 + 2, c3 = 17 + 2, c4 = 17 + 3, c5 = 17 + 3;
+        }
+        s.bin(c0, 1);
+        s.term(0);
+        s.bin(c1, cbpl != 0);
+        if (cbpc == 0)
+            s.bin(c2, 0);
+        else {
+            s.bin(c2, 1);
+            s.bin(c3, cbpc >> 1);
+        }
+        s.bin(c4, mb.i16_mode >> 1);
+        s.bin(c5, mb.i16_mode & 1);
+    } else {
+        s.bin(14, 0);
+        s.bin(15, 0);
+        s.bin(16, 0);
+    }
+    if (intra) {
+        int inc = (A && is_intra(A->type) && A->chroma_mode != 0) + (B && is_intra(B->type) && B->chroma_mode != 0);
+        int m = mb.chroma_mode;
+        s.bin(64 + inc, m > 0);
+        if (m > 0) {
+            s.bin(64 + 3, m > 1);
+            if (m > 1)
+                s.bin(64 + 3, m > 2);
+        }
+    } else {
+        for (int k = 0; k < 2; k++) {
+            int sa = (A && A->type == MB_P16x16 ? iabs_(A->mvd[k]) : 0) + (B && B->type == MB_P16x16 ? iabs_(B->mvd[k]) : 0);
+            cabac_mvd(s, k ? 47 : 40, mb.mvd[k], sa);
+        }
+    }
+    if (mb.type != MB_I16x16) {
+        int cbp_a = A ? (A->cbp & 15) : 15, cbp_b = B ? (B->cbp & 15) : 15;
+        for (int b8 = 0; b8 < 4; b8++) {
+            int la = (b8 & 1) ? (cbpl >> (b8 - 1)) & 1 : (cbp_a >> (b8 + 1)) & 1;
+            int lb = (b8 & 2) ? (cbpl >> (b8 - 2)) & 1 : (cbp_b >> (b8 + 2)) & 1;
+            s.bin(73 + (!la) + 2 * (!lb), (cbpl >> b8) & 1);
+        }
+        int ca = A ? (A->cbp >> 4) : 0, cb = B ? (B->cbp >> 4) : 0;
+        s.bin(77 + (ca > 0) + 2 * (cb > 0), cbpc > 0);
+        if (cbpc > 0)
+            s.bin(77 + 4 + (ca == 2) + 2 * (cb == 2), cbpc == 2);
+    }
+    if (mb.type == MB_I16x16 || mb.cbp)
+        s.bin(60, 0); // mb_qp_delta == 0 everywhere => ctxIdxInc 0
+    if (mb.type == MB_I16x16) {
+        int inc = cbf_neighbour(fs, mbx, mby, 0, 0, 0, 1, intra) + 2 * cbf_neighbour(fs, mbx, mby, 0, 0, 0, 0, intra);
+        cabac_block(s, coef + 16 * 16, 16, 0, inc);
+        if (cbpl)
+            for (int b = 0; b < 16; b++) {
+                inc = cbf_neighbour(fs, mbx, mby, 1, 0, b, 1, intra) + 2 * cbf_neighbour(fs, mbx, mby, 1, 0, b, 0, intra);
+                cabac_block(s, coef + b * 16 + 1, 15, 1, inc);
+            }
+    } else {
+        for (int b = 0; b < 16; b++)
+            if (cbpl & (1 << (b >> 2))) {
+                int inc = cbf_neighbour(fs, mbx, mby, 2, 0, b, 1, intra) + 2 * cbf_neighbour(fs, mbx, mby, 2, 0, b, 0, intra);
+                cabac_block(s, coef + b * 16, 16, 2, inc);
+            }
+    }
+    if (cbpc)
+        for (int comp = 0; comp < 2; comp++) {
+            int inc = cbf_neighbour(fs, mbx, mby, 3, comp, 0, 1, intra) + 2 * cbf_neighbour(fs, mbx, mby, 3, comp, 0, 0, intra);
+            cabac_block(s, coef + 17 * 16 + comp * 4, 4, 3, inc);
+        }
+    if (cbpc == 2)
+        for (int comp = 0; comp < 2; comp++)
+            for (int b = 0; b < 4; b++) {
+                int inc = cbf_neighbour(fs, mbx, mby, 4, comp, b, 1, intra) + 2 * cbf_neighbour(fs, mbx, mby, 4, comp, b, 0, intra);
+                cabac_block(s, coef + (18 + comp * 4 + b) * 16 + 1, 15, 4, inc);
+            }
+    s.term(end);
+}
+
+// =============================================================================================
+// Serial CABAC arithmetic coder (H.264 9.3.4) with byte-wise output and carry propagation.
+// `low` keeps the 10-bit coding window in bits 9..0 and queue+8 not-yet-written bits above it.
+// =============================================================================================
+struct CabacCoder {
+    uint8_t *out;      // output bytes (first byte written at out[0])
+    unsigned pos = 0;  // bytes written
+    uint32_t low = 0, range = 510;
+    int queue = -9, outstanding = 0;
+    uint8_t *state;    // [460] pStateIdx << 1 | valMPS
+
+    HD void init_states(int frame_i, int qp)
+    {
+        for (int i = 0; i < 460; i++) {
+            int m = frame_i ? h264_cabac_init_I[i][0] : h264_cabac_init_P0[i][0];
+            int n = frame_i ? h264_cabac_init_I[i][1] : h264_cabac_init_P0[i][1];
+            int pre = clip3_(1, 126, ((m * clip3_(0, 51, qp)) >> 4) + n);
+            state[i] = (uint8_t)(pre <= 63 ? (63 - pre) << 1 : (((pre - 64) << 1) | 1));
+        }
+    }
+    HD void put_byte()
+    {
+        uint32_t o = low >> (queue + 10);
+        low &= (0x400u << queue) - 1;
+        queue -= 8;
+        if ((o & 0xff) == 0xff) {
+            outstanding++;
+            return;
+        }
+        uint32_t carry = o >> 8;
+        if (pos > 0)
+            out[pos - 1] = (uint8_t)(out[pos - 1] + carry);
+        while (outstanding > 0) {
+            out[pos++] = (uint8_t)(carry - 1);
+            outstanding--;
+        }
+        out[pos++] = (uint8_t)o;
+    }
+    HD void renorm()
+    {
+        // range in [2, 510]; shift so that range >= 256
+        int shift = range >= 256 ? 0 : (8 - ilog2_(range));
+        range <<= shift;
+        low <<= shift;
+        queue += shift;
+        if (queue >= 0)
+            put_byte();
+    }
+    HD void decision(int ctx, int bin)
+    {
+        int st = state[ctx] >> 1, mps = state[ctx] & 1;
+        uint32_t lps = h264_range_lps[st][(range >> 6) & 3];
+        range -= lps;
+        if (bin != mps) {
+            low += range;
+            range = lps;
+            if (st == 0)
+                mps ^= 1;
+            st = h264_next_state_lps[st];
+        } else
+            st = h264_next_state_mps[st];
+        state[ctx] = (uint8_t)((st << 1) | mps);
+        renorm();
+    }
+    HD void bypass(int bin)
+    {
+        low <<= 1;
+        if (bin)
+            low += range;
+        queue++;
+        if (queue >= 0)
+            put_byte();
+    }
+    HD void terminate(int bin)
+    {
+        range -= 2;
+        if (bin) {
+            low += range;
+            range = 2;
+        }
+        renorm();
+        if (bin) {
+            // 9.3.4.5: put_bit(low >> 9 & 1); write_bits((low >> 7 & 3) | 1, 2): push window bits 9, 8
+            // and the stop bit out, then pad the last byte with zeros.
+            low = (low & ~0x7fu) | 0x80u;
+            low <<= 3;
+            queue += 3;
+            if (queue >= 0)
+                put_byte();
+            if (queue > -8) {
+                int k = -queue;
+                low <<= k;
+                queue += k;
+                put_byte();
+            }
+            while (outstanding > 0) {
+                out[pos++] = 0xff;
+                outstanding--;
+            }
+        }
+    }
+    HD void code(uint16_t b)
+    {
+        int v = (b & BIN_VAL) != 0;
+        if (b & BIN_BYPASS)
+            bypass(v);
+        else if (b & BIN_TERM)
+            terminate(v);
+        else
+            decision(b & 0x3ff, v);
+    }
+};
+
+// Emulation prevention: an escape byte 0x03 goes before byte i iff byte i <= 3 and the run of zero
+// bytes directly before it has an even length >= 2 (equivalent to the sequential rule
+// "after 00 00 insert 03 if the next byte <= 3, then restart counting").
+HD int epb_needed(int byte, unsigned zero_run) { return byte <= 3 && zero_run >= 2 && !(zero_run & 1); }
+
+} // namespace cedar

@@ -1,0 +1,1285 @@
+// sm_100a CUDA kernels of the B200 H.264 encoder: the replacement for the Cedar VE frame encode that
+// the reference triggers with one register write (kernel/cedar.c:1176) and has no source for.
+// Row numbers K0..K9 are SURVEY.md 8a's kernel rows.  None of this is a dense contraction, so
+// there are no tensor-core instructions here: integer SIMD-video (VABSDIFF4) for motion search,
+// HBM / L2 streaming and dependency-ordered wavefronts for everything else.
+//
+// Many closed GOPs ("lanes") are encoded in lock step: blockIdx.y = lane, lane l holds stream
+// frame step.frame0 + l * step.lane_stride.
+#pragma once
+#include "entropy.cuh"
+
+namespace cedar {
+
+struct Step {
+    int nlanes;      // lanes launched
+    int frame0;      // clip frame index held by lane 0
+    int lane_stride; // frames between consecutive lanes (the GOP length)
+    int nframes;     // frames in the clip; lanes beyond it idle
+};
+__device__ __forceinline__ int lane_frame(const Step &s, int lane)
+{
+    int f = s.frame0 + lane * s.lane_stride;
+    return f < s.nframes ? f : -1;
+}
+
+__device__ __forceinline__ int ld_volatile(const int *p) { return *(const volatile int *)p; }
+__device__ __forceinline__ void st_volatile(int *p, int v) { *(volatile int *)p = v; }
+
+// ================================================================================================
+// K0 ingest: packed NV12 / NV16 (w x h) -> planar 4:2:0 at the coded size with edge replication.
+// Replaces the ISP input stage (cedar.c:1068-1080).  One thread = 4 output bytes.  HBM bound.
+// ================================================================================================
+__global__ void ingest_kernel(Geom g, Step s, const uint8_t *__restrict__ raw, size_t raw_frame_bytes,
+                              uint8_t *__restrict__ src)
+{
+    int f = lane_frame(s, blockIdx.y);
+    if (f < 0)
+        return;
+    size_t o = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (o >= g.frame_bytes)
+        return;
+    const uint8_t *luma = raw + (size_t)f * raw_frame_bytes;
+    const uint8_t *chroma = luma + (size_t)g.src_w * g.src_h;
+    uint8_t *dst = src + (size_t)blockIdx.y * g.frame_bytes;
+    size_t ysz = (size_t)g.W * g.H, csz = (size_t)g.CW * g.CH;
+    uint32_t out = 0;
+    if (o < ysz) {
+        int y = (int)(o / g.W), x = (int)(o % g.W);
+        const uint8_t *row = luma + (size_t)imin_(y, g.src_h - 1) * g.src_w;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            out |= (uint32_t)row[imin_(x + k, g.src_w - 1)] << (8 * k);
+    } else {
+        size_t o2 = o - ysz;
+        int c = o2 >= csz;
+        size_t o3 = o2 - (c ? csz : 0);
+        int y = (int)(o3 / g.CW), x = (int)(o3 % g.CW);
+        int sy = imin_(y, g.src_h / 2 - 1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int sx = imin_(x + k, g.src_w / 2 - 1);
+            int v;
+            if (g.src_format == 1) { // NV16 -> 4:2:0: rounding average of the two chroma rows
+                int a = chroma[(size_t)(2 * sy) * g.src_w + 2 * sx + c];
+                int b = chroma[(size_t)(2 * sy + 1) * g.src_w + 2 * sx + c];
+                v = (a + b + 1) >> 1;
+            } else
+                v = chroma[(size_t)sy * g.src_w + 2 * sx + c];
+            out |= (uint32_t)v << (8 * k);
+        }
+    }
+    *(uint32_t *)(dst + o) = out;
+}
+
+// ================================================================================================
+// K1 integer motion estimation: exhaustive +-R SAD search against the previous deblocked
+// reconstruction (edge clamped).  One CTA per macroblock.  The search window is staged in shared
+// memory four times, byte-shifted by 0..3, so that every candidate reads aligned 32-bit words;
+// each thread owns one column offset and four consecutive row offsets, keeps the current block in
+// 64 registers and issues 256 VABSDIFF4-with-accumulate for 76 shared loads.
+// argmin over key = cost << 15 | raster rank (order independent => deterministic).
+// Bound: integer SIMD-video issue rate.
+// ================================================================================================
+#define ME_THREADS 320
+
+__device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__host__ __device__ inline int me_row_words(int R) { return (2 * R + 19) / 4 + 2; }
+__host__ __device__ inline int me_copy_words(int R)
+{
+    int cw = (16 + 2 * R + 3) * me_row_words(R);
+    return cw + ((8 - (cw & 31)) & 31); // == 8 (mod 32): the four copies start 8 banks apart
+}
+__host__ __device__ inline size_t me_smem_bytes(int R) { return (size_t)(64 + 4 * me_copy_words(R)) * 4; }
+
+__global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, const uint8_t *__restrict__ src,
+                                                       const uint8_t *__restrict__ ref, MbInfo *__restrict__ mbi)
+{
+    extern __shared__ uint32_t sm[];
+    __shared__ uint32_t warp_best[ME_THREADS / 32];
+    if (lane_frame(s, blockIdx.y) < 0)
+        return;
+    const int R = g.R, nd = 2 * R + 1;
+    const int WR = 16 + 2 * R + 3, RSW = me_row_words(R), CWs = me_copy_words(R);
+    const int mb = blockIdx.x, mbx = mb % g.mbw, mby = mb / g.mbw;
+    const int x0 = mbx * 16, y0 = mby * 16;
+    const uint8_t *srcY = src + (size_t)blockIdx.y * g.frame_bytes;
+    const uint8_t *refY = ref + (size_t)blockIdx.y * g.frame_bytes;
+    uint32_t *cur_s = sm, *cp = sm + 64;
+    const int tid = threadIdx.x;
+
+    if (tid < 64)
+        cur_s[tid] = *(const uint32_t *)(srcY + (size_t)(y0 + (tid >> 2)) * g.W + x0 + 4 * (tid & 3));
+    for (int idx = tid; idx < WR * RSW; idx += ME_THREADS) {
+        int r = idx / RSW, k = idx - r * RSW;
+        int fy = clip3_(0, g.H - 1, y0 - R + r), fx = x0 - R + 4 * k;
+        const uint8_t *row = refY + (size_t)fy * g.W;
+        uint32_t v;
+        if (fx >= 0 && fx + 3 < g.W && !(fx & 3))
+            v = *(const uint32_t *)(row + fx);
+        else {
+            v = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                v |= (uint32_t)row[clip3_(0, g.W - 1, fx + i)] << (8 * i);
+        }
+        cp[idx] = v;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < WR * RSW; idx += ME_THREADS) {
+        int k = idx % RSW;
+        if (k < RSW - 1) {
+            uint32_t lo = cp[idx], hi = cp[idx + 1];
+            cp[CWs + idx] = __byte_perm(lo, hi, 0x4321);
+            cp[2 * CWs + idx] = __byte_perm(lo, hi, 0x5432);
+            cp[3 * CWs + idx] = __byte_perm(lo, hi, 0x6543);
+        }
+    }
+    __syncthreads();
+
+    uint32_t cur[64];
+#pragma unroll
+    for (int i = 0; i < 64; i++)
+        cur[i] = cur_s[i];
+
+    const int warp = tid >> 5, lane = tid & 31, nwarps = ME_THREADS / 32;
+    const int nfull = nd >> 5, nleft = nd & 31, ndyg = (nd + 3) >> 2;
+    const int ntask_full = nfull * ndyg, nitems_left = nleft * ndyg;
+    const int ntask = ntask_full + ((nitems_left + 31) >> 5);
+    uint32_t best = 0xffffffffu;
+    for (int task = warp; task < ntask; task += nwarps) {
+        int ox, dyg;
+        bool valid = true;
+        if (task < ntask_full) {
+            ox = (task / ndyg) * 32 + lane;
+            dyg = task % ndyg;
+        } else {
+            int j = (task - ntask_full) * 32 + lane;
+            valid = j < nitems_left;
+            ox = nfull * 32 + j / ndyg;
+            dyg = j % ndyg;
+        }
+        if (!valid)
+            continue;
+        const int oy0 = dyg * 4;
+        const uint32_t *wp = cp + (ox & 3) * CWs + oy0 * RSW + (ox >> 2);
+        uint32_t acc[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < 19; r++) {
+            uint32_t w0 = wp[r * RSW], w1 = wp[r * RSW + 1], w2 = wp[r * RSW + 2], w3 = wp[r * RSW + 3];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int cr = r - j; // candidate row offset oy0 + j compares window row r with block row r - j
+                if (cr >= 0 && cr < 16) {
+                    acc[j] = sad4_acc(w0, cur[cr * 4 + 0], acc[j]);
+                    acc[j] = sad4_acc(w1, cur[cr * 4 + 1], acc[j]);
+                    acc[j] = sad4_acc(w2, cur[cr * 4 + 2], acc[j]);
+                    acc[j] = sad4_acc(w3, cur[cr * 4 + 3], acc[j]);
+                }
+            }
+        }
+        const int bx = mv_bits(ox - R);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int oy = oy0 + j;
+            if (oy < nd) {
+                uint32_t cost = acc[j] + (uint32_t)(g.lambda * (bx + mv_bits(oy - R)));
+                uint32_t key = (cost << 15) | (uint32_t)(oy * nd + ox);
+                best = key < best ? key : best;
+            }
+        }
+    }
+    best = __reduce_min_sync(0xffffffffu, best);
+    if (lane == 0)
+        warp_best[warp] = best;
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 1; w < nwarps; w++)
+            best = warp_best[w] < best ? warp_best[w] : best;
+        int rank = (int)(best & 0x7fff);
+        MbInfo m;
+        m.type = MB_P16x16;
+        m.i16_mode = m.chroma_mode = m.cbp = 0;
+        m.mv[0] = (int16_t)((rank % nd - R) * 4);
+        m.mv[1] = (int16_t)((rank / nd - R) * 4);
+        m.mvd[0] = m.mvd[1] = 0;
+        m.pad = best >> 15; // best cost, for statistics
+        mbi[(size_t)blockIdx.y * g.nmb + mb] = m;
+    }
+}
+
+// ================================================================================================
+// Shared per-lane chroma path (used by the inter and intra kernels): lanes 16..23 of the warp
+// own the eight 4x4 chroma blocks (16..19 Cb, 20..23 Cr).  `w` = forward-transformed residual.
+// ================================================================================================
+struct ChromaOut {
+    int zdc;   // quantised DC level owned by this lane (index cb of its plane)
+    int dcq;   // dequantised DC for this lane's block
+    int cbpc;  // chroma CBP of the macroblock (warp uniform)
+    unsigned m_dc; // ballot of non-zero DC levels
+};
+
+__device__ __forceinline__ ChromaOut chroma_dc_path(const int *w, int nz_ac, bool chroma, int lane, int qpc, int intra)
+{
+    ChromaOut o;
+    const int base = 16 + ((lane - 16) & 4), cb = lane & 3;
+    int d0 = __shfl_sync(0xffffffffu, w[0], base + 0), d1 = __shfl_sync(0xffffffffu, w[0], base + 1);
+    int d2 = __shfl_sync(0xffffffffu, w[0], base + 2), d3 = __shfl_sync(0xffffffffu, w[0], base + 3);
+    int qbits = 15 + qpc / 6, f = (1 << qbits) / (intra ? 3 : 6);
+    o.zdc = chroma ? quant1(hadamard2x2_elem(cb, d0, d1, d2, d3), h264_quant_mf[qpc % 6][0], 2 * f, qbits + 1) : 0;
+    unsigned m_ac = __ballot_sync(0xffffffffu, chroma && nz_ac > 0);
+    o.m_dc = __ballot_sync(0xffffffffu, chroma && o.zdc != 0);
+    o.cbpc = m_ac ? 2 : (o.m_dc ? 1 : 0);
+    int z0 = __shfl_sync(0xffffffffu, o.zdc, base + 0), z1 = __shfl_sync(0xffffffffu, o.zdc, base + 1);
+    int z2 = __shfl_sync(0xffffffffu, o.zdc, base + 2), z3 = __shfl_sync(0xffffffffu, o.zdc, base + 3);
+    o.dcq = dequant_chroma_dc(hadamard2x2_elem(cb, z0, z1, z2, z3), qpc);
+    return o;
+}
+
+__device__ __forceinline__ uint32_t pack4(const int *v)
+{
+    return (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+}
+
+__device__ __forceinline__ void store_levels(int16_t *dst, const int16_t *lev)
+{
+    uint4 a, b;
+    a.x = (uint16_t)lev[0] | ((uint32_t)(uint16_t)lev[1] << 16);
+    a.y = (uint16_t)lev[2] | ((uint32_t)(uint16_t)lev[3] << 16);
+    a.z = (uint16_t)lev[4] | ((uint32_t)(uint16_t)lev[5] << 16);
+    a.w = (uint16_t)lev[6] | ((uint32_t)(uint16_t)lev[7] << 16);
+    b.x = (uint16_t)lev[8] | ((uint32_t)(uint16_t)lev[9] << 16);
+    b.y = (uint16_t)lev[10] | ((uint32_t)(uint16_t)lev[11] << 16);
+    b.z = (uint16_t)lev[12] | ((uint32_t)(uint16_t)lev[13] << 16);
+    b.w = (uint16_t)lev[14] | ((uint32_t)(uint16_t)lev[15] << 16);
+    ((uint4 *)dst)[0] = a;
+    ((uint4 *)dst)[1] = b;
+}
+
+// ================================================================================================
+// K3 inter macroblock: integer luma MC, bilinear chroma MC (xFrac, yFrac in {0, 4}), 4x4 transform,
+// quantisation, CBP, dequantisation, inverse transform, reconstruction (before deblocking).
+// One warp per macroblock: lanes 0..15 luma 4x4 blocks, 16..23 chroma, 24/25 clear unused levels.
+// All macroblocks of all lanes in parallel.  HBM / L2 bound.
+// ================================================================================================
+__global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_t *__restrict__ src,
+                                                    const uint8_t *__restrict__ ref, uint8_t *__restrict__ unf,
+                                                    MbInfo *__restrict__ mbi, uint8_t *__restrict__ nnz,
+                                                    int16_t *__restrict__ coef)
+{
+    if (lane_frame(s, blockIdx.y) < 0)
+        return;
+    const int lane = threadIdx.x & 31;
+    const int mb = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (mb >= g.nmb)
+        return;
+    const int mbx = mb % g.mbw, mby = mb / g.mbw;
+    const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
+    const size_t rec = (size_t)blockIdx.y * g.nmb + mb;
+    const MbInfo me = mbi[rec];
+    const int dx = me.mv[0] >> 2, dy = me.mv[1] >> 2;
+    const bool luma = lane < 16, chroma = lane >= 16 && lane < 24;
+    const int qp = g.qp, qpc = g.qpc;
+
+    int pred[16], w[16];
+    int16_t lev[16];
+    int nz = 0;
+    size_t out_off = 0;
+    int out_stride = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++)
+        w[i] = 0, lev[i] = 0, pred[i] = 0;
+    if (luma) {
+        int px = mbx * 16 + blk_x(lane) * 4, py = mby * 16 + blk_y(lane) * 4;
+        const uint8_t *sp = src + fo + (size_t)py * g.W + px;
+        const uint8_t *rp = ref + fo;
+        int d[16];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.W);
+            const uint8_t *rr = rp + (size_t)clip3_(0, g.H - 1, py + y + dy) * g.W;
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                int p = rr[clip3_(0, g.W - 1, px + x + dx)];
+                pred[y * 4 + x] = p;
+                d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
+            }
+        }
+        fdct4x4(d, w);
+        nz = quant_block(w, qp, 0, 0, lev);
+        out_off = fo + (size_t)py * g.W + px;
+        out_stride = g.W;
+    } else if (chroma) {
+        int c = (lane - 16) >> 2, cb = lane & 3;
+        int px = mbx * 8 + (cb & 1) * 4, py = mby * 8 + (cb >> 1) * 4;
+        size_t po = fo + (size_t)g.W * g.H + (size_t)c * g.CW * g.CH;
+        const uint8_t *sp = src + po + (size_t)py * g.CW + px;
+        const uint8_t *rp = ref + po;
+        int mvx = me.mv[0], mvy = me.mv[1];
+        int xi = mvx >> 3, yi = mvy >> 3, xf = mvx & 7, yf = mvy & 7;
+        int d[16];
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.CW);
+            const uint8_t *r0 = rp + (size_t)clip3_(0, g.CH - 1, py + y + yi) * g.CW;
+            const uint8_t *r1 = rp + (size_t)clip3_(0, g.CH - 1, py + y + yi + 1) * g.CW;
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                int xa = clip3_(0, g.CW - 1, px + x + xi), xb = clip3_(0, g.CW - 1, px + x + xi + 1);
+                int A = r0[xa], B = r0[xb], C = r1[xa], D = r1[xb];
+                int p = ((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6;
+                pred[y * 4 + x] = p;
+                d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
+            }
+        }
+        fdct4x4(d, w);
+        nz = quant_block(w, qpc, 0, 1, lev);
+        out_off = po + (size_t)py * g.CW + px;
+        out_stride = g.CW;
+    }
+    ChromaOut co = chroma_dc_path(w, nz, chroma, lane, qpc, 0);
+    unsigned m_l = __ballot_sync(0xffffffffu, luma && nz > 0);
+    int cbpl = ((m_l & 0x000f) ? 1 : 0) | ((m_l & 0x00f0) ? 2 : 0) | ((m_l & 0x0f00) ? 4 : 0) | ((m_l & 0xf000) ? 8 : 0);
+
+    if (luma || chroma) {
+        int d[16], r[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            d[i] = 0;
+        if (luma) {
+            if (nz)
+                dequant_block(lev, qp, 0, d);
+        } else {
+            if (co.cbpc == 2)
+                dequant_block(lev, qpc, 1, d);
+            d[0] = co.cbpc ? co.dcq : 0;
+        }
+        idct4x4(d, r);
+        uint8_t *op = unf + out_off;
+#pragma unroll
+        for (int y = 0; y < 4; y++) {
+            int v[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++)
+                v[x] = clip255_(pred[y * 4 + x] + r[y * 4 + x]);
+            *(uint32_t *)(op + (size_t)y * out_stride) = pack4(v);
+        }
+    }
+    // syntax records
+    int16_t *cf = coef + rec * COEF_STRIDE;
+    uint8_t *nn = nnz + rec * NNZ_STRIDE;
+    if (luma) {
+        store_levels(cf + lane * 16, lev);
+        nn[lane] = (uint8_t)nz;
+    } else if (chroma) {
+        int c = (lane - 16) >> 2, cb = lane & 3;
+        store_levels(cf + (18 + c * 4 + cb) * 16, lev);
+        nn[NNZ_CB + c * 4 + cb] = (uint8_t)nz;
+        cf[17 * 16 + c * 4 + cb] = (int16_t)co.zdc;
+        if (cb == 0)
+            nn[NNZ_CBDC + c] = (uint8_t)__popc(co.m_dc & (0xfu << (16 + 4 * c)));
+    } else if (lane == 24) {
+        store_levels(cf + 16 * 16, lev); // zeros: no Intra16x16 DC block
+        nn[NNZ_DC16] = 0;
+    } else if (lane == 25) {
+        *(uint4 *)(cf + 17 * 16 + 8) = make_uint4(0, 0, 0, 0);
+    }
+    if (lane == 0) {
+        MbInfo m = me;
+        m.type = MB_P16x16;
+        m.cbp = (uint8_t)(cbpl | (co.cbpc << 4));
+        mbi[rec] = m;
+    }
+}
+
+// ================================================================================================
+// K2 median MV prediction, mvd and the P_Skip decision.  One thread per macroblock; runs after all
+// MVs of the frame are final (they never change here), so it is order independent.
+// ================================================================================================
+__global__ void mvp_skip_kernel(Geom g, Step s, MbInfo *__restrict__ mbi)
+{
+    if (lane_frame(s, blockIdx.y) < 0)
+        return;
+    int mb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (mb >= g.nmb)
+        return;
+    MbInfo *frame = mbi + (size_t)blockIdx.y * g.nmb;
+    MbInfo m = frame[mb];
+    if (m.type != MB_P16x16 && m.type != MB_PSKIP)
+        return;
+    int mvp[2], smv[2];
+    predict_mv(frame, g.mbw, mb % g.mbw, mb / g.mbw, mvp, smv);
+    int16_t mvdx = (int16_t)(m.mv[0] - mvp[0]), mvdy = (int16_t)(m.mv[1] - mvp[1]);
+    uint8_t type = MB_P16x16;
+    if (m.cbp == 0 && m.mv[0] == smv[0] && m.mv[1] == smv[1]) {
+        type = MB_PSKIP;
+        mvdx = mvdy = 0;
+    }
+    // only fields nobody else reads in this kernel are written (type is read, but P16x16 and PSKIP
+    // are treated alike by predict_mv)
+    frame[mb].mvd[0] = mvdx;
+    frame[mb].mvd[1] = mvdy;
+    frame[mb].type = type;
+}
+
+// ================================================================================================
+// K4 intra macroblocks of I frames: Intra16x16 (V/H/DC/Plane) + chroma (DC/H/V/Plane), mode by SAD,
+// transform / quant / recon.  Neighbours are the UNFILTERED reconstruction, so macroblock (x, y)
+// depends on (x-1, y) and on row y-1 up to x: one warp walks one macroblock row and publishes its
+// progress in flags[row]; the row below spins on it (wavefront).  Lanes as in K3.
+// Bound: dependency latency (mbw + mbh steps per frame) -- many lanes run side by side.
+// ================================================================================================
+__global__ void __launch_bounds__(32) intra_kernel(Geom g, Step s, const uint8_t *__restrict__ src,
+                                                   uint8_t *unf, MbInfo *__restrict__ mbi,
+                                                   uint8_t *__restrict__ nnz, int16_t *__restrict__ coef, int *flags)
+{
+    if (lane_frame(s, blockIdx.y) < 0)
+        return;
+    __shared__ uint8_t topY[20], leftY[16], topC[2][12], leftC[2][8];
+    const int lane = threadIdx.x, row = blockIdx.x;
+    const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
+    int *fl = flags + (size_t)blockIdx.y * g.mbh;
+    const bool luma = lane < 16, chroma = lane >= 16 && lane < 24;
+    const int qp = g.qp, qpc = g.qpc;
+    const int c = (lane - 16) >> 2, cb = lane & 3;
+    const int bx = luma ? blk_x(lane) * 4 : (cb & 1) * 4, by = luma ? blk_y(lane) * 4 : (cb >> 1) * 4;
+    const size_t plane_off = luma ? fo : fo + (size_t)g.W * g.H + (size_t)(chroma ? c : 0) * g.CW * g.CH;
+    const int stride = luma ? g.W : g.CW, mbsz = luma ? 16 : 8;
+    const uint8_t izz[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};
+
+    for (int mbx = 0; mbx < g.mbw; mbx++) {
+        const int has_top = row > 0, has_left = mbx > 0;
+        const size_t rec = (size_t)blockIdx.y * g.nmb + (size_t)row * g.mbw + mbx;
+        // source block (independent of the wavefront)
+        uint32_t sv[4] = {0, 0, 0, 0};
+        const size_t blk_off = plane_off + (size_t)(row * mbsz + by) * stride + mbx * mbsz + bx;
+        if (luma || chroma) {
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+                sv[y] = *(const uint32_t *)(src + blk_off + (size_t)y * stride);
+        }
+        if (has_top) {
+            if (lane == 0) {
+                while (ld_volatile(fl + row - 1) < mbx + 1)
+                    ;
+                __threadfence();
+            }
+            __syncwarp();
+            const uint8_t *ty = unf + fo + (size_t)(row * 16 - 1) * g.W + mbx * 16 - 1;
+            if (lane < 17 && (lane > 0 || has_left))
+                topY[lane] = __ldcg(ty + lane);
+            if (lane < 9 || (lane >= 16 && lane < 25)) {
+                int pl = lane >> 4, i = lane & 15;
+                const uint8_t *tc = unf + fo + (size_t)g.W * g.H + (size_t)pl * g.CW * g.CH +
+                                    (size_t)(row * 8 - 1) * g.CW + mbx * 8 - 1;
+                if (i > 0 || has_left)
+                    topC[pl][i] = __ldcg(tc + i);
+            }
+        }
+        __syncwarp();
+
+        // ---- mode decision: SAD of every available mode, summed over the 16-lane group ----
+        const uint8_t *tp = luma ? topY : topC[chroma ? c : 0];
+        const uint8_t *lp = luma ? leftY : leftC[chroma ? c : 0];
+        uint32_t best = 0xffffffffu;
+#pragma unroll 1
+        for (int mode = 0; mode < 4; mode++) {
+            // luma: 0 V 1 H 2 DC 3 P ; chroma: 0 DC 1 H 2 V 3 P  (availability per group)
+            int need_top = luma ? (mode == 0 || mode == 3) : (mode == 2 || mode == 3);
+            int need_left = (mode == 1 || mode == 3);
+            bool avail = (!need_top || has_top) && (!need_left || has_left);
+            int sad = 0;
+            if (avail && (luma || chroma)) {
+                int p[16];
+                if (luma)
+                    pred16_block(mode, tp, lp, has_top, has_left, bx, by, p);
+                else
+                    predc_block(mode, tp, lp, has_top, has_left, bx, by, p);
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    sad += iabs_((int)((sv[i >> 2] >> (8 * (i & 3))) & 0xff) - p[i]);
+            }
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1)
+                sad += __shfl_xor_sync(0xffffffffu, sad, o);
+            uint32_t key = avail ? (((uint32_t)sad << 2) | (uint32_t)mode) : 0xffffffffu;
+            best = key < best ? key : best;
+        }
+        const int mode = (int)(best & 3);
+        int pred[16], d[16], w[16];
+        int16_t lev[16];
+        int nz = 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            pred[i] = 0, w[i] = 0, lev[i] = 0;
+        if (luma || chroma) {
+            if (luma)
+                pred16_block(mode, tp, lp, has_top, has_left, bx, by, pred);
+            else
+                predc_block(mode, tp, lp, has_top, has_left, bx, by, pred);
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                d[i] = (int)((sv[i >> 2] >> (8 * (i & 3))) & 0xff) - pred[i];
+            fdct4x4(d, w);
+            nz = quant_block(w, luma ? qp : qpc, 1, 1, lev);
+        }
+        // ---- Intra16x16 DC: 4x4 Hadamard across the 16 luma lanes ----
+        int D[16], Y[16];
+#pragma unroll
+        for (int p = 0; p < 16; p++)
+            D[p] = __shfl_sync(0xffffffffu, w[0], xy2blk(p & 3, p >> 2));
+        hadamard4x4(D, Y);
+        int qbits = 15 + qp / 6, f = (1 << qbits) / 3;
+        int ydc = 0;
+#pragma unroll
+        for (int p = 0; p < 16; p++)
+            ydc = (lane == p) ? Y[p] : ydc;
+        int zdc16 = luma ? quant1(ydc, h264_quant_mf[qp % 6][0], 4 * f, qbits + 2) : 0; // raster position = lane
+        unsigned m_dc16 = __ballot_sync(0xffffffffu, zdc16 != 0);
+#pragma unroll
+        for (int p = 0; p < 16; p++)
+            D[p] = __shfl_sync(0xffffffffu, zdc16, p);
+        hadamard4x4(D, Y);
+        int fdc = 0;
+        {
+            int mypos = blk_y(lane & 15) * 4 + blk_x(lane & 15);
+#pragma unroll
+            for (int p = 0; p < 16; p++)
+                fdc = (mypos == p) ? Y[p] : fdc;
+        }
+        unsigned m_ac = __ballot_sync(0xffffffffu, luma && nz > 0);
+        const int any_ac = m_ac != 0;
+        ChromaOut co = chroma_dc_path(w, nz, chroma, lane, qpc, 1);
+
+        // ---- reconstruction ----
+        int recv[16];
+        if (luma || chroma) {
+            int dd[16], r[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                dd[i] = 0;
+            if (luma) {
+                if (any_ac)
+                    dequant_block(lev, qp, 1, dd);
+                dd[0] = dequant_luma_dc(fdc, qp);
+            } else {
+                if (co.cbpc == 2)
+                    dequant_block(lev, qpc, 1, dd);
+                dd[0] = co.cbpc ? co.dcq : 0;
+            }
+            idct4x4(dd, r);
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                recv[i] = clip255_(pred[i] + r[i]);
+            uint8_t *op = unf + blk_off;
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+                *(uint32_t *)(op + (size_t)y * stride) = pack4(recv + y * 4);
+        }
+        __syncwarp(); // everybody is done reading top/left of this macroblock
+        if (luma && bx == 12) {
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+                leftY[by + y] = (uint8_t)recv[y * 4 + 3];
+        }
+        if (chroma && bx == 4) {
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+                leftC[c][by + y] = (uint8_t)recv[y * 4 + 3];
+        }
+        // ---- syntax records ----
+        int16_t *cf = coef + rec * COEF_STRIDE;
+        uint8_t *nn = nnz + rec * NNZ_STRIDE;
+        if (luma) {
+            store_levels(cf + lane * 16, lev);
+            nn[lane] = (uint8_t)(any_ac ? nz : 0);
+            cf[16 * 16 + izz[lane]] = (int16_t)zdc16;
+        } else if (chroma) {
+            store_levels(cf + (18 + c * 4 + cb) * 16, lev);
+            nn[NNZ_CB + c * 4 + cb] = (uint8_t)nz;
+            cf[17 * 16 + c * 4 + cb] = (int16_t)co.zdc;
+            if (cb == 0)
+                nn[NNZ_CBDC + c] = (uint8_t)__popc(co.m_dc & (0xfu << (16 + 4 * c)));
+        } else if (lane == 24) {
+            nn[NNZ_DC16] = (uint8_t)__popc(m_dc16 & 0xffffu);
+        } else if (lane == 25) {
+            *(uint4 *)(cf + 17 * 16 + 8) = make_uint4(0, 0, 0, 0);
+        }
+        int cmode = __shfl_sync(0xffffffffu, mode, 16);
+        if (lane == 0) {
+            MbInfo m;
+            m.type = MB_I16x16;
+            m.i16_mode = (uint8_t)mode;
+            m.chroma_mode = (uint8_t)cmode;
+            m.cbp = (uint8_t)((any_ac ? 15 : 0) | (co.cbpc << 4));
+            m.mv[0] = m.mv[1] = m.mvd[0] = m.mvd[1] = 0;
+            m.pad = 0;
+            mbi[rec] = m;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0)
+            st_volatile(fl + row, mbx + 1);
+    }
+}
+
+// ================================================================================================
+// K5 in-loop deblocking filter (H.264 8.7; slice offsets 0, cedar.c:1024-1029), standard-exact
+// macroblock raster order realised as a 2:1 wavefront: macroblock (x, y) needs (x-1, y) and
+// (x+1, y-1).  One CTA per macroblock row: warp 0 filters luma, warp 1 filters Cb and Cr; they have
+// independent progress flags.  Reads the unfiltered frame `unf`, writes the reference frame `rec`.
+// Bound: dependency latency (mbw + 2 * mbh steps per frame).
+// ================================================================================================
+__device__ __forceinline__ int mb_bs(const MbInfo &cur, const uint8_t *ncur, const MbInfo &left, const uint8_t *nleft,
+                                     const MbInfo &top, const uint8_t *ntop, int dir, int e, int sg, bool has_left,
+                                     bool has_top)
+{
+    if (dir == 0) { // vertical edge e, rows 4*sg..
+        if (e == 0) {
+            if (!has_left)
+                return 0;
+            return boundary_strength(left, nleft[xy2blk(3, sg)], cur, ncur[xy2blk(0, sg)], 1);
+        }
+        return boundary_strength(cur, ncur[xy2blk(e - 1, sg)], cur, ncur[xy2blk(e, sg)], 0);
+    }
+    if (e == 0) {
+        if (!has_top)
+            return 0;
+        return boundary_strength(top, ntop[xy2blk(sg, 3)], cur, ncur[xy2blk(sg, 0)], 1);
+    }
+    return boundary_strength(cur, ncur[xy2blk(sg, e - 1)], cur, ncur[xy2blk(sg, e)], 0);
+}
+
+__global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8_t *__restrict__ unf, uint8_t *rec,
+                                                     const MbInfo *__restrict__ mbi, const uint8_t *__restrict__ nnz,
+                                                     int *flags_y, int *flags_c)
+{
+    if (lane_frame(s, blockIdx.y) < 0)
+        return;
+    __shared__ uint32_t tileY[20 * 6];     // 20 rows x 24 bytes: rows 0..3 top MB, cols 0..3 left MB
+    __shared__ uint32_t tileC[2][10 * 3];  // per plane 10 rows x 12 bytes: rows 0..1 top, cols 0..3 left
+    __shared__ uint8_t bsY[32], bsC[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = blockIdx.x;
+    const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
+    const MbInfo *fm = mbi + (size_t)blockIdx.y * g.nmb;
+    const uint8_t *fn = nnz + (size_t)blockIdx.y * g.nmb * NNZ_STRIDE;
+    const bool has_top = row > 0;
+
+    if (warp == 0) {
+        int *fl = flags_y + (size_t)blockIdx.y * g.mbh;
+        const int alpha = h264_deblock_alpha[g.qp], beta = h264_deblock_beta[g.qp];
+        uint8_t *tb = (uint8_t *)tileY;
+        for (int mbx = 0; mbx < g.mbw; mbx++) {
+            const bool has_left = mbx > 0;
+            const int mb = row * g.mbw + mbx;
+            const int x0 = mbx * 16, y0 = row * 16;
+            if (lane < 16) {
+                if (has_left)
+                    tileY[(4 + lane) * 6 + 0] = tileY[(4 + lane) * 6 + 4];
+                uint4 v = *(const uint4 *)(unf + fo + (size_t)(y0 + lane) * g.W + x0);
+                uint32_t *t = tileY + (4 + lane) * 6 + 1;
+                t[0] = v.x, t[1] = v.y, t[2] = v.z, t[3] = v.w;
+            }
+            {
+                int dir = lane >> 4, e = (lane >> 2) & 3, sg = lane & 3;
+                bsY[lane] = (uint8_t)mb_bs(fm[mb], fn + (size_t)mb * NNZ_STRIDE, fm[has_left ? mb - 1 : mb],
+                                           fn + (size_t)(has_left ? mb - 1 : mb) * NNZ_STRIDE,
+                                           fm[has_top ? mb - g.mbw : mb],
+                                           fn + (size_t)(has_top ? mb - g.mbw : mb) * NNZ_STRIDE, dir, e, sg, has_left,
+                                           has_top);
+            }
+            if (has_top) {
+                if (lane == 0) {
+                    int need = imin_(mbx + 2, g.mbw);
+                    while (ld_volatile(fl + row - 1) < need)
+                        ;
+                    __threadfence();
+                }
+                __syncwarp();
+                if (lane < 4) {
+                    uint4 v = __ldcg((const uint4 *)(rec + fo + (size_t)(y0 - 4 + lane) * g.W + x0));
+                    uint32_t *t = tileY + lane * 6 + 1;
+                    t[0] = v.x, t[1] = v.y, t[2] = v.z, t[3] = v.w;
+                }
+            }
+            __syncwarp();
+            if (lane < 16) { // vertical edges: lane = row
+                uint32_t *t = tileY + (4 + lane) * 6;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    int bS = bsY[e * 4 + (lane >> 2)];
+                    if (bS) {
+                        uint32_t a = t[e], b = t[e + 1];
+                        int v[8];
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            v[i] = (a >> (8 * i)) & 0xff, v[4 + i] = (b >> (8 * i)) & 0xff;
+                        filter_luma8(v, bS, alpha, beta, bS < 4 ? h264_deblock_tc0[g.qp][bS - 1] : 0);
+                        t[e] = pack4(v);
+                        t[e + 1] = pack4(v + 4);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane < 16) { // horizontal edges: lane = column
+                uint8_t *col = tb + 4 + lane;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    int bS = bsY[16 + e * 4 + (lane >> 2)];
+                    if (bS) {
+                        int v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            v[i] = col[(4 * e + i) * 24];
+                        filter_luma8(v, bS, alpha, beta, bS < 4 ? h264_deblock_tc0[g.qp][bS - 1] : 0);
+#pragma unroll
+                        for (int i = 1; i < 7; i++)
+                            col[(4 * e + i) * 24] = (uint8_t)v[i];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane < 16) {
+                const uint32_t *t = tileY + (4 + lane) * 6;
+                uint8_t *o = rec + fo + (size_t)(y0 + lane) * g.W + x0;
+                *(uint4 *)o = make_uint4(t[1], t[2], t[3], t[4]);
+                if (has_left)
+                    *(uint32_t *)(o - 4) = t[0];
+            } else if (lane < 19 && has_top) {
+                int r = lane - 15; // tile rows 1..3
+                const uint32_t *t = tileY + r * 6;
+                *(uint4 *)(rec + fo + (size_t)(y0 - 4 + r) * g.W + x0) = make_uint4(t[1], t[2], t[3], t[4]);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0)
+                st_volatile(fl + row, mbx + 1);
+        }
+    } else {
+        int *fl = flags_c + (size_t)blockIdx.y * g.mbh;
+        const int alpha = h264_deblock_alpha[g.qpc], beta = h264_deblock_beta[g.qpc];
+        const int pl = (lane >> 3) & 1, r8 = lane & 7;
+        const size_t po = fo + (size_t)g.W * g.H + (size_t)pl * g.CW * g.CH;
+        uint32_t *tw = tileC[pl];
+        uint8_t *tb = (uint8_t *)tileC[pl];
+        for (int mbx = 0; mbx < g.mbw; mbx++) {
+            const bool has_left = mbx > 0;
+            const int mb = row * g.mbw + mbx;
+            const int x0 = mbx * 8, y0 = row * 8;
+            if (lane < 16) {
+                if (has_left)
+                    tw[(2 + r8) * 3 + 0] = tw[(2 + r8) * 3 + 2];
+                uint2 v = *(const uint2 *)(unf + po + (size_t)(y0 + r8) * g.CW + x0);
+                tw[(2 + r8) * 3 + 1] = v.x;
+                tw[(2 + r8) * 3 + 2] = v.y;
+            }
+            if (lane < 16) { // bS of luma edges 0 and 2 only
+                int dir = lane >> 3, e = ((lane >> 2) & 1) * 2, sg = lane & 3;
+                bsC[lane] = (uint8_t)mb_bs(fm[mb], fn + (size_t)mb * NNZ_STRIDE, fm[has_left ? mb - 1 : mb],
+                                           fn + (size_t)(has_left ? mb - 1 : mb) * NNZ_STRIDE,
+                                           fm[has_top ? mb - g.mbw : mb],
+                                           fn + (size_t)(has_top ? mb - g.mbw : mb) * NNZ_STRIDE, dir, e, sg, has_left,
+                                           has_top);
+            }
+            if (has_top) {
+                if (lane == 0) {
+                    int need = imin_(mbx + 2, g.mbw);
+                    while (ld_volatile(fl + row - 1) < need)
+                        ;
+                    __threadfence();
+                }
+                __syncwarp();
+                if (lane < 16 && r8 < 2) {
+                    uint2 v = __ldcg((const uint2 *)(rec + po + (size_t)(y0 - 2 + r8) * g.CW + x0));
+                    tw[r8 * 3 + 1] = v.x;
+                    tw[r8 * 3 + 2] = v.y;
+                }
+            }
+            __syncwarp();
+            if (lane < 16) { // vertical edges at chroma x = 0, 4: lane = (plane, row)
+                uint8_t *t = tb + (2 + r8) * 12;
+#pragma unroll
+                for (int ce = 0; ce < 2; ce++) {
+                    int bS = bsC[ce * 4 + (r8 >> 1)];
+                    if (bS) {
+                        int v[4] = {t[2 + 4 * ce], t[3 + 4 * ce], t[4 + 4 * ce], t[5 + 4 * ce]};
+                        filter_chroma4(v, bS, alpha, beta, bS < 4 ? h264_deblock_tc0[g.qpc][bS - 1] : 0);
+                        t[3 + 4 * ce] = (uint8_t)v[1];
+                        t[4 + 4 * ce] = (uint8_t)v[2];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane < 16) { // horizontal edges at chroma y = 0, 4: lane = (plane, column)
+                uint8_t *col = tb + 4 + r8;
+#pragma unroll
+                for (int ce = 0; ce < 2; ce++) {
+                    int bS = bsC[8 + ce * 4 + (r8 >> 1)];
+                    if (bS) {
+                        int v[4] = {col[(4 * ce) * 12], col[(4 * ce + 1) * 12], col[(4 * ce + 2) * 12], col[(4 * ce + 3) * 12]};
+                        filter_chroma4(v, bS, alpha, beta, bS < 4 ? h264_deblock_tc0[g.qpc][bS - 1] : 0);
+                        col[(4 * ce + 1) * 12] = (uint8_t)v[1];
+                        col[(4 * ce + 2) * 12] = (uint8_t)v[2];
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane < 16) {
+                uint8_t *o = rec + po + (size_t)(y0 + r8) * g.CW + x0;
+                *(uint2 *)o = make_uint2(tw[(2 + r8) * 3 + 1], tw[(2 + r8) * 3 + 2]);
+                if (has_left)
+                    *(uint32_t *)(o - 4) = tw[(2 + r8) * 3 + 0];
+            } else if (lane < 18 && has_top) {
+                int p2 = lane - 16;
+                const uint32_t *t = tileC[p2] + 1 * 3;
+                *(uint2 *)(rec + fo + (size_t)g.W * g.H + (size_t)p2 * g.CW * g.CH + (size_t)(y0 - 1) * g.CW + x0) =
+                    make_uint2(t[1], t[2]);
+            }
+            __threadfence();
+            __syncwarp();
+            if (lane == 0)
+                st_volatile(fl + row, mbx + 1);
+        }
+    }
+}
+
+// ================================================================================================
+// K9 statistics: sum of squared luma error per frame (exact integer), for Y-PSNR.
+// ================================================================================================
+__global__ void sse_kernel(Geom g, Step s, const uint8_t *__restrict__ src, const uint8_t *__restrict__ rec,
+                           unsigned long long *__restrict__ sse)
+{
+    int f = lane_frame(s, blockIdx.y);
+    if (f < 0)
+        return;
+    const size_t fo = (size_t)blockIdx.y * g.frame_bytes, n4 = (size_t)g.W * g.H / 4;
+    unsigned acc = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t a = ((const uint32_t *)(src + fo))[i], b = ((const uint32_t *)(rec + fo))[i];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int d = (int)((a >> (8 * k)) & 0xff) - (int)((b >> (8 * k)) & 0xff);
+            acc += (unsigned)(d * d);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1)
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0)
+        atomicAdd(sse + f, (unsigned long long)acc);
+}
+
+// ================================================================================================
+// K6 / K7 entropy coding, pass structure: sizes per macroblock -> exclusive prefix sum per frame ->
+// scatter.  CAVLC scatters bits; CABAC scatters bins and a serial arithmetic coder (one per frame,
+// many frames at once) turns them into bytes.
+// ================================================================================================
+struct EntropyBufs {
+    uint32_t *mb_size;       // [L][nmb + 1] bits (CAVLC) or bins (CABAC) per macroblock
+    uint32_t *mb_off;        // [L][nmb + 1] exclusive prefix
+    const uint32_t *hdr_bits; // [F] slice header bits (host written, cedar.c:984-1030)
+    const int *hdr_nbits;     // [F]
+    uint8_t *rbsp;           // [F][rbsp_cap]
+    unsigned rbsp_cap;
+    uint32_t *rbsp_len;      // [F] bytes of RBSP (header + slice data + trailing)
+    uint16_t *bins;          // CABAC bin pool
+    unsigned long long bins_cap;
+    unsigned long long *bins_cursor; // pool bump pointer
+    unsigned long long *bins_off;    // [F]
+    uint32_t *bins_len;      // [F]
+    int *error;              // sticky overflow flag
+};
+
+__device__ __forceinline__ FrameSyntax lane_syntax(const Geom &g, int lane, const MbInfo *mbi, const uint8_t *nnz,
+                                                   const int16_t *coef)
+{
+    FrameSyntax fs;
+    fs.mbi = mbi + (size_t)lane * g.nmb;
+    fs.nnz = nnz + (size_t)lane * g.nmb * NNZ_STRIDE;
+    fs.coef = coef + (size_t)lane * g.nmb * COEF_STRIDE;
+    fs.mbw = g.mbw;
+    fs.mbh = g.mbh;
+    return fs;
+}
+
+__device__ __forceinline__ int skip_run_before(const FrameSyntax &fs, int i)
+{
+    int run = 0;
+    for (int j = i - 1; j >= 0 && fs.mbi[j].type == MB_PSKIP; j--)
+        run++;
+    return run;
+}
+
+__global__ void entropy_size_kernel(Geom g, Step s, int frame_i, const MbInfo *__restrict__ mbi,
+                                    const uint8_t *__restrict__ nnz, const int16_t *__restrict__ coef, EntropyBufs eb)
+{
+    if (lane_frame(s, blockIdx.y) < 0)
+        return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > g.nmb)
+        return;
+    FrameSyntax fs = lane_syntax(g, blockIdx.y, mbi, nnz, coef);
+    unsigned n;
+    if (g.cabac) {
+        BinCount c;
+        if (i < g.nmb)
+            cabac_mb(c, fs, i, frame_i);
+        n = c.n;
+    } else {
+        BitCount c;
+        bool emits = i == g.nmb || fs.mbi[i].type != MB_PSKIP;
+        if (emits)
+            cavlc_mb(c, fs, i, frame_i, frame_i ? 0 : skip_run_before(fs, i));
+        n = c.n;
+    }
+    eb.mb_size[(size_t)blockIdx.y * (g.nmb + 1) + i] = n;
+}
+
+// Exclusive prefix sum of nmb + 1 sizes per lane (one 1024-thread CTA per lane) + per-frame totals.
+__global__ void __launch_bounds__(1024) entropy_scan_kernel(Geom g, Step s, EntropyBufs eb)
+{
+    int f = lane_frame(s, blockIdx.y);
+    if (f < 0)
+        return;
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry_s;
+    const int n = g.nmb + 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t *in = eb.mb_size + (size_t)blockIdx.y * n;
+    uint32_t *out = eb.mb_off + (size_t)blockIdx.y * n;
+    const uint32_t base = g.cabac ? 0u : (uint32_t)eb.hdr_nbits[f];
+    if (tid == 0)
+        carry_s = base;
+    __syncthreads();
+    for (int start = 0; start < n; start += 1024) {
+        int i = start + tid;
+        uint32_t v = i < n ? in[i] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o)
+                x += y;
+        }
+        if (lane == 31)
+            warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = warp_sum[lane], z = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+                if (lane >= o)
+                    z += y;
+            }
+            warp_sum[lane] = z - ws; // exclusive
+        }
+        __syncthreads();
+        uint32_t carry = carry_s;
+        uint32_t incl = carry + warp_sum[warp] + x;
+        if (i < n)
+            out[i] = incl - v;
+        __syncthreads();
+        if (tid == 1023)
+            carry_s = incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        uint32_t total = carry_s;
+        if (g.cabac) {
+            unsigned long long off = atomicAdd(eb.bins_cursor, (unsigned long long)total);
+            if (off + total > eb.bins_cap) {
+                atomicExch(eb.error, 1);
+                off = 0;
+                total = 0;
+            }
+            eb.bins_off[f] = off;
+            eb.bins_len[f] = total;
+        } else {
+            uint32_t bytes = (total + 7) >> 3;
+            if (bytes + 8 > eb.rbsp_cap) {
+                atomicExch(eb.error, 2);
+                bytes = 0;
+            }
+            eb.rbsp_len[f] = bytes;
+        }
+    }
+}
+
+__global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *__restrict__ mbi,
+                                     const uint8_t *__restrict__ nnz, const int16_t *__restrict__ coef, EntropyBufs eb)
+{
+    int f = lane_frame(s, blockIdx.y);
+    if (f < 0)
+        return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > g.nmb)
+        return;
+    FrameSyntax fs = lane_syntax(g, blockIdx.y, mbi, nnz, coef);
+    uint32_t off = eb.mb_off[(size_t)blockIdx.y * (g.nmb + 1) + i];
+    if (g.cabac) {
+        if (i == g.nmb || eb.bins_len[f] == 0)
+            return;
+        BinWrite w(eb.bins + eb.bins_off[f] + off);
+        cabac_mb(w, fs, i, frame_i);
+    } else {
+        if (eb.rbsp_len[f] == 0)
+            return;
+        uint32_t *buf = (uint32_t *)(eb.rbsp + (size_t)f * eb.rbsp_cap);
+        if (i == 0) {
+            BitScatter h(buf, 0);
+            h.put(eb.hdr_bits[f], eb.hdr_nbits[f]);
+            h.flush();
+        }
+        bool emits = i == g.nmb || fs.mbi[i].type != MB_PSKIP;
+        if (!emits)
+            return;
+        BitScatter w(buf, off);
+        cavlc_mb(w, fs, i, frame_i, frame_i ? 0 : skip_run_before(fs, i));
+        w.flush();
+    }
+}
+
+// K7 serial arithmetic coder: one warp per frame, lane 0 codes.  Context states live in shared
+// memory; bins are streamed through registers eight at a time.
+__global__ void __launch_bounds__(32) cabac_encode_kernel(Geom g, int first_frame, int nframes, int gop_len,
+                                                          int gop_pos0, EntropyBufs eb)
+{
+    __shared__ uint8_t state[464];
+    int f = first_frame + blockIdx.x;
+    if (f >= nframes || threadIdx.x != 0)
+        return;
+    uint8_t *out = eb.rbsp + (size_t)f * eb.rbsp_cap;
+    const int frame_i = ((gop_pos0 + f) % gop_len) == 0;
+    uint32_t nb = eb.bins_len[f];
+    if (nb == 0) {
+        eb.rbsp_len[f] = 0;
+        return;
+    }
+    int hn = eb.hdr_nbits[f], hb = (hn + 7) >> 3;
+    unsigned long long h = ((unsigned long long)eb.hdr_bits[f] << (hb * 8 - hn)) | ((1ull << (hb * 8 - hn)) - 1);
+    for (int i = 0; i < hb; i++)
+        out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
+    CabacCoder c;
+    c.out = out + hb;
+    c.state = state;
+    c.init_states(frame_i, g.qp);
+    const uint16_t *bins = eb.bins + eb.bins_off[f];
+    const unsigned limit = eb.rbsp_cap - hb - 16;
+    // bins_off is a multiple of nothing in particular: peel to 16-byte alignment, then stream uint4
+    uint32_t i = 0;
+    while (i < nb && (((size_t)(bins + i)) & 15)) {
+        c.code(bins[i]);
+        i++;
+    }
+    uint4 nxt = make_uint4(0, 0, 0, 0);
+    if (i + 8 <= nb)
+        nxt = *(const uint4 *)(bins + i);
+    while (i + 8 <= nb) {
+        uint4 v = nxt;
+        if (i + 16 <= nb)
+            nxt = *(const uint4 *)(bins + i + 8);
+        c.code((uint16_t)(v.x & 0xffff));
+        c.code((uint16_t)(v.x >> 16));
+        c.code((uint16_t)(v.y & 0xffff));
+        c.code((uint16_t)(v.y >> 16));
+        c.code((uint16_t)(v.z & 0xffff));
+        c.code((uint16_t)(v.z >> 16));
+        c.code((uint16_t)(v.w & 0xffff));
+        c.code((uint16_t)(v.w >> 16));
+        i += 8;
+        if (c.pos > limit) {
+            atomicExch(eb.error, 3);
+            eb.rbsp_len[f] = 0;
+            return;
+        }
+    }
+    while (i < nb) {
+        c.code(bins[i]);
+        i++;
+    }
+    eb.rbsp_len[f] = (uint32_t)(hb + c.pos);
+}
+
+// ================================================================================================
+// K8 emulation prevention + NAL assembly.  Each thread owns a 64-byte chunk of a frame's RBSP:
+// pass 1 counts the 0x03 bytes it must insert (order-independent rule, epb_needed), a scan gives
+// chunk and frame offsets, pass 2 writes start code, NAL header and escaped payload into the packed
+// output stream.
+// ================================================================================================
+#define EPB_CHUNK 64
+
+__device__ __forceinline__ unsigned zero_run_before(const uint8_t *p, long i)
+{
+    unsigned run = 0;
+    for (long j = i - 1; j >= 0 && p[j] == 0; j--)
+        run++;
+    return run;
+}
+
+__global__ void epb_count_kernel(int nframes, const uint8_t *__restrict__ rbsp, unsigned rbsp_cap,
+                                 const uint32_t *__restrict__ rbsp_len, uint32_t *__restrict__ chunk_cnt,
+                                 unsigned chunks_per_frame)
+{
+    int f = blockIdx.y;
+    unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes || ch >= chunks_per_frame)
+        return;
+    const uint8_t *p = rbsp + (size_t)f * rbsp_cap;
+    long n = rbsp_len[f], b = (long)ch * EPB_CHUNK, e = b + EPB_CHUNK < n ? b + EPB_CHUNK : n;
+    uint32_t cnt = 0;
+    if (b < n) {
+        unsigned run = zero_run_before(p, b);
+        for (long i = b; i < e; i++) {
+            int v = p[i];
+            cnt += epb_needed(v, run);
+            run = v ? 0 : run + 1;
+        }
+    }
+    chunk_cnt[(size_t)f * chunks_per_frame + ch] = cnt;
+}
+
+// One CTA per frame: exclusive scan of its chunk counts (in place) and the frame's NAL size.
+__global__ void __launch_bounds__(1024) epb_scan_kernel(int nframes, const uint32_t *__restrict__ rbsp_len,
+                                                        uint32_t *chunk_cnt, unsigned chunks_per_frame,
+                                                        uint32_t *__restrict__ nal_bytes)
+{
+    int f = blockIdx.x;
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned n = (rbsp_len[f] + EPB_CHUNK - 1) / EPB_CHUNK;
+    uint32_t *c = chunk_cnt + (size_t)f * chunks_per_frame;
+    if (tid == 0)
+        carry_s = 0;
+    __syncthreads();
+    for (unsigned start = 0; start < n; start += 1024) {
+        unsigned i = start + tid;
+        uint32_t v = i < n ? c[i] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o)
+                x += y;
+        }
+        if (lane == 31)
+            warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t ws = warp_sum[lane], z = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+                if (lane >= o)
+                    z += y;
+            }
+            warp_sum[lane] = z - ws;
+        }
+        __syncthreads();
+        uint32_t incl = carry_s + warp_sum[warp] + x;
+        if (i < n)
+            c[i] = incl - v;
+        __syncthreads();
+        if (tid == 1023)
+            carry_s = incl;
+        __syncthreads();
+    }
+    if (tid == 0)
+        nal_bytes[f] = rbsp_len[f] ? 5 + rbsp_len[f] + carry_s : 0; // start code + NAL header + payload
+}
+
+// Single CTA: exclusive scan of the per-frame NAL sizes -> offsets in the packed stream.
+// frame_bytes[f] additionally counts the parameter sets that precede frame 0 (cedar.c:1058-1061).
+__global__ void __launch_bounds__(1024) pack_scan_kernel(int nframes, const uint32_t *__restrict__ nal_bytes,
+                                                         unsigned prefix_bytes, unsigned long long *__restrict__ nal_off,
+                                                         int *__restrict__ frame_bytes, unsigned long long *total,
+                                                         unsigned long long out_cap, int *error)
+{
+    __shared__ unsigned long long warp_sum[32];
+    __shared__ unsigned long long carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0)
+        carry_s = prefix_bytes;
+    __syncthreads();
+    for (int start = 0; start < nframes; start += 1024) {
+        int i = start + tid;
+        unsigned long long v = i < nframes ? nal_bytes[i] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o)
+                x += y;
+        }
+        if (lane == 31)
+            warp_sum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long ws = warp_sum[lane], z = ws;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long y = __shfl_up_sync(0xffffffffu, z, o);
+                if (lane >= o)
+                    z += y;
+            }
+            warp_sum[lane] = z - ws;
+        }
+        __syncthreads();
+        unsigned long long incl = carry_s + warp_sum[warp] + x;
+        if (i < nframes) {
+            nal_off[i] = incl - v;
+            frame_bytes[i] = (int)v + (i == 0 ? (int)prefix_bytes : 0);
+        }
+        __syncthreads();
+        if (tid == 1023)
+            carry_s = incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        *total = carry_s;
+        if (carry_s > out_cap) {
+            atomicExch(error, 4);
+            *total = 0;
+        }
+    }
+}
+
+__global__ void epb_write_kernel(int nframes, int gop_len, int first_frame_index,
+                                 const uint8_t *__restrict__ rbsp, unsigned rbsp_cap,
+                                 const uint32_t *__restrict__ rbsp_len, const uint32_t *__restrict__ chunk_off,
+                                 unsigned chunks_per_frame, const unsigned long long *__restrict__ nal_off,
+                                 const unsigned long long *__restrict__ total, uint8_t *__restrict__ out)
+{
+    int f = blockIdx.y;
+    unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nframes || ch >= chunks_per_frame || *total == 0)
+        return;
+    const uint8_t *p = rbsp + (size_t)f * rbsp_cap;
+    long n = rbsp_len[f], b = (long)ch * EPB_CHUNK, e = b + EPB_CHUNK < n ? b + EPB_CHUNK : n;
+    if (n == 0)
+        return;
+    uint8_t *o = out + nal_off[f];
+    if (ch == 0) {
+        // cedar.c:868-881 start code + NAL header: IDR ref_idc 3 type 5, P ref_idc 2 type 1 (:987-990)
+        int frame_i = ((first_frame_index + f) % gop_len) == 0;
+        o[0] = 0, o[1] = 0, o[2] = 0, o[3] = 1;
+        o[4] = frame_i ? 0x65 : 0x41;
+    }
+    if (b >= n)
+        return;
+    o += 5 + b + chunk_off[(size_t)f * chunks_per_frame + ch];
+    unsigned run = zero_run_before(p, b);
+    for (long i = b; i < e; i++) {
+        int v = p[i];
+        if (epb_needed(v, run))
+            *o++ = 3;
+        *o++ = (uint8_t)v;
+        run = v ? 0 : run + 1;
+    }
+}
+
+} // namespace cedar

@@ -1,0 +1,134 @@
+/*
+ * cedar_b200 -- C ABI of the B200-native drop-in for libv/cedarx_h264_encoder's encode path.
+ *
+ * The reference's userspace talks to the Allwinner Cedar VE through two ioctls and three mmaps
+ * (/root/reference/kernel/cedar_ioctl.h:7-46, userspace/h264enc.c:47-117,178-198).  This header
+ * is what a maintainer binds instead; every entry point cites the interface it replaces.
+ * Plain C: pointers and sizes only.  All buffers are owned by the library (as the kernel owns
+ * the DMA buffers in the reference); the caller never frees them.
+ *
+ * There is NO CPU fallback: every encode call runs hand-written sm_100a CUDA kernels and fails
+ * with a negative errno if no CUDA device is usable.
+ */
+#ifndef CEDAR_B200_H
+#define CEDAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CEDAR_B200_FORMAT_NV12 0 /* CEDAR_IOCTL_CONFIG_FORMAT_NV12, cedar_ioctl.h:15 */
+#define CEDAR_B200_FORMAT_NV16 1 /* CEDAR_IOCTL_CONFIG_FORMAT_NV16, cedar_ioctl.h:16 */
+#define CEDAR_B200_ENTROPY_CAVLC 0 /* CEDAR_IOCTL_ENTROPY_CODING_CAVLC, cedar_ioctl.h:30 */
+#define CEDAR_B200_ENTROPY_CABAC 1 /* CEDAR_IOCTL_ENTROPY_CODING_CABAC, cedar_ioctl.h:31 */
+
+/*
+ * Replaces the input half of struct cedar_ioctl_config (cedar_ioctl.h:12-32): same field names,
+ * same meaning, same validation (kernel/cedar.c:744-789).  Fields after entropy_coding_mode are
+ * extensions; zero means "reference behaviour / default".
+ */
+struct cedar_b200_config {
+    int src_width;
+    int src_height;
+    int src_format;
+    int dst_width;
+    int dst_height;
+    int profile;
+    int level;
+    int qp;
+    int keyframe_interval;
+    int thumbnail;           /* accepted and reported back as 0: the ISP thumbnail scaler is out of scope */
+    int thumbnail_downscale;
+    int entropy_coding_mode;
+    /* extensions */
+    int me_range;            /* integer-pel full-search radius, 1..64; 0 = 16 */
+    int relax_gop;           /* non-zero: accept keyframe_interval >= 32 (cedar.c:784-789 rejects it) */
+    int device;              /* CUDA device ordinal */
+    int gops_in_flight;      /* clip mode: closed GOPs encoded concurrently on this GPU; 0 = auto */
+    int max_clip_frames;     /* clip mode: capacity of the clip buffers in frames; 0 = clip mode off */
+};
+
+/*
+ * Replaces the output half of struct cedar_ioctl_config (cedar_ioctl.h:34-45) and the three
+ * mmap() calls of userspace/h264enc.c:76-106: host pointers (pinned memory) instead of DMA
+ * addresses.  The caller fills input_luma / input_chroma before every encode_frame call and
+ * reads `ret` bytes from bytestream after it (userspace/h264enc.c:181-197).
+ */
+struct cedar_b200_io {
+    void *input_luma;
+    int input_luma_size;   /* src_width * src_height rounded up to 4096 (cedar.c:610-615) */
+    void *input_chroma;
+    int input_chroma_size; /* NV12: w*h/2, NV16: w*h, rounded up to 4096 (cedar.c:621-624) */
+    void *bytestream;
+    int bytestream_size;   /* worst-case frame; the reference's fixed 1 MiB (cedar.c:663) is too small for 4K */
+};
+
+typedef struct cedar_b200_handle cedar_b200_handle;
+
+/* open("/dev/cedar_dev") + ioctl(CEDAR_IOCTL_CONFIG) + 3x mmap (userspace/h264enc.c:149,68,76-106;
+ * kernel/cedar.c:457-474,732-866).  Returns 0 or -EINVAL / -ENOMEM / -ENODEV. */
+int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *io, cedar_b200_handle **h);
+
+/* ioctl(CEDAR_IOCTL_ENCODE) (kernel/cedar.c:1032-1209): synchronous; encodes the frame currently in
+ * io->input_luma / io->input_chroma; returns the number of bytes now valid at io->bytestream
+ * (SPS+PPS precede the first frame only, cedar.c:1058-1061) or a negative errno. */
+int cedar_b200_encode_frame(cedar_b200_handle *h);
+
+/* close(fd) -> cedar_slashdev_release (kernel/cedar.c:706-730): frees everything and prints the
+ * busy/total time line the reference prints. */
+void cedar_b200_close(cedar_b200_handle *h);
+
+/* ---------------------------------------------------------------------------------------------
+ * Clip mode (the queued / GOP-parallel path of SURVEY 8b): a whole clip is encoded with several
+ * closed GOPs in flight.  Output is byte-identical to calling encode_frame once per frame.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Pinned host staging for `max_clip_frames` packed input frames (luma then chroma, back to back,
+ * exactly the bytes the reference's read loop consumes per frame, userspace/h264enc.c:181-187). */
+void *cedar_b200_clip_input(cedar_b200_handle *h, size_t *frame_bytes);
+
+/* Host -> device copy of the first nframes of the staging area. */
+int cedar_b200_clip_upload(cedar_b200_handle *h, int nframes);
+
+/* Encode nframes already resident in device memory; frame `first_frame_index + i` of the stream
+ * (this decides which frames are IDR and whether SPS/PPS are emitted: only before stream frame 0).
+ * Leaves the packed Annex-B stream in device memory.  Returns 0 or a negative errno. */
+int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_index);
+
+/* Device -> host copy of the packed stream.  *out receives a pointer to pinned host memory valid
+ * until the next clip call; frame_bytes (may be NULL) receives nframes per-frame byte counts.
+ * Returns total bytes or a negative errno. */
+long long cedar_b200_clip_download(cedar_b200_handle *h, const uint8_t **out, int *frame_bytes);
+
+/* Statistics of the last encode_frame / clip_encode: sum of squared luma error per frame
+ * (for Y-PSNR) -- sse_y must hold nframes doubles. */
+int cedar_b200_stats(cedar_b200_handle *h, double *sse_y, int nframes);
+
+/* Per-kernel device timing of the work issued since the last call with reset != 0.
+ * When enabled every launch is bracketed by CUDA events on the launching stream.
+ * names/ms/launches hold up to `cap` entries; returns the number of kernel classes. */
+int cedar_b200_profile_enable(cedar_b200_handle *h, int enable);
+int cedar_b200_profile_read(cedar_b200_handle *h, const char **names, float *ms, int *launches, int cap, int reset);
+
+/* Total kernels launched by this handle so far (bench.py's gpu_launches). */
+long long cedar_b200_launch_count(cedar_b200_handle *h);
+
+/* Debug / parity-test access to intermediates of the last encode_frame call (lane 0):
+ * what = 0 source planes, 1 unfiltered recon, 2 deblocked recon (Y then U then V, coded size),
+ *        3 macroblock info records, 4 nnz records, 5 coefficient levels.  Returns bytes copied. */
+long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_t cap);
+
+/* Header writer on its own (host C; restates kernel/cedar.c:868-1030) for byte-identity tests. */
+int cedar_b200_write_sps(const struct cedar_b200_config *cfg, uint8_t *out, int cap);
+int cedar_b200_write_pps(const struct cedar_b200_config *cfg, uint8_t *out, int cap);
+int cedar_b200_slice_header(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits);
+
+const char *cedar_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CEDAR_B200_H */

@@ -1,0 +1,113 @@
+// CPU unit-test harness: compiles the product's per-macroblock entropy logic (entropy.cuh,
+// h264_core.cuh) as ordinary C++ and drives it the way the CUDA kernels do (count pass, prefix sum,
+// scatter pass; binarise then serial arithmetic coder; parallel-rule emulation prevention).
+// TEST ONLY: it lets `pytest -m "not gpu"` compare this logic with the oracle without a GPU.
+// It is not linked into the product library and does not link the oracle.
+#include "../cedarx_h264_encoder_b200/csrc/entropy.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace cedar;
+
+static int skip_run_before(const FrameSyntax &fs, int i)
+{
+    int run = 0;
+    for (int j = i - 1; j >= 0 && fs.mbi[j].type == MB_PSKIP; j--)
+        run++;
+    return run;
+}
+
+extern "C" {
+
+// Returns RBSP length in bytes (header bits + slice data + trailing bits, byte aligned).
+long hh_cavlc_frame(const void *mbi, const uint8_t *nnz, const int16_t *coef, int mbw, int mbh, int frame_i,
+                    uint32_t hdr_bits, int hdr_nbits, uint8_t *out, long cap)
+{
+    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh};
+    int nmb = mbw * mbh;
+    std::vector<unsigned long long> off(nmb + 2);
+    unsigned long long pos = (unsigned long long)hdr_nbits;
+    for (int i = 0; i <= nmb; i++) {
+        BitCount c;
+        cavlc_mb(c, fs, i, frame_i, skip_run_before(fs, i));
+        off[i] = pos;
+        pos += c.n;
+    }
+    long bytes = (long)((pos + 7) >> 3);
+    if (bytes > cap)
+        return -1;
+    std::vector<uint32_t> buf((size_t)(bytes + 8) / 4 + 2, 0);
+    {
+        BitScatter s(buf.data(), 0);
+        s.put(hdr_bits, hdr_nbits);
+        s.flush();
+    }
+    // scatter in reverse order to show the order does not matter
+    for (int i = nmb; i >= 0; i--) {
+        BitScatter s(buf.data(), off[i]);
+        cavlc_mb(s, fs, i, frame_i, skip_run_before(fs, i));
+        s.flush();
+    }
+    memcpy(out, buf.data(), (size_t)bytes);
+    return bytes;
+}
+
+long hh_cabac_frame(const void *mbi, const uint8_t *nnz, const int16_t *coef, int mbw, int mbh, int frame_i, int qp,
+                    uint32_t hdr_bits, int hdr_nbits, uint8_t *out, long cap)
+{
+    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh};
+    int nmb = mbw * mbh;
+    std::vector<size_t> off(nmb + 1);
+    size_t total = 0;
+    for (int i = 0; i < nmb; i++) {
+        BinCount c;
+        cabac_mb(c, fs, i, frame_i);
+        off[i] = total;
+        total += c.n;
+    }
+    std::vector<uint16_t> bins(total + 1);
+    for (int i = nmb - 1; i >= 0; i--) {
+        BinWrite w(bins.data() + off[i]);
+        cabac_mb(w, fs, i, frame_i);
+    }
+    // header bits followed by cabac_alignment_one_bit up to the byte boundary
+    int hb = (hdr_nbits + 7) >> 3;
+    unsigned long long h = ((unsigned long long)hdr_bits << (hb * 8 - hdr_nbits)) | ((1ull << (hb * 8 - hdr_nbits)) - 1);
+    for (int i = 0; i < hb; i++)
+        out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
+    uint8_t state[460];
+    CabacCoder c;
+    c.out = out + hb;
+    c.state = state;
+    c.init_states(frame_i, qp);
+    for (size_t i = 0; i < total; i++) {
+        if ((long)(hb + c.pos + 8) > cap)
+            return -1;
+        c.code(bins[i]);
+    }
+    return hb + (long)c.pos;
+}
+
+// Emulation prevention with the order-independent rule used by the GPU kernel.
+long hh_epb(const uint8_t *in, long n, uint8_t *out, long cap)
+{
+    long o = 0;
+    for (long i = 0; i < n; i++) {
+        unsigned run = 0;
+        for (long j = i - 1; j >= 0 && in[j] == 0; j--)
+            run++;
+        if (epb_needed(in[i], run)) {
+            if (o >= cap)
+                return -1;
+            out[o++] = 3;
+        }
+        if (o >= cap)
+            return -1;
+        out[o++] = in[i];
+    }
+    return o;
+}
+
+int hh_sizeof_mbinfo() { return (int)sizeof(MbInfo); }
+}
