@@ -1,0 +1,353 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: 1080p CQP I+P H.264 encode, frames/s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+A "step" is one pass of the hot path over one batch: the whole synthetic clip of the workload
+(default: BASELINE.json configs[2], 1920x1088 NV12, 600 frames, GOP 60, QP 25, +-16 full search,
+CABAC -- the configuration the metric is quoted on; it fits one GPU) encoded GOP-parallel.
+With N > 1 (torchrun, one rank per GPU) every rank encodes its own 600-frame share of a 600*N-frame
+clip (GOP g -> rank g % N): closed GOPs share no data, so there is no data-path collective and
+the scaling is weak.  `value` = all frames of all ranks / max-over-ranks device time with the clip
+already resident in HBM; `e2e` = the same through the C ABI with pinned HOST buffers, H2D of the
+raw frames and D2H of the bytestream inside the timed region.
+
+--impl reference times the CPU implementation of the same path (the golden model under oracle/,
+the reference itself having no CPU macroblock encoder: its encoder is Allwinner silicon,
+kernel/cedar.c:1176) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (width, height, fmt, frames, gop, qp, me_range, cabac)
+    "1080p_nv12_600f_gop60_qp25": (1920, 1088, 0, 600, 60, 25, 16, 1),
+    "720p_nv12_300f_gop30_qp25": (1280, 720, 0, 300, 30, 25, 16, 1),
+    "1080p_nv16_300f_gop60_qp25": (1920, 1088, 1, 300, 60, 25, 16, 1),
+    "2160p_nv12_1200f_gop60_qp25_me64": (3840, 2160, 0, 1200, 60, 25, 64, 1),
+    "480p_nv12_30f_gop25_qp24": (854, 480, 0, 30, 25, 24, 16, 1),
+}
+DEFAULT_WORKLOAD = "1080p_nv12_600f_gop60_qp25"
+METRIC = "1080p CQP I+P frames/sec (GOP-parallel)"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region (B200_PROFILING.md: clocks line)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the golden model on the host cores (cpu_baseline leg and --impl reference)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    (w, h, fmt, gop, qp, me, cabac, first, n) = args
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    enc = O.Encoder(O.make_config(w, h, qp=qp, gop=gop, cabac=cabac, fmt=fmt, me_range=me))
+    frames = [O.synth_frame(w, h, first + i, fmt) for i in range(n)]
+    t0 = time.perf_counter()
+    nbytes = 0
+    for y, c in frames:
+        nbytes += len(enc.encode(y, c))
+    dt = time.perf_counter() - t0
+    enc.close()
+    return n, dt, nbytes
+
+
+def cpu_sample(workload, frames_per_core, cores):
+    """Every core encodes the first `frames_per_core` frames of a different GOP of the workload."""
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    O.build()
+    w, h, fmt, nframes, gop, qp, me, cabac = WORKLOADS[workload]
+    jobs = [(w, h, fmt, gop, qp, me, cabac, (i * gop) % max(nframes, 1), frames_per_core) for i in range(cores)]
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return total / slowest, total, wall
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    w, h, fmt, nframes, gop, qp, me, cabac = WORKLOADS[args.workload]
+    fpc = args.cpu_frames
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_sample(args.workload, 1, cores)
+    vals, t_all = [], 0.0
+    for _ in range(args.steps):
+        fps, total, wall = cpu_sample(args.workload, fpc, cores)
+        vals.append(fps)
+        t_all += wall
+    value = sum(vals) / len(vals)
+    sample = "%d cores x first %d frames (1 I + %d P) of distinct GOPs of the workload clip" % (cores, fpc, fpc - 1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": args.workload, "width": w, "height": h, "frames": nframes, "gop": gop, "qp": qp,
+                   "me_range": me, "entropy": "cabac" if cabac else "cavlc", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "reference has no CPU macroblock encoder (Cedar VE silicon); this is the C golden "
+                                 "model of the same algorithm, GOP-parallel across processes"},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import cedarx_h264_encoder_b200 as cx
+    from cedarx_h264_encoder_b200 import api, partition, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the encoder has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    w, h, fmt, nframes, gop, qp, me, cabac = WORKLOADS[args.workload]
+    total_frames = nframes * world
+    my_frames = partition.frames_for_rank(total_frames, gop, rank, world)
+    n = len(my_frames)
+
+    cfg = api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, fmt=fmt, me_range=me, device=local_rank,
+                          max_clip_frames=n, gops_in_flight=args.lanes)
+    enc = cx.Encoder(cfg)
+    stream = torch.cuda.ExternalStream(enc.stream_ptr(), device=torch.device("cuda", local_rank))
+
+    # synthetic clip: generated on the GPU (plumbing), staged into the library's pinned host buffer
+    staging = torch.from_numpy(enc.clip_input(n))
+    chunk = 20
+    for i in range(0, n, chunk):
+        part = synth.synth_clip(w, h, my_frames[i:i + chunk], fmt, device="cuda")
+        staging[i:i + len(part)].copy_(part)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # -------- device-resident throughput (`value`) --------
+    enc.clip_upload(n)
+    for _ in range(max(args.warmup, 0)):
+        enc.clip_encode(n, 0)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = enc.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        enc.clip_encode(n, 0)
+    e1.record(stream)
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = enc.launch_count() - launches0
+    data, sizes = enc.clip_download(n)
+    stream_bytes = int(len(data))
+    sse = enc.sse_y(n)
+
+    # -------- end to end through the C ABI with host buffers (`e2e`) --------
+    for _ in range(min(args.warmup, 1)):
+        enc.clip_upload(n)
+        enc.clip_encode(n, 0)
+        enc.clip_download(n)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        enc.clip_upload(n)
+        enc.clip_encode(n, 0)
+        enc.clip_download(n)
+    e3.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+
+    # -------- per-kernel device times with CUDA events on the launching stream --------
+    enc.profile_enable(True)
+    enc.profile_read(reset=True)
+    enc.clip_encode(n, 0)
+    prof = enc.profile_read(reset=True)
+    enc.profile_enable(False)
+    torch.cuda.synchronize()
+
+    value = total_frames * args.steps / (ms_dev * 1e-3)
+    e2e = total_frames * args.steps / (ms_e2e * 1e-3)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+        simd_peak = 18.54e12  # VABSDIFF4 lane-instr/s measured with tools/vabsdiff_bench.cu (profiles/)
+        try:
+            simd_peak = float(json.load(open(os.path.join(ROOT, "profiles", "vabsdiff4_peak.json")))["vabsdiff4_lane_instr_per_s"])
+        except Exception:
+            pass
+        nmb = (((w + 15) // 16) * ((h + 15) // 16))
+        W16, H16 = ((w + 15) // 16) * 16, ((h + 15) // 16) * 16
+        kernels = {}
+        tot_ms = sum(v[0] for v in prof.values()) or 1.0
+        for name, (ms, cnt) in prof.items():
+            kernels[name] = {"ms_total": round(ms, 4), "launches": cnt, "share": round(ms / tot_ms, 4)}
+        dominant = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
+        roofline = None
+        if "me_kernel" in prof:
+            ms, cnt = prof["me_kernel"]
+            p_frames = n - len(partition.gops_for_rank(total_frames, gop, rank, world))
+            instr = p_frames * nmb * (2 * me + 1) ** 2 * 64.0  # algorithmic VABSDIFF4 lane-instructions
+            ach = instr / (ms * 1e-3)
+            roofline = {"kernel": "me_kernel", "bound": "int-simd (VABSDIFF4 issue rate; neither hbm nor tensor)",
+                        "achieved": ach / 1e12, "peak": simd_peak / 1e12, "unit": "T VABSDIFF4 lane-instr/s",
+                        "frac": ach / simd_peak, "traffic": None,
+                        "peak_source": "measured on this pool with tools/vabsdiff_bench.cu (63.8 /SM/clk)",
+                        "algorithmic_per_launch": instr / cnt, "avg_launch_ms": ms / cnt,
+                        "dominant_by_time": dominant}
+        hbm = {}
+        frame_bytes = W16 * H16 * 3 // 2
+        alg = {"inter_kernel": 3 * frame_bytes, "deblock_kernel": 2 * frame_bytes, "ingest_kernel": 2 * frame_bytes,
+               "intra_kernel": 2 * frame_bytes, "sse_kernel": 2 * W16 * H16}
+        for name, per_frame in alg.items():
+            if name in prof:
+                ms, cnt = prof[name]
+                nfr = {"inter_kernel": n - len(partition.gops_for_rank(total_frames, gop, rank, world)),
+                       "intra_kernel": len(partition.gops_for_rank(total_frames, gop, rank, world))}.get(name, n)
+                gbs = per_frame * nfr / (ms * 1e-3) / 1e9
+                hbm[name] = {"bound": "hbm", "achieved": round(gbs, 2), "peak": hbm_peak, "unit": "GB/s",
+                             "frac": round(gbs / hbm_peak, 5), "traffic": None, "peak_source": hbm_src}
+        mse = float(sse.sum()) / (n * W16 * H16)
+        import math
+        line = {
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "width": w, "height": h, "format": "nv16" if fmt else "nv12",
+                       "frames_per_gpu": n, "gop": gop, "qp": qp, "me_range": me, "entropy": "cabac" if cabac else "cavlc",
+                       "gops_in_flight": int(enc.cfg.gops_in_flight) or "auto", "parallelism": "gop-parallel x%d" % world,
+                       "l2": "inputs larger than L2 (%.0f MB raw clip per GPU vs 126 MB)" % (n * enc.frame_bytes / 1e6),
+                       "scaling_ceiling_strong": partition.scaling_ceiling(nframes, gop, world)},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n * enc.frame_bytes) * world,
+                    "d2h_bytes_per_step": (stream_bytes + 4 * n + 16) * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "roofline_hbm_kernels": hbm,
+            "kernels": kernels,
+            "quality": {"y_psnr_db": round(10 * math.log10(255.0 ** 2 / mse), 3) if mse > 0 else None,
+                        "kbit_per_frame": round(stream_bytes * 8 / 1000.0 / n, 2)},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            cores = os.cpu_count() or 1
+            fps, total, wall = cpu_sample(args.workload, args.cpu_frames, cores)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": "%d cores x first %d frames of distinct GOPs (%.1f s wall)" % (
+                                        cores, args.cpu_frames, wall)}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    enc.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--lanes", type=int, default=0, help="GOPs in flight per GPU (0 = auto)")
+    ap.add_argument("--cpu-frames", type=int, default=2, help="frames per core in the CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    return run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

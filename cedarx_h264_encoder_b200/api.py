@@ -77,6 +77,8 @@ def load_library():
                                           C.c_int, C.c_int]
     L.cedar_b200_launch_count.argtypes = [H]
     L.cedar_b200_launch_count.restype = C.c_longlong
+    L.cedar_b200_stream.argtypes = [H]
+    L.cedar_b200_stream.restype = C.c_void_p
     L.cedar_b200_debug_read.argtypes = [H, C.c_int, C.c_void_p, C.c_size_t]
     L.cedar_b200_debug_read.restype = C.c_longlong
     L.cedar_b200_write_sps.argtypes = [C.POINTER(CedarConfig), C.c_void_p, C.c_int]
@@ -195,6 +197,9 @@ class Encoder:
         names, ms, n = (C.c_char_p * cap)(), (C.c_float * cap)(), (C.c_int * cap)()
         k = self.L.cedar_b200_profile_read(self.h, names, ms, n, cap, int(reset))
         return {names[i].decode(): (ms[i], n[i]) for i in range(k)}
+
+    def stream_ptr(self):
+        return self.L.cedar_b200_stream(self.h)
 
     def launch_count(self):
         return self.L.cedar_b200_launch_count(self.h)

@@ -659,6 +659,8 @@ int cedar_b200_profile_read(cedar_b200_handle *h, const char **names, float *ms,
 
 long long cedar_b200_launch_count(cedar_b200_handle *h) { return h ? h->launches : 0; }
 
+void *cedar_b200_stream(cedar_b200_handle *h) { return h ? (void *)h->stream : nullptr; }
+
 long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_t cap)
 {
     if (!h || !dst)

@@ -113,6 +113,10 @@ int cedar_b200_stats(cedar_b200_handle *h, double *sse_y, int nframes);
 int cedar_b200_profile_enable(cedar_b200_handle *h, int enable);
 int cedar_b200_profile_read(cedar_b200_handle *h, const char **names, float *ms, int *launches, int cap, int reset);
 
+/* The CUDA stream (cudaStream_t) every kernel and copy of this handle is issued on, so a caller can
+ * bracket calls with its own CUDA events. */
+void *cedar_b200_stream(cedar_b200_handle *h);
+
 /* Total kernels launched by this handle so far (bench.py's gpu_launches). */
 long long cedar_b200_launch_count(cedar_b200_handle *h);
 
