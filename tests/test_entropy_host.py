@@ -1,0 +1,64 @@
+"""The product's entropy logic (csrc/entropy.cuh: CAVLC count/scan/scatter, CABAC binarisation +
+byte-wise arithmetic coder, order-independent emulation prevention) compiled for the host and driven
+like the CUDA kernels drive it, against the oracle's bitstream -- no GPU needed."""
+import numpy as np
+import pytest
+
+import avdec
+from common import content
+
+MBI = np.dtype([("type", "u1"), ("i16_mode", "u1"), ("chroma_mode", "u1"), ("cbp", "u1"), ("mv", "<i2", (2,)),
+                ("mvd", "<i2", (2,)), ("pad", "<u4")])
+
+
+def to_product_layout(mbs):
+    n = len(mbs)
+    mbi = np.zeros(n, MBI)
+    for k in ("type", "i16_mode", "chroma_mode", "cbp", "mv", "mvd"):
+        mbi[k] = mbs[k]
+    nnz = np.zeros((n, 32), np.uint8)
+    nnz[:, :27] = mbs["nnz"]
+    coef = np.ascontiguousarray(mbs["coef"]).reshape(n, 26 * 16)
+    return mbi, nnz, coef
+
+
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("kind,qp", [("synth", 24), ("noise", 1), ("noise", 12), ("noise", 40), ("static", 36)])
+def test_entropy_logic_matches_oracle(oracle, harness, kind, qp, cabac):
+    w, h, gop = 96, 64, 3
+    enc = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8))
+    for t in range(5):
+        y, c = content(kind, w, h, t)
+        payload = avdec.split_nals(enc.encode(y, c))[-1][1][5:]
+        mbi, nnz, coef = to_product_layout(enc.mbs())
+        fi = int(enc.frame_is_i())
+        bits = oracle.slice_header_bits(fi, t % gop, cabac)
+        out = np.zeros(len(payload) * 2 + 4096, np.uint8)
+        if cabac:
+            n = harness.hh_cabac_frame(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, w // 16, h // 16, fi, qp,
+                                       int(bits, 2), len(bits), out.ctypes.data, out.size)
+        else:
+            n = harness.hh_cavlc_frame(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, w // 16, h // 16, fi,
+                                       int(bits, 2), len(bits), out.ctypes.data, out.size)
+        assert n > 0
+        esc = np.zeros(n * 2 + 16, np.uint8)
+        m = harness.hh_epb(out.ctypes.data, n, esc.ctypes.data, esc.size)
+        assert esc[:m].tobytes() == payload, "frame %d (%s)" % (t, "I" if fi else "P")
+
+
+def test_parallel_emulation_prevention_rule(harness):
+    """epb_needed(byte, zero_run) must reproduce the sequential rule on adversarial zero runs."""
+    rng = np.random.default_rng(3)
+    for trial in range(200):
+        n = int(rng.integers(1, 200))
+        data = rng.choice(np.array([0, 0, 0, 1, 2, 3, 4, 255], np.uint8), size=n)
+        want, zeros = bytearray(), 0
+        for b in data.tolist():
+            if zeros >= 2 and b <= 3:
+                want.append(3)
+                zeros = 0
+            want.append(b)
+            zeros = zeros + 1 if b == 0 else 0
+        out = np.zeros(2 * n + 8, np.uint8)
+        m = harness.hh_epb(data.ctypes.data, n, out.ctypes.data, out.size)
+        assert out[:m].tobytes() == bytes(want)

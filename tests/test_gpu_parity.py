@@ -1,0 +1,156 @@
+"""Parity tests proper (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(include/cedar_b200.h via ctypes).  Bar: bit-exact -- bytestream, every intermediate (macroblock
+records, levels, reconstruction before and after deblocking) and the luma SSE equal the CPU golden
+model's on the same seeded inputs; at BASELINE.json's full sizes, size-independent properties:
+an independent decoder reproduces the encoder's reconstruction, and the GOP-parallel clip path
+equals the frame-at-a-time path and is independent of the number of GOPs in flight."""
+import numpy as np
+import pytest
+import torch
+
+import avdec
+from common import content, make_clip, oracle_encode_clip, split_frame
+
+pytestmark = pytest.mark.gpu
+
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import cedarx_h264_encoder_b200 as cx  # noqa: E402
+from cedarx_h264_encoder_b200 import api, synth  # noqa: E402
+
+
+def test_library_is_loaded_and_launches_kernels(product_lib):
+    with cx.Encoder(api.make_config(64, 48)) as enc:
+        y, c = content("synth", 64, 48, 0)
+        assert len(enc.encode(y, c)) > 0
+        assert enc.launch_count() >= 10
+
+
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("kind,qp,me", [("synth", 24, 8), ("noise", 30, 8), ("static", 30, 8), ("shift", 24, 16),
+                                        ("noise", 1, 8), ("synth", 47, 8), ("flat", 12, 8)])
+def test_frame_mode_every_stage_matches_oracle(oracle, kind, qp, me, cabac):
+    w, h, gop, n = 96, 80, 3, 5
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=me))
+    with cx.Encoder(api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=me)) as enc:
+        for t in range(n):
+            y, c = content(kind, w, h, t)
+            want, got = gold.encode(y, c), enc.encode(y, c)
+            for p, (a, b) in enumerate(zip(gold.source(), enc.debug_planes(0))):
+                assert np.array_equal(a, b), "ingest plane %d frame %d" % (p, t)
+            mbs = gold.mbs()
+            mbi, nnz, coef = enc.debug_syntax()
+            for k in ("type", "i16_mode", "chroma_mode", "cbp", "mv", "mvd"):
+                assert np.array_equal(mbs[k], mbi[k]), "mb.%s frame %d" % (k, t)
+            assert np.array_equal(mbs["nnz"], nnz[:, :27]), "nnz frame %d" % t
+            assert np.array_equal(mbs["coef"], coef), "levels frame %d" % t
+            for p, (a, b) in enumerate(zip(gold.recon_unfiltered(), enc.debug_planes(1))):
+                assert np.array_equal(a, b), "recon before deblocking plane %d frame %d" % (p, t)
+            for p, (a, b) in enumerate(zip(gold.recon(), enc.debug_planes(2))):
+                assert np.array_equal(a, b), "recon after deblocking plane %d frame %d" % (p, t)
+            assert got == want, "bytestream frame %d" % t
+            assert gold.sse_y() == enc.sse_y(1)[0]
+    gold.close()
+
+
+@pytest.mark.parametrize("w,h,fmt,me", [(854, 480, 0, 16), (86, 50, 0, 8), (64, 48, 1, 8), (16, 16, 0, 8), (32, 16, 0, 4),
+                                        (16, 64, 0, 16), (176, 144, 0, 16), (352, 288, 0, 32)])
+def test_frame_mode_shapes_and_formats(oracle, w, h, fmt, me):
+    """ragged sizes (edge replication), NV16 ingest, single-macroblock pictures, other search ranges"""
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=25, gop=25, cabac=1, fmt=fmt, me_range=me))
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=25, cabac=1, fmt=fmt, me_range=me)) as enc:
+        for t in range(3):
+            y, c = content("synth", w, h, t, fmt)
+            assert enc.encode(y, c) == gold.encode(y, c), "frame %d" % t
+    gold.close()
+
+
+def test_me_range_64(oracle):
+    w, h = 208, 160
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=25, gop=25, cabac=0, me_range=64))
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=25, cabac=0, me_range=64)) as enc:
+        for t in range(2):
+            y, c = content("shift", w, h, 3 * t)
+            assert enc.encode(y, c) == gold.encode(y, c)
+            assert np.array_equal(gold.mbs()["mv"], enc.debug_syntax()[0]["mv"])
+    gold.close()
+
+
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("lanes", [0, 1, 3])
+def test_clip_mode_matches_oracle(oracle, cabac, lanes):
+    w, h, n, gop = 96, 80, 14, 4
+    clip = make_clip("synth", w, h, n)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=24, gop=gop, cabac=cabac, me_range=8)
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=gop, cabac=cabac, me_range=8, max_clip_frames=n,
+                                    gops_in_flight=lanes)) as enc:
+        got, gsz = enc.encode_clip(clip)
+        assert got == want and gsz.tolist() == sizes
+        got2, _ = enc.encode_clip(clip)  # the handle is reusable and deterministic
+        assert got2 == want
+
+
+def test_clip_mode_later_gops_carry_no_parameter_sets(oracle):
+    """first_frame_index != 0: a rank that owns later GOPs emits no SPS/PPS (cedar.c:1058-1061), so
+    rank streams concatenate to the single stream."""
+    w, h, n, gop = 64, 48, 9, 3
+    clip = make_clip("synth", w, h, n)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=26, gop=gop, cabac=1, me_range=8)
+    with cx.Encoder(api.make_config(w, h, qp=26, gop=gop, cabac=1, me_range=8, max_clip_frames=n)) as enc:
+        a, _ = enc.encode_clip(clip[:3], first_frame_index=0)
+        b, _ = enc.encode_clip(clip[3:], first_frame_index=3)
+        assert a + b == want
+        with pytest.raises(OSError):
+            enc.encode_clip(clip[1:4], first_frame_index=1)  # clips start at a GOP boundary
+
+
+def test_overflow_is_reported_not_silent(monkeypatch):
+    monkeypatch.setenv("CEDAR_B200_BINS_PER_MB", "8")
+    clip = make_clip("noise", 64, 48, 2)
+    with cx.Encoder(api.make_config(64, 48, qp=10, gop=25, cabac=1, me_range=8, max_clip_frames=2)) as enc:
+        with pytest.raises(OSError):
+            enc.encode_clip(clip)
+
+
+@pytest.mark.parametrize("name,w,h,fmt,gop,n", [("720p", 1280, 720, 0, 30, 31), ("1080p", 1920, 1088, 0, 60, 61),
+                                                ("1080p-nv16", 1920, 1088, 1, 60, 3)])
+def test_full_size_properties(name, w, h, fmt, gop, n):
+    """BASELINE.json shapes: (1) clip path == frame-at-a-time path, (2) independent of GOPs in flight,
+    (3) libavcodec decodes the stream to exactly the encoder's reconstruction (last frame of each path),
+    (4) Y-PSNR is sane."""
+    clip = synth.synth_clip(w, h, list(range(n)), fmt).numpy()
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, fmt=fmt, max_clip_frames=n, gops_in_flight=2)) as enc:
+        stream, sizes = enc.encode_clip(clip)
+        sse = enc.sse_y(n)
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, fmt=fmt, max_clip_frames=n, gops_in_flight=1)) as enc:
+        stream1, _ = enc.encode_clip(clip)
+    assert stream == stream1, "result depends on the number of GOPs in flight"
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, fmt=fmt)) as enc:
+        frames = b""
+        for t in range(n):
+            frames += enc.encode(*split_frame(clip[t], w, h, fmt))
+        last_recon = enc.debug_planes(2)
+    assert frames == stream, "clip path differs from the frame-at-a-time path"
+    dec = avdec.decode(stream)
+    assert len(dec) == n
+    W16, H16 = (w + 15) // 16 * 16, (h + 15) // 16 * 16
+    for p in range(3):
+        assert np.array_equal(dec[-1][p], last_recon[p]), "decoder != encoder reconstruction (plane %d)" % p
+    # SSE reported by the encoder == SSE of the decoded picture against the (padded) input
+    y_in = np.pad(split_frame(clip[-1], w, h, fmt)[0], ((0, H16 - h), (0, W16 - w)), mode="edge").astype(np.int64)
+    assert int(((dec[-1][0].astype(np.int64) - y_in) ** 2).sum()) == int(sse[-1])
+    psnr = 10 * np.log10(255.0 ** 2 / (sse.sum() / (n * W16 * H16)))
+    assert psnr > 34.0, psnr
+
+
+def test_gpu_stream_decodes_bit_exactly_small(oracle):
+    w, h, n = 176, 144, 6
+    clip = make_clip("synth", w, h, n)
+    _, _, recs = oracle_encode_clip(clip, w, h, keep_recon=True, qp=24, gop=3, cabac=1, me_range=16)
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=3, cabac=1, max_clip_frames=n)) as enc:
+        stream, _ = enc.encode_clip(clip)
+    dec = avdec.decode(stream)
+    for r, d in zip(recs, dec):
+        for p in range(3):
+            assert np.array_equal(r[p], d[p])

@@ -1,0 +1,107 @@
+"""Pins the oracle: (1) an independent conformant decoder (FFmpeg's h264 in the bundled libavcodec)
+must reproduce the golden model's reconstruction bit-exactly -- north star correctness part 3;
+(2) committed bitstream hashes (tests/golden/stream_hashes.json, made by tools/make_golden.py)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import avdec
+from common import content, make_clip, oracle_encode_clip
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+needs_decoder = pytest.mark.skipif(not avdec.available(), reason="bundled libavcodec not loadable")
+
+
+def roundtrip(oracle, kind, w, h, n, fmt=0, **cfg):
+    clip = make_clip(kind, w, h, n, fmt)
+    stream, sizes, recs = oracle_encode_clip(clip, w, h, fmt, keep_recon=True, **cfg)
+    dec = avdec.decode(stream)
+    assert len(dec) == n
+    for i, (r, d) in enumerate(zip(recs, dec)):
+        for p in range(3):
+            assert np.array_equal(r[p], d[p]), "frame %d plane %d: decoder != encoder reconstruction" % (i, p)
+    return stream
+
+
+@needs_decoder
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("kind,qp", [("synth", 24), ("noise", 1), ("noise", 30), ("static", 36), ("shift", 24),
+                                     ("flat", 10), ("synth", 47)])
+def test_decode_matches_recon(oracle, kind, qp, cabac):
+    roundtrip(oracle, kind, 96, 80, 5, qp=qp, gop=3, cabac=cabac, me_range=8 if kind != "shift" else 16)
+
+
+@needs_decoder
+def test_decode_matches_recon_nv16(oracle):
+    roundtrip(oracle, "synth", 64, 48, 3, fmt=1, qp=25, gop=25, cabac=1, me_range=8)
+
+
+@needs_decoder
+def test_decode_matches_recon_padded_size(oracle):
+    """src not a multiple of 16 (the README's 854x480 case, scaled down): edge replication to ALIGN16."""
+    roundtrip(oracle, "synth", 86, 50, 3, qp=24, gop=25, cabac=1, me_range=8)
+
+
+@needs_decoder
+def test_config1_shape_runs_on_cpu(oracle):
+    """BASELINE.json configs[0]: 854x480 NV12, reference defaults (QP 24, GOP 25, CABAC), CPU golden model."""
+    stream = roundtrip(oracle, "synth", 854, 480, 2, qp=24, gop=25, cabac=1, me_range=16)
+    assert stream.startswith(bytes.fromhex("000000016742".replace("42", "4d")))
+
+
+def test_golden_stream_hashes(oracle):
+    gold = json.load(open(os.path.join(HERE, "golden", "stream_hashes.json")))
+    for case in gold["cases"]:
+        clip = make_clip(case["kind"], case["w"], case["h"], case["n"], case["fmt"])
+        stream, sizes, _ = oracle_encode_clip(clip, case["w"], case["h"], case["fmt"], qp=case["qp"], gop=case["gop"],
+                                              cabac=case["cabac"], me_range=case["me"])
+        assert sizes == case["sizes"], case
+        assert hashlib.sha256(stream).hexdigest() == case["sha256"], case
+
+
+def test_config_validation_matches_reference_rules(oracle):
+    """kernel/cedar.c:744-789: same accept/reject decisions, -EINVAL."""
+    import ctypes as C
+    L = oracle.lib()
+
+    def rc(**kw):
+        base = dict(width=64, height=48)
+        base.update(kw)
+        relax = base.pop("relax_gop", 0)
+        cfg = oracle.make_config(relax_gop=relax, **base)
+        h = C.c_void_p()
+        r = L.gm_open(C.byref(cfg), C.byref(h))
+        if r == 0:
+            L.gm_close(h)
+        return r
+
+    assert rc() == 0
+    assert rc(width=63) == -22 and rc(height=47) == -22          # src not even
+    assert rc(dst_width=70) == -22                                # dst not multiple of 16
+    assert rc(width=80, dst_width=64) == -22                      # src > dst
+    assert rc(qp=0) == -22 and rc(qp=48) == -22 and rc(qp=47) == 0 and rc(qp=1) == 0
+    assert rc(fmt=2) == -22
+    assert rc(gop=0) == -22 and rc(gop=32) == -22 and rc(gop=31) == 0
+    assert rc(gop=60, relax_gop=1) == 0                           # documented extension
+
+
+def test_gop_structure_and_frame_num(oracle):
+    enc = oracle.Encoder(oracle.make_config(64, 48, gop=3))
+    kinds = []
+    for t in range(7):
+        y, c = oracle.synth_frame(64, 48, t)
+        enc.encode(y, c)
+        kinds.append(enc.frame_is_i())
+    assert kinds == [True, False, False, True, False, False, True]
+
+
+def test_skip_macroblocks_appear_on_static_content(oracle):
+    enc = oracle.Encoder(oracle.make_config(96, 80, qp=36, gop=5, cabac=0, me_range=8))
+    for t in range(2):
+        y, c = content("static", 96, 80, t)
+        enc.encode(y, c)
+    assert (enc.mbs()["type"] == 2).sum() >= 15
