@@ -16,6 +16,8 @@ raw frames and D2H of the bytestream inside the timed region.
 the reference itself having no CPU macroblock encoder: its encoder is Allwinner silicon,
 kernel/cedar.c:1176) on all host cores, on a bounded sample of the same workload.
 """
+import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA initialises: side streams must not share queues
 import argparse
 import json
 import os

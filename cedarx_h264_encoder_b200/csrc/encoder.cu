@@ -26,13 +26,13 @@ using namespace cedar;
 namespace {
 
 enum KernelId {
-    K_INGEST, K_ME, K_INTER, K_MVP, K_INTRA, K_DEBLOCK, K_SSE, K_ESIZE, K_ESCAN, K_EZERO, K_EWRITE,
-    K_CABAC, K_EPBCOUNT, K_EPBSCAN, K_PACKSCAN, K_EPBWRITE, K_COUNT
+    K_INGEST, K_ME, K_INTER, K_MVP, K_INTRA, K_BS, K_DEBLOCK, K_SSE, K_ESIZE, K_ESCAN, K_EZERO, K_EWRITE,
+    K_RESOLVE, K_CABAC, K_EPBCOUNT, K_EPBSCAN, K_PACKSCAN, K_EPBWRITE, K_COUNT
 };
 const char *kKernelNames[K_COUNT] = {
-    "ingest_kernel", "me_kernel", "inter_kernel", "mvp_skip_kernel", "intra_kernel", "deblock_kernel",
+    "ingest_kernel", "me_kernel", "inter_kernel", "mvp_skip_kernel", "intra_kernel", "bs_kernel", "deblock_kernel",
     "sse_kernel", "entropy_size_kernel", "entropy_scan_kernel", "rbsp_zero_kernel", "entropy_write_kernel",
-    "cabac_encode_kernel", "epb_count_kernel", "epb_scan_kernel", "pack_scan_kernel", "epb_write_kernel"};
+    "cabac_resolve_kernel", "cabac_encode_kernel", "epb_count_kernel", "epb_scan_kernel", "pack_scan_kernel", "epb_write_kernel"};
 
 const uint8_t kChromaQp[52] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17,
                                18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32, 32, 33,
@@ -63,7 +63,14 @@ struct cedar_b200_handle {
     int F;                 // clip capacity in frames (>= 1)
     int L;                 // lanes (GOPs in flight)
     size_t raw_frame_bytes;
-    cudaStream_t stream;
+    cudaStream_t stream;      // recon + parallel entropy stages
+    // serial CABAC stages run on a pool of side streams so that the coders of successive steps overlap
+    // each other and the following frames' reconstruction
+    enum { NSIDE = 32 };
+    cudaStream_t stream_cabac[NSIDE];
+    cudaEvent_t ev_bins, ev_cabac[NSIDE];
+    unsigned side_used; // bit i: side stream i has work the main stream has not joined yet
+    int side_next;
 
     // cedar.c:118-119 counters and the ping-pong reference (frame mode, lane 0)
     int frame_p_count, frame_count;
@@ -84,6 +91,7 @@ struct cedar_b200_handle {
     uint8_t *d_nnz;
     int16_t *d_coef;
     int *d_flags; // [3][L][mbh]
+    uint8_t *d_bs; // [L][nmb][32] boundary strengths
     unsigned long long *d_sse;
     EntropyBufs eb;
     uint32_t *d_hdr_bits;
@@ -132,43 +140,59 @@ cudaEvent_t get_event(cedar_b200_handle *h)
 
 struct LaunchScope {
     cedar_b200_handle *h;
+    cudaStream_t st;
     ProfEntry pe;
-    LaunchScope(cedar_b200_handle *hh, int id) : h(hh)
+    LaunchScope(cedar_b200_handle *hh, int id, cudaStream_t s) : h(hh), st(s)
     {
         pe.id = id;
         h->launches++;
         if (h->prof) {
             pe.a = get_event(h);
             pe.b = get_event(h);
-            cudaEventRecord(pe.a, h->stream);
+            cudaEventRecord(pe.a, st);
         }
     }
     ~LaunchScope()
     {
         if (h->prof) {
-            cudaEventRecord(pe.b, h->stream);
+            cudaEventRecord(pe.b, st);
             h->prof_pending.push_back(pe);
         }
     }
 };
 
-#define LAUNCH(id, kern, grid, block, smem, ...)              \
-    do {                                                      \
-        LaunchScope ls_(h, id);                               \
-        kern<<<grid, block, smem, h->stream>>>(__VA_ARGS__);  \
+#define LAUNCH_ON(st, id, kern, grid, block, smem, ...)  \
+    do {                                                 \
+        LaunchScope ls_(h, id, st);                      \
+        kern<<<grid, block, smem, st>>>(__VA_ARGS__);    \
     } while (0)
+#define LAUNCH(id, kern, grid, block, smem, ...) LAUNCH_ON(h->stream, id, kern, grid, block, smem, __VA_ARGS__)
 
 void prof_collect(cedar_b200_handle *h)
 {
     cudaStreamSynchronize(h->stream);
+    for (int i = 0; i < cedar_b200_handle::NSIDE; i++)
+        cudaStreamSynchronize(h->stream_cabac[i]);
+    // CEDAR_B200_TIMELINE=<file> (diagnosis): start/end of every launch relative to the first one
+    FILE *tl = nullptr;
+    if (const char *path = getenv("CEDAR_B200_TIMELINE"))
+        if (!h->prof_pending.empty())
+            tl = fopen(path, "a");
     for (auto &pe : h->prof_pending) {
         float ms = 0;
         cudaEventElapsedTime(&ms, pe.a, pe.b);
+        if (tl) {
+            float t0 = 0;
+            cudaEventElapsedTime(&t0, h->prof_pending.front().a, pe.a);
+            fprintf(tl, "%s,%.4f,%.4f\n", kKernelNames[pe.id], t0, t0 + ms);
+        }
         h->prof_ms[pe.id] += ms;
         h->prof_n[pe.id]++;
         h->ev_pool.push_back(pe.a);
         h->ev_pool.push_back(pe.b);
     }
+    if (tl)
+        fclose(tl);
     h->prof_pending.clear();
 }
 
@@ -252,7 +276,7 @@ int alloc_buffers(cedar_b200_handle *h)
     size_t bins_per_mb = F > 1 ? (g.qp < 12 ? 8192 : (g.qp < 20 ? 2048 : 640)) : 16384;
     if (const char *e = getenv("CEDAR_B200_BINS_PER_MB"))
         bins_per_mb = (size_t)atoll(e);
-    h->eb.bins_cap = g.cabac ? (unsigned long long)bins_per_mb * g.nmb * F + 64 : 0;
+    h->eb.bins_cap = g.cabac ? (unsigned long long)(bins_per_mb * g.nmb + 8) * F + 64 : 0;
 
     if (F > 1) {
         r |= hmalloc(&h->h_clip_in, h->raw_frame_bytes * F);
@@ -267,6 +291,7 @@ int alloc_buffers(cedar_b200_handle *h)
     r |= dmalloc(&h->d_nnz, (size_t)g.nmb * L * NNZ_STRIDE);
     r |= dmalloc(&h->d_coef, (size_t)g.nmb * L * COEF_STRIDE);
     r |= dmalloc(&h->d_flags, (size_t)3 * L * g.mbh);
+    r |= dmalloc(&h->d_bs, (size_t)g.nmb * L * 32);
     r |= dmalloc(&h->d_sse, F);
     r |= dmalloc(&h->eb.mb_size, (size_t)L * (g.nmb + 1));
     r |= dmalloc(&h->eb.mb_off, (size_t)L * (g.nmb + 1));
@@ -274,8 +299,10 @@ int alloc_buffers(cedar_b200_handle *h)
     r |= dmalloc(&h->d_hdr_nbits, F);
     r |= dmalloc(&h->eb.rbsp, (size_t)h->eb.rbsp_cap * F);
     r |= dmalloc(&h->eb.rbsp_len, F);
-    if (g.cabac)
+    if (g.cabac) {
         r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap);
+        r |= dmalloc(&h->eb.pre, (size_t)h->eb.bins_cap);
+    }
     r |= dmalloc(&h->eb.bins_cursor, 1);
     r |= dmalloc(&h->eb.bins_off, F);
     r |= dmalloc(&h->eb.bins_len, F);
@@ -300,9 +327,9 @@ int alloc_buffers(cedar_b200_handle *h)
 
 void free_buffers(cedar_b200_handle *h)
 {
-    void *dev[] = {h->d_raw, h->d_src, h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi, h->d_nnz, h->d_coef, h->d_flags,
+    void *dev[] = {h->d_raw, h->d_src, h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi, h->d_nnz, h->d_coef, h->d_flags, h->d_bs,
                    h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp, h->eb.rbsp_len,
-                   h->eb.bins, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
+                   h->eb.bins, h->eb.pre, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
                    h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes, h->d_out};
     for (void *p : dev)
         if (p)
@@ -316,7 +343,7 @@ void free_buffers(cedar_b200_handle *h)
 
 // One lock-step pass over `nl` lanes: the macroblock pipeline of one frame per lane plus the
 // parallel part of entropy coding.  t = position inside the GOP (0 => IDR).
-int encode_step(cedar_b200_handle *h, const Step &s, int t)
+int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0)
 {
     const Geom &g = h->g;
     const int nl = s.nlanes, cur = t & 1, frame_i = t == 0;
@@ -336,7 +363,8 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t)
                h->d_nnz, h->d_coef);
         LAUNCH(K_MVP, mvp_skip_kernel, dim3((g.nmb + 127) / 128, nl), 128, 0, g, s, h->d_mbi);
     }
-    LAUNCH(K_DEBLOCK, deblock_kernel, dim3(g.mbh, nl), 64, 0, g, s, h->d_unf, rec, h->d_mbi, h->d_nnz, fl_y, fl_c);
+    LAUNCH(K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, h->d_mbi, h->d_nnz, h->d_bs);
+    LAUNCH(K_DEBLOCK, deblock_kernel, dim3(g.mbh, nl), 64, 0, g, s, h->d_unf, rec, h->d_bs, fl_y, fl_c);
     LAUNCH(K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, h->d_src, rec, h->d_sse);
 
     dim3 egrid((g.nmb + 1 + 127) / 128, nl);
@@ -345,6 +373,18 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t)
     if (!g.cabac)
         LAUNCH(K_EZERO, rbsp_zero_kernel, dim3(8, nl), 256, 0, s, h->eb.rbsp, h->eb.rbsp_cap, h->eb.rbsp_len);
     LAUNCH(K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, h->d_mbi, h->d_nnz, h->d_coef, h->eb);
+    if (g.cabac) {
+        // the bins of these frames are final: code them on the side stream while the next frames are reconstructed
+        // CEDAR_B200_NO_OVERLAP=1 (diagnosis): run the serial stages in line on the main stream
+        static const bool no_overlap = getenv("CEDAR_B200_NO_OVERLAP") != nullptr;
+        cudaStream_t side = no_overlap ? h->stream : h->stream_cabac[h->side_next];
+        CK(cudaEventRecord(h->ev_bins, h->stream));
+        CK(cudaStreamWaitEvent(side, h->ev_bins, 0));
+        LAUNCH_ON(side, K_RESOLVE, cabac_resolve_kernel, nl, 512, 0, g, s, h->K, gop_pos0, h->eb);
+        LAUNCH_ON(side, K_CABAC, cabac_encode_kernel, nl, 32, 0, g, s, h->eb);
+        h->side_used |= 1u << h->side_next;
+        h->side_next = (h->side_next + 1) % cedar_b200_handle::NSIDE;
+    }
     h->last_cur = cur;
     return 0;
 }
@@ -353,8 +393,12 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t)
 int finish_stream(cedar_b200_handle *h, int nframes, int gop_pos0, bool with_param_sets)
 {
     const Geom &g = h->g;
-    if (g.cabac)
-        LAUNCH(K_CABAC, cabac_encode_kernel, nframes, 32, 0, g, 0, nframes, h->K, gop_pos0, h->eb);
+    for (int i = 0; i < cedar_b200_handle::NSIDE; i++)
+        if (h->side_used & (1u << i)) {
+            CK(cudaEventRecord(h->ev_cabac[i], h->stream_cabac[i]));
+            CK(cudaStreamWaitEvent(h->stream, h->ev_cabac[i], 0));
+        }
+    h->side_used = 0;
     unsigned cpf = h->chunks_per_frame;
     LAUNCH(K_EPBCOUNT, epb_count_kernel, dim3((cpf + 255) / 256, nframes), 256, 0, nframes, h->eb.rbsp, h->eb.rbsp_cap,
            h->eb.rbsp_len, h->d_chunk_cnt, cpf);
@@ -432,6 +476,10 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     int r = validate(cfg);
     if (r)
         return r;
+    // The serial CABAC stages of successive steps run concurrently on side streams; with the default of
+    // 8 hardware connections streams share queues and serialise.  Only effective before CUDA initialises
+    // in this process (a host that initialises CUDA earlier should export it itself).
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev) {
         fprintf(stderr, "cedar_b200: no usable CUDA device (this encoder has no CPU fallback).\n");
@@ -476,7 +524,14 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     h->prof = false;
     memset(h->prof_ms, 0, sizeof(h->prof_ms));
     memset(h->prof_n, 0, sizeof(h->prof_n));
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&h->ev_bins, cudaEventDisableTiming) == cudaSuccess;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); // the few serial-coder CTAs go first when an SM frees up
+    for (int i = 0; ok && i < cedar_b200_handle::NSIDE; i++)
+        ok = cudaStreamCreateWithPriority(&h->stream_cabac[i], cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_cabac[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
         delete h;
         return -ENODEV;
     }
@@ -519,7 +574,7 @@ int cedar_b200_encode_frame(cedar_b200_handle *h)
     if ((r = begin_stream(h, 1)))
         return r;
     Step s = {1, 0, 1, 1};
-    if ((r = encode_step(h, s, h->frame_p_count)))
+    if ((r = encode_step(h, s, h->frame_p_count, h->frame_p_count)))
         return r;
     if ((r = finish_stream(h, 1, h->frame_p_count, h->frame_count == 0)))
         return r;
@@ -578,7 +633,7 @@ int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_in
             Step s = {nl, gop0 * K + t, K, nframes};
             if (s.frame0 >= nframes)
                 break;
-            if ((r = encode_step(h, s, t)))
+            if ((r = encode_step(h, s, t, 0)))
                 return r;
         }
     }
@@ -675,6 +730,7 @@ long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_
     case 3: src = h->d_mbi, n = sizeof(MbInfo) * g.nmb; break;
     case 4: src = h->d_nnz, n = (size_t)NNZ_STRIDE * g.nmb; break;
     case 5: src = h->d_coef, n = sizeof(int16_t) * COEF_STRIDE * g.nmb; break;
+    case 6: src = h->eb.bins_len, n = sizeof(uint32_t) * (h->last_nframes > 0 ? h->last_nframes : 1); break;
     default: return -EINVAL;
     }
     if (n > cap)
@@ -688,7 +744,6 @@ void cedar_b200_close(cedar_b200_handle *h)
 {
     if (!h)
         return;
-    cudaStreamSynchronize(h->stream);
     prof_collect(h);
     double total_ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - h->t_open).count();
     // cedar.c:715-719 prints "Time spent: <waiting>/<total>ns" at release
@@ -696,6 +751,11 @@ void cedar_b200_close(cedar_b200_handle *h)
     for (cudaEvent_t e : h->ev_pool)
         cudaEventDestroy(e);
     free_buffers(h);
+    cudaEventDestroy(h->ev_bins);
+    for (int i = 0; i < cedar_b200_handle::NSIDE; i++) {
+        cudaEventDestroy(h->ev_cabac[i]);
+        cudaStreamDestroy(h->stream_cabac[i]);
+    }
     cudaStreamDestroy(h->stream);
     delete h;
 }

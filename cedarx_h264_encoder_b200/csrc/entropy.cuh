@@ -507,22 +507,54 @@ template <class S> HD void cabac_mb(S &s, const FrameSyntax &fs, int mb_index, i
 // Serial CABAC arithmetic coder (H.264 9.3.4) with byte-wise output and carry propagation.
 // `low` keeps the 10-bit coding window in bits 9..0 and queue+8 not-yet-written bits above it.
 // =============================================================================================
+// Lookup tables of the coder, rebuilt per coder instance (in shared memory on the GPU):
+// lpsw[pStateIdx] = the four rangeTabLPS entries packed little-endian by qRangeIdx;
+// trans[s] (s = pStateIdx << 1 | valMPS) = next s after an MPS in bits 0..7, after an LPS in bits 8..15.
+struct CabacTables {
+    uint32_t lpsw[64];
+    uint16_t trans[128];
+    HD void build(int tid, int nthreads)
+    {
+        for (int i = tid; i < 64; i += nthreads)
+            lpsw[i] = (uint32_t)h264_range_lps[i][0] | ((uint32_t)h264_range_lps[i][1] << 8) |
+                      ((uint32_t)h264_range_lps[i][2] << 16) | ((uint32_t)h264_range_lps[i][3] << 24);
+        for (int s = tid; s < 128; s += nthreads) {
+            int st = s >> 1, mps = s & 1;
+            int after_mps = (h264_next_state_mps[st] << 1) | mps;
+            int after_lps = (h264_next_state_lps[st] << 1) | (st == 0 ? mps ^ 1 : mps);
+            trans[s] = (uint16_t)(after_mps | (after_lps << 8));
+        }
+    }
+};
+
+// State after coding `bin` in state s (s = pStateIdx << 1 | valMPS).
+HD uint32_t cabac_next_state(const CabacTables &t, uint32_t s, int bin)
+{
+    uint32_t tr = t.trans[s];
+    return ((uint32_t)bin != (s & 1)) ? (tr >> 8) : (tr & 0xff);
+}
+HD uint32_t cabac_init_state(int ctx, int frame_i, int qp)
+{
+    int m = frame_i ? h264_cabac_init_I[ctx][0] : h264_cabac_init_P0[ctx][0];
+    int n = frame_i ? h264_cabac_init_I[ctx][1] : h264_cabac_init_P0[ctx][1];
+    int pre = clip3_(1, 126, ((m * clip3_(0, 51, qp)) >> 4) + n);
+    return (uint32_t)(pre <= 63 ? (63 - pre) << 1 : (((pre - 64) << 1) | 1));
+}
+
+// The interval coder proper.  It does not own the context states: the state each regular bin is
+// coded in ("pre-state") is resolved beforehand -- per context the state sequence depends only on that
+// context's own bins, so all contexts are resolved in parallel -- and the serial part only tracks
+// range / low.
 struct CabacCoder {
     uint8_t *out;      // output bytes (first byte written at out[0])
     unsigned pos = 0;  // bytes written
     uint32_t low = 0, range = 510;
     int queue = -9, outstanding = 0;
-    uint8_t *state;    // [460] pStateIdx << 1 | valMPS
+    int last = -1;     // most recent byte, held back until a later carry can no longer reach it
 
-    HD void init_states(int frame_i, int qp)
-    {
-        for (int i = 0; i < 460; i++) {
-            int m = frame_i ? h264_cabac_init_I[i][0] : h264_cabac_init_P0[i][0];
-            int n = frame_i ? h264_cabac_init_I[i][1] : h264_cabac_init_P0[i][1];
-            int pre = clip3_(1, 126, ((m * clip3_(0, 51, qp)) >> 4) + n);
-            state[i] = (uint8_t)(pre <= 63 ? (63 - pre) << 1 : (((pre - 64) << 1) | 1));
-        }
-    }
+    // Pops the top byte of `low`.  o has 9 bits: a carry (only ever together with a 0x00 byte, because
+    // low < 2^(queue+18) + range) and the byte.  0xff bytes are counted, not written, until the next
+    // non-0xff byte shows whether a carry ripples through them.
     HD void put_byte()
     {
         uint32_t o = low >> (queue + 10);
@@ -533,38 +565,42 @@ struct CabacCoder {
             return;
         }
         uint32_t carry = o >> 8;
-        if (pos > 0)
-            out[pos - 1] = (uint8_t)(out[pos - 1] + carry);
+        if (last >= 0)
+            out[pos++] = (uint8_t)(last + carry);
+#pragma unroll 1
         while (outstanding > 0) {
             out[pos++] = (uint8_t)(carry - 1);
             outstanding--;
         }
-        out[pos++] = (uint8_t)o;
+        last = (int)(o & 0xff);
     }
     HD void renorm()
     {
         // range in [2, 510]; shift so that range >= 256
+#ifdef __CUDACC__
+        int shift = __clz((int)range) - 23;
+#else
         int shift = range >= 256 ? 0 : (8 - ilog2_(range));
+#endif
         range <<= shift;
         low <<= shift;
         queue += shift;
         if (queue >= 0)
             put_byte();
     }
-    HD void decision(int ctx, int bin)
+    // lps4 = the four rangeTabLPS entries of the bin's pre-state; is_lps = bin != valMPS
+    HD void decision(uint32_t lps4, int is_lps)
     {
-        int st = state[ctx] >> 1, mps = state[ctx] & 1;
-        uint32_t lps = h264_range_lps[st][(range >> 6) & 3];
+#ifdef __CUDACC__
+        uint32_t lps = __byte_perm(lps4, 0, 0x4440u | ((range >> 6) & 3));
+#else
+        uint32_t lps = (lps4 >> (((range >> 6) & 3) * 8)) & 0xff;
+#endif
         range -= lps;
-        if (bin != mps) {
+        if (is_lps) {
             low += range;
             range = lps;
-            if (st == 0)
-                mps ^= 1;
-            st = h264_next_state_lps[st];
-        } else
-            st = h264_next_state_mps[st];
-        state[ctx] = (uint8_t)((st << 1) | mps);
+        }
         renorm();
     }
     HD void bypass(int bin)
@@ -598,21 +634,26 @@ struct CabacCoder {
                 queue += k;
                 put_byte();
             }
+            if (last >= 0)
+                out[pos++] = (uint8_t)last;
+            last = -1;
+#pragma unroll 1
             while (outstanding > 0) {
                 out[pos++] = 0xff;
                 outstanding--;
             }
         }
     }
-    HD void code(uint16_t b)
+    // b = bin record, lps4 = packed LPS ranges of its pre-state, mps = valMPS of its pre-state
+    HD void code(uint16_t b, uint32_t lps4, uint32_t mps)
     {
-        int v = (b & BIN_VAL) != 0;
+        uint32_t v = (b >> 15) & 1;
         if (b & BIN_BYPASS)
-            bypass(v);
+            bypass((int)v);
         else if (b & BIN_TERM)
-            terminate(v);
+            terminate((int)v);
         else
-            decision(b & 0x3ff, v);
+            decision(lps4, v != mps);
     }
 };
 

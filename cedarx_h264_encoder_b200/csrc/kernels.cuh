@@ -23,8 +23,19 @@ __device__ __forceinline__ int lane_frame(const Step &s, int lane)
     return f < s.nframes ? f : -1;
 }
 
-__device__ __forceinline__ int ld_volatile(const int *p) { return *(const volatile int *)p; }
-__device__ __forceinline__ void st_volatile(int *p, int v) { *(volatile int *)p = v; }
+// Wavefront progress flags: the producer warp stores its pixels, __syncwarp()s, and lane 0 publishes
+// the count with a gpu-scope release; the consumer's lane 0 spins with acquire loads, __syncwarp()s, and
+// the warp then reads the neighbour's pixels from L2 (__ldcg).
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ================================================================================================
 // K0 ingest: packed NV12 / NV16 (w x h) -> planar 4:2:0 at the coded size with edge replication.
@@ -467,9 +478,8 @@ __global__ void __launch_bounds__(32) intra_kernel(Geom g, Step s, const uint8_t
         }
         if (has_top) {
             if (lane == 0) {
-                while (ld_volatile(fl + row - 1) < mbx + 1)
+                while (ld_acquire(fl + row - 1) < mbx + 1)
                     ;
-                __threadfence();
             }
             __syncwarp();
             const uint8_t *ty = unf + fo + (size_t)(row * 16 - 1) * g.W + mbx * 16 - 1;
@@ -623,84 +633,102 @@ __global__ void __launch_bounds__(32) intra_kernel(Geom g, Step s, const uint8_t
             m.pad = 0;
             mbi[rec] = m;
         }
-        __threadfence();
         __syncwarp();
         if (lane == 0)
-            st_volatile(fl + row, mbx + 1);
+            st_release(fl + row, mbx + 1);
     }
 }
 
 // ================================================================================================
-// K5 in-loop deblocking filter (H.264 8.7; slice offsets 0, cedar.c:1024-1029), standard-exact
-// macroblock raster order realised as a 2:1 wavefront: macroblock (x, y) needs (x-1, y) and
-// (x+1, y-1).  One CTA per macroblock row: warp 0 filters luma, warp 1 filters Cb and Cr; they have
-// independent progress flags.  Reads the unfiltered frame `unf`, writes the reference frame `rec`.
+// K5 in-loop deblocking filter (H.264 8.7; slice offsets 0, cedar.c:1024-1029).
+//
+// bs_kernel: boundary strengths of all 32 edge segments of every macroblock, fully parallel
+// (record = [dir][edge][segment] bytes: dir 0 vertical edges, 1 horizontal).
+//
+// deblock_kernel: standard-exact macroblock raster order realised as a 2:1 wavefront: macroblock
+// (x, y) needs (x-1, y) and (x+1, y-1).  One CTA per macroblock row: warp 0 filters luma, warp 1
+// filters Cb and Cr; they have independent progress flags.  Reads the unfiltered frame `unf`, writes
+// the reference frame `rec`.  The next macroblock's pixels and strengths are prefetched into registers
+// before the current one waits on the row above.
 // Bound: dependency latency (mbw + 2 * mbh steps per frame).
 // ================================================================================================
-__device__ __forceinline__ int mb_bs(const MbInfo &cur, const uint8_t *ncur, const MbInfo &left, const uint8_t *nleft,
-                                     const MbInfo &top, const uint8_t *ntop, int dir, int e, int sg, bool has_left,
-                                     bool has_top)
+__global__ void bs_kernel(Geom g, Step s, const MbInfo *__restrict__ mbi, const uint8_t *__restrict__ nnz,
+                          uint8_t *__restrict__ bs)
 {
-    if (dir == 0) { // vertical edge e, rows 4*sg..
-        if (e == 0) {
-            if (!has_left)
-                return 0;
-            return boundary_strength(left, nleft[xy2blk(3, sg)], cur, ncur[xy2blk(0, sg)], 1);
-        }
-        return boundary_strength(cur, ncur[xy2blk(e - 1, sg)], cur, ncur[xy2blk(e, sg)], 0);
-    }
+    if (lane_frame(s, blockIdx.y) < 0)
+        return;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x; // (macroblock, dir, edge)
+    int mb = idx >> 3, dir = (idx >> 2) & 1, e = idx & 3;
+    if (mb >= g.nmb)
+        return;
+    const MbInfo *fm = mbi + (size_t)blockIdx.y * g.nmb;
+    const uint8_t *fn = nnz + (size_t)blockIdx.y * g.nmb * NNZ_STRIDE;
+    const int mbx = mb % g.mbw, mby = mb / g.mbw;
+    const MbInfo cur = fm[mb];
+    const uint8_t *ncur = fn + (size_t)mb * NNZ_STRIDE;
+    uint32_t out = 0;
     if (e == 0) {
-        if (!has_top)
-            return 0;
-        return boundary_strength(top, ntop[xy2blk(sg, 3)], cur, ncur[xy2blk(sg, 0)], 1);
+        bool avail = dir == 0 ? mbx > 0 : mby > 0;
+        if (avail) {
+            int nb = dir == 0 ? mb - 1 : mb - g.mbw;
+            const MbInfo nbm = fm[nb];
+            const uint8_t *nn = fn + (size_t)nb * NNZ_STRIDE;
+#pragma unroll
+            for (int sg = 0; sg < 4; sg++) {
+                int bp = dir == 0 ? xy2blk(3, sg) : xy2blk(sg, 3), bq = dir == 0 ? xy2blk(0, sg) : xy2blk(sg, 0);
+                out |= (uint32_t)boundary_strength(nbm, nn[bp], cur, ncur[bq], 1) << (8 * sg);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int sg = 0; sg < 4; sg++) {
+            int bp = dir == 0 ? xy2blk(e - 1, sg) : xy2blk(sg, e - 1), bq = dir == 0 ? xy2blk(e, sg) : xy2blk(sg, e);
+            out |= (uint32_t)boundary_strength(cur, ncur[bp], cur, ncur[bq], 0) << (8 * sg);
+        }
     }
-    return boundary_strength(cur, ncur[xy2blk(sg, e - 1)], cur, ncur[xy2blk(sg, e)], 0);
+    ((uint32_t *)bs)[((size_t)blockIdx.y * g.nmb + mb) * 8 + dir * 4 + e] = out;
 }
 
 __global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8_t *__restrict__ unf, uint8_t *rec,
-                                                     const MbInfo *__restrict__ mbi, const uint8_t *__restrict__ nnz,
-                                                     int *flags_y, int *flags_c)
+                                                     const uint8_t *__restrict__ bs, int *flags_y, int *flags_c)
 {
     if (lane_frame(s, blockIdx.y) < 0)
         return;
     __shared__ uint32_t tileY[20 * 6];     // 20 rows x 24 bytes: rows 0..3 top MB, cols 0..3 left MB
     __shared__ uint32_t tileC[2][10 * 3];  // per plane 10 rows x 12 bytes: rows 0..1 top, cols 0..3 left
-    __shared__ uint8_t bsY[32], bsC[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = blockIdx.x;
     const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
-    const MbInfo *fm = mbi + (size_t)blockIdx.y * g.nmb;
-    const uint8_t *fn = nnz + (size_t)blockIdx.y * g.nmb * NNZ_STRIDE;
+    const uint4 *fbs = (const uint4 *)bs + ((size_t)blockIdx.y * g.nmb + (size_t)row * g.mbw) * 2;
     const bool has_top = row > 0;
+    const int sh = (lane >> 2) * 8; // byte of a strength word that belongs to this lane's 4-sample segment
 
     if (warp == 0) {
         int *fl = flags_y + (size_t)blockIdx.y * g.mbh;
         const int alpha = h264_deblock_alpha[g.qp], beta = h264_deblock_beta[g.qp];
+        const int tc0_1 = h264_deblock_tc0[g.qp][0], tc0_2 = h264_deblock_tc0[g.qp][1], tc0_3 = h264_deblock_tc0[g.qp][2];
         uint8_t *tb = (uint8_t *)tileY;
+        const uint8_t *urow = unf + fo + (size_t)(row * 16 + (lane & 15)) * g.W;
+        uint4 nx_px = *(const uint4 *)urow, nx_v = fbs[0], nx_h = fbs[1];
         for (int mbx = 0; mbx < g.mbw; mbx++) {
             const bool has_left = mbx > 0;
-            const int mb = row * g.mbw + mbx;
             const int x0 = mbx * 16, y0 = row * 16;
-            if (lane < 16) {
-                if (has_left)
-                    tileY[(4 + lane) * 6 + 0] = tileY[(4 + lane) * 6 + 4];
-                uint4 v = *(const uint4 *)(unf + fo + (size_t)(y0 + lane) * g.W + x0);
-                uint32_t *t = tileY + (4 + lane) * 6 + 1;
-                t[0] = v.x, t[1] = v.y, t[2] = v.z, t[3] = v.w;
+            const uint4 px = nx_px, bv = nx_v, bh = nx_h;
+            if (mbx + 1 < g.mbw) { // prefetch the next macroblock
+                nx_px = *(const uint4 *)(urow + x0 + 16);
+                nx_v = fbs[(mbx + 1) * 2];
+                nx_h = fbs[(mbx + 1) * 2 + 1];
             }
-            {
-                int dir = lane >> 4, e = (lane >> 2) & 3, sg = lane & 3;
-                bsY[lane] = (uint8_t)mb_bs(fm[mb], fn + (size_t)mb * NNZ_STRIDE, fm[has_left ? mb - 1 : mb],
-                                           fn + (size_t)(has_left ? mb - 1 : mb) * NNZ_STRIDE,
-                                           fm[has_top ? mb - g.mbw : mb],
-                                           fn + (size_t)(has_top ? mb - g.mbw : mb) * NNZ_STRIDE, dir, e, sg, has_left,
-                                           has_top);
+            if (lane < 16) {
+                uint32_t *t = tileY + (4 + lane) * 6;
+                if (has_left)
+                    t[0] = t[4];
+                t[1] = px.x, t[2] = px.y, t[3] = px.z, t[4] = px.w;
             }
             if (has_top) {
                 if (lane == 0) {
                     int need = imin_(mbx + 2, g.mbw);
-                    while (ld_volatile(fl + row - 1) < need)
+                    while (ld_acquire(fl + row - 1) < need)
                         ;
-                    __threadfence();
                 }
                 __syncwarp();
                 if (lane < 4) {
@@ -712,16 +740,17 @@ __global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8
             __syncwarp();
             if (lane < 16) { // vertical edges: lane = row
                 uint32_t *t = tileY + (4 + lane) * 6;
+                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    int bS = bsY[e * 4 + (lane >> 2)];
+                    int bS = (bw[e] >> sh) & 0xff;
                     if (bS) {
                         uint32_t a = t[e], b = t[e + 1];
                         int v[8];
 #pragma unroll
                         for (int i = 0; i < 4; i++)
                             v[i] = (a >> (8 * i)) & 0xff, v[4 + i] = (b >> (8 * i)) & 0xff;
-                        filter_luma8(v, bS, alpha, beta, bS < 4 ? h264_deblock_tc0[g.qp][bS - 1] : 0);
+                        filter_luma8(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
                         t[e] = pack4(v);
                         t[e + 1] = pack4(v + 4);
                     }
@@ -730,15 +759,16 @@ __global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8
             __syncwarp();
             if (lane < 16) { // horizontal edges: lane = column
                 uint8_t *col = tb + 4 + lane;
+                const uint32_t bw[4] = {bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    int bS = bsY[16 + e * 4 + (lane >> 2)];
+                    int bS = (bw[e] >> sh) & 0xff;
                     if (bS) {
                         int v[8];
 #pragma unroll
                         for (int i = 0; i < 8; i++)
                             v[i] = col[(4 * e + i) * 24];
-                        filter_luma8(v, bS, alpha, beta, bS < 4 ? h264_deblock_tc0[g.qp][bS - 1] : 0);
+                        filter_luma8(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
 #pragma unroll
                         for (int i = 1; i < 7; i++)
                             col[(4 * e + i) * 24] = (uint8_t)v[i];
@@ -757,43 +787,43 @@ __global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8
                 const uint32_t *t = tileY + r * 6;
                 *(uint4 *)(rec + fo + (size_t)(y0 - 4 + r) * g.W + x0) = make_uint4(t[1], t[2], t[3], t[4]);
             }
-            __threadfence();
             __syncwarp();
             if (lane == 0)
-                st_volatile(fl + row, mbx + 1);
+                st_release(fl + row, mbx + 1);
         }
     } else {
         int *fl = flags_c + (size_t)blockIdx.y * g.mbh;
         const int alpha = h264_deblock_alpha[g.qpc], beta = h264_deblock_beta[g.qpc];
+        const int tc0_1 = h264_deblock_tc0[g.qpc][0], tc0_2 = h264_deblock_tc0[g.qpc][1], tc0_3 = h264_deblock_tc0[g.qpc][2];
         const int pl = (lane >> 3) & 1, r8 = lane & 7;
         const size_t po = fo + (size_t)g.W * g.H + (size_t)pl * g.CW * g.CH;
         uint32_t *tw = tileC[pl];
         uint8_t *tb = (uint8_t *)tileC[pl];
+        const int shc = (r8 >> 1) * 8; // chroma row / column k <-> luma segment k >> 1
+        const uint8_t *urow = unf + po + (size_t)(row * 8 + r8) * g.CW;
+        uint2 nx_px = *(const uint2 *)urow;
+        uint4 nx_v = fbs[0], nx_h = fbs[1];
         for (int mbx = 0; mbx < g.mbw; mbx++) {
             const bool has_left = mbx > 0;
-            const int mb = row * g.mbw + mbx;
             const int x0 = mbx * 8, y0 = row * 8;
+            const uint2 px = nx_px;
+            const uint4 bv = nx_v, bh = nx_h;
+            if (mbx + 1 < g.mbw) {
+                nx_px = *(const uint2 *)(urow + x0 + 8);
+                nx_v = fbs[(mbx + 1) * 2];
+                nx_h = fbs[(mbx + 1) * 2 + 1];
+            }
             if (lane < 16) {
                 if (has_left)
                     tw[(2 + r8) * 3 + 0] = tw[(2 + r8) * 3 + 2];
-                uint2 v = *(const uint2 *)(unf + po + (size_t)(y0 + r8) * g.CW + x0);
-                tw[(2 + r8) * 3 + 1] = v.x;
-                tw[(2 + r8) * 3 + 2] = v.y;
-            }
-            if (lane < 16) { // bS of luma edges 0 and 2 only
-                int dir = lane >> 3, e = ((lane >> 2) & 1) * 2, sg = lane & 3;
-                bsC[lane] = (uint8_t)mb_bs(fm[mb], fn + (size_t)mb * NNZ_STRIDE, fm[has_left ? mb - 1 : mb],
-                                           fn + (size_t)(has_left ? mb - 1 : mb) * NNZ_STRIDE,
-                                           fm[has_top ? mb - g.mbw : mb],
-                                           fn + (size_t)(has_top ? mb - g.mbw : mb) * NNZ_STRIDE, dir, e, sg, has_left,
-                                           has_top);
+                tw[(2 + r8) * 3 + 1] = px.x;
+                tw[(2 + r8) * 3 + 2] = px.y;
             }
             if (has_top) {
                 if (lane == 0) {
                     int need = imin_(mbx + 2, g.mbw);
-                    while (ld_volatile(fl + row - 1) < need)
+                    while (ld_acquire(fl + row - 1) < need)
                         ;
-                    __threadfence();
                 }
                 __syncwarp();
                 if (lane < 16 && r8 < 2) {
@@ -803,14 +833,15 @@ __global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8
                 }
             }
             __syncwarp();
-            if (lane < 16) { // vertical edges at chroma x = 0, 4: lane = (plane, row)
+            if (lane < 16) { // vertical edges at chroma x = 0, 4 (luma edges 0, 2): lane = (plane, row)
                 uint8_t *t = tb + (2 + r8) * 12;
+                const uint32_t bw[2] = {bv.x, bv.z};
 #pragma unroll
                 for (int ce = 0; ce < 2; ce++) {
-                    int bS = bsC[ce * 4 + (r8 >> 1)];
+                    int bS = (bw[ce] >> shc) & 0xff;
                     if (bS) {
                         int v[4] = {t[2 + 4 * ce], t[3 + 4 * ce], t[4 + 4 * ce], t[5 + 4 * ce]};
-                        filter_chroma4(v, bS, alpha, beta, bS < 4 ? h264_deblock_tc0[g.qpc][bS - 1] : 0);
+                        filter_chroma4(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
                         t[3 + 4 * ce] = (uint8_t)v[1];
                         t[4 + 4 * ce] = (uint8_t)v[2];
                     }
@@ -819,12 +850,13 @@ __global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8
             __syncwarp();
             if (lane < 16) { // horizontal edges at chroma y = 0, 4: lane = (plane, column)
                 uint8_t *col = tb + 4 + r8;
+                const uint32_t bw[2] = {bh.x, bh.z};
 #pragma unroll
                 for (int ce = 0; ce < 2; ce++) {
-                    int bS = bsC[8 + ce * 4 + (r8 >> 1)];
+                    int bS = (bw[ce] >> shc) & 0xff;
                     if (bS) {
                         int v[4] = {col[(4 * ce) * 12], col[(4 * ce + 1) * 12], col[(4 * ce + 2) * 12], col[(4 * ce + 3) * 12]};
-                        filter_chroma4(v, bS, alpha, beta, bS < 4 ? h264_deblock_tc0[g.qpc][bS - 1] : 0);
+                        filter_chroma4(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
                         col[(4 * ce + 1) * 12] = (uint8_t)v[1];
                         col[(4 * ce + 2) * 12] = (uint8_t)v[2];
                     }
@@ -842,10 +874,9 @@ __global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8
                 *(uint2 *)(rec + fo + (size_t)g.W * g.H + (size_t)p2 * g.CW * g.CH + (size_t)(y0 - 1) * g.CW + x0) =
                     make_uint2(t[1], t[2]);
             }
-            __threadfence();
             __syncwarp();
             if (lane == 0)
-                st_volatile(fl + row, mbx + 1);
+                st_release(fl + row, mbx + 1);
         }
     }
 }
@@ -890,6 +921,7 @@ struct EntropyBufs {
     unsigned rbsp_cap;
     uint32_t *rbsp_len;      // [F] bytes of RBSP (header + slice data + trailing)
     uint16_t *bins;          // CABAC bin pool
+    uint8_t *pre;            // pre-state of every bin (same indexing as bins)
     unsigned long long bins_cap;
     unsigned long long *bins_cursor; // pool bump pointer
     unsigned long long *bins_off;    // [F]
@@ -992,7 +1024,7 @@ __global__ void __launch_bounds__(1024) entropy_scan_kernel(Geom g, Step s, Entr
     if (tid == 0) {
         uint32_t total = carry_s;
         if (g.cabac) {
-            unsigned long long off = atomicAdd(eb.bins_cursor, (unsigned long long)total);
+            unsigned long long off = atomicAdd(eb.bins_cursor, (unsigned long long)((total + 7u) & ~7u));
             if (off + total > eb.bins_cap) {
                 atomicExch(eb.error, 1);
                 off = 0;
@@ -1045,65 +1077,141 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
     }
 }
 
-// K7 serial arithmetic coder: one warp per frame, lane 0 codes.  Context states live in shared
-// memory; bins are streamed through registers eight at a time.
-__global__ void __launch_bounds__(32) cabac_encode_kernel(Geom g, int first_frame, int nframes, int gop_len,
-                                                          int gop_pos0, EntropyBufs eb)
+// K7a context-state resolution.  The state a regular bin is coded in depends only on the earlier bins of
+// the SAME context, so the 460 contexts are independent chains: one CTA per frame, each thread owns one
+// context and walks the frame's bin stream (staged through shared memory in tiles), recording the state
+// before each of its bins.  This removes every context-state access from the serial coder below.
+// Matches serialise inside a warp, so neighbouring (equally hot) contexts are dealt to different warps.
+#define RESOLVE_TILE 4096
+__global__ void __launch_bounds__(512) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0, EntropyBufs eb)
 {
-    __shared__ uint8_t state[464];
-    int f = first_frame + blockIdx.x;
-    if (f >= nframes || threadIdx.x != 0)
+    __shared__ CabacTables tab;
+    __shared__ uint2 tile[RESOLVE_TILE / 4];
+    __shared__ uint8_t ptile[RESOLVE_TILE];
+    int f = lane_frame(s, blockIdx.x);
+    if (f < 0)
         return;
-    uint8_t *out = eb.rbsp + (size_t)f * eb.rbsp_cap;
     const int frame_i = ((gop_pos0 + f) % gop_len) == 0;
-    uint32_t nb = eb.bins_len[f];
+    const uint32_t nb = eb.bins_len[f];
+    const uint16_t *bins = eb.bins + eb.bins_off[f]; // bins_off is a multiple of 8 bins => 16-byte aligned
+    uint8_t *pre = eb.pre + eb.bins_off[f];
+    const int tid = threadIdx.x;
+    tab.build(tid, 512);
+    const uint32_t c = (uint32_t)((tid & 15) * 32 + (tid >> 4)); // context c -> warp c % 16
+    const uint32_t c2 = c | (c << 16);
+    uint32_t st = c < 460 ? cabac_init_state((int)c, frame_i, g.qp) : 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += RESOLVE_TILE) {
+        const uint32_t n = nb - base < RESOLVE_TILE ? nb - base : RESOLVE_TILE;
+        const uint32_t nq = (n + 3) >> 2;
+        for (uint32_t i = tid; i < nq; i += 512)
+            tile[i] = ((const uint2 *)(bins + base))[i];
+        __syncthreads();
+        if (c < 460) {
+#pragma unroll 2
+            for (uint32_t i = 0; i < nq; i++) {
+                const uint2 w = tile[i]; // four bins; same address for the whole warp => broadcast
+                const uint32_t m0 = __vcmpeq2(w.x & 0x0fff0fffu, c2), m1 = __vcmpeq2(w.y & 0x0fff0fffu, c2);
+                if (m0 | m1) {
+                    if (m0 & 0xffffu) {
+                        ptile[4 * i] = (uint8_t)st;
+                        st = cabac_next_state(tab, st, (w.x >> 15) & 1);
+                    }
+                    if (m0 >> 16) {
+                        ptile[4 * i + 1] = (uint8_t)st;
+                        st = cabac_next_state(tab, st, (w.x >> 31) & 1);
+                    }
+                    if (m1 & 0xffffu) {
+                        ptile[4 * i + 2] = (uint8_t)st;
+                        st = cabac_next_state(tab, st, (w.y >> 15) & 1);
+                    }
+                    if (m1 >> 16) {
+                        ptile[4 * i + 3] = (uint8_t)st;
+                        st = cabac_next_state(tab, st, (w.y >> 31) & 1);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < nq; i += 512)
+            ((uint32_t *)(pre + base))[i] = ((const uint32_t *)ptile)[i];
+        __syncthreads();
+    }
+}
+
+// K7b serial interval coder: one warp per frame (slice).  All lanes stage the next 32 bins (global ->
+// registers -> shared, with the LPS ranges of each bin's pre-state looked up in parallel); lane 0 then
+// codes them in a compact loop that only updates range / low (about a dozen dependent integer
+// instructions per bin).  Output bytes are written once (the byte a carry could still reach is held in a
+// register).  Runs on side streams so that it overlaps the reconstruction of the following frames.
+__global__ void __launch_bounds__(32) cabac_encode_kernel(Geom g, Step s, EntropyBufs eb)
+{
+    __shared__ CabacTables tab;
+    __shared__ uint2 stage[32]; // x = packed LPS ranges, y = bit0 value-or-isLPS, bit1 bypass, bit2 terminate
+    int f = lane_frame(s, blockIdx.x);
+    if (f < 0)
+        return;
+    const int lane = threadIdx.x;
+    tab.build(lane, 32);
+    __syncwarp();
+    uint8_t *out = eb.rbsp + (size_t)f * eb.rbsp_cap;
+    const uint32_t nb = eb.bins_len[f];
     if (nb == 0) {
-        eb.rbsp_len[f] = 0;
+        if (lane == 0)
+            eb.rbsp_len[f] = 0;
         return;
     }
-    int hn = eb.hdr_nbits[f], hb = (hn + 7) >> 3;
-    unsigned long long h = ((unsigned long long)eb.hdr_bits[f] << (hb * 8 - hn)) | ((1ull << (hb * 8 - hn)) - 1);
-    for (int i = 0; i < hb; i++)
-        out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
+    const int hn = eb.hdr_nbits[f], hb = (hn + 7) >> 3;
+    if (lane == 0) {
+        unsigned long long h = ((unsigned long long)eb.hdr_bits[f] << (hb * 8 - hn)) | ((1ull << (hb * 8 - hn)) - 1);
+        for (int i = 0; i < hb; i++)
+            out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
+    }
     CabacCoder c;
     c.out = out + hb;
-    c.state = state;
-    c.init_states(frame_i, g.qp);
     const uint16_t *bins = eb.bins + eb.bins_off[f];
-    const unsigned limit = eb.rbsp_cap - hb - 16;
-    // bins_off is a multiple of nothing in particular: peel to 16-byte alignment, then stream uint4
-    uint32_t i = 0;
-    while (i < nb && (((size_t)(bins + i)) & 15)) {
-        c.code(bins[i]);
-        i++;
+    const uint8_t *pre = eb.pre + eb.bins_off[f];
+    const unsigned limit = eb.rbsp_cap - hb - 64;
+    uint32_t nb_b = lane < nb ? bins[lane] : 0, nb_p = lane < nb ? pre[lane] : 0;
+    bool overflow = false;
+    for (uint32_t base = 0; base < nb; base += 32) {
+        const uint32_t b = nb_b, ps = nb_p;
+        if (base + 32 + lane < nb) { // prefetch the next 32 bins while lane 0 codes these
+            nb_b = bins[base + 32 + lane];
+            nb_p = pre[base + 32 + lane];
+        }
+        const uint32_t special = (b >> 10) & 3; // bit0 bypass, bit1 terminate
+        const uint32_t v = (b >> 15) & 1;
+        stage[lane] = make_uint2(tab.lpsw[(ps >> 1) & 63], special ? (v | (special << 1)) : (v ^ (ps & 1)));
+        __syncwarp();
+        if (lane == 0) {
+            const int cnt = nb - base < 32 ? (int)(nb - base) : 32;
+            uint2 e = stage[0];
+#pragma unroll 1
+            for (int k = 0; k < cnt; k++) {
+                const uint2 cur = e;
+                e = stage[(k + 1) & 31];
+                if (cur.y & 6) {
+                    if (cur.y & 2)
+                        c.bypass((int)(cur.y & 1));
+                    else
+                        c.terminate((int)(cur.y & 1));
+                } else
+                    c.decision(cur.x, (int)cur.y);
+            }
+            overflow = c.pos + c.outstanding > limit;
+        }
+        overflow = __shfl_sync(0xffffffffu, overflow, 0);
+        if (overflow)
+            break;
     }
-    uint4 nxt = make_uint4(0, 0, 0, 0);
-    if (i + 8 <= nb)
-        nxt = *(const uint4 *)(bins + i);
-    while (i + 8 <= nb) {
-        uint4 v = nxt;
-        if (i + 16 <= nb)
-            nxt = *(const uint4 *)(bins + i + 8);
-        c.code((uint16_t)(v.x & 0xffff));
-        c.code((uint16_t)(v.x >> 16));
-        c.code((uint16_t)(v.y & 0xffff));
-        c.code((uint16_t)(v.y >> 16));
-        c.code((uint16_t)(v.z & 0xffff));
-        c.code((uint16_t)(v.z >> 16));
-        c.code((uint16_t)(v.w & 0xffff));
-        c.code((uint16_t)(v.w >> 16));
-        i += 8;
-        if (c.pos > limit) {
+    if (lane == 0) {
+        if (overflow) {
             atomicExch(eb.error, 3);
             eb.rbsp_len[f] = 0;
-            return;
-        }
+        } else
+            eb.rbsp_len[f] = (uint32_t)(hb + c.pos);
     }
-    while (i < nb) {
-        c.code(bins[i]);
-        i++;
-    }
-    eb.rbsp_len[f] = (uint32_t)(hb + c.pos);
 }
 
 // ================================================================================================

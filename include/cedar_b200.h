@@ -122,7 +122,8 @@ long long cedar_b200_launch_count(cedar_b200_handle *h);
 
 /* Debug / parity-test access to intermediates of the last encode_frame call (lane 0):
  * what = 0 source planes, 1 unfiltered recon, 2 deblocked recon (Y then U then V, coded size),
- *        3 macroblock info records, 4 nnz records, 5 coefficient levels.  Returns bytes copied. */
+ *        3 macroblock info records, 4 nnz records, 5 coefficient levels,
+ *        6 CABAC bins per frame of the last call (uint32 each).  Returns bytes copied. */
 long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_t cap);
 
 /* Header writer on its own (host C; restates kernel/cedar.c:868-1030) for byte-identity tests. */

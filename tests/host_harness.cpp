@@ -76,15 +76,27 @@ long hh_cabac_frame(const void *mbi, const uint8_t *nnz, const int16_t *coef, in
     unsigned long long h = ((unsigned long long)hdr_bits << (hb * 8 - hdr_nbits)) | ((1ull << (hb * 8 - hdr_nbits)) - 1);
     for (int i = 0; i < hb; i++)
         out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
-    uint8_t state[460];
+    // pre-state resolution (sequential here; per-context parallel in cabac_resolve_kernel), then the coder
+    CabacTables tab;
+    tab.build(0, 1);
+    uint32_t state[460];
+    for (int i = 0; i < 460; i++)
+        state[i] = cabac_init_state(i, frame_i, qp);
+    std::vector<uint8_t> pre(total + 1, 0);
+    for (size_t i = 0; i < total; i++) {
+        uint16_t b = bins[i];
+        if (!(b & (BIN_BYPASS | BIN_TERM))) {
+            int ctx = b & 0x3ff;
+            pre[i] = (uint8_t)state[ctx];
+            state[ctx] = cabac_next_state(tab, state[ctx], (b >> 15) & 1);
+        }
+    }
     CabacCoder c;
     c.out = out + hb;
-    c.state = state;
-    c.init_states(frame_i, qp);
     for (size_t i = 0; i < total; i++) {
         if ((long)(hb + c.pos + 8) > cap)
             return -1;
-        c.code(bins[i]);
+        c.code(bins[i], tab.lpsw[pre[i] >> 1], pre[i] & 1);
     }
     return hb + (long)c.pos;
 }
