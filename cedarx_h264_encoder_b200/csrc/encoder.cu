@@ -27,12 +27,12 @@ namespace {
 
 enum KernelId {
     K_INGEST, K_ME, K_INTER, K_MVP, K_INTRA, K_BS, K_DEBLOCK, K_SSE, K_ESIZE, K_ESCAN, K_EZERO, K_EWRITE,
-    K_RESOLVE, K_CABAC, K_EPBCOUNT, K_EPBSCAN, K_PACKSCAN, K_EPBWRITE, K_COUNT
+    K_CABAC, K_EPBCOUNT, K_EPBSCAN, K_PACKSCAN, K_EPBWRITE, K_COUNT
 };
 const char *kKernelNames[K_COUNT] = {
     "ingest_kernel", "me_kernel", "inter_kernel", "mvp_skip_kernel", "intra_kernel", "bs_kernel", "deblock_kernel",
     "sse_kernel", "entropy_size_kernel", "entropy_scan_kernel", "rbsp_zero_kernel", "entropy_write_kernel",
-    "cabac_resolve_kernel", "cabac_encode_kernel", "epb_count_kernel", "epb_scan_kernel", "pack_scan_kernel", "epb_write_kernel"};
+    "cabac_kernel", "epb_count_kernel", "epb_scan_kernel", "pack_scan_kernel", "epb_write_kernel"};
 
 const uint8_t kChromaQp[52] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17,
                                18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32, 32, 33,
@@ -68,7 +68,12 @@ struct cedar_b200_handle {
     // each other and the following frames' reconstruction
     enum { NSIDE = 32 };
     cudaStream_t stream_cabac[NSIDE];
+    enum { MAXGRP = 4 };
+    cudaStream_t stream_grp[MAXGRP]; // [0] == stream; lane groups 1.. run on their own streams
+    cudaEvent_t ev_grp[MAXGRP], ev_bins_grp[MAXGRP], ev_begin;
+    int ngroups;
     cudaEvent_t ev_bins, ev_cabac[NSIDE];
+    size_t cabac_excl_smem; // dummy dynamic smem that leaves no room for another CTA on the SM
     unsigned side_used; // bit i: side stream i has work the main stream has not joined yet
     int side_next;
 
@@ -299,10 +304,8 @@ int alloc_buffers(cedar_b200_handle *h)
     r |= dmalloc(&h->d_hdr_nbits, F);
     r |= dmalloc(&h->eb.rbsp, (size_t)h->eb.rbsp_cap * F);
     r |= dmalloc(&h->eb.rbsp_len, F);
-    if (g.cabac) {
+    if (g.cabac)
         r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap);
-        r |= dmalloc(&h->eb.pre, (size_t)h->eb.bins_cap);
-    }
     r |= dmalloc(&h->eb.bins_cursor, 1);
     r |= dmalloc(&h->eb.bins_off, F);
     r |= dmalloc(&h->eb.bins_len, F);
@@ -329,7 +332,7 @@ void free_buffers(cedar_b200_handle *h)
 {
     void *dev[] = {h->d_raw, h->d_src, h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi, h->d_nnz, h->d_coef, h->d_flags, h->d_bs,
                    h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp, h->eb.rbsp_len,
-                   h->eb.bins, h->eb.pre, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
+                   h->eb.bins, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
                    h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes, h->d_out};
     for (void *p : dev)
         if (p)
@@ -341,49 +344,66 @@ void free_buffers(cedar_b200_handle *h)
             cudaFreeHost(p);
 }
 
-// One lock-step pass over `nl` lanes: the macroblock pipeline of one frame per lane plus the
-// parallel part of entropy coding.  t = position inside the GOP (0 => IDR).
-int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0)
+// One lock-step pass over the lanes [lane0, lane0 + s.nlanes): the macroblock pipeline of one frame per lane
+// plus the parallel part of entropy coding, issued on stream `st`.  t = position inside the GOP (0 => IDR).
+// Lane groups run on different streams so that one group's latency-bound wavefronts overlap another
+// group's throughput-bound motion search.
+int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int lane0, cudaStream_t st, cudaEvent_t ev_bins)
 {
     const Geom &g = h->g;
     const int nl = s.nlanes, cur = t & 1, frame_i = t == 0;
-    const size_t flag_n = (size_t)h->L * g.mbh;
-    int *fl_intra = h->d_flags, *fl_y = h->d_flags + flag_n, *fl_c = h->d_flags + 2 * flag_n;
-    uint8_t *rec = h->d_rec[cur], *ref = h->d_rec[cur ^ 1];
+    const size_t flag_n = (size_t)h->L * g.mbh, fl_off = (size_t)lane0 * g.mbh;
+    int *fl_intra = h->d_flags + fl_off, *fl_y = h->d_flags + flag_n + fl_off, *fl_c = h->d_flags + 2 * flag_n + fl_off;
+    const size_t po = (size_t)lane0 * g.frame_bytes, mo = (size_t)lane0 * g.nmb;
+    uint8_t *src = h->d_src + po, *unf = h->d_unf + po, *rec = h->d_rec[cur] + po, *ref = h->d_rec[cur ^ 1] + po;
+    MbInfo *mbi = h->d_mbi + mo;
+    uint8_t *nnz = h->d_nnz + mo * NNZ_STRIDE, *bs = h->d_bs + mo * 32;
+    int16_t *coef = h->d_coef + mo * COEF_STRIDE;
+    EntropyBufs eb = h->eb;
+    eb.mb_size += (size_t)lane0 * (g.nmb + 1);
+    eb.mb_off += (size_t)lane0 * (g.nmb + 1);
 
-    LAUNCH(K_INGEST, ingest_kernel, dim3((unsigned)((g.frame_bytes / 4 + 255) / 256), nl), 256, 0, g, s, h->d_raw,
-           h->raw_frame_bytes, h->d_src);
-    CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 3 * flag_n, h->stream));
+    LAUNCH_ON(st, K_INGEST, ingest_kernel, dim3((unsigned)((g.frame_bytes / 4 + 255) / 256), nl), 256, 0, g, s, h->d_raw,
+              h->raw_frame_bytes, src);
+    for (int k = 0; k < 3; k++)
+        CK(cudaMemsetAsync(h->d_flags + k * flag_n + fl_off, 0, sizeof(int) * nl * g.mbh, st));
     if (frame_i) {
-        LAUNCH(K_INTRA, intra_kernel, dim3(g.mbh, nl), 32, 0, g, s, h->d_src, h->d_unf, h->d_mbi, h->d_nnz, h->d_coef,
-               fl_intra);
+        LAUNCH_ON(st, K_INTRA, intra_kernel, dim3(g.mbh, nl), 32, 0, g, s, src, unf, mbi, nnz, coef, fl_intra);
     } else {
-        LAUNCH(K_ME, me_kernel, dim3(g.nmb, nl), ME_THREADS, me_smem_bytes(g.R), g, s, h->d_src, ref, h->d_mbi);
-        LAUNCH(K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, h->d_src, ref, h->d_unf, h->d_mbi,
-               h->d_nnz, h->d_coef);
-        LAUNCH(K_MVP, mvp_skip_kernel, dim3((g.nmb + 127) / 128, nl), 128, 0, g, s, h->d_mbi);
+        const int nstrip = me_strip(g.R);
+        LAUNCH_ON(st, K_ME, me_kernel, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
+                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi);
+        LAUNCH_ON(st, K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, src, ref, unf, mbi, nnz, coef);
+        LAUNCH_ON(st, K_MVP, mvp_skip_kernel, dim3((g.nmb + 127) / 128, nl), 128, 0, g, s, mbi);
     }
-    LAUNCH(K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, h->d_mbi, h->d_nnz, h->d_bs);
-    LAUNCH(K_DEBLOCK, deblock_kernel, dim3(g.mbh, nl), 64, 0, g, s, h->d_unf, rec, h->d_bs, fl_y, fl_c);
-    LAUNCH(K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, h->d_src, rec, h->d_sse);
+    LAUNCH_ON(st, K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, mbi, nnz, bs);
+    LAUNCH_ON(st, K_DEBLOCK, deblock_kernel, dim3(g.mbh, nl), 256, 0, g, s, unf, rec, bs, fl_y, fl_c);
+    LAUNCH_ON(st, K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, src, rec, h->d_sse);
 
     dim3 egrid((g.nmb + 1 + 127) / 128, nl);
-    LAUNCH(K_ESIZE, entropy_size_kernel, egrid, 128, 0, g, s, frame_i, h->d_mbi, h->d_nnz, h->d_coef, h->eb);
-    LAUNCH(K_ESCAN, entropy_scan_kernel, dim3(1, nl), 1024, 0, g, s, h->eb);
+    LAUNCH_ON(st, K_ESIZE, entropy_size_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, eb);
+    LAUNCH_ON(st, K_ESCAN, entropy_scan_kernel, dim3(1, nl), 1024, 0, g, s, eb);
     if (!g.cabac)
-        LAUNCH(K_EZERO, rbsp_zero_kernel, dim3(8, nl), 256, 0, s, h->eb.rbsp, h->eb.rbsp_cap, h->eb.rbsp_len);
-    LAUNCH(K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, h->d_mbi, h->d_nnz, h->d_coef, h->eb);
+        LAUNCH_ON(st, K_EZERO, rbsp_zero_kernel, dim3(8, nl), 256, 0, s, eb.rbsp, eb.rbsp_cap, eb.rbsp_len);
+    LAUNCH_ON(st, K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, eb);
     if (g.cabac) {
-        // the bins of these frames are final: code them on the side stream while the next frames are reconstructed
-        // CEDAR_B200_NO_OVERLAP=1 (diagnosis): run the serial stages in line on the main stream
+        // the bins of these frames are final: code them on a side stream while the next frames are reconstructed
+        // CEDAR_B200_NO_OVERLAP=1 (diagnosis): run the serial stages in line
         static const bool no_overlap = getenv("CEDAR_B200_NO_OVERLAP") != nullptr;
-        cudaStream_t side = no_overlap ? h->stream : h->stream_cabac[h->side_next];
-        CK(cudaEventRecord(h->ev_bins, h->stream));
-        CK(cudaStreamWaitEvent(side, h->ev_bins, 0));
-        LAUNCH_ON(side, K_RESOLVE, cabac_resolve_kernel, nl, 512, 0, g, s, h->K, gop_pos0, h->eb);
-        LAUNCH_ON(side, K_CABAC, cabac_encode_kernel, nl, 32, 0, g, s, h->eb);
-        h->side_used |= 1u << h->side_next;
-        h->side_next = (h->side_next + 1) % cedar_b200_handle::NSIDE;
+        cudaStream_t side = no_overlap ? st : h->stream_cabac[h->side_next];
+        CK(cudaEventRecord(ev_bins, st));
+        CK(cudaStreamWaitEvent(side, ev_bins, 0));
+        // The coders that sit on the critical path (the long I frames; the last frames, whose coding is the
+        // tail after reconstruction ends) get an SM each: a dummy dynamic shared-memory request keeps the
+        // throughput kernels off that SM, so the two serial warps are not starved of issue slots.
+        static const int tail_steps = getenv("CEDAR_B200_EXCL_TAIL") ? atoi(getenv("CEDAR_B200_EXCL_TAIL")) : 4;
+        const bool exclusive = t == 0 || t >= h->K - tail_steps;
+        LAUNCH_ON(side, K_CABAC, cabac_kernel, nl, CABAC_THREADS, exclusive ? h->cabac_excl_smem : 0, g, s, h->K, gop_pos0,
+                  eb);
+        if (!no_overlap) {
+            h->side_used |= 1u << h->side_next;
+            h->side_next = (h->side_next + 1) % cedar_b200_handle::NSIDE;
+        }
     }
     h->last_cur = cur;
     return 0;
@@ -526,6 +546,19 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     memset(h->prof_n, 0, sizeof(h->prof_n));
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_bins, cudaEventDisableTiming) == cudaSuccess;
+    h->ngroups = getenv("CEDAR_B200_GROUPS") ? atoi(getenv("CEDAR_B200_GROUPS")) : 1; // measured: more groups do not pay (profiles/)
+    if (h->ngroups < 1)
+        h->ngroups = 1;
+    if (h->ngroups > cedar_b200_handle::MAXGRP)
+        h->ngroups = cedar_b200_handle::MAXGRP;
+    h->stream_grp[0] = h->stream;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_begin, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < cedar_b200_handle::MAXGRP; i++) {
+        if (i > 0)
+            ok = cudaStreamCreateWithFlags(&h->stream_grp[i], cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&h->ev_grp[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_bins_grp[i], cudaEventDisableTiming) == cudaSuccess;
+    }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); // the few serial-coder CTAs go first when an SM frees up
     for (int i = 0; ok && i < cedar_b200_handle::NSIDE; i++)
@@ -535,8 +568,23 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
         delete h;
         return -ENODEV;
     }
-    if (me_smem_bytes(g.R) > 48 * 1024)
-        cudaFuncSetAttribute(me_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)me_smem_bytes(g.R));
+    {
+        cudaDeviceProp prop;
+        cudaGetDeviceProperties(&prop, cfg->device);
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, cabac_kernel);
+        size_t want = prop.sharedMemPerMultiprocessor > (size_t)200 * 1024 ? (size_t)176 * 1024 : 0;
+        if (want + fa.sharedSizeBytes > prop.sharedMemPerBlockOptin)
+            want = prop.sharedMemPerBlockOptin > fa.sharedSizeBytes ? prop.sharedMemPerBlockOptin - fa.sharedSizeBytes : 0;
+        if (getenv("CEDAR_B200_NO_EXCL"))
+            want = 0;
+        if (want && cudaFuncSetAttribute(cabac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) != cudaSuccess)
+            want = 0;
+        h->cabac_excl_smem = want;
+    }
+    if (me_smem_bytes(g.R, me_strip(g.R)) > 48 * 1024)
+        cudaFuncSetAttribute(me_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)me_smem_bytes(g.R, me_strip(g.R)));
     r = alloc_buffers(h);
     if (r) {
         free_buffers(h);
@@ -574,7 +622,7 @@ int cedar_b200_encode_frame(cedar_b200_handle *h)
     if ((r = begin_stream(h, 1)))
         return r;
     Step s = {1, 0, 1, 1};
-    if ((r = encode_step(h, s, h->frame_p_count, h->frame_p_count)))
+    if ((r = encode_step(h, s, h->frame_p_count, h->frame_p_count, 0, h->stream, h->ev_bins)))
         return r;
     if ((r = finish_stream(h, 1, h->frame_p_count, h->frame_count == 0)))
         return r;
@@ -627,15 +675,27 @@ int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_in
     if ((r = begin_stream(h, nframes)))
         return r;
     const int K = h->K, gops = (nframes + K - 1) / K;
+    // the group streams start after the uploads / clears issued on the main stream
+    CK(cudaEventRecord(h->ev_begin, h->stream));
+    for (int gi = 1; gi < h->ngroups; gi++)
+        CK(cudaStreamWaitEvent(h->stream_grp[gi], h->ev_begin, 0));
     for (int gop0 = 0; gop0 < gops; gop0 += h->L) {
         int nl = gops - gop0 < h->L ? gops - gop0 : h->L;
+        int ng = h->ngroups < nl ? h->ngroups : nl;
         for (int t = 0; t < K; t++) {
-            Step s = {nl, gop0 * K + t, K, nframes};
-            if (s.frame0 >= nframes)
-                break;
-            if ((r = encode_step(h, s, t, 0)))
-                return r;
+            for (int gi = 0; gi < ng; gi++) {
+                int l0 = (int)((long)nl * gi / ng), l1 = (int)((long)nl * (gi + 1) / ng);
+                Step s = {l1 - l0, (gop0 + l0) * K + t, K, nframes};
+                if (s.frame0 >= nframes)
+                    continue;
+                if ((r = encode_step(h, s, t, 0, l0, h->stream_grp[gi], h->ev_bins_grp[gi])))
+                    return r;
+            }
         }
+    }
+    for (int gi = 1; gi < h->ngroups; gi++) {
+        CK(cudaEventRecord(h->ev_grp[gi], h->stream_grp[gi]));
+        CK(cudaStreamWaitEvent(h->stream, h->ev_grp[gi], 0));
     }
     if ((r = finish_stream(h, nframes, 0, first_frame_index == 0)))
         return r;
@@ -752,6 +812,13 @@ void cedar_b200_close(cedar_b200_handle *h)
         cudaEventDestroy(e);
     free_buffers(h);
     cudaEventDestroy(h->ev_bins);
+    cudaEventDestroy(h->ev_begin);
+    for (int i = 0; i < cedar_b200_handle::MAXGRP; i++) {
+        cudaEventDestroy(h->ev_grp[i]);
+        cudaEventDestroy(h->ev_bins_grp[i]);
+        if (i > 0)
+            cudaStreamDestroy(h->stream_grp[i]);
+    }
     for (int i = 0; i < cedar_b200_handle::NSIDE; i++) {
         cudaEventDestroy(h->ev_cabac[i]);
         cudaStreamDestroy(h->stream_cabac[i]);

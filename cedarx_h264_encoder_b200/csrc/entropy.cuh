@@ -509,15 +509,24 @@ template <class S> HD void cabac_mb(S &s, const FrameSyntax &fs, int mb_index, i
 // =============================================================================================
 // Lookup tables of the coder, rebuilt per coder instance (in shared memory on the GPU):
 // lpsw[pStateIdx] = the four rangeTabLPS entries packed little-endian by qRangeIdx;
+// shw[pStateIdx]  = their renormalisation shifts (3 bits each);
 // trans[s] (s = pStateIdx << 1 | valMPS) = next s after an MPS in bits 0..7, after an LPS in bits 8..15.
 struct CabacTables {
     uint32_t lpsw[64];
+    uint16_t shw[64];
     uint16_t trans[128];
     HD void build(int tid, int nthreads)
     {
-        for (int i = tid; i < 64; i += nthreads)
-            lpsw[i] = (uint32_t)h264_range_lps[i][0] | ((uint32_t)h264_range_lps[i][1] << 8) |
-                      ((uint32_t)h264_range_lps[i][2] << 16) | ((uint32_t)h264_range_lps[i][3] << 24);
+        for (int i = tid; i < 64; i += nthreads) {
+            uint32_t w = 0, sh = 0;
+            for (int q = 0; q < 4; q++) {
+                uint32_t lps = h264_range_lps[i][q];
+                w |= lps << (8 * q);
+                sh |= (uint32_t)(8 - ilog2_(lps)) << (3 * q);
+            }
+            lpsw[i] = w;
+            shw[i] = (uint16_t)sh;
+        }
         for (int s = tid; s < 128; s += nthreads) {
             int st = s >> 1, mps = s & 1;
             int after_mps = (h264_next_state_mps[st] << 1) | mps;
@@ -541,14 +550,96 @@ HD uint32_t cabac_init_state(int ctx, int frame_i, int qp)
     return (uint32_t)(pre <= 63 ? (63 - pre) << 1 : (((pre - 64) << 1) | 1));
 }
 
-// The interval coder proper.  It does not own the context states: the state each regular bin is
-// coded in ("pre-state") is resolved beforehand -- per context the state sequence depends only on that
-// context's own bins, so all contexts are resolved in parallel -- and the serial part only tracks
-// range / low.
-struct CabacCoder {
+// The arithmetic coder (H.264 9.3.4) is split into three stages so that only a minimal recurrence stays
+// serial:
+//   1. context-state resolution: the state each regular bin is coded in ("pre-state") depends only on the
+//      earlier bins of the same context => all contexts in parallel (cabac_next_state);
+//   2. CabacRange: the codIRange recurrence.  Per bin it emits an "interval step" word: what to add to
+//      codILow and by how much to shift, which no longer depends on anything but the step itself;
+//   3. CabacBytes: the codILow recurrence + byte output with carry propagation.
+// Stages 2 and 3 are two independent serial chains that run pipelined on different warps.
+//
+// Interval step word: bits 0..8 add, 9..11 shift after the add, 12 shift-by-one before the add (bypass),
+// 13 end of slice (flush).
+enum { STEP_PRE1 = 1 << 12, STEP_FINAL = 1 << 13 };
+
+// meta word of a staged bin: bit 0 = isLPS (regular) or value (bypass / terminate), bit 1 bypass,
+// bit 2 terminate, bits 4..15 = LPS renormalisation shifts (shw)
+HD uint32_t cabac_stage_meta(uint16_t b, uint32_t pre_state, const CabacTables &t)
+{
+    uint32_t special = (b >> 10) & 3, v = (b >> 15) & 1;
+    return (special ? (v | (special << 1)) : (v ^ (pre_state & 1))) | ((uint32_t)t.shw[(pre_state >> 1) & 63] << 4);
+}
+
+struct CabacRange {
+    uint32_t range = 510;
+    HD uint32_t step(uint32_t lps4, uint32_t meta)
+    {
+        if (meta & 6) {
+            if (meta & 2) // bypass: low = (low << 1) + (bin ? range : 0)
+                return ((meta & 1) ? range : 0) | STEP_PRE1;
+            range -= 2; // terminate
+            if (meta & 1) {
+                uint32_t add = range;
+                range = 2;
+                return add | (7u << 9) | STEP_FINAL;
+            }
+            uint32_t sh = (range >> 8) ^ 1; // range in [254, 508]
+            range <<= sh;
+            return sh << 9;
+        }
+        uint32_t q = (range >> 6) & 3;
+#ifdef __CUDACC__
+        uint32_t lps = __byte_perm(lps4, 0, 0x4440u | q);
+#else
+        uint32_t lps = (lps4 >> (q * 8)) & 0xff;
+#endif
+        uint32_t rm = range - lps; // >= 128: the MPS path renormalises by at most one bit
+        if (meta & 1) {
+            uint32_t sh = (meta >> (4 + 3 * q)) & 7;
+            range = lps << sh;
+            return rm | (sh << 9);
+        }
+        uint32_t sh = (rm >> 8) ^ 1;
+        range = rm << sh;
+        return sh << 9;
+    }
+};
+
+// Same recurrence as CabacRange::step with the regular-bin path written without branches (both the MPS and
+// the LPS continuation are computed and selected), so that an unrolled loop overlaps the independent work
+// of neighbouring bins and only the short range -> range dependency stays serial.
+HD uint32_t cabac_range_step_flat(uint32_t &range, uint32_t lps4, uint32_t meta)
+{
+    const uint32_t q = (range >> 6) & 3;
+#ifdef __CUDACC__
+    const uint32_t lps = __byte_perm(lps4, 0, 0x4440u | q);
+#else
+    const uint32_t lps = (lps4 >> (q * 8)) & 0xff;
+#endif
+    const uint32_t rm = range - lps;
+    const uint32_t sh_m = (rm >> 8) ^ 1, sh_l = (meta >> (4 + 3 * q)) & 7;
+    const bool isl = meta & 1;
+    uint32_t nr = isl ? (lps << sh_l) : (rm << sh_m);
+    uint32_t w = isl ? (rm | (sh_l << 9)) : (sh_m << 9);
+    if (meta & 6) { // bypass / terminate: rare enough for a branch
+        if (meta & 2) {
+            nr = range;
+            w = (isl ? range : 0) | STEP_PRE1;
+        } else {
+            const uint32_t r2 = range - 2, sh = (r2 >> 8) ^ 1;
+            nr = isl ? 2u : (r2 << sh);
+            w = isl ? (r2 | (7u << 9) | STEP_FINAL) : (sh << 9);
+        }
+    }
+    range = nr;
+    return w;
+}
+
+struct CabacBytes {
     uint8_t *out;      // output bytes (first byte written at out[0])
     unsigned pos = 0;  // bytes written
-    uint32_t low = 0, range = 510;
+    uint32_t low = 0;  // the 10-bit coding window in bits 9..0 and queue + 8 not-yet-written bits above it
     int queue = -9, outstanding = 0;
     int last = -1;     // most recent byte, held back until a later carry can no longer reach it
 
@@ -574,53 +665,18 @@ struct CabacCoder {
         }
         last = (int)(o & 0xff);
     }
-    HD void renorm()
+    HD void step_fast(uint32_t w) // any step but the final one
     {
-        // range in [2, 510]; shift so that range >= 256
-#ifdef __CUDACC__
-        int shift = __clz((int)range) - 23;
-#else
-        int shift = range >= 256 ? 0 : (8 - ilog2_(range));
-#endif
-        range <<= shift;
-        low <<= shift;
-        queue += shift;
+        uint32_t pre1 = (w >> 12) & 1, sh = (w >> 9) & 7;
+        low = ((low << pre1) + (w & 0x1ff)) << sh;
+        queue += (int)(pre1 + sh);
         if (queue >= 0)
             put_byte();
     }
-    // lps4 = the four rangeTabLPS entries of the bin's pre-state; is_lps = bin != valMPS
-    HD void decision(uint32_t lps4, int is_lps)
+    HD void step(uint32_t w)
     {
-#ifdef __CUDACC__
-        uint32_t lps = __byte_perm(lps4, 0, 0x4440u | ((range >> 6) & 3));
-#else
-        uint32_t lps = (lps4 >> (((range >> 6) & 3) * 8)) & 0xff;
-#endif
-        range -= lps;
-        if (is_lps) {
-            low += range;
-            range = lps;
-        }
-        renorm();
-    }
-    HD void bypass(int bin)
-    {
-        low <<= 1;
-        if (bin)
-            low += range;
-        queue++;
-        if (queue >= 0)
-            put_byte();
-    }
-    HD void terminate(int bin)
-    {
-        range -= 2;
-        if (bin) {
-            low += range;
-            range = 2;
-        }
-        renorm();
-        if (bin) {
+        step_fast(w);
+        if (w & STEP_FINAL) {
             // 9.3.4.5: put_bit(low >> 9 & 1); write_bits((low >> 7 & 3) | 1, 2): push window bits 9, 8
             // and the stop bit out, then pad the last byte with zeros.
             low = (low & ~0x7fu) | 0x80u;
@@ -643,17 +699,6 @@ struct CabacCoder {
                 outstanding--;
             }
         }
-    }
-    // b = bin record, lps4 = packed LPS ranges of its pre-state, mps = valMPS of its pre-state
-    HD void code(uint16_t b, uint32_t lps4, uint32_t mps)
-    {
-        uint32_t v = (b >> 15) & 1;
-        if (b & BIN_BYPASS)
-            bypass((int)v);
-        else if (b & BIN_TERM)
-            terminate((int)v);
-        else
-            decision(lps4, v != mps);
     }
 };
 

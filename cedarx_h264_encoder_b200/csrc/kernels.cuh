@@ -8,6 +8,7 @@
 // frame step.frame0 + l * step.lane_stride.
 #pragma once
 #include "entropy.cuh"
+#include <cstdio>
 
 namespace cedar {
 
@@ -85,14 +86,15 @@ __global__ void ingest_kernel(Geom g, Step s, const uint8_t *__restrict__ raw, s
 
 // ================================================================================================
 // K1 integer motion estimation: exhaustive +-R SAD search against the previous deblocked
-// reconstruction (edge clamped).  One CTA per macroblock.  The search window is staged in shared
-// memory four times, byte-shifted by 0..3, so that every candidate reads aligned 32-bit words;
-// each thread owns one column offset and four consecutive row offsets, keeps the current block in
-// 64 registers and issues 256 VABSDIFF4-with-accumulate for 76 shared loads.
-// argmin over key = cost << 15 | raster rank (order independent => deterministic).
-// Bound: integer SIMD-video issue rate.
+// reconstruction (edge clamped).  One CTA per horizontal strip of `nstrip` macroblocks that share one
+// search window.  The window is staged in shared memory four times, byte-shifted by 0..3, so that every
+// candidate reads aligned 32-bit words; a warp task = 32 column offsets x 4 consecutive row offsets of one
+// macroblock: each thread keeps that macroblock's 16x16 block in 64 registers and issues 256
+// VABSDIFF4-with-accumulate for 76 shared loads.  argmin over key = cost << 15 | raster rank
+// (order independent => deterministic).  Bound: integer SIMD-video issue rate.
 // ================================================================================================
 #define ME_THREADS 320
+#define ME_MAX_STRIP 4
 
 __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -101,32 +103,44 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
     return d;
 }
 
-__host__ __device__ inline int me_row_words(int R) { return (2 * R + 19) / 4 + 2; }
-__host__ __device__ inline int me_copy_words(int R)
+__host__ __device__ inline int me_strip(int R) { return R > 32 ? 2 : ME_MAX_STRIP; }
+__host__ __device__ inline int me_row_words(int R, int nstrip)
 {
-    int cw = (16 + 2 * R + 3) * me_row_words(R);
+    int w = (16 * nstrip + 2 * R + 3) / 4 + 2;
+    return w | 1; // odd: consecutive row groups of the transposed (left-over column) tasks hit different banks
+}
+__host__ __device__ inline int me_copy_words(int R, int nstrip)
+{
+    int cw = (16 + 2 * R + 3) * me_row_words(R, nstrip);
     return cw + ((8 - (cw & 31)) & 31); // == 8 (mod 32): the four copies start 8 banks apart
 }
-__host__ __device__ inline size_t me_smem_bytes(int R) { return (size_t)(64 + 4 * me_copy_words(R)) * 4; }
+__host__ __device__ inline size_t me_smem_bytes(int R, int nstrip)
+{
+    return (size_t)(64 * nstrip + 4 * me_copy_words(R, nstrip)) * 4;
+}
 
-__global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, const uint8_t *__restrict__ src,
+__global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstrip, const uint8_t *__restrict__ src,
                                                        const uint8_t *__restrict__ ref, MbInfo *__restrict__ mbi)
 {
     extern __shared__ uint32_t sm[];
-    __shared__ uint32_t warp_best[ME_THREADS / 32];
+    __shared__ uint32_t warp_best[ME_MAX_STRIP][ME_THREADS / 32];
     if (lane_frame(s, blockIdx.y) < 0)
         return;
     const int R = g.R, nd = 2 * R + 1;
-    const int WR = 16 + 2 * R + 3, RSW = me_row_words(R), CWs = me_copy_words(R);
-    const int mb = blockIdx.x, mbx = mb % g.mbw, mby = mb / g.mbw;
-    const int x0 = mbx * 16, y0 = mby * 16;
+    const int WR = 16 + 2 * R + 3, RSW = me_row_words(R, nstrip), CWs = me_copy_words(R, nstrip);
+    const int strips_per_row = (g.mbw + nstrip - 1) / nstrip;
+    const int mby = blockIdx.x / strips_per_row, mbx0 = (blockIdx.x % strips_per_row) * nstrip;
+    const int nm = imin_(nstrip, g.mbw - mbx0); // macroblocks in this strip
+    const int x0 = mbx0 * 16, y0 = mby * 16;
     const uint8_t *srcY = src + (size_t)blockIdx.y * g.frame_bytes;
     const uint8_t *refY = ref + (size_t)blockIdx.y * g.frame_bytes;
-    uint32_t *cur_s = sm, *cp = sm + 64;
+    uint32_t *cur_s = sm, *cp = sm + 64 * nstrip;
     const int tid = threadIdx.x;
 
-    if (tid < 64)
-        cur_s[tid] = *(const uint32_t *)(srcY + (size_t)(y0 + (tid >> 2)) * g.W + x0 + 4 * (tid & 3));
+    for (int i = tid; i < 64 * nm; i += ME_THREADS) { // current blocks: [mb][row][4 words]
+        int m = i >> 6, row = (i >> 2) & 15, k = i & 3;
+        cur_s[i] = *(const uint32_t *)(srcY + (size_t)(y0 + row) * g.W + x0 + 16 * m + 4 * k);
+    }
     for (int idx = tid; idx < WR * RSW; idx += ME_THREADS) {
         int r = idx / RSW, k = idx - r * RSW;
         int fy = clip3_(0, g.H - 1, y0 - R + r), fx = x0 - R + 4 * k;
@@ -154,32 +168,45 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, const ui
     }
     __syncthreads();
 
-    uint32_t cur[64];
-#pragma unroll
-    for (int i = 0; i < 64; i++)
-        cur[i] = cur_s[i];
-
     const int warp = tid >> 5, lane = tid & 31, nwarps = ME_THREADS / 32;
     const int nfull = nd >> 5, nleft = nd & 31, ndyg = (nd + 3) >> 2;
-    const int ntask_full = nfull * ndyg, nitems_left = nleft * ndyg;
-    const int ntask = ntask_full + ((nitems_left + 31) >> 5);
-    uint32_t best = 0xffffffffu;
+    const int ntask_full = nfull * ndyg;               // per macroblock: 32 columns x one row group
+    const int nitems_left = nleft * ndyg * nm;         // left-over columns of all macroblocks, one item per lane
+    const int ntask = ntask_full * nm + ((nitems_left + 31) >> 5);
+    uint32_t best[ME_MAX_STRIP];
+#pragma unroll
+    for (int m = 0; m < ME_MAX_STRIP; m++)
+        best[m] = 0xffffffffu;
     for (int task = warp; task < ntask; task += nwarps) {
-        int ox, dyg;
+        int m, ox, dyg;
         bool valid = true;
-        if (task < ntask_full) {
-            ox = (task / ndyg) * 32 + lane;
-            dyg = task % ndyg;
+        if (task < ntask_full * nm) {
+            m = task / ntask_full;
+            int t = task - m * ntask_full;
+            ox = (t / ndyg) * 32 + lane;
+            dyg = t % ndyg;
         } else {
-            int j = (task - ntask_full) * 32 + lane;
+            int j = (task - ntask_full * nm) * 32 + lane;
             valid = j < nitems_left;
-            ox = nfull * 32 + j / ndyg;
-            dyg = j % ndyg;
+            int per_mb = nleft * ndyg;
+            m = valid ? j / per_mb : 0;
+            int jj = j - m * per_mb;
+            ox = nfull * 32 + jj / ndyg;
+            dyg = jj % ndyg;
         }
         if (!valid)
             continue;
+        uint32_t cur[64];
+        {
+            const uint4 *c4 = (const uint4 *)(cur_s + 64 * m);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                uint4 v = c4[i];
+                cur[4 * i] = v.x, cur[4 * i + 1] = v.y, cur[4 * i + 2] = v.z, cur[4 * i + 3] = v.w;
+            }
+        }
         const int oy0 = dyg * 4;
-        const uint32_t *wp = cp + (ox & 3) * CWs + oy0 * RSW + (ox >> 2);
+        const uint32_t *wp = cp + (ox & 3) * CWs + oy0 * RSW + 4 * m + (ox >> 2);
         uint32_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int r = 0; r < 19; r++) {
@@ -196,33 +223,42 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, const ui
             }
         }
         const int bx = mv_bits(ox - R);
+        uint32_t b = 0xffffffffu;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int oy = oy0 + j;
             if (oy < nd) {
                 uint32_t cost = acc[j] + (uint32_t)(g.lambda * (bx + mv_bits(oy - R)));
                 uint32_t key = (cost << 15) | (uint32_t)(oy * nd + ox);
-                best = key < best ? key : best;
+                b = key < b ? key : b;
             }
         }
+#pragma unroll
+        for (int mm = 0; mm < ME_MAX_STRIP; mm++)
+            if (mm == m)
+                best[mm] = b < best[mm] ? b : best[mm];
     }
-    best = __reduce_min_sync(0xffffffffu, best);
-    if (lane == 0)
-        warp_best[warp] = best;
+#pragma unroll
+    for (int m = 0; m < ME_MAX_STRIP; m++) {
+        uint32_t b = __reduce_min_sync(0xffffffffu, best[m]);
+        if (lane == 0)
+            warp_best[m][warp] = b;
+    }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < nm) {
+        uint32_t b = warp_best[tid][0];
 #pragma unroll
         for (int w = 1; w < nwarps; w++)
-            best = warp_best[w] < best ? warp_best[w] : best;
-        int rank = (int)(best & 0x7fff);
-        MbInfo m;
-        m.type = MB_P16x16;
-        m.i16_mode = m.chroma_mode = m.cbp = 0;
-        m.mv[0] = (int16_t)((rank % nd - R) * 4);
-        m.mv[1] = (int16_t)((rank / nd - R) * 4);
-        m.mvd[0] = m.mvd[1] = 0;
-        m.pad = best >> 15; // best cost, for statistics
-        mbi[(size_t)blockIdx.y * g.nmb + mb] = m;
+            b = warp_best[tid][w] < b ? warp_best[tid][w] : b;
+        int rank = (int)(b & 0x7fff);
+        MbInfo mi;
+        mi.type = MB_P16x16;
+        mi.i16_mode = mi.chroma_mode = mi.cbp = 0;
+        mi.mv[0] = (int16_t)((rank % nd - R) * 4);
+        mi.mv[1] = (int16_t)((rank / nd - R) * 4);
+        mi.mvd[0] = mi.mvd[1] = 0;
+        mi.pad = b >> 15; // best cost, for statistics
+        mbi[(size_t)blockIdx.y * g.nmb + (size_t)mby * g.mbw + mbx0 + tid] = mi;
     }
 }
 
@@ -689,26 +725,128 @@ __global__ void bs_kernel(Geom g, Step s, const MbInfo *__restrict__ mbi, const 
     ((uint32_t *)bs)[((size_t)blockIdx.y * g.nmb + mb) * 8 + dir * 4 + e] = out;
 }
 
-__global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8_t *__restrict__ unf, uint8_t *rec,
-                                                     const uint8_t *__restrict__ bs, int *flags_y, int *flags_c)
+// Shared-memory mailbox between a filtering warp and its two helper warps.
+struct DeblockMail {
+    volatile int top_ready;    // loader -> main: top rows of macroblocks [0, top_ready) are in the ring
+    volatile int top_consumed; // main -> loader: ring slots of macroblocks [0, top_consumed) are free again
+    volatile int done;         // main -> publisher: macroblocks [0, done) are completely stored
+};
+
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Loader warp: as soon as the row above has progressed far enough, fetches the top neighbour rows of the
+// next macroblock from L2 into a 2-slot shared ring, so the filtering warp never waits on a global round
+// trip.  `load_top(slot, mbx)` is executed by the whole warp.
+template <class LoadTop>
+__device__ __forceinline__ void deblock_loader(DeblockMail *mail, const int *fl_above, int mbw, int lane, LoadTop load_top)
+{
+    for (int x = 0; x < mbw; x++) {
+        const int need = imin_(x + 2, mbw);
+        if (lane == 0) {
+            while (mail->top_consumed + 2 <= x) // both ring slots still in use
+                __nanosleep(64);
+            while (ld_relaxed(fl_above) < need)
+                __nanosleep(32);
+            asm volatile("fence.acq_rel.gpu;" ::: "memory"); // acquire: the row above's pixels before its flag
+        }
+        __syncwarp();
+        load_top(x & 1, x);
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0)
+            mail->top_ready = x + 1;
+    }
+}
+
+// Publisher warp: publishes the filtering warp's progress with a gpu-scope release (the fence inside
+// st.release covers the filtering warp's stores, observed through the shared `done` counter), so the
+// filtering warp itself never stalls on a memory fence.
+__device__ __forceinline__ void deblock_publisher(DeblockMail *mail, int *fl_mine, int mbw, int lane)
+{
+    if (lane != 0)
+        return;
+    int published = 0;
+    while (published < mbw) {
+        int d = mail->done;
+        if (d > published) {
+            __threadfence_block();
+            st_release(fl_mine, d);
+            published = d;
+        } else
+            __nanosleep(64);
+    }
+}
+
+__device__ __forceinline__ void mail_wait(volatile int *p, int want, int lane)
+{
+    if (lane == 0)
+        while (*p < want)
+            __nanosleep(32);
+    __syncwarp();
+    __threadfence_block();
+}
+
+// Warps: 0 luma filter, 1 chroma filter, 2 luma loader, 3 chroma loader, 6 luma publisher, 7 chroma
+// publisher (4 and 5 exit at once: the spinning helpers then share schedulers 2 and 3 and leave the
+// schedulers of the two filtering warps alone).
+__global__ void __launch_bounds__(256) deblock_kernel(Geom g, Step s, const uint8_t *__restrict__ unf, uint8_t *rec,
+                                                      const uint8_t *__restrict__ bs, int *flags_y, int *flags_c)
 {
     if (lane_frame(s, blockIdx.y) < 0)
         return;
-    __shared__ uint32_t tileY[20 * 6];     // 20 rows x 24 bytes: rows 0..3 top MB, cols 0..3 left MB
-    __shared__ uint32_t tileC[2][10 * 3];  // per plane 10 rows x 12 bytes: rows 0..1 top, cols 0..3 left
+    __shared__ uint32_t tileY[16 * 6];     // 16 rows x 24 bytes: cols 0..3 = left MB's last 4 columns
+    __shared__ uint32_t tileC[2][8 * 3];   // per plane 8 rows x 12 bytes: cols 0..3 left
+    __shared__ uint4 ringY[2][4];          // top-neighbour rows staged by the loader: [slot][row]
+    __shared__ uint2 ringC[2][2][2];       // [slot][plane][row]
+    __shared__ DeblockMail mailY, mailC;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = blockIdx.x;
     const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
     const uint4 *fbs = (const uint4 *)bs + ((size_t)blockIdx.y * g.nmb + (size_t)row * g.mbw) * 2;
     const bool has_top = row > 0;
     const int sh = (lane >> 2) * 8; // byte of a strength word that belongs to this lane's 4-sample segment
+    int *fly = flags_y + (size_t)blockIdx.y * g.mbh, *flc = flags_c + (size_t)blockIdx.y * g.mbh;
+    if (threadIdx.x == 0) {
+        mailY.top_ready = mailY.top_consumed = mailY.done = 0;
+        mailC.top_ready = mailC.top_consumed = mailC.done = 0;
+    }
+    __syncthreads();
 
-    if (warp == 0) {
-        int *fl = flags_y + (size_t)blockIdx.y * g.mbh;
+    if (warp == 2) {
+        if (has_top)
+            deblock_loader(&mailY, fly + row - 1, g.mbw, lane, [&](int slot, int mbx) {
+                if (lane < 4)
+                    ringY[slot][lane] = __ldcg((const uint4 *)(rec + fo + (size_t)(row * 16 - 4 + lane) * g.W + mbx * 16));
+            });
+    } else if (warp == 3) {
+        if (has_top)
+            deblock_loader(&mailC, flc + row - 1, g.mbw, lane, [&](int slot, int mbx) {
+                if (lane < 4) {
+                    int pl = lane >> 1, r = lane & 1;
+                    ringC[slot][pl][r] = __ldcg((const uint2 *)(rec + fo + (size_t)g.W * g.H + (size_t)pl * g.CW * g.CH +
+                                                                (size_t)(row * 8 - 2 + r) * g.CW + mbx * 8));
+                }
+            });
+    } else if (warp == 6) {
+        deblock_publisher(&mailY, fly + row, g.mbw, lane);
+    } else if (warp == 7) {
+        deblock_publisher(&mailC, flc + row, g.mbw, lane);
+    } else if (warp == 0) {
         const int alpha = h264_deblock_alpha[g.qp], beta = h264_deblock_beta[g.qp];
         const int tc0_1 = h264_deblock_tc0[g.qp][0], tc0_2 = h264_deblock_tc0[g.qp][1], tc0_3 = h264_deblock_tc0[g.qp][2];
         uint8_t *tb = (uint8_t *)tileY;
         const uint8_t *urow = unf + fo + (size_t)(row * 16 + (lane & 15)) * g.W;
         uint4 nx_px = *(const uint4 *)urow, nx_v = fbs[0], nx_h = fbs[1];
+#ifdef DEBLOCK_PROFILE
+        long long tp[6] = {0, 0, 0, 0, 0, 0}, tq = clock64();
+#define DBP(i) { long long tn = clock64(); tp[i] += tn - tq; tq = tn; }
+#else
+#define DBP(i)
+#endif
         for (int mbx = 0; mbx < g.mbw; mbx++) {
             const bool has_left = mbx > 0;
             const int x0 = mbx * 16, y0 = row * 16;
@@ -718,81 +856,89 @@ __global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8
                 nx_v = fbs[(mbx + 1) * 2];
                 nx_h = fbs[(mbx + 1) * 2 + 1];
             }
+            DBP(0)
+            // ---- vertical edges, lane = row: the whole row (left MB's last 4 + own 16 pixels) stays in
+            // registers across the four dependent edges ----
             if (lane < 16) {
-                uint32_t *t = tileY + (4 + lane) * 6;
-                if (has_left)
-                    t[0] = t[4];
-                t[1] = px.x, t[2] = px.y, t[3] = px.z, t[4] = px.w;
-            }
-            if (has_top) {
-                if (lane == 0) {
-                    int need = imin_(mbx + 2, g.mbw);
-                    while (ld_acquire(fl + row - 1) < need)
-                        ;
-                }
-                __syncwarp();
-                if (lane < 4) {
-                    uint4 v = __ldcg((const uint4 *)(rec + fo + (size_t)(y0 - 4 + lane) * g.W + x0));
-                    uint32_t *t = tileY + lane * 6 + 1;
-                    t[0] = v.x, t[1] = v.y, t[2] = v.z, t[3] = v.w;
-                }
-            }
-            __syncwarp();
-            if (lane < 16) { // vertical edges: lane = row
-                uint32_t *t = tileY + (4 + lane) * 6;
+                uint32_t *t = tileY + lane * 6;
+                uint32_t w[5] = {has_left ? t[4] : 0u, px.x, px.y, px.z, px.w};
                 const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     int bS = (bw[e] >> sh) & 0xff;
                     if (bS) {
-                        uint32_t a = t[e], b = t[e + 1];
                         int v[8];
 #pragma unroll
                         for (int i = 0; i < 4; i++)
-                            v[i] = (a >> (8 * i)) & 0xff, v[4 + i] = (b >> (8 * i)) & 0xff;
+                            v[i] = (w[e] >> (8 * i)) & 0xff, v[4 + i] = (w[e + 1] >> (8 * i)) & 0xff;
                         filter_luma8(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
-                        t[e] = pack4(v);
-                        t[e + 1] = pack4(v + 4);
+                        w[e] = pack4(v);
+                        w[e + 1] = pack4(v + 4);
                     }
                 }
+#pragma unroll
+                for (int i = 0; i < 5; i++)
+                    t[i] = w[i];
             }
-            __syncwarp();
-            if (lane < 16) { // horizontal edges: lane = column
+            DBP(1)
+            if (has_top)
+                mail_wait(&mailY.top_ready, mbx + 1, lane);
+            else
+                __syncwarp();
+            DBP(2)
+            // ---- horizontal edges, lane = column: the 20-sample column (4 from the ring) stays in registers ----
+            uint8_t *ring = (uint8_t *)ringY[mbx & 1];
+            if (lane < 16) {
                 uint8_t *col = tb + 4 + lane;
+                int cpx[20];
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    cpx[i] = has_top ? ring[i * 16 + lane] : 0;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    cpx[4 + i] = col[i * 24];
                 const uint32_t bw[4] = {bh.x, bh.y, bh.z, bh.w};
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
                     int bS = (bw[e] >> sh) & 0xff;
-                    if (bS) {
-                        int v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; i++)
-                            v[i] = col[(4 * e + i) * 24];
-                        filter_luma8(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
-#pragma unroll
-                        for (int i = 1; i < 7; i++)
-                            col[(4 * e + i) * 24] = (uint8_t)v[i];
-                    }
+                    if (bS)
+                        filter_luma8(cpx + 4 * e, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
                 }
+                if (has_top) {
+#pragma unroll
+                    for (int i = 1; i < 4; i++)
+                        ring[i * 16 + lane] = (uint8_t)cpx[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 15; i++)
+                    col[i * 24] = (uint8_t)cpx[4 + i];
             }
             __syncwarp();
+            DBP(4)
             if (lane < 16) {
-                const uint32_t *t = tileY + (4 + lane) * 6;
+                const uint32_t *t = tileY + lane * 6;
                 uint8_t *o = rec + fo + (size_t)(y0 + lane) * g.W + x0;
                 *(uint4 *)o = make_uint4(t[1], t[2], t[3], t[4]);
                 if (has_left)
                     *(uint32_t *)(o - 4) = t[0];
             } else if (lane < 19 && has_top) {
-                int r = lane - 15; // tile rows 1..3
-                const uint32_t *t = tileY + r * 6;
-                *(uint4 *)(rec + fo + (size_t)(y0 - 4 + r) * g.W + x0) = make_uint4(t[1], t[2], t[3], t[4]);
+                int r = lane - 15; // ring rows 1..3
+                *(uint4 *)(rec + fo + (size_t)(y0 - 4 + r) * g.W + x0) = ringY[mbx & 1][r];
             }
+            __threadfence_block();
             __syncwarp();
-            if (lane == 0)
-                st_release(fl + row, mbx + 1);
+            if (lane == 0) {
+                mailY.top_consumed = mbx + 1;
+                mailY.done = mbx + 1;
+            }
+            DBP(5)
         }
-    } else {
-        int *fl = flags_c + (size_t)blockIdx.y * g.mbh;
+#ifdef DEBLOCK_PROFILE
+        if (lane == 0 && blockIdx.y == 0 && (row < 3 || row == 8 || row == g.mbh / 2 || row == g.mbh - 1))
+            printf("deblock row %d: per MB cycles: pre %lld V %lld wait %lld H %lld store %lld\n", row, tp[0] / g.mbw,
+                   tp[1] / g.mbw, tp[2] / g.mbw, tp[4] / g.mbw, tp[5] / g.mbw);
+#endif
+    } else if (warp == 1) {
         const int alpha = h264_deblock_alpha[g.qpc], beta = h264_deblock_beta[g.qpc];
         const int tc0_1 = h264_deblock_tc0[g.qpc][0], tc0_2 = h264_deblock_tc0[g.qpc][1], tc0_3 = h264_deblock_tc0[g.qpc][2];
         const int pl = (lane >> 3) & 1, r8 = lane & 7;
@@ -813,70 +959,66 @@ __global__ void __launch_bounds__(64) deblock_kernel(Geom g, Step s, const uint8
                 nx_v = fbs[(mbx + 1) * 2];
                 nx_h = fbs[(mbx + 1) * 2 + 1];
             }
-            if (lane < 16) {
-                if (has_left)
-                    tw[(2 + r8) * 3 + 0] = tw[(2 + r8) * 3 + 2];
-                tw[(2 + r8) * 3 + 1] = px.x;
-                tw[(2 + r8) * 3 + 2] = px.y;
-            }
-            if (has_top) {
-                if (lane == 0) {
-                    int need = imin_(mbx + 2, g.mbw);
-                    while (ld_acquire(fl + row - 1) < need)
-                        ;
-                }
-                __syncwarp();
-                if (lane < 16 && r8 < 2) {
-                    uint2 v = __ldcg((const uint2 *)(rec + po + (size_t)(y0 - 2 + r8) * g.CW + x0));
-                    tw[r8 * 3 + 1] = v.x;
-                    tw[r8 * 3 + 2] = v.y;
-                }
-            }
-            __syncwarp();
             if (lane < 16) { // vertical edges at chroma x = 0, 4 (luma edges 0, 2): lane = (plane, row)
-                uint8_t *t = tb + (2 + r8) * 12;
+                uint32_t *t = tw + r8 * 3;
+                uint32_t w[3] = {has_left ? t[2] : 0u, px.x, px.y};
                 const uint32_t bw[2] = {bv.x, bv.z};
 #pragma unroll
                 for (int ce = 0; ce < 2; ce++) {
                     int bS = (bw[ce] >> shc) & 0xff;
                     if (bS) {
-                        int v[4] = {t[2 + 4 * ce], t[3 + 4 * ce], t[4 + 4 * ce], t[5 + 4 * ce]};
+                        int v[4] = {(int)((w[ce] >> 16) & 0xff), (int)(w[ce] >> 24), (int)(w[ce + 1] & 0xff),
+                                    (int)((w[ce + 1] >> 8) & 0xff)};
                         filter_chroma4(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
-                        t[3 + 4 * ce] = (uint8_t)v[1];
-                        t[4 + 4 * ce] = (uint8_t)v[2];
+                        w[ce] = (w[ce] & 0x00ffffffu) | ((uint32_t)v[1] << 24);
+                        w[ce + 1] = (w[ce + 1] & 0xffffff00u) | (uint32_t)v[2];
                     }
                 }
+                t[0] = w[0], t[1] = w[1], t[2] = w[2];
             }
-            __syncwarp();
+            if (has_top)
+                mail_wait(&mailC.top_ready, mbx + 1, lane);
+            else
+                __syncwarp();
+            uint8_t *ring = (uint8_t *)ringC[mbx & 1][pl]; // 2 rows x 8 bytes
             if (lane < 16) { // horizontal edges at chroma y = 0, 4: lane = (plane, column)
                 uint8_t *col = tb + 4 + r8;
+                int cpx[8];
+                cpx[0] = has_top ? ring[r8] : 0;
+                cpx[1] = has_top ? ring[8 + r8] : 0;
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+                    cpx[2 + i] = col[i * 12];
                 const uint32_t bw[2] = {bh.x, bh.z};
 #pragma unroll
                 for (int ce = 0; ce < 2; ce++) {
                     int bS = (bw[ce] >> shc) & 0xff;
-                    if (bS) {
-                        int v[4] = {col[(4 * ce) * 12], col[(4 * ce + 1) * 12], col[(4 * ce + 2) * 12], col[(4 * ce + 3) * 12]};
-                        filter_chroma4(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
-                        col[(4 * ce + 1) * 12] = (uint8_t)v[1];
-                        col[(4 * ce + 2) * 12] = (uint8_t)v[2];
-                    }
+                    if (bS)
+                        filter_chroma4(cpx + 4 * ce, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
                 }
+                if (has_top)
+                    ring[8 + r8] = (uint8_t)cpx[1];
+                col[0 * 12] = (uint8_t)cpx[2];
+                col[3 * 12] = (uint8_t)cpx[5];
+                col[4 * 12] = (uint8_t)cpx[6];
             }
             __syncwarp();
             if (lane < 16) {
                 uint8_t *o = rec + po + (size_t)(y0 + r8) * g.CW + x0;
-                *(uint2 *)o = make_uint2(tw[(2 + r8) * 3 + 1], tw[(2 + r8) * 3 + 2]);
+                *(uint2 *)o = make_uint2(tw[r8 * 3 + 1], tw[r8 * 3 + 2]);
                 if (has_left)
-                    *(uint32_t *)(o - 4) = tw[(2 + r8) * 3 + 0];
+                    *(uint32_t *)(o - 4) = tw[r8 * 3 + 0];
             } else if (lane < 18 && has_top) {
                 int p2 = lane - 16;
-                const uint32_t *t = tileC[p2] + 1 * 3;
                 *(uint2 *)(rec + fo + (size_t)g.W * g.H + (size_t)p2 * g.CW * g.CH + (size_t)(y0 - 1) * g.CW + x0) =
-                    make_uint2(t[1], t[2]);
+                    ringC[mbx & 1][p2][1];
             }
+            __threadfence_block();
             __syncwarp();
-            if (lane == 0)
-                st_release(fl + row, mbx + 1);
+            if (lane == 0) {
+                mailC.top_consumed = mbx + 1;
+                mailC.done = mbx + 1;
+            }
         }
     }
 }
@@ -921,7 +1063,6 @@ struct EntropyBufs {
     unsigned rbsp_cap;
     uint32_t *rbsp_len;      // [F] bytes of RBSP (header + slice data + trailing)
     uint16_t *bins;          // CABAC bin pool
-    uint8_t *pre;            // pre-state of every bin (same indexing as bins)
     unsigned long long bins_cap;
     unsigned long long *bins_cursor; // pool bump pointer
     unsigned long long *bins_off;    // [F]
@@ -1077,140 +1218,163 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
     }
 }
 
-// K7a context-state resolution.  The state a regular bin is coded in depends only on the earlier bins of
-// the SAME context, so the 460 contexts are independent chains: one CTA per frame, each thread owns one
-// context and walks the frame's bin stream (staged through shared memory in tiles), recording the state
-// before each of its bins.  This removes every context-state access from the serial coder below.
-// Matches serialise inside a warp, so neighbouring (equally hot) contexts are dealt to different warps.
-#define RESOLVE_TILE 4096
-__global__ void __launch_bounds__(512) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0, EntropyBufs eb)
+// K7 CABAC arithmetic coding: one CTA per frame (one slice per picture, cedar.c:992-993), software
+// pipelined over tiles of CABAC_TILE bins with three stages running on different warps at the same time
+// (entropy.cuh explains the split):
+//   warps 0..15  tile i    context-state resolution: thread c owns context c (neighbouring, equally hot
+//                          contexts dealt to different warps because matches serialise inside a warp),
+//                          walks the tile in shared memory and records the state before each of its bins;
+//   warp 16      tile i-1  range recurrence (lane 0; all lanes stage 32 bins at a time) -> interval steps;
+//   warp 17      tile i-2  low recurrence + byte output with carry propagation (lane 0).
+// Only the two short recurrences are serial (about a dozen dependent integer instructions per bin each).
+// Runs on side streams so that it overlaps the reconstruction of the following frames.
+#define CABAC_TILE 2048
+#define CABAC_THREADS 576
+__global__ void __launch_bounds__(CABAC_THREADS) cabac_kernel(Geom g, Step s, int gop_len, int gop_pos0, EntropyBufs eb)
 {
     __shared__ CabacTables tab;
-    __shared__ uint2 tile[RESOLVE_TILE / 4];
-    __shared__ uint8_t ptile[RESOLVE_TILE];
-    int f = lane_frame(s, blockIdx.x);
+    __shared__ uint2 binsT[3][CABAC_TILE / 4];
+    __shared__ uint8_t preT[2][CABAC_TILE];
+    __shared__ uint32_t stepT[2][CABAC_TILE];
+    __shared__ uint2 stage[32];
+    const int f = lane_frame(s, blockIdx.x);
     if (f < 0)
         return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int frame_i = ((gop_pos0 + f) % gop_len) == 0;
     const uint32_t nb = eb.bins_len[f];
-    const uint16_t *bins = eb.bins + eb.bins_off[f]; // bins_off is a multiple of 8 bins => 16-byte aligned
-    uint8_t *pre = eb.pre + eb.bins_off[f];
-    const int tid = threadIdx.x;
-    tab.build(tid, 512);
-    const uint32_t c = (uint32_t)((tid & 15) * 32 + (tid >> 4)); // context c -> warp c % 16
-    const uint32_t c2 = c | (c << 16);
-    uint32_t st = c < 460 ? cabac_init_state((int)c, frame_i, g.qp) : 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < nb; base += RESOLVE_TILE) {
-        const uint32_t n = nb - base < RESOLVE_TILE ? nb - base : RESOLVE_TILE;
-        const uint32_t nq = (n + 3) >> 2;
-        for (uint32_t i = tid; i < nq; i += 512)
-            tile[i] = ((const uint2 *)(bins + base))[i];
-        __syncthreads();
-        if (c < 460) {
-#pragma unroll 2
-            for (uint32_t i = 0; i < nq; i++) {
-                const uint2 w = tile[i]; // four bins; same address for the whole warp => broadcast
-                const uint32_t m0 = __vcmpeq2(w.x & 0x0fff0fffu, c2), m1 = __vcmpeq2(w.y & 0x0fff0fffu, c2);
-                if (m0 | m1) {
-                    if (m0 & 0xffffu) {
-                        ptile[4 * i] = (uint8_t)st;
-                        st = cabac_next_state(tab, st, (w.x >> 15) & 1);
-                    }
-                    if (m0 >> 16) {
-                        ptile[4 * i + 1] = (uint8_t)st;
-                        st = cabac_next_state(tab, st, (w.x >> 31) & 1);
-                    }
-                    if (m1 & 0xffffu) {
-                        ptile[4 * i + 2] = (uint8_t)st;
-                        st = cabac_next_state(tab, st, (w.y >> 15) & 1);
-                    }
-                    if (m1 >> 16) {
-                        ptile[4 * i + 3] = (uint8_t)st;
-                        st = cabac_next_state(tab, st, (w.y >> 31) & 1);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (uint32_t i = tid; i < nq; i += 512)
-            ((uint32_t *)(pre + base))[i] = ((const uint32_t *)ptile)[i];
-        __syncthreads();
-    }
-}
-
-// K7b serial interval coder: one warp per frame (slice).  All lanes stage the next 32 bins (global ->
-// registers -> shared, with the LPS ranges of each bin's pre-state looked up in parallel); lane 0 then
-// codes them in a compact loop that only updates range / low (about a dozen dependent integer
-// instructions per bin).  Output bytes are written once (the byte a carry could still reach is held in a
-// register).  Runs on side streams so that it overlaps the reconstruction of the following frames.
-__global__ void __launch_bounds__(32) cabac_encode_kernel(Geom g, Step s, EntropyBufs eb)
-{
-    __shared__ CabacTables tab;
-    __shared__ uint2 stage[32]; // x = packed LPS ranges, y = bit0 value-or-isLPS, bit1 bypass, bit2 terminate
-    int f = lane_frame(s, blockIdx.x);
-    if (f < 0)
-        return;
-    const int lane = threadIdx.x;
-    tab.build(lane, 32);
-    __syncwarp();
-    uint8_t *out = eb.rbsp + (size_t)f * eb.rbsp_cap;
-    const uint32_t nb = eb.bins_len[f];
     if (nb == 0) {
-        if (lane == 0)
+        if (tid == 0)
             eb.rbsp_len[f] = 0;
         return;
     }
+    const uint2 *gbins = (const uint2 *)(eb.bins + eb.bins_off[f]); // bins_off is a multiple of 8 bins
+    const int ntiles = (int)((nb + CABAC_TILE - 1) / CABAC_TILE);
+    tab.build(tid, CABAC_THREADS);
+
+    // resolve state
+    const uint32_t c = (uint32_t)((tid & 15) * 32 + ((tid >> 4) & 31)); // context c -> warp c % 16
+    const uint32_t c2 = c | (c << 16);
+    uint32_t st = (warp < 16 && c < 460) ? cabac_init_state((int)c, frame_i, g.qp) : 0;
+    uint2 nx = make_uint2(0, 0);
+    if (warp < 16 && (uint32_t)tid * 4 < nb)
+        nx = gbins[tid];
+    // coder state
+    CabacRange rc;
+    CabacBytes cb;
+    uint8_t *out = eb.rbsp + (size_t)f * eb.rbsp_cap;
     const int hn = eb.hdr_nbits[f], hb = (hn + 7) >> 3;
-    if (lane == 0) {
+    cb.out = out + hb;
+    const unsigned limit = eb.rbsp_cap - hb - 64;
+    bool overflow = false;
+    if (tid == 17 * 32) { // header bits, then cabac_alignment_one_bit up to the byte boundary
         unsigned long long h = ((unsigned long long)eb.hdr_bits[f] << (hb * 8 - hn)) | ((1ull << (hb * 8 - hn)) - 1);
         for (int i = 0; i < hb; i++)
             out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
     }
-    CabacCoder c;
-    c.out = out + hb;
-    const uint16_t *bins = eb.bins + eb.bins_off[f];
-    const uint8_t *pre = eb.pre + eb.bins_off[f];
-    const unsigned limit = eb.rbsp_cap - hb - 64;
-    uint32_t nb_b = lane < nb ? bins[lane] : 0, nb_p = lane < nb ? pre[lane] : 0;
-    bool overflow = false;
-    for (uint32_t base = 0; base < nb; base += 32) {
-        const uint32_t b = nb_b, ps = nb_p;
-        if (base + 32 + lane < nb) { // prefetch the next 32 bins while lane 0 codes these
-            nb_b = bins[base + 32 + lane];
-            nb_p = pre[base + 32 + lane];
-        }
-        const uint32_t special = (b >> 10) & 3; // bit0 bypass, bit1 terminate
-        const uint32_t v = (b >> 15) & 1;
-        stage[lane] = make_uint2(tab.lpsw[(ps >> 1) & 63], special ? (v | (special << 1)) : (v ^ (ps & 1)));
-        __syncwarp();
-        if (lane == 0) {
-            const int cnt = nb - base < 32 ? (int)(nb - base) : 32;
-            uint2 e = stage[0];
-#pragma unroll 1
-            for (int k = 0; k < cnt; k++) {
-                const uint2 cur = e;
-                e = stage[(k + 1) & 31];
-                if (cur.y & 6) {
-                    if (cur.y & 2)
-                        c.bypass((int)(cur.y & 1));
-                    else
-                        c.terminate((int)(cur.y & 1));
-                } else
-                    c.decision(cur.x, (int)cur.y);
+    __syncthreads();
+
+    for (int it = 0; it < ntiles + 2; it++) {
+        if (warp < 16) {
+            if (it < ntiles) {
+                const uint32_t base = (uint32_t)it * CABAC_TILE;
+                const uint32_t n = nb - base < CABAC_TILE ? nb - base : CABAC_TILE;
+                const uint32_t nq = (n + 3) >> 2;
+                uint2 *tile = binsT[it % 3];
+                uint8_t *ptile = preT[it & 1];
+                tile[tid] = nx;
+                if (it + 1 < ntiles && base + CABAC_TILE + (uint32_t)tid * 4 < nb)
+                    nx = gbins[(base + CABAC_TILE) / 4 + tid];
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (c < 460) {
+#pragma unroll 2
+                    for (uint32_t i = 0; i < nq; i++) {
+                        const uint2 w = tile[i]; // four bins; same address for the whole warp => broadcast
+                        const uint32_t m0 = __vcmpeq2(w.x & 0x0fff0fffu, c2), m1 = __vcmpeq2(w.y & 0x0fff0fffu, c2);
+                        if (m0 | m1) {
+                            if (m0 & 0xffffu) {
+                                ptile[4 * i] = (uint8_t)st;
+                                st = cabac_next_state(tab, st, (w.x >> 15) & 1);
+                            }
+                            if (m0 >> 16) {
+                                ptile[4 * i + 1] = (uint8_t)st;
+                                st = cabac_next_state(tab, st, (w.x >> 31) & 1);
+                            }
+                            if (m1 & 0xffffu) {
+                                ptile[4 * i + 2] = (uint8_t)st;
+                                st = cabac_next_state(tab, st, (w.y >> 15) & 1);
+                            }
+                            if (m1 >> 16) {
+                                ptile[4 * i + 3] = (uint8_t)st;
+                                st = cabac_next_state(tab, st, (w.y >> 31) & 1);
+                            }
+                        }
+                    }
+                }
             }
-            overflow = c.pos + c.outstanding > limit;
+        } else if (warp == 16) {
+            const int t = it - 1;
+            if (t >= 0 && t < ntiles) {
+                const uint32_t base = (uint32_t)t * CABAC_TILE;
+                const uint32_t n = nb - base < CABAC_TILE ? nb - base : CABAC_TILE;
+                const uint16_t *tb = (const uint16_t *)binsT[t % 3];
+                const uint8_t *ptile = preT[t & 1];
+                uint32_t *steps = stepT[t & 1];
+                for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+                    const uint32_t ps = ptile[k0 + lane];
+                    stage[lane] = make_uint2(tab.lpsw[(ps >> 1) & 63], cabac_stage_meta(tb[k0 + lane], ps, tab));
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int cnt = n - k0 < 32 ? (int)(n - k0) : 32;
+                        uint32_t range = rc.range;
+                        if (cnt == 32) {
+#pragma unroll 8
+                            for (int k = 0; k < 32; k++) {
+                                const uint2 e = stage[k];
+                                steps[k0 + k] = cabac_range_step_flat(range, e.x, e.y);
+                            }
+                        } else {
+#pragma unroll 1
+                            for (int k = 0; k < cnt; k++) {
+                                const uint2 e = stage[k];
+                                steps[k0 + k] = cabac_range_step_flat(range, e.x, e.y);
+                            }
+                        }
+                        rc.range = range;
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            const int t = it - 2;
+            if (t >= 0 && t < ntiles && lane == 0 && !overflow) {
+                const uint32_t base = (uint32_t)t * CABAC_TILE;
+                const int n = nb - base < CABAC_TILE ? (int)(nb - base) : CABAC_TILE;
+                const uint32_t *steps = stepT[t & 1];
+                const int nfast = (t == ntiles - 1) ? n - 1 : n; // the slice's last step carries the flush
+                int k = 0;
+                for (; k + 4 <= nfast; k += 4) {
+                    const uint4 e = *(const uint4 *)(steps + k);
+                    cb.step_fast(e.x);
+                    cb.step_fast(e.y);
+                    cb.step_fast(e.z);
+                    cb.step_fast(e.w);
+                }
+                for (; k < nfast; k++)
+                    cb.step_fast(steps[k]);
+                if (nfast < n)
+                    cb.step(steps[n - 1]);
+                overflow = cb.pos + cb.outstanding > limit;
+            }
         }
-        overflow = __shfl_sync(0xffffffffu, overflow, 0);
-        if (overflow)
-            break;
+        __syncthreads();
     }
-    if (lane == 0) {
+    if (tid == 17 * 32) {
         if (overflow) {
             atomicExch(eb.error, 3);
             eb.rbsp_len[f] = 0;
         } else
-            eb.rbsp_len[f] = (uint32_t)(hb + c.pos);
+            eb.rbsp_len[f] = (uint32_t)(hb + cb.pos);
     }
 }
 

@@ -91,12 +91,25 @@ long hh_cabac_frame(const void *mbi, const uint8_t *nnz, const int16_t *coef, in
             state[ctx] = cabac_next_state(tab, state[ctx], (b >> 15) & 1);
         }
     }
-    CabacCoder c;
+    // stage 2 (range recurrence -> interval steps) and stage 3 (low recurrence -> bytes)
+    CabacRange rc;
+    std::vector<uint32_t> steps(total + 1);
+    uint32_t flat_range = 510;
+    for (size_t i = 0; i < total; i++) {
+        uint32_t lps4 = tab.lpsw[(pre[i] >> 1) & 63], meta = cabac_stage_meta(bins[i], pre[i], tab);
+        steps[i] = rc.step(lps4, meta);
+        if (cabac_range_step_flat(flat_range, lps4, meta) != steps[i] || (flat_range != rc.range && i + 1 < total))
+            return -2; // the branch-free variant the GPU uses must agree step by step
+    }
+    CabacBytes c;
     c.out = out + hb;
     for (size_t i = 0; i < total; i++) {
         if ((long)(hb + c.pos + 8) > cap)
             return -1;
-        c.code(bins[i], tab.lpsw[pre[i] >> 1], pre[i] & 1);
+        if (i + 1 < total)
+            c.step_fast(steps[i]);
+        else
+            c.step(steps[i]);
     }
     return hb + (long)c.pos;
 }
@@ -122,4 +135,15 @@ long hh_epb(const uint8_t *in, long n, uint8_t *out, long cap)
 }
 
 int hh_sizeof_mbinfo() { return (int)sizeof(MbInfo); }
+
+// Property the range stage relies on: on the MPS path the interval never needs more than a one-bit
+// renormalisation (range - rangeTabLPS >= 128 for every state and every range of the quantiser cell).
+int hh_mps_renorm_at_most_one()
+{
+    for (int s = 0; s < 64; s++)
+        for (int range = 256; range <= 510; range++)
+            if (range - (int)h264_range_lps[s][(range >> 6) & 3] < 128)
+                return 0;
+    return 1;
+}
 }

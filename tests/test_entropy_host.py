@@ -62,3 +62,8 @@ def test_parallel_emulation_prevention_rule(harness):
         out = np.zeros(2 * n + 8, np.uint8)
         m = harness.hh_epb(data.ctypes.data, n, out.ctypes.data, out.size)
         assert out[:m].tobytes() == bytes(want)
+
+
+def test_mps_path_renormalises_by_at_most_one_bit(harness):
+    """CabacRange::step computes the MPS shift as (rm >> 8) ^ 1; valid iff range - rangeLPS >= 128 always."""
+    assert harness.hh_mps_renorm_at_most_one() == 1
