@@ -72,6 +72,11 @@ struct cedar_b200_handle {
     cudaStream_t stream_grp[MAXGRP]; // [0] == stream; lane groups 1.. run on their own streams
     cudaEvent_t ev_grp[MAXGRP], ev_bins_grp[MAXGRP], ev_begin;
     int ngroups;
+    // clip upload: host->device copies run on their own stream in step order; step t waits for ev_upload[t] only
+    cudaStream_t stream_copy;
+    std::vector<cudaEvent_t> ev_upload;
+    cudaEvent_t ev_encode_done;
+    bool upload_pending;
     cudaEvent_t ev_bins, ev_cabac[NSIDE];
     size_t cabac_excl_smem; // dummy dynamic smem that leaves no room for another CTA on the SM
     unsigned side_used; // bit i: side stream i has work the main stream has not joined yet
@@ -552,6 +557,11 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     if (h->ngroups > cedar_b200_handle::MAXGRP)
         h->ngroups = cedar_b200_handle::MAXGRP;
     h->stream_grp[0] = h->stream;
+    ok = ok && cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->ev_encode_done, cudaEventDisableTiming) == cudaSuccess;
+    h->ev_upload.resize(h->F > 1 ? h->K : 0);
+    for (auto &e : h->ev_upload)
+        ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->ev_begin, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; ok && i < cedar_b200_handle::MAXGRP; i++) {
         if (i > 0)
@@ -660,7 +670,21 @@ int cedar_b200_clip_upload(cedar_b200_handle *h, int nframes)
 {
     if (!h || !h->h_clip_in || nframes <= 0 || nframes > h->F)
         return -EINVAL;
-    CK(cudaMemcpyAsync(h->d_raw, h->h_clip_in, h->raw_frame_bytes * nframes, cudaMemcpyHostToDevice, h->stream));
+    // Copies are issued in the order the encoder consumes the frames (step t needs frame t of every GOP) on a
+    // dedicated stream; clip_encode's step t waits for ev_upload[t] only, so the transfer overlaps the encode.
+    CK(cudaEventRecord(h->ev_encode_done, h->stream)); // do not overwrite frames a running encode still reads
+    CK(cudaStreamWaitEvent(h->stream_copy, h->ev_encode_done, 0));
+    const int K = h->K, gops = (nframes + K - 1) / K;
+    const size_t fb = h->raw_frame_bytes;
+    for (int t = 0; t < K; t++) {
+        for (int gp = 0; gp < gops; gp++) {
+            size_t f = (size_t)gp * K + t;
+            if (f < (size_t)nframes)
+                CK(cudaMemcpyAsync(h->d_raw + f * fb, h->h_clip_in + f * fb, fb, cudaMemcpyHostToDevice, h->stream_copy));
+        }
+        CK(cudaEventRecord(h->ev_upload[t], h->stream_copy));
+    }
+    h->upload_pending = true;
     return 0;
 }
 
@@ -688,6 +712,8 @@ int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_in
                 Step s = {l1 - l0, (gop0 + l0) * K + t, K, nframes};
                 if (s.frame0 >= nframes)
                     continue;
+                if (h->upload_pending)
+                    CK(cudaStreamWaitEvent(h->stream_grp[gi], h->ev_upload[t], 0));
                 if ((r = encode_step(h, s, t, 0, l0, h->stream_grp[gi], h->ev_bins_grp[gi])))
                     return r;
             }
@@ -697,6 +723,7 @@ int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_in
         CK(cudaEventRecord(h->ev_grp[gi], h->stream_grp[gi]));
         CK(cudaStreamWaitEvent(h->stream, h->ev_grp[gi], 0));
     }
+    h->upload_pending = false;
     if ((r = finish_stream(h, nframes, 0, first_frame_index == 0)))
         return r;
     h->last_nframes = nframes;
@@ -813,6 +840,10 @@ void cedar_b200_close(cedar_b200_handle *h)
     free_buffers(h);
     cudaEventDestroy(h->ev_bins);
     cudaEventDestroy(h->ev_begin);
+    cudaEventDestroy(h->ev_encode_done);
+    for (auto &e : h->ev_upload)
+        cudaEventDestroy(e);
+    cudaStreamDestroy(h->stream_copy);
     for (int i = 0; i < cedar_b200_handle::MAXGRP; i++) {
         cudaEventDestroy(h->ev_grp[i]);
         cudaEventDestroy(h->ev_bins_grp[i]);

@@ -113,20 +113,21 @@ def test_overflow_is_reported_not_silent(monkeypatch):
             enc.encode_clip(clip)
 
 
-@pytest.mark.parametrize("name,w,h,fmt,gop,n", [("720p", 1280, 720, 0, 30, 31), ("1080p", 1920, 1088, 0, 60, 61),
-                                                ("1080p-nv16", 1920, 1088, 1, 60, 3)])
-def test_full_size_properties(name, w, h, fmt, gop, n):
+@pytest.mark.parametrize("name,w,h,fmt,gop,n,me", [("720p", 1280, 720, 0, 30, 31, 16), ("1080p", 1920, 1088, 0, 60, 61, 16),
+                                                   ("1080p-nv16", 1920, 1088, 1, 60, 3, 16),
+                                                   ("2160p-me64", 3840, 2160, 0, 60, 3, 64)])
+def test_full_size_properties(name, w, h, fmt, gop, n, me):
     """BASELINE.json shapes: (1) clip path == frame-at-a-time path, (2) independent of GOPs in flight,
     (3) libavcodec decodes the stream to exactly the encoder's reconstruction (last frame of each path),
     (4) Y-PSNR is sane."""
     clip = synth.synth_clip(w, h, list(range(n)), fmt).numpy()
-    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, fmt=fmt, max_clip_frames=n, gops_in_flight=2)) as enc:
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, fmt=fmt, me_range=me, max_clip_frames=n, gops_in_flight=2)) as enc:
         stream, sizes = enc.encode_clip(clip)
         sse = enc.sse_y(n)
-    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, fmt=fmt, max_clip_frames=n, gops_in_flight=1)) as enc:
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, fmt=fmt, me_range=me, max_clip_frames=n, gops_in_flight=1)) as enc:
         stream1, _ = enc.encode_clip(clip)
     assert stream == stream1, "result depends on the number of GOPs in flight"
-    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, fmt=fmt)) as enc:
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, fmt=fmt, me_range=me)) as enc:
         frames = b""
         for t in range(n):
             frames += enc.encode(*split_frame(clip[t], w, h, fmt))
