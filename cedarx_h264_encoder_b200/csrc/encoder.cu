@@ -382,7 +382,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int la
         LAUNCH_ON(st, K_MVP, mvp_skip_kernel, dim3((g.nmb + 127) / 128, nl), 128, 0, g, s, mbi);
     }
     LAUNCH_ON(st, K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, mbi, nnz, bs);
-    LAUNCH_ON(st, K_DEBLOCK, deblock_kernel, dim3(g.mbh, nl), 256, 0, g, s, unf, rec, bs, fl_y, fl_c);
+    LAUNCH_ON(st, K_DEBLOCK, deblock_kernel, dim3((g.mbh + DB_ROWS - 1) / DB_ROWS, nl, 2), (DB_ROWS + 2) * 32, 0, g, s, unf, rec, bs, fl_y, fl_c);
     LAUNCH_ON(st, K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, src, rec, h->d_sse);
 
     dim3 egrid((g.nmb + 1 + 127) / 128, nl);

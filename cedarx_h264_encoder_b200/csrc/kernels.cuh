@@ -791,62 +791,91 @@ __device__ __forceinline__ void mail_wait(volatile int *p, int want, int lane)
     __threadfence_block();
 }
 
-// Warps: 0 luma filter, 1 chroma filter, 2 luma loader, 3 chroma loader, 6 luma publisher, 7 chroma
-// publisher (4 and 5 exit at once: the spinning helpers then share schedulers 2 and 3 and leave the
-// schedulers of the two filtering warps alone).
-__global__ void __launch_bounds__(256) deblock_kernel(Geom g, Step s, const uint8_t *__restrict__ unf, uint8_t *rec,
-                                                      const uint8_t *__restrict__ bs, int *flags_y, int *flags_c)
+// One CTA filters DB_ROWS consecutive macroblock rows of one plane type (blockIdx.z: 0 luma, 1 Cb+Cr) of one
+// frame: warp j owns row j and hands the bottom rows of every finished macroblock to warp j+1 through a
+// shared-memory line buffer (a hop of a few hundred cycles); only the first row of a CTA gets its top
+// neighbours from global memory (loader warp, progress flag of the CTA above) and only the last row
+// publishes its progress globally (publisher warp).
+#define DB_ROWS 16
+#define DB_NB 8 // line-buffer depth in macroblocks
+struct DeblockRow {
+    uint32_t tile[16 * 6];   // luma: 16 rows x 24 bytes (cols 0..3 = left MB's last 4 columns);
+                             // chroma: 2 planes x 8 rows x 12 bytes
+    uint4 lb[DB_NB][4];      // bottom rows of finished macroblocks: luma 4 rows x 16 B; chroma [plane][2 rows] x 8 B
+    volatile int ready;      // macroblocks [0, ready) of lb are final (left edge of the next MB applied)
+    volatile int consumed;   // this row has consumed the top neighbours of macroblocks [0, consumed)
+};
+
+__device__ __forceinline__ void spin_until_ge(volatile int *p, int want, int lane)
+{
+    if (lane == 0)
+        while (*p < want)
+            __nanosleep(20);
+    __syncwarp();
+    __threadfence_block();
+}
+
+__global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Step s, const uint8_t *__restrict__ unf,
+                                                                      uint8_t *rec, const uint8_t *__restrict__ bs,
+                                                                      int *flags_y, int *flags_c)
 {
     if (lane_frame(s, blockIdx.y) < 0)
         return;
-    __shared__ uint32_t tileY[16 * 6];     // 16 rows x 24 bytes: cols 0..3 = left MB's last 4 columns
-    __shared__ uint32_t tileC[2][8 * 3];   // per plane 8 rows x 12 bytes: cols 0..3 left
-    __shared__ uint4 ringY[2][4];          // top-neighbour rows staged by the loader: [slot][row]
-    __shared__ uint2 ringC[2][2][2];       // [slot][plane][row]
-    __shared__ DeblockMail mailY, mailC;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, row = blockIdx.x;
+    __shared__ DeblockRow rows[DB_ROWS];
+    __shared__ uint4 ring[2][4]; // top neighbours of the CTA's first row, staged by the loader: [slot][...]
+    __shared__ DeblockMail mail;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool chroma = blockIdx.z != 0;
+    const int row0 = blockIdx.x * DB_ROWS, nr = imin_(DB_ROWS, g.mbh - row0);
     const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
-    const uint4 *fbs = (const uint4 *)bs + ((size_t)blockIdx.y * g.nmb + (size_t)row * g.mbw) * 2;
-    const bool has_top = row > 0;
-    const int sh = (lane >> 2) * 8; // byte of a strength word that belongs to this lane's 4-sample segment
-    int *fly = flags_y + (size_t)blockIdx.y * g.mbh, *flc = flags_c + (size_t)blockIdx.y * g.mbh;
-    if (threadIdx.x == 0) {
-        mailY.top_ready = mailY.top_consumed = mailY.done = 0;
-        mailC.top_ready = mailC.top_consumed = mailC.done = 0;
+    int *fl = (chroma ? flags_c : flags_y) + (size_t)blockIdx.y * g.mbh;
+    if (threadIdx.x < DB_ROWS) {
+        rows[threadIdx.x].ready = 0;
+        rows[threadIdx.x].consumed = 0;
     }
+    if (threadIdx.x == 0)
+        mail.top_ready = mail.top_consumed = mail.done = 0;
     __syncthreads();
 
-    if (warp == 2) {
-        if (has_top)
-            deblock_loader(&mailY, fly + row - 1, g.mbw, lane, [&](int slot, int mbx) {
-                if (lane < 4)
-                    ringY[slot][lane] = __ldcg((const uint4 *)(rec + fo + (size_t)(row * 16 - 4 + lane) * g.W + mbx * 16));
-            });
-    } else if (warp == 3) {
-        if (has_top)
-            deblock_loader(&mailC, flc + row - 1, g.mbw, lane, [&](int slot, int mbx) {
-                if (lane < 4) {
-                    int pl = lane >> 1, r = lane & 1;
-                    ringC[slot][pl][r] = __ldcg((const uint2 *)(rec + fo + (size_t)g.W * g.H + (size_t)pl * g.CW * g.CH +
-                                                                (size_t)(row * 8 - 2 + r) * g.CW + mbx * 8));
-                }
-            });
-    } else if (warp == 6) {
-        deblock_publisher(&mailY, fly + row, g.mbw, lane);
-    } else if (warp == 7) {
-        deblock_publisher(&mailC, flc + row, g.mbw, lane);
-    } else if (warp == 0) {
+    if (warp == DB_ROWS) { // loader: top neighbours of row0 from the CTA above
+        if (row0 > 0) {
+            if (!chroma)
+                deblock_loader(&mail, fl + row0 - 1, g.mbw, lane, [&](int slot, int mbx) {
+                    if (lane < 4)
+                        ring[slot][lane] = __ldcg((const uint4 *)(rec + fo + (size_t)(row0 * 16 - 4 + lane) * g.W + mbx * 16));
+                });
+            else
+                deblock_loader(&mail, fl + row0 - 1, g.mbw, lane, [&](int slot, int mbx) {
+                    if (lane < 4) {
+                        int pl = lane >> 1, r = lane & 1;
+                        ((uint2 *)ring[slot])[lane] =
+                            __ldcg((const uint2 *)(rec + fo + (size_t)g.W * g.H + (size_t)pl * g.CW * g.CH +
+                                                   (size_t)(row0 * 8 - 2 + r) * g.CW + mbx * 8));
+                    }
+                });
+        }
+        return;
+    }
+    if (warp == DB_ROWS + 1) { // publisher: progress of the CTA's last row, for the CTA below
+        if (row0 + nr < g.mbh)
+            deblock_publisher(&mail, fl + row0 + nr - 1, g.mbw, lane);
+        return;
+    }
+    if (warp >= nr)
+        return;
+
+    const int j = warp, row = row0 + j;
+    DeblockRow &me = rows[j];
+    const bool has_top = row > 0, top_local = j > 0, below_local = j + 1 < nr, publish = j == nr - 1 && row + 1 < g.mbh;
+    const uint4 *fbs = (const uint4 *)bs + ((size_t)blockIdx.y * g.nmb + (size_t)row * g.mbw) * 2;
+
+    if (!chroma) {
+        const int sh = (lane >> 2) * 8; // byte of a strength word that belongs to this lane's 4-sample segment
         const int alpha = h264_deblock_alpha[g.qp], beta = h264_deblock_beta[g.qp];
         const int tc0_1 = h264_deblock_tc0[g.qp][0], tc0_2 = h264_deblock_tc0[g.qp][1], tc0_3 = h264_deblock_tc0[g.qp][2];
-        uint8_t *tb = (uint8_t *)tileY;
+        uint8_t *tb = (uint8_t *)me.tile;
         const uint8_t *urow = unf + fo + (size_t)(row * 16 + (lane & 15)) * g.W;
         uint4 nx_px = *(const uint4 *)urow, nx_v = fbs[0], nx_h = fbs[1];
-#ifdef DEBLOCK_PROFILE
-        long long tp[6] = {0, 0, 0, 0, 0, 0}, tq = clock64();
-#define DBP(i) { long long tn = clock64(); tp[i] += tn - tq; tq = tn; }
-#else
-#define DBP(i)
-#endif
         for (int mbx = 0; mbx < g.mbw; mbx++) {
             const bool has_left = mbx > 0;
             const int x0 = mbx * 16, y0 = row * 16;
@@ -856,11 +885,9 @@ __global__ void __launch_bounds__(256) deblock_kernel(Geom g, Step s, const uint
                 nx_v = fbs[(mbx + 1) * 2];
                 nx_h = fbs[(mbx + 1) * 2 + 1];
             }
-            DBP(0)
-            // ---- vertical edges, lane = row: the whole row (left MB's last 4 + own 16 pixels) stays in
-            // registers across the four dependent edges ----
+            // ---- vertical edges, lane = row: the row (left MB's last 4 + own 16 pixels) stays in registers ----
             if (lane < 16) {
-                uint32_t *t = tileY + lane * 6;
+                uint32_t *t = me.tile + lane * 6;
                 uint32_t w[5] = {has_left ? t[4] : 0u, px.x, px.y, px.z, px.w};
                 const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
@@ -879,21 +906,37 @@ __global__ void __launch_bounds__(256) deblock_kernel(Geom g, Step s, const uint
 #pragma unroll
                 for (int i = 0; i < 5; i++)
                     t[i] = w[i];
+                // The left edge just changed columns 13..15 of the previous macroblock.  They are final for this row
+                // now: store them before the row below is told it may filter (and store) across them.
+                if (has_left) {
+                    *(uint32_t *)(rec + fo + (size_t)(y0 + lane) * g.W + x0 - 4) = w[0];
+                    if (below_local && lane >= 12)
+                        ((uint32_t *)&me.lb[(mbx - 1) % DB_NB][lane - 12])[3] = w[0];
+                }
             }
-            DBP(1)
-            if (has_top)
-                mail_wait(&mailY.top_ready, mbx + 1, lane);
-            else
+            if (below_local && has_left) {
+                __threadfence_block();
                 __syncwarp();
-            DBP(2)
-            // ---- horizontal edges, lane = column: the 20-sample column (4 from the ring) stays in registers ----
-            uint8_t *ring = (uint8_t *)ringY[mbx & 1];
+                if (lane == 0)
+                    me.ready = mbx;
+            }
+            // ---- top neighbours ----
+            uint8_t *top = nullptr;
+            if (top_local) {
+                spin_until_ge(&rows[j - 1].ready, mbx + 1, lane);
+                top = (uint8_t *)rows[j - 1].lb[mbx % DB_NB];
+            } else if (has_top) {
+                mail_wait(&mail.top_ready, mbx + 1, lane);
+                top = (uint8_t *)ring[mbx & 1];
+            } else
+                __syncwarp();
+            // ---- horizontal edges, lane = column: the 20-sample column stays in registers ----
             if (lane < 16) {
                 uint8_t *col = tb + 4 + lane;
                 int cpx[20];
 #pragma unroll
                 for (int i = 0; i < 4; i++)
-                    cpx[i] = has_top ? ring[i * 16 + lane] : 0;
+                    cpx[i] = has_top ? top[i * 16 + lane] : 0;
 #pragma unroll
                 for (int i = 0; i < 16; i++)
                     cpx[4 + i] = col[i * 24];
@@ -907,44 +950,45 @@ __global__ void __launch_bounds__(256) deblock_kernel(Geom g, Step s, const uint
                 if (has_top) {
 #pragma unroll
                     for (int i = 1; i < 4; i++)
-                        ring[i * 16 + lane] = (uint8_t)cpx[i];
+                        top[i * 16 + lane] = (uint8_t)cpx[i];
                 }
 #pragma unroll
                 for (int i = 0; i < 15; i++)
                     col[i * 24] = (uint8_t)cpx[4 + i];
             }
             __syncwarp();
-            DBP(4)
+            if (below_local) // the slot is free once the row below has consumed macroblock mbx - DB_NB
+                spin_until_ge(&rows[j + 1].consumed, mbx - DB_NB + 1, lane);
             if (lane < 16) {
-                const uint32_t *t = tileY + lane * 6;
+                const uint32_t *t = me.tile + lane * 6;
                 uint8_t *o = rec + fo + (size_t)(y0 + lane) * g.W + x0;
-                *(uint4 *)o = make_uint4(t[1], t[2], t[3], t[4]);
-                if (has_left)
-                    *(uint32_t *)(o - 4) = t[0];
+                const uint4 mine = make_uint4(t[1], t[2], t[3], t[4]);
+                *(uint4 *)o = mine;
+                if (below_local && lane >= 12)
+                    me.lb[mbx % DB_NB][lane - 12] = mine;
             } else if (lane < 19 && has_top) {
-                int r = lane - 15; // ring rows 1..3
-                *(uint4 *)(rec + fo + (size_t)(y0 - 4 + r) * g.W + x0) = ringY[mbx & 1][r];
+                int r = lane - 15; // top rows 1..3 were modified
+                *(uint4 *)(rec + fo + (size_t)(y0 - 4 + r) * g.W + x0) = ((const uint4 *)top)[r];
             }
             __threadfence_block();
             __syncwarp();
             if (lane == 0) {
-                mailY.top_consumed = mbx + 1;
-                mailY.done = mbx + 1;
+                me.consumed = mbx + 1;
+                if (below_local && mbx == g.mbw - 1)
+                    me.ready = g.mbw;
+                if (!top_local && has_top)
+                    mail.top_consumed = mbx + 1;
+                if (publish)
+                    mail.done = mbx + 1;
             }
-            DBP(5)
         }
-#ifdef DEBLOCK_PROFILE
-        if (lane == 0 && blockIdx.y == 0 && (row < 3 || row == 8 || row == g.mbh / 2 || row == g.mbh - 1))
-            printf("deblock row %d: per MB cycles: pre %lld V %lld wait %lld H %lld store %lld\n", row, tp[0] / g.mbw,
-                   tp[1] / g.mbw, tp[2] / g.mbw, tp[4] / g.mbw, tp[5] / g.mbw);
-#endif
-    } else if (warp == 1) {
+    } else {
         const int alpha = h264_deblock_alpha[g.qpc], beta = h264_deblock_beta[g.qpc];
         const int tc0_1 = h264_deblock_tc0[g.qpc][0], tc0_2 = h264_deblock_tc0[g.qpc][1], tc0_3 = h264_deblock_tc0[g.qpc][2];
         const int pl = (lane >> 3) & 1, r8 = lane & 7;
         const size_t po = fo + (size_t)g.W * g.H + (size_t)pl * g.CW * g.CH;
-        uint32_t *tw = tileC[pl];
-        uint8_t *tb = (uint8_t *)tileC[pl];
+        uint32_t *tw = me.tile + pl * 24;
+        uint8_t *tb = (uint8_t *)tw;
         const int shc = (r8 >> 1) * 8; // chroma row / column k <-> luma segment k >> 1
         const uint8_t *urow = unf + po + (size_t)(row * 8 + r8) * g.CW;
         uint2 nx_px = *(const uint2 *)urow;
@@ -975,17 +1019,34 @@ __global__ void __launch_bounds__(256) deblock_kernel(Geom g, Step s, const uint
                     }
                 }
                 t[0] = w[0], t[1] = w[1], t[2] = w[2];
+                // line buffer entry: [plane][row 6, 7] x 8 bytes; the left edge finalises columns 4..7 of the previous MB
+                if (has_left) {
+                    *(uint32_t *)(rec + po + (size_t)(y0 + r8) * g.CW + x0 - 4) = w[0];
+                    if (below_local && r8 >= 6)
+                        ((uint32_t *)me.lb[(mbx - 1) % DB_NB])[(pl * 2 + (r8 - 6)) * 2 + 1] = w[0];
+                }
             }
-            if (has_top)
-                mail_wait(&mailC.top_ready, mbx + 1, lane);
-            else
+            if (below_local && has_left) {
+                __threadfence_block();
                 __syncwarp();
-            uint8_t *ring = (uint8_t *)ringC[mbx & 1][pl]; // 2 rows x 8 bytes
+                if (lane == 0)
+                    me.ready = mbx;
+            }
+            uint8_t *topb = nullptr; // [plane][2 rows][8 bytes]
+            if (top_local) {
+                spin_until_ge(&rows[j - 1].ready, mbx + 1, lane);
+                topb = (uint8_t *)rows[j - 1].lb[mbx % DB_NB];
+            } else if (has_top) {
+                mail_wait(&mail.top_ready, mbx + 1, lane);
+                topb = (uint8_t *)ring[mbx & 1];
+            } else
+                __syncwarp();
+            uint8_t *top = topb + pl * 16;
             if (lane < 16) { // horizontal edges at chroma y = 0, 4: lane = (plane, column)
                 uint8_t *col = tb + 4 + r8;
                 int cpx[8];
-                cpx[0] = has_top ? ring[r8] : 0;
-                cpx[1] = has_top ? ring[8 + r8] : 0;
+                cpx[0] = has_top ? top[r8] : 0;
+                cpx[1] = has_top ? top[8 + r8] : 0;
 #pragma unroll
                 for (int i = 0; i < 6; i++)
                     cpx[2 + i] = col[i * 12];
@@ -997,27 +1058,35 @@ __global__ void __launch_bounds__(256) deblock_kernel(Geom g, Step s, const uint
                         filter_chroma4(cpx + 4 * ce, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
                 }
                 if (has_top)
-                    ring[8 + r8] = (uint8_t)cpx[1];
+                    top[8 + r8] = (uint8_t)cpx[1];
                 col[0 * 12] = (uint8_t)cpx[2];
                 col[3 * 12] = (uint8_t)cpx[5];
                 col[4 * 12] = (uint8_t)cpx[6];
             }
             __syncwarp();
+            if (below_local)
+                spin_until_ge(&rows[j + 1].consumed, mbx - DB_NB + 1, lane);
             if (lane < 16) {
                 uint8_t *o = rec + po + (size_t)(y0 + r8) * g.CW + x0;
-                *(uint2 *)o = make_uint2(tw[r8 * 3 + 1], tw[r8 * 3 + 2]);
-                if (has_left)
-                    *(uint32_t *)(o - 4) = tw[r8 * 3 + 0];
+                const uint2 mine = make_uint2(tw[r8 * 3 + 1], tw[r8 * 3 + 2]);
+                *(uint2 *)o = mine;
+                if (below_local && r8 >= 6)
+                    ((uint2 *)me.lb[mbx % DB_NB])[pl * 2 + (r8 - 6)] = mine;
             } else if (lane < 18 && has_top) {
                 int p2 = lane - 16;
                 *(uint2 *)(rec + fo + (size_t)g.W * g.H + (size_t)p2 * g.CW * g.CH + (size_t)(y0 - 1) * g.CW + x0) =
-                    ringC[mbx & 1][p2][1];
+                    ((const uint2 *)topb)[p2 * 2 + 1];
             }
             __threadfence_block();
             __syncwarp();
             if (lane == 0) {
-                mailC.top_consumed = mbx + 1;
-                mailC.done = mbx + 1;
+                me.consumed = mbx + 1;
+                if (below_local && mbx == g.mbw - 1)
+                    me.ready = g.mbw;
+                if (!top_local && has_top)
+                    mail.top_consumed = mbx + 1;
+                if (publish)
+                    mail.done = mbx + 1;
             }
         }
     }
