@@ -141,29 +141,34 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
         int m = i >> 6, row = (i >> 2) & 15, k = i & 3;
         cur_s[i] = *(const uint32_t *)(srcY + (size_t)(y0 + row) * g.W + x0 + 16 * m + 4 * k);
     }
-    for (int idx = tid; idx < WR * RSW; idx += ME_THREADS) {
-        int r = idx / RSW, k = idx - r * RSW;
-        int fy = clip3_(0, g.H - 1, y0 - R + r), fx = x0 - R + 4 * k;
-        const uint8_t *row = refY + (size_t)fy * g.W;
-        uint32_t v;
-        if (fx >= 0 && fx + 3 < g.W && !(fx & 3))
-            v = *(const uint32_t *)(row + fx);
-        else {
-            v = 0;
+    // Window staging: warp = window row (round robin), lane = 32-bit word of the row.  Each lane fetches its
+    // word and the next one (the second fetch hits L1) and builds the three byte-shifted copies in
+    // registers; no integer division, no shared-memory round trip.
+    {
+        const int warp_ = tid >> 5, lane_ = tid & 31;
+        const bool interior_x = x0 - R >= 0 && x0 - R + 4 * RSW + 4 <= g.W && !((x0 - R) & 3);
+        for (int r = warp_; r < WR; r += ME_THREADS / 32) {
+            const uint8_t *row = refY + (size_t)clip3_(0, g.H - 1, y0 - R + r) * g.W;
+            for (int k = lane_; k < RSW; k += 32) {
+                const int fx = x0 - R + 4 * k;
+                uint32_t lo, hi;
+                if (interior_x) {
+                    lo = *(const uint32_t *)(row + fx);
+                    hi = *(const uint32_t *)(row + fx + 4);
+                } else {
+                    lo = hi = 0;
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-                v |= (uint32_t)row[clip3_(0, g.W - 1, fx + i)] << (8 * i);
-        }
-        cp[idx] = v;
-    }
-    __syncthreads();
-    for (int idx = tid; idx < WR * RSW; idx += ME_THREADS) {
-        int k = idx % RSW;
-        if (k < RSW - 1) {
-            uint32_t lo = cp[idx], hi = cp[idx + 1];
-            cp[CWs + idx] = __byte_perm(lo, hi, 0x4321);
-            cp[2 * CWs + idx] = __byte_perm(lo, hi, 0x5432);
-            cp[3 * CWs + idx] = __byte_perm(lo, hi, 0x6543);
+                    for (int i = 0; i < 4; i++) {
+                        lo |= (uint32_t)row[clip3_(0, g.W - 1, fx + i)] << (8 * i);
+                        hi |= (uint32_t)row[clip3_(0, g.W - 1, fx + 4 + i)] << (8 * i);
+                    }
+                }
+                uint32_t *d = cp + r * RSW + k;
+                d[0] = lo;
+                d[CWs] = __byte_perm(lo, hi, 0x4321);
+                d[2 * CWs] = __byte_perm(lo, hi, 0x5432);
+                d[3 * CWs] = __byte_perm(lo, hi, 0x6543);
+            }
         }
     }
     __syncthreads();

@@ -19,6 +19,7 @@ static inline int clip255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
 static inline int iabs(int v) { return v < 0 ? -v : v; }
 static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int me_lambda(int qp);
 
 /* luma4x4BlkIdx <-> position inside the macroblock (in 4x4 units) */
 static const uint8_t blk_x[16] = {0, 1, 0, 1, 2, 3, 2, 3, 0, 1, 0, 1, 2, 3, 2, 3};
@@ -660,6 +661,201 @@ static int sad_block(const uint8_t *a, int as, const uint8_t *b, int bs, int w, 
     return s;
 }
 
+
+/* ------------------------------------------------------------------------------------------
+ * Intra4x4 (H.264 8.3.1): nine prediction modes from the reconstructed neighbours of each 4x4
+ * block, blocks coded in luma4x4BlkIdx order.  edge layout: t[0..7] = A..H (above, above-right),
+ * l[0..3] = I..L (left), m = M (above-left).
+ * ------------------------------------------------------------------------------------------ */
+static void pred4x4(int mode, const int *t, const int *l, int m, int has_top, int has_left, uint8_t *pred /* 16 */)
+{
+#define PT(x) ((x) < 0 ? m : t[x])
+#define PL(y) ((y) < 0 ? m : l[y])
+    for (int y = 0; y < 4; y++)
+        for (int x = 0; x < 4; x++) {
+            int v;
+            switch (mode) {
+            case 0: v = t[x]; break;
+            case 1: v = l[y]; break;
+            case 2: {
+                int s = 0;
+                if (has_top)
+                    s += t[0] + t[1] + t[2] + t[3];
+                if (has_left)
+                    s += l[0] + l[1] + l[2] + l[3];
+                v = (has_top && has_left) ? (s + 4) >> 3 : ((has_top || has_left) ? (s + 2) >> 2 : 128);
+                break;
+            }
+            case 3: /* diagonal down left */
+                v = (x == 3 && y == 3) ? (t[6] + 3 * t[7] + 2) >> 2 : (t[x + y] + 2 * t[x + y + 1] + t[x + y + 2] + 2) >> 2;
+                break;
+            case 4: /* diagonal down right */
+                if (x > y)
+                    v = (PT(x - y - 2) + 2 * PT(x - y - 1) + PT(x - y) + 2) >> 2;
+                else if (x < y)
+                    v = (PL(y - x - 2) + 2 * PL(y - x - 1) + PL(y - x) + 2) >> 2;
+                else
+                    v = (t[0] + 2 * m + l[0] + 2) >> 2;
+                break;
+            case 5: { /* vertical right */
+                int z = 2 * x - y;
+                if (z >= 0 && !(z & 1))
+                    v = (PT(x - (y >> 1) - 1) + PT(x - (y >> 1)) + 1) >> 1;
+                else if (z >= 0)
+                    v = (PT(x - (y >> 1) - 2) + 2 * PT(x - (y >> 1) - 1) + PT(x - (y >> 1)) + 2) >> 2;
+                else if (z == -1)
+                    v = (l[0] + 2 * m + t[0] + 2) >> 2;
+                else
+                    v = (PL(y - 1) + 2 * PL(y - 2) + PL(y - 3) + 2) >> 2;
+                break;
+            }
+            case 6: { /* horizontal down */
+                int z = 2 * y - x;
+                if (z >= 0 && !(z & 1))
+                    v = (PL(y - (x >> 1) - 1) + PL(y - (x >> 1)) + 1) >> 1;
+                else if (z >= 0)
+                    v = (PL(y - (x >> 1) - 2) + 2 * PL(y - (x >> 1) - 1) + PL(y - (x >> 1)) + 2) >> 2;
+                else if (z == -1)
+                    v = (l[0] + 2 * m + t[0] + 2) >> 2;
+                else
+                    v = (PT(x - 1) + 2 * PT(x - 2) + PT(x - 3) + 2) >> 2;
+                break;
+            }
+            case 7: /* vertical left */
+                if (!(y & 1))
+                    v = (t[x + (y >> 1)] + t[x + (y >> 1) + 1] + 1) >> 1;
+                else
+                    v = (t[x + (y >> 1)] + 2 * t[x + (y >> 1) + 1] + t[x + (y >> 1) + 2] + 2) >> 2;
+                break;
+            default: { /* 8: horizontal up */
+                int z = x + 2 * y;
+                if (z > 5)
+                    v = l[3];
+                else if (z == 5)
+                    v = (l[2] + 3 * l[3] + 2) >> 2;
+                else if (!(z & 1))
+                    v = (l[y + (x >> 1)] + l[y + (x >> 1) + 1] + 1) >> 1;
+                else
+                    v = (l[y + (x >> 1)] + 2 * l[y + (x >> 1) + 1] + l[y + (x >> 1) + 2] + 2) >> 2;
+                break;
+            }
+            }
+            pred[y * 4 + x] = (uint8_t)v;
+        }
+#undef PT
+#undef PL
+}
+
+/* Intra4x4PredMode of the 4x4 block left of / above block blk of macroblock (mbx, mby) for the
+ * prediction of the mode: -1 = not available (=> predicted mode 2), 2 when the neighbour MB is
+ * not Intra4x4 (8.3.1.1; constrained_intra_pred_flag = 0). */
+static int i4_neighbour_mode(const gm_encoder *e, int mbx, int mby, int blk, int left)
+{
+    const gm_mb *cur = &e->mbs[mby * e->mbw + mbx];
+    int bx = blk_x[blk], by = blk_y[blk];
+    const gm_mb *n = cur;
+    int nb;
+    if (left) {
+        if (bx > 0)
+            nb = xy2blk[by][bx - 1];
+        else {
+            if (mbx == 0)
+                return -1;
+            n = cur - 1;
+            nb = xy2blk[by][3];
+        }
+    } else {
+        if (by > 0)
+            nb = xy2blk[by - 1][bx];
+        else {
+            if (mby == 0)
+                return -1;
+            n = cur - e->mbw;
+            nb = xy2blk[3][bx];
+        }
+    }
+    return n->type == GM_MB_I4x4 ? n->i4_mode[nb] : 2;
+}
+
+static int i4_pred_mode(const gm_encoder *e, int mbx, int mby, int blk)
+{
+    int a = i4_neighbour_mode(e, mbx, mby, blk, 1), b = i4_neighbour_mode(e, mbx, mby, blk, 0);
+    if (a < 0 || b < 0)
+        return 2;
+    return a < b ? a : b;
+}
+
+/* Tries to code the macroblock's luma as Intra4x4.  Block by block: mode = argmin over available modes of
+ * (SAD + lambda * modebits) << 4 | mode with modebits = 1 for the predicted mode, 4 otherwise; the block is
+ * reconstructed at once because the next blocks predict from it.  Gives up (returns 0) as soon as the
+ * accumulated cost reaches cost16, the cost of the best Intra16x16 mode. */
+static int try_intra4x4(gm_encoder *e, int mbx, int mby, uint32_t cost16)
+{
+    int W = e->W, qp = e->qp, lam = me_lambda(qp);
+    gm_mb *mb = &e->mbs[mby * e->mbw + mbx];
+    const uint8_t *src = e->src.p[0] + (size_t)(mby * 16) * W + mbx * 16;
+    uint8_t *dst = e->unf.p[0] + (size_t)(mby * 16) * W + mbx * 16;
+    uint32_t cost4 = 0;
+    int cbp = 0;
+    mb->type = GM_MB_I4x4; /* i4_pred_mode of later blocks looks at the blocks already decided */
+    for (int b = 0; b < 16; b++) {
+        int bx = blk_x[b], by = blk_y[b];
+        int has_top = by > 0 || mby > 0, has_left = bx > 0 || mbx > 0;
+        int has_tl = (bx > 0 || mbx > 0) && (by > 0 || mby > 0);
+        int has_tr;
+        if (by == 0)
+            has_tr = mby > 0 && (bx < 3 || mbx + 1 < e->mbw);
+        else
+            has_tr = bx < 3 && xy2blk[by - 1][bx + 1] < b;
+        const uint8_t *s4 = src + by * 4 * W + bx * 4;
+        uint8_t *d4 = dst + by * 4 * W + bx * 4;
+        int t[8] = {0}, l[4] = {0}, m = 0;
+        if (has_top)
+            for (int i = 0; i < 8; i++)
+                t[i] = d4[-W + (i < 4 || has_tr ? i : 3)];
+        if (has_left)
+            for (int i = 0; i < 4; i++)
+                l[i] = d4[i * W - 1];
+        if (has_tl)
+            m = d4[-W - 1];
+        int pm = i4_pred_mode(e, mbx, mby, b);
+        uint32_t best = 0xffffffffu;
+        uint8_t pred[16], bpred[16];
+        for (int mode = 0; mode < 9; mode++) {
+            int need_top = mode == 0 || mode == 3 || mode == 7 || mode == 4 || mode == 5 || mode == 6;
+            int need_left = mode == 1 || mode == 8 || mode == 4 || mode == 5 || mode == 6;
+            if ((need_top && !has_top) || (need_left && !has_left) || ((mode >= 4 && mode <= 6) && !has_tl))
+                continue;
+            pred4x4(mode, t, l, m, has_top, has_left, pred);
+            uint32_t cost = (uint32_t)sad_block(s4, W, pred, 4, 4, 4) + (uint32_t)(lam * (mode == pm ? 1 : 4));
+            uint32_t key = (cost << 4) | (uint32_t)mode;
+            if (key < best) {
+                best = key;
+                memcpy(bpred, pred, 16);
+            }
+        }
+        cost4 += best >> 4;
+        if (cost4 >= cost16)
+            return 0;
+        mb->i4_mode[b] = (uint8_t)(best & 15);
+        int16_t d[16];
+        int w[16];
+        resid4x4(s4, W, bpred, 4, d);
+        fdct4x4(d, w);
+        int n = quant_block(w, qp, 1, 0, mb->coef[b]);
+        mb->nnz[b] = (uint8_t)n;
+        if (n)
+            cbp |= 1 << (b >> 2);
+        int dq[16] = {0};
+        if (n)
+            dequant_block(mb->coef[b], qp, 0, dq);
+        idct4x4_add(dq, d4, W, bpred, 4);
+    }
+    /* an 8x8 quadrant without coefficients in any of its blocks is not coded: its cbp bit is 0 already */
+    mb->cbp = (uint8_t)cbp;
+    return 1;
+}
+
 static void encode_mb_intra(gm_encoder *e, int mbx, int mby)
 {
     int W = e->W, CW = W / 2, qp = e->qp;
@@ -699,6 +895,14 @@ static void encode_mb_intra(gm_encoder *e, int mbx, int mby)
         }
     }
     mb->i16_mode = (uint8_t)(best & 3);
+    int use_i4 = e->cfg.intra4x4 && try_intra4x4(e, mbx, mby, best >> 2);
+    if (use_i4) {
+        mb->i16_mode = 0;
+    } else {
+        memset(mb->coef, 0, sizeof(mb->coef));
+        memset(mb->nnz, 0, sizeof(mb->nnz));
+        memset(mb->i4_mode, 0, sizeof(mb->i4_mode));
+        mb->type = GM_MB_I16x16;
 
     /* luma: 16 x (transform, AC quant), DC Hadamard + quant */
     int wblk[16][16], dcm[16]; /* dcm raster [by*4+bx] */
@@ -776,6 +980,8 @@ static void encode_mb_intra(gm_encoder *e, int mbx, int mby)
             idct4x4_add(d, dst + by * W + bx, W, best_pred + by * 16 + bx, 16);
         }
     }
+
+    } /* !use_i4 */
 
     /* chroma */
     uint8_t cpred[2][64], cbest[2][64];
@@ -1307,6 +1513,21 @@ static void cavlc_slice_data(gm_encoder *e, bitw *bw, int frame_i)
                 bw_ue(bw, (uint32_t)(t + (frame_i ? 0 : 5)));
                 bw_ue(bw, mb->chroma_mode);
                 bw_se(bw, 0); /* mb_qp_delta */
+            } else if (mb->type == GM_MB_I4x4) {
+                bw_ue(bw, frame_i ? 0 : 5); /* I_NxN */
+                for (int b = 0; b < 16; b++) {
+                    int pm = i4_pred_mode(e, mbx, mby, b), mode = mb->i4_mode[b];
+                    if (mode == pm)
+                        bw_put(bw, 1, 1); /* prev_intra4x4_pred_mode_flag */
+                    else {
+                        bw_put(bw, 0, 1);
+                        bw_put(bw, (uint32_t)(mode < pm ? mode : mode - 1), 3); /* rem_intra4x4_pred_mode */
+                    }
+                }
+                bw_ue(bw, mb->chroma_mode);
+                bw_ue(bw, h264_cbp_to_codenum_intra[mb->cbp]);
+                if (mb->cbp)
+                    bw_se(bw, 0); /* mb_qp_delta */
             } else {          /* P_L0_16x16 */
                 bw_ue(bw, 0);
                 bw_se(bw, mb->mvd[0]);
@@ -1564,6 +1785,24 @@ static void cabac_mb(gm_encoder *e, cabac_t *c, int mbx, int mby, int frame_i)
         }
         cabac_decision(c, c4, mb->i16_mode >> 1);
         cabac_decision(c, c5, mb->i16_mode & 1);
+    } else if (mb->type == GM_MB_I4x4) {
+        if (frame_i) {
+            int inc = (A && A->type != GM_MB_I4x4) + (B && B->type != GM_MB_I4x4);
+            cabac_decision(c, 3 + inc, 0); /* I_NxN */
+        } else {
+            cabac_decision(c, 14, 1);
+            cabac_decision(c, 17, 0);
+        }
+        for (int b = 0; b < 16; b++) {
+            int pm = i4_pred_mode(e, mbx, mby, b), mode = mb->i4_mode[b];
+            cabac_decision(c, 68, mode == pm);
+            if (mode != pm) {
+                int rem = mode < pm ? mode : mode - 1;
+                cabac_decision(c, 69, rem & 1);
+                cabac_decision(c, 69, (rem >> 1) & 1);
+                cabac_decision(c, 69, (rem >> 2) & 1);
+            }
+        }
     } else { /* P_L0_16x16 */
         cabac_decision(c, 14, 0);
         cabac_decision(c, 15, 0);

@@ -105,3 +105,18 @@ def test_skip_macroblocks_appear_on_static_content(oracle):
         y, c = content("static", 96, 80, t)
         enc.encode(y, c)
     assert (enc.mbs()["type"] == 2).sum() >= 15
+
+
+@needs_decoder
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("kind,qp", [("synth", 24), ("noise", 12), ("shift", 36)])
+def test_intra4x4_option_decodes_bit_exactly(oracle, kind, qp, cabac):
+    """Opt-in Intra4x4 (oracle only so far): nine prediction modes, I_NxN syntax for both
+    entropy coders.  Off by default: with the SAD-based I4x4/I16x16 decision it costs bits."""
+    clip = make_clip(kind, 96, 80, 3)
+    stream, sizes, recs = oracle_encode_clip(clip, 96, 80, keep_recon=True, qp=qp, gop=2, cabac=cabac, me_range=8, intra4x4=1)
+    dec = avdec.decode(stream)
+    assert len(dec) == 3
+    for r, d in zip(recs, dec):
+        for p in range(3):
+            assert np.array_equal(r[p], d[p])
