@@ -345,7 +345,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--lanes", type=int, default=0, help="GOPs in flight per GPU (0 = auto)")
-    ap.add_argument("--cpu-frames", type=int, default=2, help="frames per core in the CPU sample")
+    ap.add_argument("--cpu-frames", type=int, default=60, help="frames per core in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)

@@ -268,6 +268,7 @@ struct gm_encoder {
     frame_t src, rec[2], unf;
     int cur;                        /* reference_current index (ping-pong, cedar.c:1198-1201) */
     gm_mb *mbs;
+    uint8_t *refpad; /* edge-extended reference luma for the motion search */
     uint8_t *rbsp;
     size_t rbsp_cap;
     int last_frame_i;
@@ -342,6 +343,7 @@ void gm_close(gm_encoder *e)
     frame_free(&e->rec[1]);
     frame_free(&e->unf);
     free(e->mbs);
+    free(e->refpad);
     free(e->rbsp);
     free(e);
 }
@@ -1035,20 +1037,36 @@ static inline int mv_bits(int d) /* se(v) length of the quarter-pel value 4*d */
 
 static inline int me_lambda(int qp) { return 1 << CLIP3(0, 5, (qp - 12) / 6); }
 
+/* The reference plane is edge-extended once per frame (pad = R + 16) so that the search loops carry no
+ * clamping and the compiler can vectorise the SAD; the result is identical to clamped fetches. */
+static void pad_reference(gm_encoder *e, const frame_t *ref)
+{
+    int W = e->W, H = e->H, P = e->cfg.me_range + 16, PW = W + 2 * P;
+    if (!e->refpad)
+        e->refpad = (uint8_t *)malloc((size_t)PW * (H + 2 * P));
+    for (int y = -P; y < H + P; y++) {
+        const uint8_t *srow = ref->p[0] + (size_t)CLIP3(0, H - 1, y) * W;
+        uint8_t *drow = e->refpad + (size_t)(y + P) * PW;
+        memset(drow, srow[0], (size_t)P);
+        memcpy(drow + P, srow, (size_t)W);
+        memset(drow + P + W, srow[W - 1], (size_t)P);
+    }
+}
+
 static void motion_search(gm_encoder *e, const frame_t *ref, int mbx, int mby, int *bdx, int *bdy)
 {
-    int W = e->W, H = e->H, R = e->cfg.me_range, lam = me_lambda(e->qp);
+    (void)ref;
+    int W = e->W, R = e->cfg.me_range, lam = me_lambda(e->qp), P = R + 16, PW = W + 2 * P;
     const uint8_t *src = e->src.p[0] + (size_t)(mby * 16) * W + mbx * 16;
     uint32_t best = 0xffffffffu;
     for (int dy = -R; dy <= R; dy++)
         for (int dx = -R; dx <= R; dx++) {
+            const uint8_t *rp = e->refpad + (size_t)(mby * 16 + dy + P) * PW + mbx * 16 + dx + P;
             int sad = 0;
             for (int y = 0; y < 16; y++) {
-                int ry = CLIP3(0, H - 1, mby * 16 + y + dy);
-                for (int x = 0; x < 16; x++) {
-                    int rx = CLIP3(0, W - 1, mbx * 16 + x + dx);
-                    sad += iabs(src[y * W + x] - ref->p[0][(size_t)ry * W + rx]);
-                }
+                const uint8_t *a = src + y * W, *b = rp + (size_t)y * PW;
+                for (int x = 0; x < 16; x++)
+                    sad += iabs(a[x] - b[x]);
             }
             uint32_t cost = (uint32_t)(sad + lam * (mv_bits(dx) + mv_bits(dy)));
             uint32_t key = (cost << 15) | (uint32_t)((dy + R) * (2 * R + 1) + (dx + R));
@@ -1916,6 +1934,7 @@ int gm_encode_frame(gm_encoder *e, const uint8_t *luma, const uint8_t *chroma, u
             for (int mbx = 0; mbx < e->mbw; mbx++)
                 encode_mb_intra(e, mbx, mby);
     } else {
+        pad_reference(e, ref);
         for (int mby = 0; mby < e->mbh; mby++)
             for (int mbx = 0; mbx < e->mbw; mbx++) {
                 int dx = 0, dy = 0;
