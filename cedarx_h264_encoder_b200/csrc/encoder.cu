@@ -68,10 +68,12 @@ struct cedar_b200_handle {
     // each other and the following frames' reconstruction
     enum { NSIDE = 32 };
     cudaStream_t stream_cabac[NSIDE];
-    enum { MAXGRP = 4 };
-    cudaStream_t stream_grp[MAXGRP]; // [0] == stream; lane groups 1.. run on their own streams
-    cudaEvent_t ev_grp[MAXGRP], ev_bins_grp[MAXGRP], ev_begin;
-    int ngroups;
+    // Per step only ME -> residual -> deblock stay on the main stream.  Ingest runs one step ahead on
+    // stream_pre, SSE and the parallel entropy passes one step behind on stream_post; source planes and
+    // syntax records are double buffered (index = step parity) so the three can overlap.
+    cudaStream_t stream_pre, stream_post;
+    cudaEvent_t ev_ingest[2], ev_main[2], ev_post[2], ev_begin, ev_post_done;
+    bool post_valid[2]; // ev_post[p] has been recorded in this stream of work
     // clip upload: host->device copies run on their own stream in step order; step t waits for ev_upload[t] only
     cudaStream_t stream_copy;
     std::vector<cudaEvent_t> ev_upload;
@@ -96,10 +98,10 @@ struct cedar_b200_handle {
     int *h_error;
 
     // device
-    uint8_t *d_raw, *d_src, *d_unf, *d_rec[2];
-    MbInfo *d_mbi;
-    uint8_t *d_nnz;
-    int16_t *d_coef;
+    uint8_t *d_raw, *d_src[2], *d_unf, *d_rec[2];
+    MbInfo *d_mbi[2];
+    uint8_t *d_nnz[2];
+    int16_t *d_coef[2];
     int *d_flags; // [3][L][mbh]
     uint8_t *d_bs; // [L][nmb][32] boundary strengths
     unsigned long long *d_sse;
@@ -114,7 +116,7 @@ struct cedar_b200_handle {
     uint8_t prefix[64];
     int prefix_len;
 
-    int last_nframes, last_cur;
+    int last_nframes, last_cur, last_par;
     long long launches;
     bool prof;
     std::vector<ProfEntry> prof_pending;
@@ -293,13 +295,16 @@ int alloc_buffers(cedar_b200_handle *h)
         r |= hmalloc(&h->h_clip_out, h->out_cap);
     }
     r |= dmalloc(&h->d_raw, h->raw_frame_bytes * F + 64);
-    r |= dmalloc(&h->d_src, g.frame_bytes * L);
+    r |= dmalloc(&h->d_src[0], g.frame_bytes * L);
+    r |= dmalloc(&h->d_src[1], g.frame_bytes * L);
     r |= dmalloc(&h->d_unf, g.frame_bytes * L);
     r |= dmalloc(&h->d_rec[0], g.frame_bytes * L);
     r |= dmalloc(&h->d_rec[1], g.frame_bytes * L);
-    r |= dmalloc(&h->d_mbi, (size_t)g.nmb * L);
-    r |= dmalloc(&h->d_nnz, (size_t)g.nmb * L * NNZ_STRIDE);
-    r |= dmalloc(&h->d_coef, (size_t)g.nmb * L * COEF_STRIDE);
+    for (int p = 0; p < 2; p++) {
+        r |= dmalloc(&h->d_mbi[p], (size_t)g.nmb * L);
+        r |= dmalloc(&h->d_nnz[p], (size_t)g.nmb * L * NNZ_STRIDE);
+        r |= dmalloc(&h->d_coef[p], (size_t)g.nmb * L * COEF_STRIDE);
+    }
     r |= dmalloc(&h->d_flags, (size_t)3 * L * g.mbh);
     r |= dmalloc(&h->d_bs, (size_t)g.nmb * L * 32);
     r |= dmalloc(&h->d_sse, F);
@@ -327,7 +332,8 @@ int alloc_buffers(cedar_b200_handle *h)
     h->eb.hdr_bits = h->d_hdr_bits;
     h->eb.hdr_nbits = h->d_hdr_nbits;
     CK(cudaMemset(h->eb.error, 0, sizeof(int)));
-    CK(cudaMemset(h->d_mbi, 0, sizeof(MbInfo) * g.nmb * L));
+    CK(cudaMemset(h->d_mbi[0], 0, sizeof(MbInfo) * g.nmb * L));
+    CK(cudaMemset(h->d_mbi[1], 0, sizeof(MbInfo) * g.nmb * L));
     CK(cudaMemset(h->d_rec[0], 0, g.frame_bytes * L));
     CK(cudaMemset(h->d_rec[1], 0, g.frame_bytes * L));
     return 0;
@@ -335,7 +341,8 @@ int alloc_buffers(cedar_b200_handle *h)
 
 void free_buffers(cedar_b200_handle *h)
 {
-    void *dev[] = {h->d_raw, h->d_src, h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi, h->d_nnz, h->d_coef, h->d_flags, h->d_bs,
+    void *dev[] = {h->d_raw, h->d_src[0], h->d_src[1], h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi[0], h->d_mbi[1],
+                   h->d_nnz[0], h->d_nnz[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_bs,
                    h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp, h->eb.rbsp_len,
                    h->eb.bins, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
                    h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes, h->d_out};
@@ -349,29 +356,41 @@ void free_buffers(cedar_b200_handle *h)
             cudaFreeHost(p);
 }
 
-// One lock-step pass over the lanes [lane0, lane0 + s.nlanes): the macroblock pipeline of one frame per lane
-// plus the parallel part of entropy coding, issued on stream `st`.  t = position inside the GOP (0 => IDR).
-// Lane groups run on different streams so that one group's latency-bound wavefronts overlap another
-// group's throughput-bound motion search.
-int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int lane0, cudaStream_t st, cudaEvent_t ev_bins)
+// One lock-step pass over s.nlanes lanes (one frame per lane).  t = position inside the GOP (0 => IDR).
+//   stream_pre : ingest(t)                                   -> src[p]                 (p = step parity)
+//   stream     : intra | ME, residual, MVP/skip; bS; deblock -> syntax[p], unf, rec[t & 1]
+//   stream_post: SSE, entropy sizes / scan / scatter          -> RBSP (CAVLC) or bins (CABAC)
+//   side stream: cabac_kernel
+// Buffers with index p are reused two steps later, hence the waits on ev_post[p].
+int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int step_index, bool wait_upload)
 {
     const Geom &g = h->g;
-    const int nl = s.nlanes, cur = t & 1, frame_i = t == 0;
-    const size_t flag_n = (size_t)h->L * g.mbh, fl_off = (size_t)lane0 * g.mbh;
-    int *fl_intra = h->d_flags + fl_off, *fl_y = h->d_flags + flag_n + fl_off, *fl_c = h->d_flags + 2 * flag_n + fl_off;
-    const size_t po = (size_t)lane0 * g.frame_bytes, mo = (size_t)lane0 * g.nmb;
-    uint8_t *src = h->d_src + po, *unf = h->d_unf + po, *rec = h->d_rec[cur] + po, *ref = h->d_rec[cur ^ 1] + po;
-    MbInfo *mbi = h->d_mbi + mo;
-    uint8_t *nnz = h->d_nnz + mo * NNZ_STRIDE, *bs = h->d_bs + mo * 32;
-    int16_t *coef = h->d_coef + mo * COEF_STRIDE;
-    EntropyBufs eb = h->eb;
-    eb.mb_size += (size_t)lane0 * (g.nmb + 1);
-    eb.mb_off += (size_t)lane0 * (g.nmb + 1);
+    const int nl = s.nlanes, cur = t & 1, frame_i = t == 0, p = step_index & 1;
+    const size_t flag_n = (size_t)h->L * g.mbh;
+    int *fl_intra = h->d_flags, *fl_y = h->d_flags + flag_n, *fl_c = h->d_flags + 2 * flag_n;
+    uint8_t *src = h->d_src[p], *unf = h->d_unf, *rec = h->d_rec[cur], *ref = h->d_rec[cur ^ 1];
+    MbInfo *mbi = h->d_mbi[p];
+    uint8_t *nnz = h->d_nnz[p], *bs = h->d_bs;
+    int16_t *coef = h->d_coef[p];
+    static const bool no_overlap = getenv("CEDAR_B200_NO_OVERLAP") != nullptr; // diagnosis: everything in line
+    cudaStream_t st = h->stream, pre = no_overlap ? st : h->stream_pre, post = no_overlap ? st : h->stream_post;
 
-    LAUNCH_ON(st, K_INGEST, ingest_kernel, dim3((unsigned)((g.frame_bytes / 4 + 255) / 256), nl), 256, 0, g, s, h->d_raw,
+    // ---- one step ahead: ingest ----
+    if (h->post_valid[p])
+        CK(cudaStreamWaitEvent(pre, h->ev_post[p], 0)); // step - 2 has finished with src[p] (and main with it)
+    if (wait_upload)
+        CK(cudaStreamWaitEvent(pre, h->ev_upload[t], 0));
+    LAUNCH_ON(pre, K_INGEST, ingest_kernel, dim3((unsigned)((g.frame_bytes / 4 + 255) / 256), nl), 256, 0, g, s, h->d_raw,
               h->raw_frame_bytes, src);
-    for (int k = 0; k < 3; k++)
-        CK(cudaMemsetAsync(h->d_flags + k * flag_n + fl_off, 0, sizeof(int) * nl * g.mbh, st));
+    CK(cudaEventRecord(h->ev_ingest[p], pre));
+
+    // ---- critical chain ----
+    CK(cudaStreamWaitEvent(st, h->ev_ingest[p], 0));
+    if (h->post_valid[p])
+        CK(cudaStreamWaitEvent(st, h->ev_post[p], 0)); // step - 2 has finished with syntax[p] and rec[cur]
+    if (t == 0 && h->post_valid[p ^ 1]) // a new wave of GOPs restarts the rec[] parity: also wait for step - 1's SSE
+        CK(cudaStreamWaitEvent(st, h->ev_post[p ^ 1], 0));
+    CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 3 * flag_n, st));
     if (frame_i) {
         LAUNCH_ON(st, K_INTRA, intra_kernel, dim3(g.mbh, nl), 32, 0, g, s, src, unf, mbi, nnz, coef, fl_intra);
     } else {
@@ -382,35 +401,39 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int la
         LAUNCH_ON(st, K_MVP, mvp_skip_kernel, dim3((g.nmb + 127) / 128, nl), 128, 0, g, s, mbi);
     }
     LAUNCH_ON(st, K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, mbi, nnz, bs);
-    LAUNCH_ON(st, K_DEBLOCK, deblock_kernel, dim3((g.mbh + DB_ROWS - 1) / DB_ROWS, nl, 2), (DB_ROWS + 2) * 32, 0, g, s, unf, rec, bs, fl_y, fl_c);
-    LAUNCH_ON(st, K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, src, rec, h->d_sse);
+    LAUNCH_ON(st, K_DEBLOCK, deblock_kernel, dim3((g.mbh + DB_ROWS - 1) / DB_ROWS, nl, 2), (DB_ROWS + 2) * 32, 0, g, s, unf,
+              rec, bs, fl_y, fl_c);
+    CK(cudaEventRecord(h->ev_main[p], st));
 
+    // ---- one step behind: statistics and the parallel entropy passes ----
+    CK(cudaStreamWaitEvent(post, h->ev_main[p], 0));
+    LAUNCH_ON(post, K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, src, rec, h->d_sse);
     dim3 egrid((g.nmb + 1 + 127) / 128, nl);
-    LAUNCH_ON(st, K_ESIZE, entropy_size_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, eb);
-    LAUNCH_ON(st, K_ESCAN, entropy_scan_kernel, dim3(1, nl), 1024, 0, g, s, eb);
+    LAUNCH_ON(post, K_ESIZE, entropy_size_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, h->eb);
+    LAUNCH_ON(post, K_ESCAN, entropy_scan_kernel, dim3(1, nl), 1024, 0, g, s, h->eb);
     if (!g.cabac)
-        LAUNCH_ON(st, K_EZERO, rbsp_zero_kernel, dim3(8, nl), 256, 0, s, eb.rbsp, eb.rbsp_cap, eb.rbsp_len);
-    LAUNCH_ON(st, K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, eb);
+        LAUNCH_ON(post, K_EZERO, rbsp_zero_kernel, dim3(8, nl), 256, 0, s, h->eb.rbsp, h->eb.rbsp_cap, h->eb.rbsp_len);
+    LAUNCH_ON(post, K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, h->eb);
+    CK(cudaEventRecord(h->ev_post[p], post));
+    h->post_valid[p] = true;
     if (g.cabac) {
         // the bins of these frames are final: code them on a side stream while the next frames are reconstructed
-        // CEDAR_B200_NO_OVERLAP=1 (diagnosis): run the serial stages in line
-        static const bool no_overlap = getenv("CEDAR_B200_NO_OVERLAP") != nullptr;
         cudaStream_t side = no_overlap ? st : h->stream_cabac[h->side_next];
-        CK(cudaEventRecord(ev_bins, st));
-        CK(cudaStreamWaitEvent(side, ev_bins, 0));
+        CK(cudaStreamWaitEvent(side, h->ev_post[p], 0));
         // The coders that sit on the critical path (the long I frames; the last frames, whose coding is the
         // tail after reconstruction ends) get an SM each: a dummy dynamic shared-memory request keeps the
         // throughput kernels off that SM, so the two serial warps are not starved of issue slots.
         static const int tail_steps = getenv("CEDAR_B200_EXCL_TAIL") ? atoi(getenv("CEDAR_B200_EXCL_TAIL")) : 4;
         const bool exclusive = t == 0 || t >= h->K - tail_steps;
         LAUNCH_ON(side, K_CABAC, cabac_kernel, nl, CABAC_THREADS, exclusive ? h->cabac_excl_smem : 0, g, s, h->K, gop_pos0,
-                  eb);
+                  h->eb);
         if (!no_overlap) {
             h->side_used |= 1u << h->side_next;
             h->side_next = (h->side_next + 1) % cedar_b200_handle::NSIDE;
         }
     }
     h->last_cur = cur;
+    h->last_par = p;
     return 0;
 }
 
@@ -418,6 +441,8 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int la
 int finish_stream(cedar_b200_handle *h, int nframes, int gop_pos0, bool with_param_sets)
 {
     const Geom &g = h->g;
+    CK(cudaEventRecord(h->ev_post_done, h->stream_post));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_post_done, 0));
     for (int i = 0; i < cedar_b200_handle::NSIDE; i++)
         if (h->side_used & (1u << i)) {
             CK(cudaEventRecord(h->ev_cabac[i], h->stream_cabac[i]));
@@ -460,6 +485,10 @@ int begin_stream(cedar_b200_handle *h, int nframes)
     CK(cudaMemsetAsync(h->d_sse, 0, sizeof(unsigned long long) * nframes, h->stream));
     CK(cudaMemsetAsync(h->eb.rbsp_len, 0, sizeof(uint32_t) * nframes, h->stream));
     CK(cudaMemsetAsync(h->eb.bins_len, 0, sizeof(uint32_t) * nframes, h->stream));
+    CK(cudaEventRecord(h->ev_begin, h->stream));
+    CK(cudaStreamWaitEvent(h->stream_pre, h->ev_begin, 0));
+    CK(cudaStreamWaitEvent(h->stream_post, h->ev_begin, 0));
+    h->post_valid[0] = h->post_valid[1] = false;
     return 0;
 }
 
@@ -551,24 +580,19 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     memset(h->prof_n, 0, sizeof(h->prof_n));
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&h->ev_bins, cudaEventDisableTiming) == cudaSuccess;
-    h->ngroups = getenv("CEDAR_B200_GROUPS") ? atoi(getenv("CEDAR_B200_GROUPS")) : 1; // measured: more groups do not pay (profiles/)
-    if (h->ngroups < 1)
-        h->ngroups = 1;
-    if (h->ngroups > cedar_b200_handle::MAXGRP)
-        h->ngroups = cedar_b200_handle::MAXGRP;
-    h->stream_grp[0] = h->stream;
+    ok = ok && cudaStreamCreateWithFlags(&h->stream_pre, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&h->stream_post, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->ev_begin, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&h->ev_post_done, cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < 2; i++)
+        ok = cudaEventCreateWithFlags(&h->ev_ingest[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_main[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&h->ev_post[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking) == cudaSuccess &&
          cudaEventCreateWithFlags(&h->ev_encode_done, cudaEventDisableTiming) == cudaSuccess;
     h->ev_upload.resize(h->F > 1 ? h->K : 0);
     for (auto &e : h->ev_upload)
         ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&h->ev_begin, cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; ok && i < cedar_b200_handle::MAXGRP; i++) {
-        if (i > 0)
-            ok = cudaStreamCreateWithFlags(&h->stream_grp[i], cudaStreamNonBlocking) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&h->ev_grp[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->ev_bins_grp[i], cudaEventDisableTiming) == cudaSuccess;
-    }
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi); // the few serial-coder CTAs go first when an SM frees up
     for (int i = 0; ok && i < cedar_b200_handle::NSIDE; i++)
@@ -632,7 +656,7 @@ int cedar_b200_encode_frame(cedar_b200_handle *h)
     if ((r = begin_stream(h, 1)))
         return r;
     Step s = {1, 0, 1, 1};
-    if ((r = encode_step(h, s, h->frame_p_count, h->frame_p_count, 0, h->stream, h->ev_bins)))
+    if ((r = encode_step(h, s, h->frame_p_count, h->frame_p_count, 0, false)))
         return r;
     if ((r = finish_stream(h, 1, h->frame_p_count, h->frame_count == 0)))
         return r;
@@ -699,29 +723,16 @@ int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_in
     if ((r = begin_stream(h, nframes)))
         return r;
     const int K = h->K, gops = (nframes + K - 1) / K;
-    // the group streams start after the uploads / clears issued on the main stream
-    CK(cudaEventRecord(h->ev_begin, h->stream));
-    for (int gi = 1; gi < h->ngroups; gi++)
-        CK(cudaStreamWaitEvent(h->stream_grp[gi], h->ev_begin, 0));
+    int step_index = 0;
     for (int gop0 = 0; gop0 < gops; gop0 += h->L) {
         int nl = gops - gop0 < h->L ? gops - gop0 : h->L;
-        int ng = h->ngroups < nl ? h->ngroups : nl;
         for (int t = 0; t < K; t++) {
-            for (int gi = 0; gi < ng; gi++) {
-                int l0 = (int)((long)nl * gi / ng), l1 = (int)((long)nl * (gi + 1) / ng);
-                Step s = {l1 - l0, (gop0 + l0) * K + t, K, nframes};
-                if (s.frame0 >= nframes)
-                    continue;
-                if (h->upload_pending)
-                    CK(cudaStreamWaitEvent(h->stream_grp[gi], h->ev_upload[t], 0));
-                if ((r = encode_step(h, s, t, 0, l0, h->stream_grp[gi], h->ev_bins_grp[gi])))
-                    return r;
-            }
+            Step s = {nl, gop0 * K + t, K, nframes};
+            if (s.frame0 >= nframes)
+                break;
+            if ((r = encode_step(h, s, t, 0, step_index++, h->upload_pending)))
+                return r;
         }
-    }
-    for (int gi = 1; gi < h->ngroups; gi++) {
-        CK(cudaEventRecord(h->ev_grp[gi], h->stream_grp[gi]));
-        CK(cudaStreamWaitEvent(h->stream, h->ev_grp[gi], 0));
     }
     h->upload_pending = false;
     if ((r = finish_stream(h, nframes, 0, first_frame_index == 0)))
@@ -811,12 +822,12 @@ long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_
     const void *src = nullptr;
     size_t n = 0;
     switch (what) {
-    case 0: src = h->d_src, n = g.frame_bytes; break;
+    case 0: src = h->d_src[h->last_par], n = g.frame_bytes; break;
     case 1: src = h->d_unf, n = g.frame_bytes; break;
     case 2: src = h->d_rec[h->last_cur], n = g.frame_bytes; break;
-    case 3: src = h->d_mbi, n = sizeof(MbInfo) * g.nmb; break;
-    case 4: src = h->d_nnz, n = (size_t)NNZ_STRIDE * g.nmb; break;
-    case 5: src = h->d_coef, n = sizeof(int16_t) * COEF_STRIDE * g.nmb; break;
+    case 3: src = h->d_mbi[h->last_par], n = sizeof(MbInfo) * g.nmb; break;
+    case 4: src = h->d_nnz[h->last_par], n = (size_t)NNZ_STRIDE * g.nmb; break;
+    case 5: src = h->d_coef[h->last_par], n = sizeof(int16_t) * COEF_STRIDE * g.nmb; break;
     case 6: src = h->eb.bins_len, n = sizeof(uint32_t) * (h->last_nframes > 0 ? h->last_nframes : 1); break;
     default: return -EINVAL;
     }
@@ -840,16 +851,18 @@ void cedar_b200_close(cedar_b200_handle *h)
     free_buffers(h);
     cudaEventDestroy(h->ev_bins);
     cudaEventDestroy(h->ev_begin);
+    cudaEventDestroy(h->ev_post_done);
     cudaEventDestroy(h->ev_encode_done);
     for (auto &e : h->ev_upload)
         cudaEventDestroy(e);
-    cudaStreamDestroy(h->stream_copy);
-    for (int i = 0; i < cedar_b200_handle::MAXGRP; i++) {
-        cudaEventDestroy(h->ev_grp[i]);
-        cudaEventDestroy(h->ev_bins_grp[i]);
-        if (i > 0)
-            cudaStreamDestroy(h->stream_grp[i]);
+    for (int i = 0; i < 2; i++) {
+        cudaEventDestroy(h->ev_ingest[i]);
+        cudaEventDestroy(h->ev_main[i]);
+        cudaEventDestroy(h->ev_post[i]);
     }
+    cudaStreamDestroy(h->stream_copy);
+    cudaStreamDestroy(h->stream_pre);
+    cudaStreamDestroy(h->stream_post);
     for (int i = 0; i < cedar_b200_handle::NSIDE; i++) {
         cudaEventDestroy(h->ev_cabac[i]);
         cudaStreamDestroy(h->stream_cabac[i]);
