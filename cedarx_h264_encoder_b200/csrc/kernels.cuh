@@ -1292,25 +1292,27 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
     }
 }
 
-// K7 CABAC arithmetic coding: one CTA per frame (one slice per picture, cedar.c:992-993), software
-// pipelined over tiles of CABAC_TILE bins with three stages running on different warps at the same time
-// (entropy.cuh explains the split):
-//   warps 0..15  tile i    context-state resolution: thread c owns context c (neighbouring, equally hot
-//                          contexts dealt to different warps because matches serialise inside a warp),
-//                          walks the tile in shared memory and records the state before each of its bins;
-//   warp 16      tile i-1  range recurrence (lane 0; all lanes stage 32 bins at a time) -> interval steps;
-//   warp 17      tile i-2  low recurrence + byte output with carry propagation (lane 0).
+// K7 CABAC arithmetic coding: one CTA (three warps) per frame (one slice per picture, cedar.c:992-993),
+// software pipelined over tiles of CABAC_TILE bins, the three stages running at the same time on different
+// warps (entropy.cuh explains the split):
+//   warp 0  tile i    context-state resolution, 32 bins at a time: __match_any_sync groups the lanes whose
+//                     bins share a context; round r lets the r-th bin of every group read / advance its
+//                     context state in shared memory (distinct contexts inside a round => no conflicts),
+//                     which yields the state each bin is coded in;
+//   warp 1  tile i-1  range recurrence (lane 0; all lanes stage 32 bins at a time) -> interval steps;
+//   warp 2  tile i-2  low recurrence + byte output with carry propagation (lane 0).
 // Only the two short recurrences are serial (about a dozen dependent integer instructions per bin each).
 // Runs on side streams so that it overlaps the reconstruction of the following frames.
 #define CABAC_TILE 2048
-#define CABAC_THREADS 576
+#define CABAC_THREADS 96
 __global__ void __launch_bounds__(CABAC_THREADS) cabac_kernel(Geom g, Step s, int gop_len, int gop_pos0, EntropyBufs eb)
 {
     __shared__ CabacTables tab;
-    __shared__ uint2 binsT[3][CABAC_TILE / 4];
+    __shared__ uint16_t binsT[3][CABAC_TILE];
     __shared__ uint8_t preT[2][CABAC_TILE];
     __shared__ uint32_t stepT[2][CABAC_TILE];
     __shared__ uint2 stage[32];
+    __shared__ uint8_t ctx_state[464];
     const int f = lane_frame(s, blockIdx.x);
     if (f < 0)
         return;
@@ -1322,17 +1324,12 @@ __global__ void __launch_bounds__(CABAC_THREADS) cabac_kernel(Geom g, Step s, in
             eb.rbsp_len[f] = 0;
         return;
     }
-    const uint2 *gbins = (const uint2 *)(eb.bins + eb.bins_off[f]); // bins_off is a multiple of 8 bins
+    const uint16_t *gbins = eb.bins + eb.bins_off[f];
     const int ntiles = (int)((nb + CABAC_TILE - 1) / CABAC_TILE);
     tab.build(tid, CABAC_THREADS);
+    for (int i = tid; i < 460; i += CABAC_THREADS)
+        ctx_state[i] = (uint8_t)cabac_init_state(i, frame_i, g.qp);
 
-    // resolve state
-    const uint32_t c = (uint32_t)((tid & 15) * 32 + ((tid >> 4) & 31)); // context c -> warp c % 16
-    const uint32_t c2 = c | (c << 16);
-    uint32_t st = (warp < 16 && c < 460) ? cabac_init_state((int)c, frame_i, g.qp) : 0;
-    uint2 nx = make_uint2(0, 0);
-    if (warp < 16 && (uint32_t)tid * 4 < nb)
-        nx = gbins[tid];
     // coder state
     CabacRange rc;
     CabacBytes cb;
@@ -1341,57 +1338,53 @@ __global__ void __launch_bounds__(CABAC_THREADS) cabac_kernel(Geom g, Step s, in
     cb.out = out + hb;
     const unsigned limit = eb.rbsp_cap - hb - 64;
     bool overflow = false;
-    if (tid == 17 * 32) { // header bits, then cabac_alignment_one_bit up to the byte boundary
+    if (tid == 64) { // header bits, then cabac_alignment_one_bit up to the byte boundary
         unsigned long long h = ((unsigned long long)eb.hdr_bits[f] << (hb * 8 - hn)) | ((1ull << (hb * 8 - hn)) - 1);
         for (int i = 0; i < hb; i++)
             out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
     }
+    // resolver prefetch: the first chunk of 32 bins
+    uint32_t nx = (warp == 0 && (uint32_t)lane < nb) ? gbins[lane] : 0;
     __syncthreads();
 
     for (int it = 0; it < ntiles + 2; it++) {
-        if (warp < 16) {
+        if (warp == 0) {
             if (it < ntiles) {
                 const uint32_t base = (uint32_t)it * CABAC_TILE;
                 const uint32_t n = nb - base < CABAC_TILE ? nb - base : CABAC_TILE;
-                const uint32_t nq = (n + 3) >> 2;
-                uint2 *tile = binsT[it % 3];
+                uint16_t *tile = binsT[it % 3];
                 uint8_t *ptile = preT[it & 1];
-                tile[tid] = nx;
-                if (it + 1 < ntiles && base + CABAC_TILE + (uint32_t)tid * 4 < nb)
-                    nx = gbins[(base + CABAC_TILE) / 4 + tid];
-                asm volatile("bar.sync 1, 512;" ::: "memory");
-                if (c < 460) {
-#pragma unroll 2
-                    for (uint32_t i = 0; i < nq; i++) {
-                        const uint2 w = tile[i]; // four bins; same address for the whole warp => broadcast
-                        const uint32_t m0 = __vcmpeq2(w.x & 0x0fff0fffu, c2), m1 = __vcmpeq2(w.y & 0x0fff0fffu, c2);
-                        if (m0 | m1) {
-                            if (m0 & 0xffffu) {
-                                ptile[4 * i] = (uint8_t)st;
-                                st = cabac_next_state(tab, st, (w.x >> 15) & 1);
-                            }
-                            if (m0 >> 16) {
-                                ptile[4 * i + 1] = (uint8_t)st;
-                                st = cabac_next_state(tab, st, (w.x >> 31) & 1);
-                            }
-                            if (m1 & 0xffffu) {
-                                ptile[4 * i + 2] = (uint8_t)st;
-                                st = cabac_next_state(tab, st, (w.y >> 15) & 1);
-                            }
-                            if (m1 >> 16) {
-                                ptile[4 * i + 3] = (uint8_t)st;
-                                st = cabac_next_state(tab, st, (w.y >> 31) & 1);
-                            }
+                for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+                    const uint32_t b = nx;
+                    const uint32_t nidx = base + k0 + 32 + lane;
+                    if (nidx < nb) // prefetch the next chunk (possibly the next tile's first)
+                        nx = gbins[nidx];
+                    const bool live = k0 + lane < n;
+                    const bool reg = live && !(b & (BIN_BYPASS | BIN_TERM));
+                    const uint32_t c = b & 0x3ff;
+                    const uint32_t grp = __match_any_sync(0xffffffffu, reg ? c : 1024u + lane);
+                    const int rank = __popc(grp & ((1u << lane) - 1));
+                    const int rounds = __reduce_max_sync(0xffffffffu, reg ? rank : 0);
+                    uint32_t st = 0;
+                    for (int r = 0; r <= rounds; r++) {
+                        if (reg && rank == r) {
+                            st = ctx_state[c];
+                            ctx_state[c] = (uint8_t)cabac_next_state(tab, st, (b >> 15) & 1);
                         }
+                        __syncwarp();
+                    }
+                    if (live) {
+                        tile[k0 + lane] = (uint16_t)b;
+                        ptile[k0 + lane] = (uint8_t)st;
                     }
                 }
             }
-        } else if (warp == 16) {
+        } else if (warp == 1) {
             const int t = it - 1;
             if (t >= 0 && t < ntiles) {
                 const uint32_t base = (uint32_t)t * CABAC_TILE;
                 const uint32_t n = nb - base < CABAC_TILE ? nb - base : CABAC_TILE;
-                const uint16_t *tb = (const uint16_t *)binsT[t % 3];
+                const uint16_t *tb = binsT[t % 3];
                 const uint8_t *ptile = preT[t & 1];
                 uint32_t *steps = stepT[t & 1];
                 for (uint32_t k0 = 0; k0 < n; k0 += 32) {
@@ -1443,7 +1436,7 @@ __global__ void __launch_bounds__(CABAC_THREADS) cabac_kernel(Geom g, Step s, in
         }
         __syncthreads();
     }
-    if (tid == 17 * 32) {
+    if (tid == 64) {
         if (overflow) {
             atomicExch(eb.error, 3);
             eb.rbsp_len[f] = 0;
