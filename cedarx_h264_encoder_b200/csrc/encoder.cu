@@ -173,10 +173,17 @@ struct LaunchScope {
     }
 };
 
-#define LAUNCH_ON(st, id, kern, grid, block, smem, ...)  \
-    do {                                                 \
-        LaunchScope ls_(h, id, st);                      \
-        kern<<<grid, block, smem, st>>>(__VA_ARGS__);    \
+#define LAUNCH_ON(st, id, kern, grid, block, smem, ...)                                                      \
+    do {                                                                                                     \
+        {                                                                                                    \
+            LaunchScope ls_(h, id, st);                                                                      \
+            kern<<<grid, block, smem, st>>>(__VA_ARGS__);                                                    \
+        }                                                                                                    \
+        cudaError_t le_ = cudaGetLastError();                                                                \
+        if (le_ != cudaSuccess) {                                                                            \
+            fprintf(stderr, "cedar_b200: launch of %s failed: %s\n", kKernelNames[id], cudaGetErrorString(le_)); \
+            return -EIO;                                                                                     \
+        }                                                                                                    \
     } while (0)
 #define LAUNCH(id, kern, grid, block, smem, ...) LAUNCH_ON(h->stream, id, kern, grid, block, smem, __VA_ARGS__)
 
@@ -616,9 +623,13 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
             want = 0;
         h->cabac_excl_smem = want;
     }
-    if (me_smem_bytes(g.R, me_strip(g.R)) > 48 * 1024)
-        cudaFuncSetAttribute(me_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)me_smem_bytes(g.R, me_strip(g.R)));
+    if (cudaFuncSetAttribute(me_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)me_smem_bytes(g.R, me_strip(g.R))) != cudaSuccess) {
+        fprintf(stderr, "cedar_b200: search range %d needs more shared memory than the device offers\n", g.R);
+        cudaGetLastError();
+        delete h;
+        return -EINVAL;
+    }
     r = alloc_buffers(h);
     if (r) {
         free_buffers(h);

@@ -114,16 +114,23 @@ __host__ __device__ inline int me_copy_words(int R, int nstrip)
     int cw = (16 + 2 * R + 3) * me_row_words(R, nstrip);
     return cw + ((8 - (cw & 31)) & 31); // == 8 (mod 32): the four copies start 8 banks apart
 }
+__host__ __device__ inline int me_item_words(int R, int nstrip) // left-over column items, padded to whole warps
+{
+    int nd = 2 * R + 1;
+    return (((nd & 31) * ((nd + 3) >> 2) * nstrip) + 31) & ~31;
+}
 __host__ __device__ inline size_t me_smem_bytes(int R, int nstrip)
 {
-    return (size_t)(64 * nstrip + 4 * me_copy_words(R, nstrip)) * 4;
+    return (size_t)(64 * nstrip + 4 * me_copy_words(R, nstrip) + me_item_words(R, nstrip)) * 4;
 }
 
 __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstrip, const uint8_t *__restrict__ src,
                                                        const uint8_t *__restrict__ ref, MbInfo *__restrict__ mbi)
 {
     extern __shared__ uint32_t sm[];
-    __shared__ uint32_t warp_best[ME_MAX_STRIP][ME_THREADS / 32];
+    __shared__ uint32_t mb_best[ME_MAX_STRIP];
+    __shared__ uint32_t mvcost[136];      // lambda * bits(offset - R); >= 0x10000 beyond the range (padded row groups)
+    __shared__ uint32_t task_tab[ME_MAX_STRIP * 4 * 33];
     if (lane_frame(s, blockIdx.y) < 0)
         return;
     const int R = g.R, nd = 2 * R + 1;
@@ -134,9 +141,26 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
     const int x0 = mbx0 * 16, y0 = mby * 16;
     const uint8_t *srcY = src + (size_t)blockIdx.y * g.frame_bytes;
     const uint8_t *refY = ref + (size_t)blockIdx.y * g.frame_bytes;
-    uint32_t *cur_s = sm, *cp = sm + 64 * nstrip;
+    uint32_t *cur_s = sm, *cp = sm + 64 * nstrip, *item_tab = cp + 4 * CWs;
     const int tid = threadIdx.x;
 
+    // Tables that take every division and every bit-length computation out of the task loop.
+    const int nfull = nd >> 5, nleft = nd & 31, ndyg = (nd + 3) >> 2;
+    const int ntask_full = nfull * ndyg;               // per macroblock: 32 columns x one row group
+    const int nitems_left = nleft * ndyg * nm;         // left-over columns of all macroblocks, one item per lane
+    for (int i = tid; i < 136; i += ME_THREADS)
+        mvcost[i] = i < nd ? (uint32_t)(g.lambda * mv_bits(i - R)) : 0x10000u;
+    for (int i = tid; i < ntask_full * nm; i += ME_THREADS) {
+        int m = i / ntask_full, t = i - m * ntask_full;
+        task_tab[i] = (uint32_t)m | ((uint32_t)((t / ndyg) * 32) << 4) | ((uint32_t)(t % ndyg) << 12);
+    }
+    for (int i = tid; i < ((nitems_left + 31) & ~31); i += ME_THREADS) {
+        int per_mb = nleft * ndyg, m = i / (per_mb > 0 ? per_mb : 1), jj = i - m * per_mb;
+        item_tab[i] = i < nitems_left ? (uint32_t)m | ((uint32_t)(nfull * 32 + jj / ndyg) << 4) | ((uint32_t)(jj % ndyg) << 12)
+                                      : 0xffffffffu;
+    }
+    if (tid < ME_MAX_STRIP)
+        mb_best[tid] = 0xffffffffu;
     for (int i = tid; i < 64 * nm; i += ME_THREADS) { // current blocks: [mb][row][4 words]
         int m = i >> 6, row = (i >> 2) & 15, k = i & 3;
         cur_s[i] = *(const uint32_t *)(srcY + (size_t)(y0 + row) * g.W + x0 + 16 * m + 4 * k);
@@ -174,87 +198,60 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31, nwarps = ME_THREADS / 32;
-    const int nfull = nd >> 5, nleft = nd & 31, ndyg = (nd + 3) >> 2;
-    const int ntask_full = nfull * ndyg;               // per macroblock: 32 columns x one row group
-    const int nitems_left = nleft * ndyg * nm;         // left-over columns of all macroblocks, one item per lane
     const int ntask = ntask_full * nm + ((nitems_left + 31) >> 5);
-    uint32_t best[ME_MAX_STRIP];
-#pragma unroll
-    for (int m = 0; m < ME_MAX_STRIP; m++)
-        best[m] = 0xffffffffu;
     for (int task = warp; task < ntask; task += nwarps) {
-        int m, ox, dyg;
-        bool valid = true;
-        if (task < ntask_full * nm) {
-            m = task / ntask_full;
-            int t = task - m * ntask_full;
-            ox = (t / ndyg) * 32 + lane;
-            dyg = t % ndyg;
-        } else {
-            int j = (task - ntask_full * nm) * 32 + lane;
-            valid = j < nitems_left;
-            int per_mb = nleft * ndyg;
-            m = valid ? j / per_mb : 0;
-            int jj = j - m * per_mb;
-            ox = nfull * 32 + jj / ndyg;
-            dyg = jj % ndyg;
-        }
-        if (!valid)
-            continue;
-        uint32_t cur[64];
-        {
-            const uint4 *c4 = (const uint4 *)(cur_s + 64 * m);
+        // task table entry: macroblock | column offset << 4 | row group << 12 (0xffffffff = idle lane)
+        const uint32_t e = task < ntask_full * nm ? task_tab[task] + ((uint32_t)lane << 4)
+                                                  : item_tab[(task - ntask_full * nm) * 32 + lane];
+        uint32_t key = 0xffffffffu;
+        const int m = (int)(e & 15);
+        if (e != 0xffffffffu) {
+            const int ox = (int)((e >> 4) & 255), oy0 = (int)(e >> 12) * 4;
+            uint32_t cur[64];
+            {
+                const uint4 *c4 = (const uint4 *)(cur_s + 64 * m);
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                uint4 v = c4[i];
-                cur[4 * i] = v.x, cur[4 * i + 1] = v.y, cur[4 * i + 2] = v.z, cur[4 * i + 3] = v.w;
-            }
-        }
-        const int oy0 = dyg * 4;
-        const uint32_t *wp = cp + (ox & 3) * CWs + oy0 * RSW + 4 * m + (ox >> 2);
-        uint32_t acc[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int r = 0; r < 19; r++) {
-            uint32_t w0 = wp[r * RSW], w1 = wp[r * RSW + 1], w2 = wp[r * RSW + 2], w3 = wp[r * RSW + 3];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                int cr = r - j; // candidate row offset oy0 + j compares window row r with block row r - j
-                if (cr >= 0 && cr < 16) {
-                    acc[j] = sad4_acc(w0, cur[cr * 4 + 0], acc[j]);
-                    acc[j] = sad4_acc(w1, cur[cr * 4 + 1], acc[j]);
-                    acc[j] = sad4_acc(w2, cur[cr * 4 + 2], acc[j]);
-                    acc[j] = sad4_acc(w3, cur[cr * 4 + 3], acc[j]);
+                for (int i = 0; i < 16; i++) {
+                    uint4 v = c4[i];
+                    cur[4 * i] = v.x, cur[4 * i + 1] = v.y, cur[4 * i + 2] = v.z, cur[4 * i + 3] = v.w;
                 }
             }
-        }
-        const int bx = mv_bits(ox - R);
-        uint32_t b = 0xffffffffu;
+            const uint32_t *wp = cp + (ox & 3) * CWs + oy0 * RSW + 4 * m + (ox >> 2);
+            uint32_t acc[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            int oy = oy0 + j;
-            if (oy < nd) {
-                uint32_t cost = acc[j] + (uint32_t)(g.lambda * (bx + mv_bits(oy - R)));
-                uint32_t key = (cost << 15) | (uint32_t)(oy * nd + ox);
-                b = key < b ? key : b;
+            for (int r = 0; r < 19; r++) {
+                uint32_t w0 = wp[r * RSW], w1 = wp[r * RSW + 1], w2 = wp[r * RSW + 2], w3 = wp[r * RSW + 3];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    int cr = r - j; // candidate row offset oy0 + j compares window row r with block row r - j
+                    if (cr >= 0 && cr < 16) {
+                        acc[j] = sad4_acc(w0, cur[cr * 4 + 0], acc[j]);
+                        acc[j] = sad4_acc(w1, cur[cr * 4 + 1], acc[j]);
+                        acc[j] = sad4_acc(w2, cur[cr * 4 + 2], acc[j]);
+                        acc[j] = sad4_acc(w3, cur[cr * 4 + 3], acc[j]);
+                    }
+                }
+            }
+            // cost = SAD + lambda * (bits(mvx) + bits(mvy)); rows beyond the search range have an infinite cost
+            const uint32_t cx = mvcost[ox], rank0 = (uint32_t)(oy0 * nd + ox);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t k = ((acc[j] + cx + mvcost[oy0 + j]) << 15) | (rank0 + (uint32_t)(j * nd));
+                k = mvcost[oy0 + j] >= 0x10000u ? 0xffffffffu : k;
+                key = k < key ? k : key;
             }
         }
-#pragma unroll
-        for (int mm = 0; mm < ME_MAX_STRIP; mm++)
-            if (mm == m)
-                best[mm] = b < best[mm] ? b : best[mm];
-    }
-#pragma unroll
-    for (int m = 0; m < ME_MAX_STRIP; m++) {
-        uint32_t b = __reduce_min_sync(0xffffffffu, best[m]);
-        if (lane == 0)
-            warp_best[m][warp] = b;
+        // the lanes of a full task share the macroblock; the left-over task mixes macroblocks
+        if (task < ntask_full * nm) {
+            key = __reduce_min_sync(0xffffffffu, key);
+            if (lane == 0)
+                atomicMin(&mb_best[m], key);
+        } else if (key != 0xffffffffu)
+            atomicMin(&mb_best[m], key);
     }
     __syncthreads();
     if (tid < nm) {
-        uint32_t b = warp_best[tid][0];
-#pragma unroll
-        for (int w = 1; w < nwarps; w++)
-            b = warp_best[tid][w] < b ? warp_best[tid][w] : b;
+        const uint32_t b = mb_best[tid];
         int rank = (int)(b & 0x7fff);
         MbInfo mi;
         mi.type = MB_P16x16;
