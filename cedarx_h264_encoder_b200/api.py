@@ -189,8 +189,9 @@ class Encoder:
         self._ck(self.L.cedar_b200_stats(self.h, a, nframes), "stats")
         return np.array(a[:])
 
-    def profile_enable(self, on=True):
-        self.L.cedar_b200_profile_enable(self.h, int(on))
+    def profile_enable(self, mode=1):
+        """0 off, 1 live (overlapped streams), 2 serialised (standalone kernel times)."""
+        self.L.cedar_b200_profile_enable(self.h, int(mode))
 
     def profile_read(self, reset=True):
         cap = 32

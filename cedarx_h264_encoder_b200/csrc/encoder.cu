@@ -119,6 +119,7 @@ struct cedar_b200_handle {
     int last_nframes, last_cur, last_par;
     long long launches;
     bool prof;
+    bool serialize; // profile mode 2: no stream overlap, so that per-kernel event times are standalone times
     std::vector<ProfEntry> prof_pending;
     std::vector<cudaEvent_t> ev_pool;
     float prof_ms[K_COUNT];
@@ -379,7 +380,8 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
     MbInfo *mbi = h->d_mbi[p];
     uint8_t *nnz = h->d_nnz[p], *bs = h->d_bs;
     int16_t *coef = h->d_coef[p];
-    static const bool no_overlap = getenv("CEDAR_B200_NO_OVERLAP") != nullptr; // diagnosis: everything in line
+    static const bool env_no_overlap = getenv("CEDAR_B200_NO_OVERLAP") != nullptr;
+    const bool no_overlap = env_no_overlap || h->serialize; // diagnosis / per-kernel timing: everything in line
     cudaStream_t st = h->stream, pre = no_overlap ? st : h->stream_pre, post = no_overlap ? st : h->stream_post;
 
     // ---- one step ahead: ingest ----
@@ -794,6 +796,7 @@ int cedar_b200_profile_enable(cedar_b200_handle *h, int enable)
     if (!enable && h->prof)
         prof_collect(h);
     h->prof = enable != 0;
+    h->serialize = enable == 2;
     return 0;
 }
 

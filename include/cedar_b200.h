@@ -108,7 +108,8 @@ long long cedar_b200_clip_download(cedar_b200_handle *h, const uint8_t **out, in
 int cedar_b200_stats(cedar_b200_handle *h, double *sse_y, int nframes);
 
 /* Per-kernel device timing of the work issued since the last call with reset != 0.
- * When enabled every launch is bracketed by CUDA events on the launching stream.
+ * enable = 1: every launch is bracketed by CUDA events on the stream it is launched on (live, overlapped);
+ * enable = 2: additionally all work is issued on one stream, so the event times are standalone kernel times.
  * names/ms/launches hold up to `cap` entries; returns the number of kernel classes. */
 int cedar_b200_profile_enable(cedar_b200_handle *h, int enable);
 int cedar_b200_profile_read(cedar_b200_handle *h, const char **names, float *ms, int *launches, int cap, int reset);
