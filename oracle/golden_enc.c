@@ -55,6 +55,8 @@ int main(int argc, char **argv)
             cfg.me_range = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--synth") && i + 1 < argc)
             synth = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--slice-rows") && i + 1 < argc)
+            cfg.slice_rows = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--cavlc"))
             cfg.entropy_coding_mode = GM_ENTROPY_CAVLC;
         else if (!strcmp(argv[i], "--nv16"))

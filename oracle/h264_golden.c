@@ -178,9 +178,9 @@ int gm_write_pps(const gm_config *cfg, uint8_t *out, int cap)
 }
 
 /* cedar.c:984-1030 (bits after the NAL header byte) */
-static void write_slice_header(bitw *b, int frame_i, int frame_p_count, int cabac)
+static void write_slice_header(bitw *b, int frame_i, int frame_p_count, int cabac, int first_mb)
 {
-    bw_ue(b, 0);                /* first_mb_in_slice */
+    bw_ue(b, (uint32_t)first_mb); /* first_mb_in_slice: 0 in the reference (cedar.c:992-993, one slice per picture) */
     bw_ue(b, frame_i ? 2 : 0);  /* slice_type */
     bw_ue(b, 0);                /* pic_parameter_set_id */
     bw_put(b, (uint32_t)frame_p_count & 0x0F, 4); /* frame_num */
@@ -201,14 +201,25 @@ static void write_slice_header(bitw *b, int frame_i, int frame_p_count, int caba
     bw_se(b, 0); /* slice_beta_offset_div2 */
 }
 
-int gm_slice_header_bits(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits)
+int gm_slice_header_bits64(int frame_i, int frame_p_count, int cabac, int first_mb, uint64_t *bits, int *nbits)
 {
-    uint8_t rb[8] = {0};
+    uint8_t rb[16] = {0};
     bitw b;
     bw_init(&b, rb, sizeof(rb));
-    write_slice_header(&b, frame_i, frame_p_count, cabac);
+    write_slice_header(&b, frame_i, frame_p_count, cabac, first_mb);
     *nbits = (int)b.nbits;
-    *bits = ((uint32_t)rb[0] << 24 | (uint32_t)rb[1] << 16 | (uint32_t)rb[2] << 8 | rb[3]) >> (32 - b.nbits);
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++)
+        v = (v << 8) | rb[i];
+    *bits = v >> (64 - b.nbits);
+    return 0;
+}
+
+int gm_slice_header_bits(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits)
+{
+    uint64_t v;
+    gm_slice_header_bits64(frame_i, frame_p_count, cabac, 0, &v, nbits);
+    *bits = (uint32_t)v;
     return 0;
 }
 
@@ -263,6 +274,7 @@ typedef struct {
 struct gm_encoder {
     gm_config cfg;
     int W, H, mbw, mbh;
+    int srows; /* macroblock rows per slice (mbh = one slice per picture, the reference's layout) */
     int qp, qpc;
     int frame_p_count, frame_count; /* cedar.c:118-119 counters */
     frame_t src, rec[2], unf;
@@ -306,7 +318,7 @@ int gm_open(const gm_config *cfg, gm_encoder **out)
         return -EINVAL;
     if (cfg->keyframe_interval <= 0 || (cfg->keyframe_interval >= 32 && !cfg->relax_gop))
         return -EINVAL;
-    if (cfg->src_width <= 0 || cfg->src_height <= 0 || cfg->me_range < 0 || cfg->me_range > 64)
+    if (cfg->src_width <= 0 || cfg->src_height <= 0 || cfg->me_range < 0 || cfg->me_range > 64 || cfg->slice_rows < 0)
         return -EINVAL;
 
     gm_encoder *e = (gm_encoder *)calloc(1, sizeof(*e));
@@ -319,6 +331,7 @@ int gm_open(const gm_config *cfg, gm_encoder **out)
     e->H = cfg->dst_height;
     e->mbw = e->W >> 4;
     e->mbh = e->H >> 4;
+    e->srows = cfg->slice_rows > 0 && cfg->slice_rows < e->mbh ? cfg->slice_rows : e->mbh;
     e->qp = cfg->qp;
     e->qpc = h264_chroma_qp[CLIP3(0, 51, cfg->qp + 4)]; /* chroma_qp_index_offset = 4, cedar.c:969 */
     int err = frame_alloc(&e->src, e->W, e->H) | frame_alloc(&e->rec[0], e->W, e->H) |
@@ -347,6 +360,12 @@ void gm_close(gm_encoder *e)
     free(e->rbsp);
     free(e);
 }
+
+/* Is the macroblock row above row mby in the same slice?  Slices are whole macroblock rows, so the left
+ * neighbour always is; neighbours in other slices are "not available" (H.264 6.4.x) for intra prediction,
+ * motion-vector prediction and every entropy-coding context -- but not for the deblocking filter, which runs
+ * across slice edges when disable_deblocking_filter_idc = 0 (cedar.c:1025). */
+static inline int top_avail(const gm_encoder *e, int mby) { return (mby % e->srows) != 0; }
 
 int gm_coded_width(const gm_encoder *e) { return e->W; }
 int gm_coded_height(const gm_encoder *e) { return e->H; }
@@ -770,7 +789,7 @@ static int i4_neighbour_mode(const gm_encoder *e, int mbx, int mby, int blk, int
         if (by > 0)
             nb = xy2blk[by - 1][bx];
         else {
-            if (mby == 0)
+            if (!top_avail(e, mby))
                 return -1;
             n = cur - e->mbw;
             nb = xy2blk[3][bx];
@@ -802,11 +821,11 @@ static int try_intra4x4(gm_encoder *e, int mbx, int mby, uint32_t cost16)
     mb->type = GM_MB_I4x4; /* i4_pred_mode of later blocks looks at the blocks already decided */
     for (int b = 0; b < 16; b++) {
         int bx = blk_x[b], by = blk_y[b];
-        int has_top = by > 0 || mby > 0, has_left = bx > 0 || mbx > 0;
-        int has_tl = (bx > 0 || mbx > 0) && (by > 0 || mby > 0);
+        int has_top = by > 0 || top_avail(e, mby), has_left = bx > 0 || mbx > 0;
+        int has_tl = (bx > 0 || mbx > 0) && (by > 0 || top_avail(e, mby));
         int has_tr;
         if (by == 0)
-            has_tr = mby > 0 && (bx < 3 || mbx + 1 < e->mbw);
+            has_tr = top_avail(e, mby) && (bx < 3 || mbx + 1 < e->mbw);
         else
             has_tr = bx < 3 && xy2blk[by - 1][bx + 1] < b;
         const uint8_t *s4 = src + by * 4 * W + bx * 4;
@@ -865,7 +884,7 @@ static void encode_mb_intra(gm_encoder *e, int mbx, int mby)
     frame_t *out = &e->unf;
     memset(mb, 0, sizeof(*mb));
     mb->type = GM_MB_I16x16;
-    int has_top = mby > 0, has_left = mbx > 0;
+    int has_top = top_avail(e, mby), has_left = mbx > 0;
     const uint8_t *src = e->src.p[0] + (size_t)(mby * 16) * W + mbx * 16;
     uint8_t *dst = out->p[0] + (size_t)(mby * 16) * W + mbx * 16;
 
@@ -1166,8 +1185,8 @@ static void predict_mv(const gm_encoder *e, int mbx, int mby, int16_t mvp[2], in
 {
     int16_t a[2], b[2], c[2];
     int ra, rb, rc;
-    int availA = mbx > 0, availB = mby > 0;
-    int availC = mby > 0 && mbx + 1 < e->mbw, availD = mby > 0 && mbx > 0;
+    int availA = mbx > 0, availB = top_avail(e, mby);
+    int availC = availB && mbx + 1 < e->mbw, availD = availB && mbx > 0;
     neighbour_mv(e, mbx - 1, mby, availA, a, &ra);
     neighbour_mv(e, mbx, mby - 1, availB, b, &rb);
     if (availC)
@@ -1374,14 +1393,14 @@ static int nnz_top(const gm_encoder *e, int mbx, int mby, int kind, int blk)
         int bx = blk_x[blk], by = blk_y[blk];
         if (by > 0)
             return cur->nnz[xy2blk[by - 1][bx]];
-        if (mby == 0)
+        if (!top_avail(e, mby))
             return -1;
         return (cur - e->mbw)->nnz[xy2blk[3][bx]];
     }
     int base = 17 + (kind - 1) * 4, bx = blk & 1, by = blk >> 1;
     if (by > 0)
         return cur->nnz[base + bx];
-    if (mby == 0)
+    if (!top_avail(e, mby))
         return -1;
     return (cur - e->mbw)->nnz[base + 2 + bx];
 }
@@ -1512,10 +1531,10 @@ static void cavlc_residual(gm_encoder *e, bitw *bw, int mbx, int mby)
                 cavlc_block(bw, mb->coef[18 + c * 4 + b] + 1, 15, calc_nc(e, mbx, mby, 1 + c, b));
 }
 
-static void cavlc_slice_data(gm_encoder *e, bitw *bw, int frame_i)
+static void cavlc_slice_data(gm_encoder *e, bitw *bw, int frame_i, int row0, int row1)
 {
     int skip_run = 0;
-    for (int mby = 0; mby < e->mbh; mby++)
+    for (int mby = row0; mby < row1; mby++)
         for (int mbx = 0; mbx < e->mbw; mbx++) {
             const gm_mb *mb = &e->mbs[mby * e->mbw + mbx];
             if (mb->type == GM_MB_PSKIP) {
@@ -1689,7 +1708,7 @@ static int cbf_neighbour(const gm_encoder *e, int mbx, int mby, int cat, int com
 {
     const gm_mb *cur = &e->mbs[mby * e->mbw + mbx];
     const gm_mb *n = left ? cur - 1 : cur - e->mbw;
-    int navail = left ? mbx > 0 : mby > 0;
+    int navail = left ? mbx > 0 : top_avail(e, mby);
     if (cat == 0) {
         if (!navail)
             return intra;
@@ -1774,7 +1793,7 @@ static void cabac_mvd(cabac_t *c, int base, int mvd, int sum_abs)
 static void cabac_mb(gm_encoder *e, cabac_t *c, int mbx, int mby, int frame_i)
 {
     const gm_mb *mb = &e->mbs[mby * e->mbw + mbx];
-    const gm_mb *A = mbx > 0 ? mb - 1 : NULL, *B = mby > 0 ? mb - e->mbw : NULL;
+    const gm_mb *A = mbx > 0 ? mb - 1 : NULL, *B = top_avail(e, mby) ? mb - e->mbw : NULL;
     int intra = mb_is_intra(mb);
     if (!frame_i) {
         int inc = (A && A->type != GM_MB_PSKIP) + (B && B->type != GM_MB_PSKIP);
@@ -1894,14 +1913,14 @@ static void cabac_mb(gm_encoder *e, cabac_t *c, int mbx, int mby, int frame_i)
             }
 }
 
-static void cabac_slice_data(gm_encoder *e, bitw *bw, int frame_i)
+static void cabac_slice_data(gm_encoder *e, bitw *bw, int frame_i, int row0, int row1)
 {
     while (bw->nbits & 7)
         bw_put(bw, 1, 1); /* cabac_alignment_one_bit */
     cabac_t c;
     cabac_init(&c, bw, frame_i, e->qp);
-    int n = e->mbw * e->mbh;
-    for (int i = 0; i < n; i++) {
+    int n = e->mbw * row1;
+    for (int i = e->mbw * row0; i < n; i++) {
         cabac_mb(e, &c, i % e->mbw, i / e->mbw, frame_i);
         cabac_terminate(&c, i == n - 1); /* end_of_slice_flag */
     }
@@ -1949,24 +1968,29 @@ int gm_encode_frame(gm_encoder *e, const uint8_t *luma, const uint8_t *chroma, u
         for (int mbx = 0; mbx < e->mbw; mbx++)
             deblock_mb(e, cur, mbx, mby);
 
-    /* slice NAL: header bits (cedar.c:1063-1066), then slice data */
-    bitw bw;
-    bw_init(&bw, e->rbsp, e->rbsp_cap);
+    /* slice NALs: header bits (cedar.c:1063-1066), then slice data.  One slice per picture as in the
+     * reference (cedar.c:992-993) unless the slice_rows extension splits the picture into slices of whole
+     * macroblock rows. */
     int cabac = e->cfg.entropy_coding_mode == GM_ENTROPY_CABAC;
-    write_slice_header(&bw, frame_i, e->frame_p_count, cabac);
-    if (cabac)
-        cabac_slice_data(e, &bw, frame_i);
-    else
-        cavlc_slice_data(e, &bw, frame_i);
-    if ((bw.nbits >> 3) >= e->rbsp_cap)
-        return -ENOMEM;
-    if (out_cap - n < 5)
-        return -ENOMEM;
-    n += (int)put_startcode(out + n, frame_i ? 3 : 2, frame_i ? 5 : 1);
-    size_t esc = epb_copy(out + n, (size_t)(out_cap - n), e->rbsp, bw.nbits >> 3);
-    if (esc > (size_t)(out_cap - n))
-        return -ENOMEM;
-    n += (int)esc;
+    for (int row0 = 0; row0 < e->mbh; row0 += e->srows) {
+        int row1 = imin(row0 + e->srows, e->mbh);
+        bitw bw;
+        bw_init(&bw, e->rbsp, e->rbsp_cap);
+        write_slice_header(&bw, frame_i, e->frame_p_count, cabac, row0 * e->mbw);
+        if (cabac)
+            cabac_slice_data(e, &bw, frame_i, row0, row1);
+        else
+            cavlc_slice_data(e, &bw, frame_i, row0, row1);
+        if ((bw.nbits >> 3) >= e->rbsp_cap)
+            return -ENOMEM;
+        if (out_cap - n < 5)
+            return -ENOMEM;
+        n += (int)put_startcode(out + n, frame_i ? 3 : 2, frame_i ? 5 : 1);
+        size_t esc = epb_copy(out + n, (size_t)(out_cap - n), e->rbsp, bw.nbits >> 3);
+        if (esc > (size_t)(out_cap - n))
+            return -ENOMEM;
+        n += (int)esc;
+    }
 
     double sse = 0;
     for (size_t i = 0; i < (size_t)e->W * e->H; i++) {

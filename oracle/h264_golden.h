@@ -45,6 +45,7 @@ typedef struct gm_config {
     int me_range;      /* extension: integer-pel full-search radius (default 16) */
     int relax_gop;     /* extension: accept keyframe_interval >= 32 (cedar.c:784-789 rejects) */
     int intra4x4;      /* extension: enable Intra4x4 macroblocks in I frames */
+    int slice_rows;    /* extension: macroblock rows per slice; 0 = one slice per picture (cedar.c:992-993) */
 } gm_config;
 
 /* Per-macroblock record: every syntax element the entropy coder needs. */
@@ -88,6 +89,8 @@ int gm_write_sps(const gm_config *cfg, uint8_t *out, int cap);
 int gm_write_pps(const gm_config *cfg, uint8_t *out, int cap);
 /* Writes start code + NAL header + slice header bits; *nbits = header bits after NAL byte. */
 int gm_slice_header_bits(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits);
+/* The same with first_mb_in_slice != 0 (slice_rows extension); up to 64 bits. */
+int gm_slice_header_bits64(int frame_i, int frame_p_count, int cabac, int first_mb, uint64_t *bits, int *nbits);
 
 /* Deterministic synthetic moving-pattern clip (integer only, stateless per pixel). */
 void gm_synth_frame(int width, int height, int format, int t, uint8_t *luma, uint8_t *chroma);

@@ -82,12 +82,22 @@ def split_nals(stream: bytes):
 
 
 def split_access_units(stream: bytes):
-    aus, cur = [], b""
+    """One access unit = parameter sets (if any) + all slices of one picture.  A slice NAL whose
+    first_mb_in_slice is 0 (first payload bit set: ue(0) = '1') starts a new picture."""
+    aus, cur, has_slice = [], b"", False
     for t, nal in split_nals(stream):
-        cur += nal
         if t in (1, 5):
-            aus.append(cur)
-            cur = b""
+            hdr = nal.index(b"\x00\x00\x01") + 3
+            if has_slice and (nal[hdr + 1] & 0x80):
+                aus.append(cur)
+                cur, has_slice = b"", False
+            cur += nal
+            has_slice = True
+        else:
+            if has_slice:
+                aus.append(cur)
+                cur, has_slice = b"", False
+            cur += nal
     if cur:
         aus.append(cur)
     return aus

@@ -14,7 +14,7 @@ LIB = os.path.join(ORACLE_DIR, "liboracle_h264.so")
 class GmConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "src_width", "src_height", "src_format", "dst_width", "dst_height", "profile", "level", "qp",
-        "keyframe_interval", "entropy_coding_mode", "me_range", "relax_gop", "intra4x4")]
+        "keyframe_interval", "entropy_coding_mode", "me_range", "relax_gop", "intra4x4", "slice_rows")]
 
 
 class GmMb(C.Structure):
@@ -57,6 +57,8 @@ def lib():
         L.gm_write_sps.argtypes = [C.POINTER(GmConfig), C.c_void_p, C.c_int]
         L.gm_write_pps.argtypes = [C.POINTER(GmConfig), C.c_void_p, C.c_int]
         L.gm_slice_header_bits.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+        L.gm_slice_header_bits64.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64),
+                                             C.POINTER(C.c_int)]
         L.gm_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         assert C.sizeof(GmMb) == MB_DTYPE.itemsize, (C.sizeof(GmMb), MB_DTYPE.itemsize)
         _lib = L
@@ -68,10 +70,10 @@ def align16(x):
 
 
 def make_config(width, height, qp=24, gop=25, cabac=1, fmt=0, me_range=16, profile=77, level=41, intra4x4=0,
-                dst_width=None, dst_height=None, relax_gop=1):
+                dst_width=None, dst_height=None, relax_gop=1, slice_rows=0):
     return GmConfig(width, height, fmt, align16(width) if dst_width is None else dst_width,
                     align16(height) if dst_height is None else dst_height, profile, level, qp, gop, cabac,
-                    me_range, relax_gop, intra4x4)
+                    me_range, relax_gop, intra4x4, slice_rows)
 
 
 def synth_frame(width, height, t, fmt=0):

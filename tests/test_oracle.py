@@ -120,3 +120,32 @@ def test_intra4x4_option_decodes_bit_exactly(oracle, kind, qp, cabac):
     for r, d in zip(recs, dec):
         for p in range(3):
             assert np.array_equal(r[p], d[p])
+
+
+@needs_decoder
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("kind,qp,rows,i4", [("synth", 24, 1, 0), ("noise", 12, 2, 0), ("shift", 36, 3, 0), ("static", 30, 2, 0),
+                                             ("synth", 26, 2, 1)])
+def test_slice_rows_option_decodes_bit_exactly(oracle, kind, qp, rows, i4, cabac):
+    """slice_rows extension (north star: "MB rows per slice configurable"): every slice is its own NAL with
+    first_mb_in_slice != 0; neighbours in other slices are unavailable for intra / MV prediction and all
+    entropy contexts, deblocking still runs across slice edges.  The independent decoder must agree."""
+    w, h, n = 96, 80, 4
+    clip = make_clip(kind, w, h, n)
+    stream, sizes, recs = oracle_encode_clip(clip, w, h, keep_recon=True, qp=qp, gop=3, cabac=cabac, me_range=8,
+                                             slice_rows=rows, intra4x4=i4)
+    nslices = -(-(h // 16) // rows)
+    assert stream.count(b"\x00\x00\x00\x01\x65") + stream.count(b"\x00\x00\x00\x01\x41") >= n * nslices
+    dec = avdec.decode(stream)
+    assert len(dec) == n
+    for r, d in zip(recs, dec):
+        for p in range(3):
+            assert np.array_equal(r[p], d[p])
+
+
+def test_slice_rows_zero_and_full_height_are_the_reference_layout(oracle):
+    clip = make_clip("synth", 64, 48, 3)
+    a, _, _ = oracle_encode_clip(clip, 64, 48, qp=24, gop=2, cabac=1, me_range=8)
+    b, _, _ = oracle_encode_clip(clip, 64, 48, qp=24, gop=2, cabac=1, me_range=8, slice_rows=3)
+    c, _, _ = oracle_encode_clip(clip, 64, 48, qp=24, gop=2, cabac=1, me_range=8, slice_rows=99)
+    assert a == b == c
