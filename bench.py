@@ -20,6 +20,7 @@ import os
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # before CUDA initialises: side streams must not share queues
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -181,7 +182,7 @@ def run_gpu(args, rank, local_rank, world):
     n = len(my_frames)
 
     cfg = api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, fmt=fmt, me_range=me, device=local_rank,
-                          max_clip_frames=n, gops_in_flight=args.lanes)
+                          max_clip_frames=n, gops_in_flight=args.lanes, slice_rows=args.slice_rows)
     enc = cx.Encoder(cfg)
     stream = torch.cuda.ExternalStream(enc.stream_ptr(), device=torch.device("cuda", local_rank))
 
@@ -258,6 +259,38 @@ def run_gpu(args, rank, local_rank, world):
 
     value = total_frames * args.steps / (ms_dev * 1e-3)
     e2e = total_frames * args.steps / (ms_e2e * 1e-3)
+
+    # -------- slice-parallel entropy coding (north star: MB rows per slice configurable, bitrate cost reported) -----
+    # Same clip, same settings, slice_rows = N: every N macroblock rows are their own slice NAL and get their own
+    # serial coder.  Not the headline (the reference writes one slice per picture, cedar.c:992-993).
+    slice_report = None
+    if world == 1 and not args.no_slice_report and args.slice_rows == 0:
+        slice_report = []
+        mbh = (h + 15) // 16
+        for rows in sorted({(mbh + 3) // 4, (mbh + 15) // 16}, reverse=True):
+            cfg2 = api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, fmt=fmt, me_range=me, device=local_rank,
+                                   max_clip_frames=n, gops_in_flight=args.lanes, slice_rows=rows)
+            enc2 = cx.Encoder(cfg2)
+            torch.from_numpy(enc2.clip_input(n)).copy_(staging[:n])
+            enc2.clip_upload(n)
+            st2 = torch.cuda.ExternalStream(enc2.stream_ptr(), device=torch.device("cuda", local_rank))
+            for _ in range(2):
+                enc2.clip_encode(n, 0)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st2)
+            for _ in range(args.steps):
+                enc2.clip_encode(n, 0)
+            b.record(st2)
+            torch.cuda.synchronize()
+            d2, _ = enc2.clip_download(n)
+            sse2 = enc2.sse_y(n)
+            slice_report.append({"slice_rows": rows, "slices_per_picture": -(-mbh // rows),
+                                 "value": n * args.steps / (a.elapsed_time(b) * 1e-3), "unit": "frames/s",
+                                 "kbit_per_frame": round(len(d2) * 8 / 1000.0 / n, 2),
+                                 "bitrate_cost_pct": round(100.0 * (len(d2) - stream_bytes) / stream_bytes, 3),
+                                 "y_psnr_delta_db": round(10 * math.log10(float(sse.sum()) / float(sse2.sum())), 4)})
+            enc2.close()
     if rank == 0:
         peaks = {}
         try:
@@ -309,13 +342,13 @@ def run_gpu(args, rank, local_rank, world):
                 hbm[name] = {"bound": "hbm", "achieved": round(gbs, 2), "peak": hbm_peak, "unit": "GB/s",
                              "frac": round(gbs / hbm_peak, 5), "traffic": None, "peak_source": hbm_src}
         mse = float(sse.sum()) / (n * W16 * H16)
-        import math
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "width": w, "height": h, "format": "nv16" if fmt else "nv12",
                        "frames_per_gpu": n, "gop": gop, "qp": qp, "me_range": me, "entropy": "cabac" if cabac else "cavlc",
+                       "slice_rows": args.slice_rows or "one slice per picture (reference layout)",
                        "gops_in_flight": int(enc.cfg.gops_in_flight) or "auto", "parallelism": "gop-parallel x%d" % world,
                        "l2": "inputs larger than L2 (%.0f MB raw clip per GPU vs 126 MB)" % (n * enc.frame_bytes / 1e6),
                        "scaling_ceiling_strong": partition.scaling_ceiling(nframes, gop, world)},
@@ -326,6 +359,7 @@ def run_gpu(args, rank, local_rank, world):
             "roofline": roofline,
             "roofline_hbm_kernels": hbm,
             "kernels": kernels,
+            "slice_parallel": slice_report,
             "quality": {"y_psnr_db": round(10 * math.log10(255.0 ** 2 / mse), 3) if mse > 0 else None,
                         "kbit_per_frame": round(stream_bytes * 8 / 1000.0 / n, 2)},
         }
@@ -355,6 +389,8 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="GOPs in flight per GPU (0 = auto)")
     ap.add_argument("--cpu-frames", type=int, default=60, help="frames per core in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slice-rows", type=int, default=0, help="macroblock rows per slice (0 = one slice per picture)")
+    ap.add_argument("--no-slice-report", action="store_true")
     args = ap.parse_args()
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
     if args.impl == "reference":

@@ -24,7 +24,7 @@ class CedarConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "src_width", "src_height", "src_format", "dst_width", "dst_height", "profile", "level", "qp",
         "keyframe_interval", "thumbnail", "thumbnail_downscale", "entropy_coding_mode",
-        "me_range", "relax_gop", "device", "gops_in_flight", "max_clip_frames")]
+        "me_range", "relax_gop", "device", "gops_in_flight", "max_clip_frames", "slice_rows")]
 
 
 class CedarIO(C.Structure):
@@ -84,6 +84,8 @@ def load_library():
     L.cedar_b200_write_sps.argtypes = [C.POINTER(CedarConfig), C.c_void_p, C.c_int]
     L.cedar_b200_write_pps.argtypes = [C.POINTER(CedarConfig), C.c_void_p, C.c_int]
     L.cedar_b200_slice_header.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    L.cedar_b200_slice_header_mb.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64),
+                                             C.POINTER(C.c_int)]
     L.cedar_b200_version.restype = C.c_char_p
     _lib = L
     return L
@@ -94,11 +96,12 @@ def align16(x):
 
 
 def make_config(width, height, qp=24, gop=25, cabac=1, fmt=FORMAT_NV12, me_range=16, profile=77, level=41,
-                dst_width=None, dst_height=None, relax_gop=1, device=0, gops_in_flight=0, max_clip_frames=0):
+                dst_width=None, dst_height=None, relax_gop=1, device=0, gops_in_flight=0, max_clip_frames=0,
+                slice_rows=0):
     """Defaults are the reference's hard-coded ones (userspace/h264enc.c:53-66)."""
     return CedarConfig(width, height, fmt, align16(width) if dst_width is None else dst_width,
                        align16(height) if dst_height is None else dst_height, profile, level, qp, gop, 0, 0,
-                       cabac, me_range, relax_gop, device, gops_in_flight, max_clip_frames)
+                       cabac, me_range, relax_gop, device, gops_in_flight, max_clip_frames, slice_rows)
 
 
 def write_sps(cfg):

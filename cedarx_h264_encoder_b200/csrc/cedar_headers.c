@@ -121,11 +121,11 @@ int cedar_hdr_pps(int qp, int cabac, uint8_t *out, int cap)
     return emit_nal(out, cap, 3, 8, &b);
 }
 
-int cedar_hdr_slice(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits)
+int cedar_hdr_slice_mb(int frame_i, int frame_p_count, int cabac, int first_mb, uint64_t *bits, int *nbits)
 {
     struct hbits b;
     memset(&b, 0, sizeof(b));
-    hb_ue(&b, 0);                /* :993 first_mb_in_slice */
+    hb_ue(&b, (uint32_t)first_mb); /* :993 first_mb_in_slice (0 in the reference) */
     hb_ue(&b, frame_i ? 2 : 0);  /* :994-997 slice_type */
     hb_ue(&b, 0);                /* :999 pic_parameter_set_id */
     hb_put(&b, (uint32_t)frame_p_count & 0x0F, 4); /* :1001 frame_num */
@@ -144,10 +144,22 @@ int cedar_hdr_slice(int frame_i, int frame_p_count, int cabac, uint32_t *bits, i
     hb_ue(&b, 0); /* :1025 disable_deblocking_filter_idc */
     hb_se(&b, 0); /* :1027 slice_alpha_c0_offset_div2 */
     hb_se(&b, 0); /* :1029 slice_beta_offset_div2 */
-    if (b.nbits > 32)
+    if (b.nbits > 64)
         return -EINVAL;
     *nbits = b.nbits;
-    *bits = (((uint32_t)b.buf[0] << 24) | ((uint32_t)b.buf[1] << 16) | ((uint32_t)b.buf[2] << 8) | b.buf[3]) >>
-            (32 - b.nbits);
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++)
+        v = (v << 8) | b.buf[i];
+    *bits = v >> (64 - b.nbits);
+    return 0;
+}
+
+int cedar_hdr_slice(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits)
+{
+    uint64_t v = 0;
+    int r = cedar_hdr_slice_mb(frame_i, frame_p_count, cabac, 0, &v, nbits);
+    if (r)
+        return r;
+    *bits = (uint32_t)v;
     return 0;
 }

@@ -50,8 +50,9 @@ __global__ void rbsp_zero_kernel(Step s, uint8_t *rbsp, unsigned rbsp_cap, const
     int f = lane_frame(s, blockIdx.y);
     if (f < 0)
         return;
-    size_t words = ((size_t)rbsp_len[f] + 8 + 3) / 4;
-    uint32_t *p = (uint32_t *)(rbsp + (size_t)f * rbsp_cap);
+    const size_t u = (size_t)f * gridDim.z + blockIdx.z; // blockIdx.z = slice
+    size_t words = ((size_t)rbsp_len[u] + 8 + 3) / 4;
+    uint32_t *p = (uint32_t *)(rbsp + u * rbsp_cap);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += (size_t)gridDim.x * blockDim.x)
         p[i] = 0;
 }
@@ -62,6 +63,7 @@ struct cedar_b200_handle {
     int K;                 // keyframe_interval
     int F;                 // clip capacity in frames (>= 1)
     int L;                 // lanes (GOPs in flight)
+    int S;                 // slices per picture (1 = the reference's layout)
     size_t raw_frame_bytes;
     cudaStream_t stream;      // recon + parallel entropy stages
     // serial CABAC stages run on a pool of side streams so that the coders of successive steps overlap
@@ -106,10 +108,10 @@ struct cedar_b200_handle {
     uint8_t *d_bs; // [L][nmb][32] boundary strengths
     unsigned long long *d_sse;
     EntropyBufs eb;
-    uint32_t *d_hdr_bits;
+    unsigned long long *d_hdr_bits;
     int *d_hdr_nbits;
     uint32_t *d_chunk_cnt, *d_nal_bytes;
-    unsigned chunks_per_frame;
+    unsigned chunks_per_frame; // per slice NAL
     unsigned long long *d_nal_off, *d_total;
     int *d_frame_bytes;
     uint8_t *d_out;
@@ -244,7 +246,7 @@ int validate(const cedar_b200_config *c) // kernel/cedar.c:744-789, same order, 
         return -EINVAL;
     }
     if (c->src_width <= 0 || c->src_height <= 0 || c->me_range < 0 || c->me_range > 64 || c->max_clip_frames < 0 ||
-        c->gops_in_flight < 0) {
+        c->gops_in_flight < 0 || c->slice_rows < 0) {
         fprintf(stderr, "cedar_b200: invalid extension field.\n");
         return -EINVAL;
     }
@@ -290,8 +292,11 @@ int alloc_buffers(cedar_b200_handle *h)
     if (r)
         return r;
 
-    h->eb.rbsp_cap = (unsigned)ALIGN_UP((size_t)g.nmb * (F > 1 ? (g.qp < 20 ? 1024 : 400) : 1024) + 4096, 256);
-    size_t per_frame_out = F > 1 ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) + 4096 : (size_t)h->bytestream_size;
+    const int S = h->S;
+    const size_t U = (size_t)F * S; // slice NALs
+    const size_t slice_mbs = (size_t)g.srows * g.mbw;
+    h->eb.rbsp_cap = (unsigned)ALIGN_UP(slice_mbs * (F > 1 ? (g.qp < 20 ? 1024 : 400) : 1024) + 4096, 256);
+    size_t per_frame_out = (F > 1 ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) + 4096 : (size_t)h->bytestream_size) + 8 * S;
     h->out_cap = per_frame_out * F;
     size_t bins_per_mb = F > 1 ? (g.qp < 12 ? 8192 : (g.qp < 20 ? 2048 : 640)) : 16384;
     if (const char *e = getenv("CEDAR_B200_BINS_PER_MB"))
@@ -316,22 +321,22 @@ int alloc_buffers(cedar_b200_handle *h)
     r |= dmalloc(&h->d_flags, (size_t)3 * L * g.mbh);
     r |= dmalloc(&h->d_bs, (size_t)g.nmb * L * 32);
     r |= dmalloc(&h->d_sse, F);
-    r |= dmalloc(&h->eb.mb_size, (size_t)L * (g.nmb + 1));
-    r |= dmalloc(&h->eb.mb_off, (size_t)L * (g.nmb + 1));
-    r |= dmalloc(&h->d_hdr_bits, F);
-    r |= dmalloc(&h->d_hdr_nbits, F);
-    r |= dmalloc(&h->eb.rbsp, (size_t)h->eb.rbsp_cap * F);
-    r |= dmalloc(&h->eb.rbsp_len, F);
+    r |= dmalloc(&h->eb.mb_size, (size_t)L * (g.nmb + S + 1));
+    r |= dmalloc(&h->eb.mb_off, (size_t)L * (g.nmb + S + 1));
+    r |= dmalloc(&h->d_hdr_bits, U);
+    r |= dmalloc(&h->d_hdr_nbits, U);
+    r |= dmalloc(&h->eb.rbsp, (size_t)h->eb.rbsp_cap * U);
+    r |= dmalloc(&h->eb.rbsp_len, U);
     if (g.cabac)
         r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap);
     r |= dmalloc(&h->eb.bins_cursor, 1);
-    r |= dmalloc(&h->eb.bins_off, F);
-    r |= dmalloc(&h->eb.bins_len, F);
+    r |= dmalloc(&h->eb.bins_off, U);
+    r |= dmalloc(&h->eb.bins_len, U);
     r |= dmalloc(&h->eb.error, 1);
     h->chunks_per_frame = (h->eb.rbsp_cap + EPB_CHUNK - 1) / EPB_CHUNK;
-    r |= dmalloc(&h->d_chunk_cnt, (size_t)h->chunks_per_frame * F);
-    r |= dmalloc(&h->d_nal_bytes, F);
-    r |= dmalloc(&h->d_nal_off, F);
+    r |= dmalloc(&h->d_chunk_cnt, (size_t)h->chunks_per_frame * U);
+    r |= dmalloc(&h->d_nal_bytes, U);
+    r |= dmalloc(&h->d_nal_off, U);
     r |= dmalloc(&h->d_total, 1);
     r |= dmalloc(&h->d_frame_bytes, F);
     r |= dmalloc(&h->d_out, h->out_cap + 64);
@@ -417,11 +422,12 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
     // ---- one step behind: statistics and the parallel entropy passes ----
     CK(cudaStreamWaitEvent(post, h->ev_main[p], 0));
     LAUNCH_ON(post, K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, src, rec, h->d_sse);
-    dim3 egrid((g.nmb + 1 + 127) / 128, nl);
+    dim3 egrid((g.nmb + g.nslices + 127) / 128, nl);
     LAUNCH_ON(post, K_ESIZE, entropy_size_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, h->eb);
     LAUNCH_ON(post, K_ESCAN, entropy_scan_kernel, dim3(1, nl), 1024, 0, g, s, h->eb);
     if (!g.cabac)
-        LAUNCH_ON(post, K_EZERO, rbsp_zero_kernel, dim3(8, nl), 256, 0, s, h->eb.rbsp, h->eb.rbsp_cap, h->eb.rbsp_len);
+        LAUNCH_ON(post, K_EZERO, rbsp_zero_kernel, dim3(8, nl, g.nslices), 256, 0, s, h->eb.rbsp, h->eb.rbsp_cap,
+                  h->eb.rbsp_len);
     LAUNCH_ON(post, K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, h->eb);
     CK(cudaEventRecord(h->ev_post[p], post));
     h->post_valid[p] = true;
@@ -434,7 +440,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         // throughput kernels off that SM, so the two serial warps are not starved of issue slots.
         static const int tail_steps = getenv("CEDAR_B200_EXCL_TAIL") ? atoi(getenv("CEDAR_B200_EXCL_TAIL")) : 4;
         const bool exclusive = t == 0 || t >= h->K - tail_steps;
-        LAUNCH_ON(side, K_CABAC, cabac_kernel, nl, CABAC_THREADS, exclusive ? h->cabac_excl_smem : 0, g, s, h->K, gop_pos0,
+        LAUNCH_ON(side, K_CABAC, cabac_kernel, nl * g.nslices, CABAC_THREADS, exclusive ? h->cabac_excl_smem : 0, g, s, h->K, gop_pos0,
                   h->eb);
         if (!no_overlap) {
             h->side_used |= 1u << h->side_next;
@@ -459,13 +465,14 @@ int finish_stream(cedar_b200_handle *h, int nframes, int gop_pos0, bool with_par
         }
     h->side_used = 0;
     unsigned cpf = h->chunks_per_frame;
-    LAUNCH(K_EPBCOUNT, epb_count_kernel, dim3((cpf + 255) / 256, nframes), 256, 0, nframes, h->eb.rbsp, h->eb.rbsp_cap,
+    const int nunits = nframes * h->S; // slice NALs
+    LAUNCH(K_EPBCOUNT, epb_count_kernel, dim3((cpf + 255) / 256, nunits), 256, 0, nunits, h->eb.rbsp, h->eb.rbsp_cap,
            h->eb.rbsp_len, h->d_chunk_cnt, cpf);
-    LAUNCH(K_EPBSCAN, epb_scan_kernel, nframes, 1024, 0, nframes, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_bytes);
+    LAUNCH(K_EPBSCAN, epb_scan_kernel, nunits, 1024, 0, nunits, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_bytes);
     unsigned prefix = with_param_sets ? (unsigned)h->prefix_len : 0;
-    LAUNCH(K_PACKSCAN, pack_scan_kernel, 1, 1024, 0, nframes, h->d_nal_bytes, prefix, h->d_nal_off, h->d_frame_bytes,
+    LAUNCH(K_PACKSCAN, pack_scan_kernel, 1, 1024, 0, nunits, h->S, h->d_nal_bytes, prefix, h->d_nal_off, h->d_frame_bytes,
            h->d_total, (unsigned long long)h->out_cap, h->eb.error);
-    LAUNCH(K_EPBWRITE, epb_write_kernel, dim3((cpf + 255) / 256, nframes), 256, 0, nframes, h->K, gop_pos0, h->eb.rbsp,
+    LAUNCH(K_EPBWRITE, epb_write_kernel, dim3((cpf + 255) / 256, nunits), 256, 0, nunits, h->S, h->K, gop_pos0, h->eb.rbsp,
            h->eb.rbsp_cap, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_off, h->d_total, h->d_out);
     if (prefix)
         CK(cudaMemcpyAsync(h->d_out, h->prefix, prefix, cudaMemcpyHostToDevice, h->stream));
@@ -474,16 +481,22 @@ int finish_stream(cedar_b200_handle *h, int nframes, int gop_pos0, bool with_par
 
 int upload_headers(cedar_b200_handle *h, int nframes, int gop_pos0)
 {
-    std::vector<uint32_t> bits(nframes);
-    std::vector<int> nbits(nframes);
+    const int S = h->S;
+    std::vector<unsigned long long> bits((size_t)nframes * S);
+    std::vector<int> nbits((size_t)nframes * S);
     for (int f = 0; f < nframes; f++) {
         int p = (gop_pos0 + f) % h->K;
-        int r = cedar_hdr_slice(p == 0, p, h->g.cabac, &bits[f], &nbits[f]);
-        if (r)
-            return r;
+        for (int k = 0; k < S; k++) { // first_mb_in_slice = first macroblock of the slice's first row (0: cedar.c:992-993)
+            uint64_t b = 0;
+            int r = cedar_hdr_slice_mb(p == 0, p, h->g.cabac, k * h->g.srows * h->g.mbw, &b, &nbits[(size_t)f * S + k]);
+            if (r)
+                return r;
+            bits[(size_t)f * S + k] = b;
+        }
     }
-    CK(cudaMemcpyAsync(h->d_hdr_bits, bits.data(), sizeof(uint32_t) * nframes, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaMemcpyAsync(h->d_hdr_nbits, nbits.data(), sizeof(int) * nframes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_hdr_bits, bits.data(), sizeof(unsigned long long) * bits.size(), cudaMemcpyHostToDevice,
+                       h->stream));
+    CK(cudaMemcpyAsync(h->d_hdr_nbits, nbits.data(), sizeof(int) * nbits.size(), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream)); // the vectors go out of scope
     return 0;
 }
@@ -492,8 +505,8 @@ int begin_stream(cedar_b200_handle *h, int nframes)
 {
     CK(cudaMemsetAsync(h->eb.bins_cursor, 0, sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->d_sse, 0, sizeof(unsigned long long) * nframes, h->stream));
-    CK(cudaMemsetAsync(h->eb.rbsp_len, 0, sizeof(uint32_t) * nframes, h->stream));
-    CK(cudaMemsetAsync(h->eb.bins_len, 0, sizeof(uint32_t) * nframes, h->stream));
+    CK(cudaMemsetAsync(h->eb.rbsp_len, 0, sizeof(uint32_t) * nframes * h->S, h->stream));
+    CK(cudaMemsetAsync(h->eb.bins_len, 0, sizeof(uint32_t) * nframes * h->S, h->stream));
     CK(cudaEventRecord(h->ev_begin, h->stream));
     CK(cudaStreamWaitEvent(h->stream_pre, h->ev_begin, 0));
     CK(cudaStreamWaitEvent(h->stream_post, h->ev_begin, 0));
@@ -530,6 +543,10 @@ int cedar_b200_write_pps(const struct cedar_b200_config *cfg, uint8_t *out, int 
 int cedar_b200_slice_header(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits)
 {
     return cedar_hdr_slice(frame_i, frame_p_count, cabac, bits, nbits);
+}
+int cedar_b200_slice_header_mb(int frame_i, int frame_p_count, int cabac, int first_mb, uint64_t *bits, int *nbits)
+{
+    return cedar_hdr_slice_mb(frame_i, frame_p_count, cabac, first_mb, bits, nbits);
 }
 
 int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *io, cedar_b200_handle **out)
@@ -572,6 +589,9 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     int lq = (cfg->qp - 12) / 6;
     g.lambda = 1 << (lq < 0 ? 0 : (lq > 5 ? 5 : lq));
     g.cabac = cfg->entropy_coding_mode == CEDAR_B200_ENTROPY_CABAC;
+    g.srows = cfg->slice_rows > 0 && cfg->slice_rows < g.mbh ? cfg->slice_rows : g.mbh;
+    g.nslices = (g.mbh + g.srows - 1) / g.srows;
+    h->S = g.nslices;
     g.frame_bytes = (unsigned long long)g.W * g.H * 3 / 2;
     h->K = cfg->keyframe_interval;
     h->F = cfg->max_clip_frames > 0 ? cfg->max_clip_frames : 1;
@@ -842,7 +862,7 @@ long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_
     case 3: src = h->d_mbi[h->last_par], n = sizeof(MbInfo) * g.nmb; break;
     case 4: src = h->d_nnz[h->last_par], n = (size_t)NNZ_STRIDE * g.nmb; break;
     case 5: src = h->d_coef[h->last_par], n = sizeof(int16_t) * COEF_STRIDE * g.nmb; break;
-    case 6: src = h->eb.bins_len, n = sizeof(uint32_t) * (h->last_nframes > 0 ? h->last_nframes : 1); break;
+    case 6: src = h->eb.bins_len, n = sizeof(uint32_t) * (h->last_nframes > 0 ? h->last_nframes : 1) * h->S; break;
     default: return -EINVAL;
     }
     if (n > cap)

@@ -16,7 +16,35 @@ struct FrameSyntax {
     const uint8_t *nnz;   // [nmb][NNZ_STRIDE]
     const int16_t *coef;  // [nmb][COEF_STRIDE]
     int mbw, mbh;
+    int srows; // macroblock rows per slice (== mbh: one slice per picture, the reference's layout)
 };
+
+// Slices are whole macroblock rows, so the left neighbour is always in the same slice; the row above is
+// "not available" (H.264 6.4.x) for every entropy context when it belongs to another slice.
+HD bool top_avail(const FrameSyntax &fs, int mby) { return (mby % fs.srows) != 0; }
+
+// Entropy work items of a picture: per slice its macroblocks in raster order followed by one terminal item
+// (CAVLC: trailing mb_skip_run + rbsp_slice_trailing_bits; CABAC: nothing).  All slices but the last have
+// srows * mbw macroblocks, so item -> (slice, macroblock) needs one division.
+struct SliceItem {
+    int slice, mb, first_mb;
+    bool is_end, is_first;
+};
+HD int slice_items_per(const FrameSyntax &fs) { return fs.srows * fs.mbw + 1; }
+HD SliceItem slice_item(const FrameSyntax &fs, int item)
+{
+    SliceItem it;
+    int per = slice_items_per(fs);
+    it.slice = item / per;
+    int local = item - it.slice * per;
+    int row0 = it.slice * fs.srows;
+    int count = imin_(fs.srows, fs.mbh - row0) * fs.mbw;
+    it.first_mb = row0 * fs.mbw;
+    it.mb = it.first_mb + local;
+    it.is_end = local == count;
+    it.is_first = local == 0;
+    return it;
+}
 
 // total_coeff of the 4x4 block left of / above block `blk`; -1 when outside the picture.
 // kind 0: luma (blk = luma4x4BlkIdx), 1: Cb AC, 2: Cr AC (blk 0..3 raster)
@@ -46,14 +74,14 @@ HD int nnz_top(const FrameSyntax &fs, int mbx, int mby, int kind, int blk)
         int bx = blk_x(blk), by = blk_y(blk);
         if (by > 0)
             return cur[xy2blk(bx, by - 1)];
-        if (mby == 0)
+        if (!top_avail(fs, mby))
             return -1;
         return (cur - (size_t)fs.mbw * NNZ_STRIDE)[xy2blk(bx, 3)];
     }
     int base = kind == 1 ? NNZ_CB : NNZ_CR, bx = blk & 1, by = blk >> 1;
     if (by > 0)
         return cur[base + bx];
-    if (mby == 0)
+    if (!top_avail(fs, mby))
         return -1;
     return (cur - (size_t)fs.mbw * NNZ_STRIDE)[base + 2 + bx];
 }
@@ -231,18 +259,27 @@ template <class S> HD void cavlc_block(S &s, const int16_t *lev, int max_coeff, 
     }
 }
 
+// Terminal item of a slice: trailing skip run + rbsp_slice_trailing_bits stop bit (alignment zeros come
+// for free from the zero-initialised buffer).
+template <class S> HD void cavlc_end(S &s, int skip_run)
+{
+    if (skip_run)
+        put_ue(s, (unsigned)skip_run);
+    s.put(1, 1);
+}
+
+// Number of P_Skip macroblocks directly before macroblock i inside its slice (which starts at first_mb).
+HD int skip_run_before(const FrameSyntax &fs, int i, int first_mb)
+{
+    int run = 0;
+    for (int j = i - 1; j >= first_mb && fs.mbi[j].type == MB_PSKIP; j--)
+        run++;
+    return run;
+}
+
 // One macroblock of slice data.  `skip_run` = number of P_Skip macroblocks directly before it.
-// mb_index == nmb is the virtual terminal element: trailing skip run + rbsp_slice_trailing_bits
-// stop bit (alignment zeros come for free from the zero-initialised buffer).
 template <class S> HD void cavlc_mb(S &s, const FrameSyntax &fs, int mb_index, int frame_i, int skip_run)
 {
-    int nmb = fs.mbw * fs.mbh;
-    if (mb_index == nmb) {
-        if (skip_run)
-            put_ue(s, (unsigned)skip_run);
-        s.put(1, 1);
-        return;
-    }
     const MbInfo &mb = fs.mbi[mb_index];
     if (mb.type == MB_PSKIP)
         return;
@@ -317,7 +354,7 @@ template <class S> HD void cabac_ueg_bypass(S &s, int k, int v)
 // coded_block_flag of the neighbour (left / top) for ctxIdxInc
 HD int cbf_neighbour(const FrameSyntax &fs, int mbx, int mby, int cat, int comp, int blk, int left, int intra)
 {
-    int navail = left ? mbx > 0 : mby > 0;
+    int navail = left ? mbx > 0 : top_avail(fs, mby);
     int nidx = mby * fs.mbw + mbx - (left ? 1 : fs.mbw);
     if (cat == 0) {
         if (!navail)
@@ -404,13 +441,13 @@ template <class S> HD void cabac_mvd(S &s, int base, int mvd, int sum_abs)
 // All bins of one macroblock including its end_of_slice_flag.
 template <class S> HD void cabac_mb(S &s, const FrameSyntax &fs, int mb_index, int frame_i)
 {
-    int nmb = fs.mbw * fs.mbh;
     int mbx = mb_index % fs.mbw, mby = mb_index / fs.mbw;
     const MbInfo &mb = fs.mbi[mb_index];
-    const MbInfo *A = mbx > 0 ? &mb - 1 : nullptr, *B = mby > 0 ? &mb - fs.mbw : nullptr;
+    const int row_in_slice = mby % fs.srows;
+    const MbInfo *A = mbx > 0 ? &mb - 1 : nullptr, *B = row_in_slice ? &mb - fs.mbw : nullptr;
     const int16_t *coef = fs.coef + (size_t)mb_index * COEF_STRIDE;
     int intra = is_intra(mb.type);
-    int end = mb_index == nmb - 1;
+    int end = mbx == fs.mbw - 1 && (row_in_slice == fs.srows - 1 || mby == fs.mbh - 1); // end_of_slice_flag
     if (!frame_i) {
         int inc = (A && A->type != MB_PSKIP) + (B && B->type != MB_PSKIP);
         s.bin(11 + inc, mb.type == MB_PSKIP);

@@ -47,6 +47,7 @@ struct Geom {
     int qp, qpc;
     int R, lambda;      // ME radius and SAD lambda
     int cabac;
+    int srows, nslices; // macroblock rows per slice (mbh = the reference's one slice per picture), slices per picture
     unsigned long long frame_bytes; // W*H*3/2 : one planar frame (Y, U, V)
 };
 
@@ -217,10 +218,11 @@ HD int median3(int a, int b, int c) { return imax_(imin_(a, b), imin_(imax_(a, b
 
 // ---- median MV prediction for 16x16 partitions + P_Skip MV (H.264 8.4.1.1 / 8.4.1.3) ---------
 // mbi: macroblock records of the frame (types are only tested for intra / inter).
-HD void predict_mv(const MbInfo *mbi, int mbw, int mbx, int mby, int *mvp, int *skip_mv)
+// srows = macroblock rows per slice: the row above is unavailable when it belongs to another slice.
+HD void predict_mv(const MbInfo *mbi, int mbw, int srows, int mbx, int mby, int *mvp, int *skip_mv)
 {
-    int availA = mbx > 0, availB = mby > 0;
-    int availC = mby > 0 && mbx + 1 < mbw, availD = mby > 0 && mbx > 0;
+    int availA = mbx > 0, availB = (mby % srows) != 0;
+    int availC = availB && mbx + 1 < mbw, availD = availB && mbx > 0;
     int a[2] = {0, 0}, b[2] = {0, 0}, c[2] = {0, 0};
     int ra = -1, rb = -1, rc = -1;
     const MbInfo *cur = mbi + mby * mbw + mbx;

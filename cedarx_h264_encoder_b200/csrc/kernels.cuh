@@ -464,7 +464,7 @@ __global__ void mvp_skip_kernel(Geom g, Step s, MbInfo *__restrict__ mbi)
     if (m.type != MB_P16x16 && m.type != MB_PSKIP)
         return;
     int mvp[2], smv[2];
-    predict_mv(frame, g.mbw, mb % g.mbw, mb / g.mbw, mvp, smv);
+    predict_mv(frame, g.mbw, g.srows, mb % g.mbw, mb / g.mbw, mvp, smv);
     int16_t mvdx = (int16_t)(m.mv[0] - mvp[0]), mvdy = (int16_t)(m.mv[1] - mvp[1]);
     uint8_t type = MB_P16x16;
     if (m.cbp == 0 && m.mv[0] == smv[0] && m.mv[1] == smv[1]) {
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(32) intra_kernel(Geom g, Step s, const uint8_t
     const uint8_t izz[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};
 
     for (int mbx = 0; mbx < g.mbw; mbx++) {
-        const int has_top = row > 0, has_left = mbx > 0;
+        const int has_top = (row % g.srows) != 0, has_left = mbx > 0; // the row above may belong to another slice
         const size_t rec = (size_t)blockIdx.y * g.nmb + (size_t)row * g.mbw + mbx;
         // source block (independent of the wavefront)
         uint32_t sv[4] = {0, 0, 0, 0};
@@ -1125,19 +1125,20 @@ __global__ void sse_kernel(Geom g, Step s, const uint8_t *__restrict__ src, cons
 // scatter.  CAVLC scatters bits; CABAC scatters bins and a serial arithmetic coder (one per frame,
 // many frames at once) turns them into bytes.
 // ================================================================================================
+// "Unit" = one slice NAL: unit index u = frame * nslices + slice (nslices = 1 in the reference's layout).
 struct EntropyBufs {
-    uint32_t *mb_size;       // [L][nmb + 1] bits (CAVLC) or bins (CABAC) per macroblock
-    uint32_t *mb_off;        // [L][nmb + 1] exclusive prefix
-    const uint32_t *hdr_bits; // [F] slice header bits (host written, cedar.c:984-1030)
-    const int *hdr_nbits;     // [F]
-    uint8_t *rbsp;           // [F][rbsp_cap]
+    uint32_t *mb_size;       // [L][nitems + 1] bits (CAVLC) or bins (CABAC) per entropy item (slice_item)
+    uint32_t *mb_off;        // [L][nitems + 1] exclusive prefix over the picture; [nitems] = total
+    const unsigned long long *hdr_bits; // [U] slice header bits (host written, cedar.c:984-1030)
+    const int *hdr_nbits;     // [U]
+    uint8_t *rbsp;           // [U][rbsp_cap]
     unsigned rbsp_cap;
-    uint32_t *rbsp_len;      // [F] bytes of RBSP (header + slice data + trailing)
+    uint32_t *rbsp_len;      // [U] bytes of RBSP (header + slice data + trailing)
     uint16_t *bins;          // CABAC bin pool
     unsigned long long bins_cap;
     unsigned long long *bins_cursor; // pool bump pointer
-    unsigned long long *bins_off;    // [F]
-    uint32_t *bins_len;      // [F]
+    unsigned long long *bins_off;    // [U]
+    uint32_t *bins_len;      // [U]
     int *error;              // sticky overflow flag
 };
 
@@ -1150,15 +1151,8 @@ __device__ __forceinline__ FrameSyntax lane_syntax(const Geom &g, int lane, cons
     fs.coef = coef + (size_t)lane * g.nmb * COEF_STRIDE;
     fs.mbw = g.mbw;
     fs.mbh = g.mbh;
+    fs.srows = g.srows;
     return fs;
-}
-
-__device__ __forceinline__ int skip_run_before(const FrameSyntax &fs, int i)
-{
-    int run = 0;
-    for (int j = i - 1; j >= 0 && fs.mbi[j].type == MB_PSKIP; j--)
-        run++;
-    return run;
 }
 
 __global__ void entropy_size_kernel(Geom g, Step s, int frame_i, const MbInfo *__restrict__ mbi,
@@ -1166,27 +1160,30 @@ __global__ void entropy_size_kernel(Geom g, Step s, int frame_i, const MbInfo *_
 {
     if (lane_frame(s, blockIdx.y) < 0)
         return;
+    const int nitems = g.nmb + g.nslices;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > g.nmb)
+    if (i >= nitems)
         return;
     FrameSyntax fs = lane_syntax(g, blockIdx.y, mbi, nnz, coef);
+    const SliceItem it = slice_item(fs, i);
     unsigned n;
     if (g.cabac) {
         BinCount c;
-        if (i < g.nmb)
-            cabac_mb(c, fs, i, frame_i);
+        if (!it.is_end)
+            cabac_mb(c, fs, it.mb, frame_i);
         n = c.n;
     } else {
         BitCount c;
-        bool emits = i == g.nmb || fs.mbi[i].type != MB_PSKIP;
-        if (emits)
-            cavlc_mb(c, fs, i, frame_i, frame_i ? 0 : skip_run_before(fs, i));
+        if (it.is_end)
+            cavlc_end(c, frame_i ? 0 : skip_run_before(fs, it.mb, it.first_mb));
+        else if (fs.mbi[it.mb].type != MB_PSKIP)
+            cavlc_mb(c, fs, it.mb, frame_i, frame_i ? 0 : skip_run_before(fs, it.mb, it.first_mb));
         n = c.n;
     }
-    eb.mb_size[(size_t)blockIdx.y * (g.nmb + 1) + i] = n;
+    eb.mb_size[(size_t)blockIdx.y * (nitems + 1) + i] = n;
 }
 
-// Exclusive prefix sum of nmb + 1 sizes per lane (one 1024-thread CTA per lane) + per-frame totals.
+// Exclusive prefix sum of the item sizes of a picture (one 1024-thread CTA per lane) + per-slice totals.
 __global__ void __launch_bounds__(1024) entropy_scan_kernel(Geom g, Step s, EntropyBufs eb)
 {
     int f = lane_frame(s, blockIdx.y);
@@ -1194,12 +1191,12 @@ __global__ void __launch_bounds__(1024) entropy_scan_kernel(Geom g, Step s, Entr
         return;
     __shared__ uint32_t warp_sum[32];
     __shared__ uint32_t carry_s;
-    const int n = g.nmb + 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t *in = eb.mb_size + (size_t)blockIdx.y * n;
-    uint32_t *out = eb.mb_off + (size_t)blockIdx.y * n;
-    const uint32_t base = g.cabac ? 0u : (uint32_t)eb.hdr_nbits[f];
+    __shared__ unsigned long long pool_off;
+    const int n = g.nmb + g.nslices, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t *in = eb.mb_size + (size_t)blockIdx.y * (n + 1);
+    uint32_t *out = eb.mb_off + (size_t)blockIdx.y * (n + 1);
     if (tid == 0)
-        carry_s = base;
+        carry_s = 0;
     __syncthreads();
     for (int start = 0; start < n; start += 1024) {
         int i = start + tid;
@@ -1234,23 +1231,32 @@ __global__ void __launch_bounds__(1024) entropy_scan_kernel(Geom g, Step s, Entr
         __syncthreads();
     }
     if (tid == 0) {
-        uint32_t total = carry_s;
-        if (g.cabac) {
+        const uint32_t total = carry_s;
+        out[n] = total;
+        if (g.cabac) { // one pool allocation per picture; its slices lie back to back
             unsigned long long off = atomicAdd(eb.bins_cursor, (unsigned long long)((total + 7u) & ~7u));
             if (off + total > eb.bins_cap) {
                 atomicExch(eb.error, 1);
-                off = 0;
-                total = 0;
+                off = ~0ull;
             }
-            eb.bins_off[f] = off;
-            eb.bins_len[f] = total;
+            pool_off = off;
+        }
+    }
+    __syncthreads();
+    const int per = g.srows * g.mbw + 1;
+    for (int k = tid; k < g.nslices; k += 1024) {
+        const size_t u = (size_t)f * g.nslices + k;
+        const uint32_t start = out[k * per], end = out[imin_((k + 1) * per, n)];
+        if (g.cabac) {
+            eb.bins_off[u] = pool_off == ~0ull ? 0 : pool_off + start;
+            eb.bins_len[u] = pool_off == ~0ull ? 0 : end - start;
         } else {
-            uint32_t bytes = (total + 7) >> 3;
+            uint32_t bytes = ((uint32_t)eb.hdr_nbits[u] + (end - start) + 7) >> 3;
             if (bytes + 8 > eb.rbsp_cap) {
                 atomicExch(eb.error, 2);
                 bytes = 0;
             }
-            eb.rbsp_len[f] = bytes;
+            eb.rbsp_len[u] = bytes;
         }
     }
 }
@@ -1261,30 +1267,40 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
     int f = lane_frame(s, blockIdx.y);
     if (f < 0)
         return;
+    const int nitems = g.nmb + g.nslices;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > g.nmb)
+    if (i >= nitems)
         return;
     FrameSyntax fs = lane_syntax(g, blockIdx.y, mbi, nnz, coef);
-    uint32_t off = eb.mb_off[(size_t)blockIdx.y * (g.nmb + 1) + i];
+    const SliceItem it = slice_item(fs, i);
+    const uint32_t *offs = eb.mb_off + (size_t)blockIdx.y * (nitems + 1);
+    const uint32_t off = offs[i] - offs[it.slice * slice_items_per(fs)]; // relative to the slice's first item
+    const size_t u = (size_t)f * g.nslices + it.slice;
     if (g.cabac) {
-        if (i == g.nmb || eb.bins_len[f] == 0)
+        if (it.is_end || eb.bins_len[u] == 0)
             return;
-        BinWrite w(eb.bins + eb.bins_off[f] + off);
-        cabac_mb(w, fs, i, frame_i);
+        BinWrite w(eb.bins + eb.bins_off[u] + off);
+        cabac_mb(w, fs, it.mb, frame_i);
     } else {
-        if (eb.rbsp_len[f] == 0)
+        if (eb.rbsp_len[u] == 0)
             return;
-        uint32_t *buf = (uint32_t *)(eb.rbsp + (size_t)f * eb.rbsp_cap);
-        if (i == 0) {
+        uint32_t *buf = (uint32_t *)(eb.rbsp + u * eb.rbsp_cap);
+        const int hn = eb.hdr_nbits[u];
+        if (it.is_first) { // slice header bits (up to 46 with first_mb_in_slice != 0)
             BitScatter h(buf, 0);
-            h.put(eb.hdr_bits[f], eb.hdr_nbits[f]);
+            const unsigned long long hb = eb.hdr_bits[u];
+            if (hn > 32)
+                h.put((uint32_t)(hb >> 32), hn - 32);
+            h.put((uint32_t)hb, hn > 32 ? 32 : hn);
             h.flush();
         }
-        bool emits = i == g.nmb || fs.mbi[i].type != MB_PSKIP;
-        if (!emits)
+        if (!it.is_end && fs.mbi[it.mb].type == MB_PSKIP)
             return;
-        BitScatter w(buf, off);
-        cavlc_mb(w, fs, i, frame_i, frame_i ? 0 : skip_run_before(fs, i));
+        BitScatter w(buf, (unsigned long long)hn + off);
+        if (it.is_end)
+            cavlc_end(w, frame_i ? 0 : skip_run_before(fs, it.mb, it.first_mb));
+        else
+            cavlc_mb(w, fs, it.mb, frame_i, frame_i ? 0 : skip_run_before(fs, it.mb, it.first_mb));
         w.flush();
     }
 }
@@ -1310,18 +1326,19 @@ __global__ void __launch_bounds__(CABAC_THREADS) cabac_kernel(Geom g, Step s, in
     __shared__ uint32_t stepT[2][CABAC_TILE];
     __shared__ uint2 stage[32];
     __shared__ uint8_t ctx_state[464];
-    const int f = lane_frame(s, blockIdx.x);
+    const int f = lane_frame(s, blockIdx.x / g.nslices); // one CTA per slice
     if (f < 0)
         return;
+    const size_t u = (size_t)f * g.nslices + blockIdx.x % g.nslices;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int frame_i = ((gop_pos0 + f) % gop_len) == 0;
-    const uint32_t nb = eb.bins_len[f];
+    const uint32_t nb = eb.bins_len[u];
     if (nb == 0) {
         if (tid == 0)
-            eb.rbsp_len[f] = 0;
+            eb.rbsp_len[u] = 0;
         return;
     }
-    const uint16_t *gbins = eb.bins + eb.bins_off[f];
+    const uint16_t *gbins = eb.bins + eb.bins_off[u];
     const int ntiles = (int)((nb + CABAC_TILE - 1) / CABAC_TILE);
     tab.build(tid, CABAC_THREADS);
     for (int i = tid; i < 460; i += CABAC_THREADS)
@@ -1330,13 +1347,13 @@ __global__ void __launch_bounds__(CABAC_THREADS) cabac_kernel(Geom g, Step s, in
     // coder state
     CabacRange rc;
     CabacBytes cb;
-    uint8_t *out = eb.rbsp + (size_t)f * eb.rbsp_cap;
-    const int hn = eb.hdr_nbits[f], hb = (hn + 7) >> 3;
+    uint8_t *out = eb.rbsp + u * eb.rbsp_cap;
+    const int hn = eb.hdr_nbits[u], hb = (hn + 7) >> 3;
     cb.out = out + hb;
     const unsigned limit = eb.rbsp_cap - hb - 64;
     bool overflow = false;
     if (tid == 64) { // header bits, then cabac_alignment_one_bit up to the byte boundary
-        unsigned long long h = ((unsigned long long)eb.hdr_bits[f] << (hb * 8 - hn)) | ((1ull << (hb * 8 - hn)) - 1);
+        unsigned long long h = (eb.hdr_bits[u] << (hb * 8 - hn)) | ((1ull << (hb * 8 - hn)) - 1);
         for (int i = 0; i < hb; i++)
             out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
     }
@@ -1436,9 +1453,9 @@ __global__ void __launch_bounds__(CABAC_THREADS) cabac_kernel(Geom g, Step s, in
     if (tid == 64) {
         if (overflow) {
             atomicExch(eb.error, 3);
-            eb.rbsp_len[f] = 0;
+            eb.rbsp_len[u] = 0;
         } else
-            eb.rbsp_len[f] = (uint32_t)(hb + cb.pos);
+            eb.rbsp_len[u] = (uint32_t)(hb + cb.pos);
     }
 }
 
@@ -1531,11 +1548,12 @@ __global__ void __launch_bounds__(1024) epb_scan_kernel(int nframes, const uint3
 
 // Single CTA: exclusive scan of the per-frame NAL sizes -> offsets in the packed stream.
 // frame_bytes[f] additionally counts the parameter sets that precede frame 0 (cedar.c:1058-1061).
-__global__ void __launch_bounds__(1024) pack_scan_kernel(int nframes, const uint32_t *__restrict__ nal_bytes,
-                                                         unsigned prefix_bytes, unsigned long long *__restrict__ nal_off,
+__global__ void __launch_bounds__(1024) pack_scan_kernel(int nunits, int nslices, const uint32_t *__restrict__ nal_bytes,
+                                                         unsigned prefix_bytes, unsigned long long *nal_off,
                                                          int *__restrict__ frame_bytes, unsigned long long *total,
                                                          unsigned long long out_cap, int *error)
 {
+    const int nframes = nunits; // scanned entries: one per slice NAL
     __shared__ unsigned long long warp_sum[32];
     __shared__ unsigned long long carry_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1566,14 +1584,19 @@ __global__ void __launch_bounds__(1024) pack_scan_kernel(int nframes, const uint
         }
         __syncthreads();
         unsigned long long incl = carry_s + warp_sum[warp] + x;
-        if (i < nframes) {
+        if (i < nframes)
             nal_off[i] = incl - v;
-            frame_bytes[i] = (int)v + (i == 0 ? (int)prefix_bytes : 0);
-        }
         __syncthreads();
         if (tid == 1023)
             carry_s = incl;
         __syncthreads();
+    }
+    // bytes per picture = its slice NALs (+ the parameter sets in front of picture 0)
+    const unsigned long long end_all = carry_s;
+    for (int fr = tid; fr < nunits / nslices; fr += 1024) {
+        unsigned long long b = fr == 0 ? 0 : nal_off[(size_t)fr * nslices];
+        unsigned long long e = (fr + 1) * nslices < nunits ? nal_off[(size_t)(fr + 1) * nslices] : end_all;
+        frame_bytes[fr] = (int)(e - b);
     }
     if (tid == 0) {
         *total = carry_s;
@@ -1584,7 +1607,7 @@ __global__ void __launch_bounds__(1024) pack_scan_kernel(int nframes, const uint
     }
 }
 
-__global__ void epb_write_kernel(int nframes, int gop_len, int first_frame_index,
+__global__ void epb_write_kernel(int nframes /* units */, int nslices, int gop_len, int first_frame_index,
                                  const uint8_t *__restrict__ rbsp, unsigned rbsp_cap,
                                  const uint32_t *__restrict__ rbsp_len, const uint32_t *__restrict__ chunk_off,
                                  unsigned chunks_per_frame, const unsigned long long *__restrict__ nal_off,
@@ -1601,7 +1624,7 @@ __global__ void epb_write_kernel(int nframes, int gop_len, int first_frame_index
     uint8_t *o = out + nal_off[f];
     if (ch == 0) {
         // cedar.c:868-881 start code + NAL header: IDR ref_idc 3 type 5, P ref_idc 2 type 1 (:987-990)
-        int frame_i = ((first_frame_index + f) % gop_len) == 0;
+        int frame_i = ((first_frame_index + f / nslices) % gop_len) == 0;
         o[0] = 0, o[1] = 0, o[2] = 0, o[3] = 1;
         o[4] = frame_i ? 0x65 : 0x41;
     }

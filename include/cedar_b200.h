@@ -49,6 +49,9 @@ struct cedar_b200_config {
     int device;              /* CUDA device ordinal */
     int gops_in_flight;      /* clip mode: closed GOPs encoded concurrently on this GPU; 0 = auto */
     int max_clip_frames;     /* clip mode: capacity of the clip buffers in frames; 0 = clip mode off */
+    int slice_rows;          /* macroblock rows per slice; 0 = one slice per picture as the reference writes it
+                              * (first_mb_in_slice always 0, cedar.c:992-993).  N > 0: every N rows start a new slice
+                              * NAL, coded by its own (parallel) entropy coder at some cost in bits. */
 };
 
 /*
@@ -131,6 +134,8 @@ long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_
 int cedar_b200_write_sps(const struct cedar_b200_config *cfg, uint8_t *out, int cap);
 int cedar_b200_write_pps(const struct cedar_b200_config *cfg, uint8_t *out, int cap);
 int cedar_b200_slice_header(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits);
+/* Slice header of a slice that starts at macroblock first_mb (slice_rows extension); up to 64 bits. */
+int cedar_b200_slice_header_mb(int frame_i, int frame_p_count, int cabac, int first_mb, uint64_t *bits, int *nbits);
 
 const char *cedar_b200_version(void);
 

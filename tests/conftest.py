@@ -38,10 +38,10 @@ def harness():
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-g", "-Wall", "-Wno-unknown-pragmas", "-fPIC", "-shared", "-std=c++17", "-o", so, src])
     H = C.CDLL(so)
-    H.hh_cavlc_frame.restype = C.c_long
-    H.hh_cabac_frame.restype = C.c_long
+    H.hh_cavlc_slice.restype = C.c_long
+    H.hh_cabac_slice.restype = C.c_long
     H.hh_epb.restype = C.c_long
-    H.hh_cavlc_frame.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_uint32, C.c_int, C.c_void_p, C.c_long]
-    H.hh_cabac_frame.argtypes = [C.c_void_p] * 3 + [C.c_int] * 4 + [C.c_uint32, C.c_int, C.c_void_p, C.c_long]
+    H.hh_cavlc_slice.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_uint64, C.c_int, C.c_void_p, C.c_long]
+    H.hh_cabac_slice.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_uint64, C.c_int, C.c_void_p, C.c_long]
     H.hh_epb.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long]
     return H

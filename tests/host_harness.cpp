@@ -10,28 +10,30 @@
 
 using namespace cedar;
 
-static int skip_run_before(const FrameSyntax &fs, int i)
-{
-    int run = 0;
-    for (int j = i - 1; j >= 0 && fs.mbi[j].type == MB_PSKIP; j--)
-        run++;
-    return run;
-}
-
 extern "C" {
 
-// Returns RBSP length in bytes (header bits + slice data + trailing bits, byte aligned).
-long hh_cavlc_frame(const void *mbi, const uint8_t *nnz, const int16_t *coef, int mbw, int mbh, int frame_i,
-                    uint32_t hdr_bits, int hdr_nbits, uint8_t *out, long cap)
+// One slice (macroblock rows [row0, row1) of a picture whose slices are srows rows tall) through the
+// count / prefix-sum / scatter passes.  Returns RBSP length in bytes (header bits + slice data + trailing
+// bits, byte aligned).
+long hh_cavlc_slice(const void *mbi, const uint8_t *nnz, const int16_t *coef, int mbw, int mbh, int srows, int slice,
+                    int frame_i, uint64_t hdr_bits, int hdr_nbits, uint8_t *out, long cap)
 {
-    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh};
-    int nmb = mbw * mbh;
-    std::vector<unsigned long long> off(nmb + 2);
+    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh, srows};
+    const int per = slice_items_per(fs), nitems = mbw * mbh + (mbh + srows - 1) / srows;
+    const int j0 = slice * per, j1 = per * (slice + 1) < nitems ? per * (slice + 1) : nitems;
+    std::vector<unsigned long long> off(j1 - j0 + 1);
     unsigned long long pos = (unsigned long long)hdr_nbits;
-    for (int i = 0; i <= nmb; i++) {
+    for (int j = j0; j < j1; j++) {
+        SliceItem it = slice_item(fs, j);
+        if (it.slice != slice || it.is_first != (j == j0) || it.is_end != (j == j1 - 1))
+            return -3;
         BitCount c;
-        cavlc_mb(c, fs, i, frame_i, skip_run_before(fs, i));
-        off[i] = pos;
+        int run = frame_i ? 0 : skip_run_before(fs, it.mb, it.first_mb);
+        if (it.is_end)
+            cavlc_end(c, run);
+        else if (fs.mbi[it.mb].type != MB_PSKIP)
+            cavlc_mb(c, fs, it.mb, frame_i, run);
+        off[j - j0] = pos;
         pos += c.n;
     }
     long bytes = (long)((pos + 7) >> 3);
@@ -40,43 +42,53 @@ long hh_cavlc_frame(const void *mbi, const uint8_t *nnz, const int16_t *coef, in
     std::vector<uint32_t> buf((size_t)(bytes + 8) / 4 + 2, 0);
     {
         BitScatter s(buf.data(), 0);
-        s.put(hdr_bits, hdr_nbits);
+        if (hdr_nbits > 32)
+            s.put((uint32_t)(hdr_bits >> 32), hdr_nbits - 32);
+        s.put((uint32_t)hdr_bits, hdr_nbits > 32 ? 32 : hdr_nbits);
         s.flush();
     }
     // scatter in reverse order to show the order does not matter
-    for (int i = nmb; i >= 0; i--) {
-        BitScatter s(buf.data(), off[i]);
-        cavlc_mb(s, fs, i, frame_i, skip_run_before(fs, i));
+    for (int j = j1 - 1; j >= j0; j--) {
+        SliceItem it = slice_item(fs, j);
+        int run = frame_i ? 0 : skip_run_before(fs, it.mb, it.first_mb);
+        if (!it.is_end && fs.mbi[it.mb].type == MB_PSKIP)
+            continue;
+        BitScatter s(buf.data(), off[j - j0]);
+        if (it.is_end)
+            cavlc_end(s, run);
+        else
+            cavlc_mb(s, fs, it.mb, frame_i, run);
         s.flush();
     }
     memcpy(out, buf.data(), (size_t)bytes);
     return bytes;
 }
 
-long hh_cabac_frame(const void *mbi, const uint8_t *nnz, const int16_t *coef, int mbw, int mbh, int frame_i, int qp,
-                    uint32_t hdr_bits, int hdr_nbits, uint8_t *out, long cap)
+long hh_cabac_slice(const void *mbi, const uint8_t *nnz, const int16_t *coef, int mbw, int mbh, int srows, int slice,
+                    int frame_i, int qp, uint64_t hdr_bits, int hdr_nbits, uint8_t *out, long cap)
 {
-    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh};
-    int nmb = mbw * mbh;
+    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh, srows};
+    const int row0 = slice * srows, row1 = row0 + srows < mbh ? row0 + srows : mbh;
+    const int mb0 = row0 * mbw, nmb = (row1 - row0) * mbw;
     std::vector<size_t> off(nmb + 1);
     size_t total = 0;
     for (int i = 0; i < nmb; i++) {
         BinCount c;
-        cabac_mb(c, fs, i, frame_i);
+        cabac_mb(c, fs, mb0 + i, frame_i);
         off[i] = total;
         total += c.n;
     }
     std::vector<uint16_t> bins(total + 1);
     for (int i = nmb - 1; i >= 0; i--) {
         BinWrite w(bins.data() + off[i]);
-        cabac_mb(w, fs, i, frame_i);
+        cabac_mb(w, fs, mb0 + i, frame_i);
     }
     // header bits followed by cabac_alignment_one_bit up to the byte boundary
     int hb = (hdr_nbits + 7) >> 3;
-    unsigned long long h = ((unsigned long long)hdr_bits << (hb * 8 - hdr_nbits)) | ((1ull << (hb * 8 - hdr_nbits)) - 1);
+    unsigned long long h = (hdr_bits << (hb * 8 - hdr_nbits)) | ((1ull << (hb * 8 - hdr_nbits)) - 1);
     for (int i = 0; i < hb; i++)
         out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
-    // pre-state resolution (sequential here; per-context parallel in cabac_resolve_kernel), then the coder
+    // pre-state resolution (sequential here; per-context parallel in cabac_kernel), then the coder
     CabacTables tab;
     tab.build(0, 1);
     uint32_t state[460];

@@ -157,7 +157,11 @@ def write_pps(cfg):
     return buf[:n].tobytes()
 
 
-def slice_header_bits(frame_i, frame_p_count, cabac):
+def slice_header_bits(frame_i, frame_p_count, cabac, first_mb=0):
+    if first_mb:
+        bits64, n = C.c_uint64(), C.c_int()
+        lib().gm_slice_header_bits64(frame_i, frame_p_count, cabac, first_mb, C.byref(bits64), C.byref(n))
+        return format(bits64.value, "0%db" % n.value)
     bits, n = C.c_uint32(), C.c_int()
     lib().gm_slice_header_bits(frame_i, frame_p_count, cabac, C.byref(bits), C.byref(n))
     return format(bits.value, "0%db" % n.value)

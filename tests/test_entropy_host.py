@@ -23,27 +23,34 @@ def to_product_layout(mbs):
 
 
 @pytest.mark.parametrize("cabac", [0, 1])
-@pytest.mark.parametrize("kind,qp", [("synth", 24), ("noise", 1), ("noise", 12), ("noise", 40), ("static", 36)])
-def test_entropy_logic_matches_oracle(oracle, harness, kind, qp, cabac):
-    w, h, gop = 96, 64, 3
-    enc = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8))
+@pytest.mark.parametrize("kind,qp,rows", [("synth", 24, 0), ("noise", 1, 0), ("noise", 12, 0), ("noise", 40, 0), ("static", 36, 0),
+                                          ("synth", 24, 1), ("static", 36, 3), ("noise", 30, 2)])
+def test_entropy_logic_matches_oracle(oracle, harness, kind, qp, rows, cabac):
+    """rows = slice_rows: every slice NAL of the picture goes through the product logic on its own."""
+    w, h, gop = 96, 80, 3
+    mbw, mbh = w // 16, h // 16
+    srows = rows if rows else mbh
+    nslices = -(-mbh // srows)
+    enc = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, slice_rows=rows))
     for t in range(5):
         y, c = content(kind, w, h, t)
-        payload = avdec.split_nals(enc.encode(y, c))[-1][1][5:]
+        payloads = [nal[5:] for ty, nal in avdec.split_nals(enc.encode(y, c)) if ty in (1, 5)]
+        assert len(payloads) == nslices
         mbi, nnz, coef = to_product_layout(enc.mbs())
         fi = int(enc.frame_is_i())
-        bits = oracle.slice_header_bits(fi, t % gop, cabac)
-        out = np.zeros(len(payload) * 2 + 4096, np.uint8)
-        if cabac:
-            n = harness.hh_cabac_frame(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, w // 16, h // 16, fi, qp,
-                                       int(bits, 2), len(bits), out.ctypes.data, out.size)
-        else:
-            n = harness.hh_cavlc_frame(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, w // 16, h // 16, fi,
-                                       int(bits, 2), len(bits), out.ctypes.data, out.size)
-        assert n > 0
-        esc = np.zeros(n * 2 + 16, np.uint8)
-        m = harness.hh_epb(out.ctypes.data, n, esc.ctypes.data, esc.size)
-        assert esc[:m].tobytes() == payload, "frame %d (%s)" % (t, "I" if fi else "P")
+        for k, payload in enumerate(payloads):
+            bits = oracle.slice_header_bits(fi, t % gop, cabac, k * srows * mbw)
+            out = np.zeros(len(payload) * 2 + 4096, np.uint8)
+            if cabac:
+                n = harness.hh_cabac_slice(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, mbw, mbh, srows, k, fi, qp,
+                                           int(bits, 2), len(bits), out.ctypes.data, out.size)
+            else:
+                n = harness.hh_cavlc_slice(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, mbw, mbh, srows, k, fi,
+                                           int(bits, 2), len(bits), out.ctypes.data, out.size)
+            assert n > 0
+            esc = np.zeros(n * 2 + 16, np.uint8)
+            m = harness.hh_epb(out.ctypes.data, n, esc.ctypes.data, esc.size)
+            assert esc[:m].tobytes() == payload, "frame %d (%s) slice %d" % (t, "I" if fi else "P", k)
 
 
 def test_parallel_emulation_prevention_rule(harness):

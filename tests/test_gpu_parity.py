@@ -155,3 +155,61 @@ def test_gpu_stream_decodes_bit_exactly_small(oracle):
     for r, d in zip(recs, dec):
         for p in range(3):
             assert np.array_equal(r[p], d[p])
+
+
+# ---- slice_rows extension (north star: "MB rows per slice configurable, bitrate cost reported") ----------------
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("kind,qp,rows", [("synth", 24, 1), ("noise", 30, 2), ("static", 30, 3), ("shift", 24, 2), ("noise", 1, 4)])
+def test_slices_every_stage_matches_oracle(oracle, kind, qp, rows, cabac):
+    w, h, gop, n = 96, 80, 3, 5
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, slice_rows=rows))
+    with cx.Encoder(api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, slice_rows=rows)) as enc:
+        for t in range(n):
+            y, c = content(kind, w, h, t)
+            want, got = gold.encode(y, c), enc.encode(y, c)
+            mbs = gold.mbs()
+            mbi, nnz, coef = enc.debug_syntax()
+            for k in ("type", "i16_mode", "chroma_mode", "cbp", "mv", "mvd"):
+                assert np.array_equal(mbs[k], mbi[k]), "mb.%s frame %d" % (k, t)
+            assert np.array_equal(mbs["coef"], coef), "levels frame %d" % t
+            for p, (a, b) in enumerate(zip(gold.recon(), enc.debug_planes(2))):
+                assert np.array_equal(a, b), "recon after deblocking plane %d frame %d" % (p, t)
+            assert got == want, "bytestream frame %d" % t
+    gold.close()
+
+
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("rows,lanes", [(1, 0), (2, 3), (4, 1), (5, 2)])
+def test_slices_clip_mode_matches_oracle(oracle, rows, lanes, cabac):
+    w, h, n, gop = 96, 80, 11, 4
+    clip = make_clip("synth", w, h, n)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=24, gop=gop, cabac=cabac, me_range=8, slice_rows=rows)
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=gop, cabac=cabac, me_range=8, max_clip_frames=n,
+                                    gops_in_flight=lanes, slice_rows=rows)) as enc:
+        got, gsz = enc.encode_clip(clip)
+        assert got == want and gsz.tolist() == sizes
+
+
+@pytest.mark.parametrize("cabac", [0, 1])
+def test_slices_full_size_decode_and_bitrate_cost(cabac):
+    """1080p, 4 rows per slice (17 slices): the independent decoder reproduces the encoder's reconstruction, the
+    frame-at-a-time path equals the clip path, and the extra bits over one slice per picture stay moderate."""
+    w, h, n, gop = 1920, 1088, 4, 60
+    clip = synth.synth_clip(w, h, list(range(n)), 0).numpy()
+    total = {}
+    for rows in (0, 4):
+        with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=cabac, max_clip_frames=n, slice_rows=rows)) as enc:
+            stream, sizes = enc.encode_clip(clip)
+        total[rows] = len(stream)
+        if rows:
+            with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=cabac, slice_rows=rows)) as enc:
+                frames = b""
+                for t in range(n):
+                    frames += enc.encode(*split_frame(clip[t], w, h, 0))
+                last_recon = enc.debug_planes(2)
+            assert frames == stream
+            dec = avdec.decode(stream)
+            assert len(dec) == n
+            for p in range(3):
+                assert np.array_equal(dec[-1][p], last_recon[p])
+    assert total[0] < total[4] < 1.10 * total[0], total
