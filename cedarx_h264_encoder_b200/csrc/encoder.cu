@@ -27,12 +27,12 @@ namespace {
 
 enum KernelId {
     K_INGEST, K_ME, K_INTER, K_MVP, K_INTRA, K_BS, K_DEBLOCK, K_SSE, K_ESIZE, K_ESCAN, K_EZERO, K_EWRITE,
-    K_CABAC, K_EPBCOUNT, K_EPBSCAN, K_PACKSCAN, K_EPBWRITE, K_COUNT
+    K_CRESOLVE, K_CCODE, K_EPBCOUNT, K_EPBSCAN, K_PACKSCAN, K_EPBWRITE, K_COUNT
 };
 const char *kKernelNames[K_COUNT] = {
     "ingest_kernel", "me_kernel", "inter_kernel", "mvp_skip_kernel", "intra_kernel", "bs_kernel", "deblock_kernel",
     "sse_kernel", "entropy_size_kernel", "entropy_scan_kernel", "rbsp_zero_kernel", "entropy_write_kernel",
-    "cabac_kernel", "epb_count_kernel", "epb_scan_kernel", "pack_scan_kernel", "epb_write_kernel"};
+    "cabac_resolve_kernel", "cabac_code_kernel", "epb_count_kernel", "epb_scan_kernel", "pack_scan_kernel", "epb_write_kernel"};
 
 const uint8_t kChromaQp[52] = {0,  1,  2,  3,  4,  5,  6,  7,  8,  9,  10, 11, 12, 13, 14, 15, 16, 17,
                                18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 29, 30, 31, 32, 32, 33,
@@ -82,7 +82,6 @@ struct cedar_b200_handle {
     cudaEvent_t ev_encode_done;
     bool upload_pending;
     cudaEvent_t ev_bins, ev_cabac[NSIDE];
-    size_t cabac_excl_smem; // dummy dynamic smem that leaves no room for another CTA on the SM
     unsigned side_used; // bit i: side stream i has work the main stream has not joined yet
     int side_next;
 
@@ -327,8 +326,11 @@ int alloc_buffers(cedar_b200_handle *h)
     r |= dmalloc(&h->d_hdr_nbits, U);
     r |= dmalloc(&h->eb.rbsp, (size_t)h->eb.rbsp_cap * U);
     r |= dmalloc(&h->eb.rbsp_len, U);
-    if (g.cabac)
+    h->eb.limb_cap = h->eb.rbsp_cap / 2 + 8;
+    if (g.cabac) {
         r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap);
+        r |= dmalloc(&h->eb.limbs, (size_t)h->eb.limb_cap * U);
+    }
     r |= dmalloc(&h->eb.bins_cursor, 1);
     r |= dmalloc(&h->eb.bins_off, U);
     r |= dmalloc(&h->eb.bins_len, U);
@@ -357,7 +359,7 @@ void free_buffers(cedar_b200_handle *h)
     void *dev[] = {h->d_raw, h->d_src[0], h->d_src[1], h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi[0], h->d_mbi[1],
                    h->d_nnz[0], h->d_nnz[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_bs,
                    h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp, h->eb.rbsp_len,
-                   h->eb.bins, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
+                   h->eb.bins, h->eb.limbs, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
                    h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes, h->d_out};
     for (void *p : dev)
         if (p)
@@ -373,7 +375,7 @@ void free_buffers(cedar_b200_handle *h)
 //   stream_pre : ingest(t)                                   -> src[p]                 (p = step parity)
 //   stream     : intra | ME, residual, MVP/skip; bS; deblock -> syntax[p], unf, rec[t & 1]
 //   stream_post: SSE, entropy sizes / scan / scatter          -> RBSP (CAVLC) or bins (CABAC)
-//   side stream: cabac_kernel
+//   side stream: cabac_resolve_kernel, cabac_code_kernel
 // Buffers with index p are reused two steps later, hence the waits on ev_post[p].
 int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int step_index, bool wait_upload)
 {
@@ -435,13 +437,8 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         // the bins of these frames are final: code them on a side stream while the next frames are reconstructed
         cudaStream_t side = no_overlap ? st : h->stream_cabac[h->side_next];
         CK(cudaStreamWaitEvent(side, h->ev_post[p], 0));
-        // The coders that sit on the critical path (the long I frames; the last frames, whose coding is the
-        // tail after reconstruction ends) get an SM each: a dummy dynamic shared-memory request keeps the
-        // throughput kernels off that SM, so the two serial warps are not starved of issue slots.
-        static const int tail_steps = getenv("CEDAR_B200_EXCL_TAIL") ? atoi(getenv("CEDAR_B200_EXCL_TAIL")) : 4;
-        const bool exclusive = t == 0 || t >= h->K - tail_steps;
-        LAUNCH_ON(side, K_CABAC, cabac_kernel, nl * g.nslices, CABAC_THREADS, exclusive ? h->cabac_excl_smem : 0, g, s, h->K, gop_pos0,
-                  h->eb);
+        LAUNCH_ON(side, K_CRESOLVE, cabac_resolve_kernel, nl * g.nslices, RES_WARPS * 32, 0, g, s, h->K, gop_pos0, h->eb);
+        LAUNCH_ON(side, K_CCODE, cabac_code_kernel, nl * g.nslices, CP_THREADS, 0, g, s, h->eb);
         if (!no_overlap) {
             h->side_used |= 1u << h->side_next;
             h->side_next = (h->side_next + 1) % cedar_b200_handle::NSIDE;
@@ -630,20 +627,6 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     if (!ok) {
         delete h;
         return -ENODEV;
-    }
-    {
-        cudaDeviceProp prop;
-        cudaGetDeviceProperties(&prop, cfg->device);
-        cudaFuncAttributes fa;
-        cudaFuncGetAttributes(&fa, cabac_kernel);
-        size_t want = prop.sharedMemPerMultiprocessor > (size_t)200 * 1024 ? (size_t)176 * 1024 : 0;
-        if (want + fa.sharedSizeBytes > prop.sharedMemPerBlockOptin)
-            want = prop.sharedMemPerBlockOptin > fa.sharedSizeBytes ? prop.sharedMemPerBlockOptin - fa.sharedSizeBytes : 0;
-        if (getenv("CEDAR_B200_NO_EXCL"))
-            want = 0;
-        if (want && cudaFuncSetAttribute(cabac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want) != cudaSuccess)
-            want = 0;
-        h->cabac_excl_smem = want;
     }
     if (cudaFuncSetAttribute(me_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)me_smem_bytes(g.R, me_strip(g.R))) != cudaSuccess) {

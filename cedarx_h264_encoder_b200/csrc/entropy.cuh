@@ -739,6 +739,114 @@ struct CabacBytes {
     }
 };
 
+// =============================================================================================
+// Parallel formulation of the arithmetic coder (what cabac_code_kernel runs; the three-stage serial coder
+// above is kept as the CPU-checkable restatement of 9.3.4 it is derived from).
+//
+// (1) codIRange.  After a regular bin coded as LPS the new range is rangeTabLPS[state][q] << shift: it depends
+//     on the range before that bin only through q = (range >> 6) & 3.  So the bin sequence is cut right after
+//     LPS bins ("chunks" of about CP_K bins); a chunk is walked for all four q hypotheses of the LPS bin in
+//     front of it, which yields a 4 -> 4 map (hypothesis -> q at the chunk's closing LPS bin) and the number
+//     of bits the chunk shifts out.  Composing the maps (an associative scan) gives every chunk its true
+//     start range; a second walk then produces the true interval steps.  All chunks run in parallel.
+// (2) codILow.  With every bin's (add, shift) known, the code word is the big integer
+//     sum_i add_i << (T_end - P_i), P_i = bits shifted out before bin i's add: additions commute, so every bin
+//     adds its 9-bit value into an array of 16-bit limbs (held in 32-bit words: deferred carries) at stream
+//     bit position P_i, and one carry-lookahead pass turns the limbs into bytes.  This replaces put_byte's
+//     outstanding-0xff bookkeeping: a carry rippling through 0xff bytes is just a propagated carry.
+//     Stream bit p <-> code-word bit T_end + 8 - p; the flush of 9.3.4.5 keeps code-word bits >= 8, then the
+//     rbsp stop bit, i.e. T_end + 2 bits in total.
+// =============================================================================================
+// per-bin record left by the context-state resolver: bit 0 = isLPS (regular) or value (bypass / terminate),
+// bit 1 bypass, bit 2 terminate, bits 3..8 pStateIdx of the bin's context when it is coded
+enum { META_LPS = 1, META_BYPASS = 2, META_TERM = 4 };
+HD uint16_t cabac_meta(uint16_t bin, uint32_t pre_state)
+{
+    uint32_t special = (bin >> 10) & 3, v = (bin >> 15) & 1;
+    return (uint16_t)(special ? (v | (special << 1)) : ((v ^ (pre_state & 1)) | ((pre_state >> 1) << 3)));
+}
+HD bool cabac_meta_is_lps(uint32_t m) { return (m & 7) == META_LPS; }
+HD uint32_t byte_of(uint32_t w, uint32_t q)
+{
+#ifdef __CUDACC__
+    return __byte_perm(w, 0, 0x4440u | q);
+#else
+    return (w >> (q * 8)) & 0xff;
+#endif
+}
+// range entering the bin after an LPS bin of state `st` that was coded with range quantiser index q
+HD uint32_t cabac_range_after_lps(uint32_t lps4, uint32_t shw, uint32_t q) { return byte_of(lps4, q) << ((shw >> (3 * q)) & 7); }
+
+// One step of the range recurrence: new range, the value added to the code word (after `pre1` bits and before
+// `sh` more bits are shifted out).  lps4 / shw = CabacTables rows of the bin's state (ignored for bypass /
+// terminate).  Branch-free on the regular path.
+HD void cabac_rstep(uint32_t &range, uint32_t m, uint32_t lps4, uint32_t shw, uint32_t &add, uint32_t &pre1, uint32_t &sh)
+{
+    const uint32_t q = (range >> 6) & 3, lps = byte_of(lps4, q), rm = range - lps;
+    const uint32_t sh_m = (rm >> 8) ^ 1, sh_l = (shw >> (3 * q)) & 7;
+    const bool v = m & 1;
+    uint32_t nr = v ? (lps << sh_l) : (rm << sh_m);
+    add = v ? rm : 0;
+    sh = v ? sh_l : sh_m;
+    pre1 = 0;
+    if (m & (META_BYPASS | META_TERM)) {
+        if (m & META_BYPASS) { // low = (low << 1) + (bin ? range : 0)
+            nr = range;
+            add = v ? range : 0;
+            pre1 = 1;
+            sh = 0;
+        } else { // terminate: range -= 2; value 1 ends the slice (low += range; range = 2; renorm by 7)
+            const uint32_t r2 = range - 2, s2 = (r2 >> 8) ^ 1;
+            nr = v ? 256u : (r2 << s2);
+            add = v ? r2 : 0;
+            sh = v ? 7u : s2;
+        }
+    }
+    range = nr;
+}
+
+// Chunk summary for the scan: hypothesis h -> q at the closing LPS bin (2 bits each in qmap) and the bits the
+// chunk shifts out under hypothesis h.  Identity = an absent chunk.
+struct ChunkMap {
+    uint32_t qmap;
+    uint32_t s[4];
+};
+HD ChunkMap chunkmap_identity()
+{
+    ChunkMap m;
+    m.qmap = 0xe4; // 3,2,1,0
+    m.s[0] = m.s[1] = m.s[2] = m.s[3] = 0;
+    return m;
+}
+HD uint32_t sel4(const uint32_t *v, uint32_t q) { return q & 2 ? (q & 1 ? v[3] : v[2]) : (q & 1 ? v[1] : v[0]); }
+// a then b
+HD ChunkMap chunkmap_compose(const ChunkMap &a, const ChunkMap &b)
+{
+    ChunkMap c;
+    c.qmap = 0;
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        uint32_t qa = (a.qmap >> (2 * h)) & 3;
+        c.qmap |= ((b.qmap >> (2 * qa)) & 3) << (2 * h);
+        c.s[h] = a.s[h] + sel4(b.s, qa);
+    }
+    return c;
+}
+
+// Adds the 9-bit value `add` at stream bit position P (its MSB lands on bit P) into 16-bit limbs held in
+// 32-bit words: limb j covers stream bits [16 j, 16 j + 16), bit 16 j is the limb's bit 15.
+template <class A> HD void limb_add(A &&adder, unsigned long long P, uint32_t add)
+{
+    unsigned long long j = P >> 4;
+    uint32_t off = (uint32_t)P & 15;
+    if (off <= 7)
+        adder(j, add << (7 - off));
+    else {
+        adder(j, add >> (off - 7));
+        adder(j + 1, (add & ((1u << (off - 7)) - 1)) << (23 - off));
+    }
+}
+
 // Emulation prevention: an escape byte 0x03 goes before byte i iff byte i <= 3 and the run of zero
 // bytes directly before it has an even length >= 2 (equivalent to the sequential rule
 // "after 00 00 insert 03 if the next byte <= 3, then restart counting").

@@ -1139,6 +1139,8 @@ struct EntropyBufs {
     unsigned long long *bins_cursor; // pool bump pointer
     unsigned long long *bins_off;    // [U]
     uint32_t *bins_len;      // [U]
+    uint32_t *limbs;         // [U][limb_cap] code-word limbs of the CABAC coder (16 stream bits per 32-bit word)
+    unsigned long long limb_cap;
     int *error;              // sticky overflow flag
 };
 
@@ -1305,158 +1307,347 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
     }
 }
 
-// K7 CABAC arithmetic coding: one CTA (three warps) per frame (one slice per picture, cedar.c:992-993),
-// software pipelined over tiles of CABAC_TILE bins, the three stages running at the same time on different
-// warps (entropy.cuh explains the split):
-//   warp 0  tile i    context-state resolution, 32 bins at a time: __match_any_sync groups the lanes whose
-//                     bins share a context; round r lets the r-th bin of every group read / advance its
-//                     context state in shared memory (distinct contexts inside a round => no conflicts),
-//                     which yields the state each bin is coded in;
-//   warp 1  tile i-1  range recurrence (lane 0; all lanes stage 32 bins at a time) -> interval steps;
-//   warp 2  tile i-2  low recurrence + byte output with carry propagation (lane 0).
-// Only the two short recurrences are serial (about a dozen dependent integer instructions per bin each).
-// Runs on side streams so that it overlaps the reconstruction of the following frames.
-#define CABAC_TILE 2048
-#define CABAC_THREADS 96
-__global__ void __launch_bounds__(CABAC_THREADS) cabac_kernel(Geom g, Step s, int gop_len, int gop_pos0, EntropyBufs eb)
+// K7 CABAC arithmetic coding, one slice per CTA (one slice per picture in the reference's layout,
+// cedar.c:992-993), in two kernels; entropy.cuh derives the parallel formulation.
+//
+// cabac_resolve_kernel: context-state resolution.  The state a regular bin is coded in depends only on the
+// earlier bins of the same context, so the contexts are split over RES_WARPS warps (ctxIdx mod RES_WARPS);
+// every warp walks the slice's bins 32 at a time, __match_any_sync groups the lanes of its own bins by
+// context and round r lets the r-th bin of every group read / advance its context state in shared memory
+// (distinct contexts inside a round => no conflicts).  Rewrites the bin stream in place as per-bin records
+// (cabac_meta: isLPS / bypass / terminate + pStateIdx).  This is the only stage that is serial along the
+// slice; it runs at a few cycles per bin.
+#define RES_WARPS 8
+#define RES_TILE 2048
+__global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0,
+                                                                       EntropyBufs eb)
 {
-    __shared__ CabacTables tab;
-    __shared__ uint16_t binsT[3][CABAC_TILE];
-    __shared__ uint8_t preT[2][CABAC_TILE];
-    __shared__ uint32_t stepT[2][CABAC_TILE];
-    __shared__ uint2 stage[32];
+    __shared__ uint16_t tile[RES_TILE], mtile[RES_TILE];
+    __shared__ uint16_t trans[128];
     __shared__ uint8_t ctx_state[464];
     const int f = lane_frame(s, blockIdx.x / g.nslices); // one CTA per slice
     if (f < 0)
         return;
     const size_t u = (size_t)f * g.nslices + blockIdx.x % g.nslices;
+    const uint32_t nb = eb.bins_len[u];
+    if (nb == 0)
+        return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int frame_i = ((gop_pos0 + f) % gop_len) == 0;
-    const uint32_t nb = eb.bins_len[u];
+    uint16_t *gb = eb.bins + eb.bins_off[u];
+    for (int st = tid; st < 128; st += RES_WARPS * 32) {
+        int ps = st >> 1, mps = st & 1;
+        int after_mps = (h264_next_state_mps[ps] << 1) | mps;
+        int after_lps = (h264_next_state_lps[ps] << 1) | (ps == 0 ? mps ^ 1 : mps);
+        trans[st] = (uint16_t)(after_mps | (after_lps << 8));
+    }
+    for (int i = tid; i < 460; i += RES_WARPS * 32)
+        ctx_state[i] = (uint8_t)cabac_init_state(i, frame_i, g.qp);
+    for (uint32_t base = 0; base < nb; base += RES_TILE) {
+        const uint32_t n = nb - base < RES_TILE ? nb - base : RES_TILE;
+        __syncthreads(); // tables ready / previous tile's records stored
+        for (uint32_t i = tid; i < n; i += RES_WARPS * 32)
+            tile[i] = gb[base + i];
+        __syncthreads();
+        for (uint32_t k0 = 0; k0 < n; k0 += 32) {
+            const bool live = k0 + lane < n;
+            const uint32_t b = live ? tile[k0 + lane] : (uint32_t)BIN_BYPASS;
+            const bool reg = !(b & (BIN_BYPASS | BIN_TERM));
+            const uint32_t c = b & 0x3ff;
+            const bool mine = reg && (int)(c & (RES_WARPS - 1)) == warp;
+            if (warp == 0 && live && !reg)
+                mtile[k0 + lane] = cabac_meta((uint16_t)b, 0);
+            if (!__any_sync(0xffffffffu, mine))
+                continue;
+            const uint32_t grp = __match_any_sync(0xffffffffu, mine ? c : 1024u + lane);
+            const int rank = __popc(grp & ((1u << lane) - 1));
+            const int rounds = __reduce_max_sync(0xffffffffu, mine ? rank : 0);
+            uint32_t st = 0;
+            for (int r = 0; r <= rounds; r++) {
+                if (mine && rank == r) {
+                    st = ctx_state[c];
+                    const uint32_t tr = trans[st];
+                    ctx_state[c] = (uint8_t)((((b >> 15) & 1) != (st & 1)) ? (tr >> 8) : (tr & 0xff));
+                }
+                __syncwarp();
+            }
+            if (mine)
+                mtile[k0 + lane] = cabac_meta((uint16_t)b, st);
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += RES_WARPS * 32)
+            gb[base + i] = mtile[i];
+    }
+}
+
+// cabac_code_kernel: the arithmetic coder proper, all bins of the slice in parallel (entropy.cuh, "parallel
+// formulation").  Per tile of CP_THREADS chunks x CP_K bins: stage the records in shared memory; find the
+// chunk starts (right after the first LPS bin of each CP_K-bin stretch); walk every chunk for the four
+// hypotheses; scan the chunk maps (warp 0); walk again with the true start range and add every bin's value
+// into the slice's limb array (global, red.add); finally one carry-lookahead pass over the limbs writes the
+// bytes.  CP_K = 62 bins = 31 words: the strided walks are bank-conflict free.
+#define CP_THREADS 128
+#define CP_K 62
+#define CP_TB (CP_THREADS * CP_K)
+__device__ __forceinline__ ChunkMap shfl_up_map(const ChunkMap &m, int off)
+{
+    ChunkMap o;
+    o.qmap = __shfl_up_sync(0xffffffffu, m.qmap, off);
+#pragma unroll
+    for (int h = 0; h < 4; h++)
+        o.s[h] = __shfl_up_sync(0xffffffffu, m.s[h], off);
+    return o;
+}
+
+__global__ void __launch_bounds__(CP_THREADS) cabac_code_kernel(Geom g, Step s, EntropyBufs eb)
+{
+    __shared__ uint16_t meta_s[CP_TB + CP_K + 2];
+    __shared__ uint2 rtab[64];
+    __shared__ int start_s[CP_THREADS + 1];
+    __shared__ uint32_t qmap_s[CP_THREADS], shift_s[4][CP_THREADS], qin_s[CP_THREADS], pbase_s[CP_THREADS];
+    __shared__ uint32_t carry_q, carry_P, wg_s[CP_THREADS / 32], wp_s[CP_THREADS / 32], cin_s;
+    const int f = lane_frame(s, blockIdx.x / g.nslices);
+    if (f < 0)
+        return;
+    const size_t u = (size_t)f * g.nslices + blockIdx.x % g.nslices;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nb = (int)eb.bins_len[u];
     if (nb == 0) {
         if (tid == 0)
             eb.rbsp_len[u] = 0;
         return;
     }
-    const uint16_t *gbins = eb.bins + eb.bins_off[u];
-    const int ntiles = (int)((nb + CABAC_TILE - 1) / CABAC_TILE);
-    tab.build(tid, CABAC_THREADS);
-    for (int i = tid; i < 460; i += CABAC_THREADS)
-        ctx_state[i] = (uint8_t)cabac_init_state(i, frame_i, g.qp);
-
-    // coder state
-    CabacRange rc;
-    CabacBytes cb;
+    const uint16_t *mg = eb.bins + eb.bins_off[u];
+    uint32_t *limbs = eb.limbs + u * eb.limb_cap;
     uint8_t *out = eb.rbsp + u * eb.rbsp_cap;
     const int hn = eb.hdr_nbits[u], hb = (hn + 7) >> 3;
-    cb.out = out + hb;
-    const unsigned limit = eb.rbsp_cap - hb - 64;
-    bool overflow = false;
     if (tid == 64) { // header bits, then cabac_alignment_one_bit up to the byte boundary
         unsigned long long h = (eb.hdr_bits[u] << (hb * 8 - hn)) | ((1ull << (hb * 8 - hn)) - 1);
         for (int i = 0; i < hb; i++)
             out[i] = (uint8_t)(h >> (8 * (hb - 1 - i)));
     }
-    // resolver prefetch: the first chunk of 32 bins
-    uint32_t nx = (warp == 0 && (uint32_t)lane < nb) ? gbins[lane] : 0;
-    __syncthreads();
-
-    for (int it = 0; it < ntiles + 2; it++) {
+    if (tid < 64) {
+        uint32_t w = 0, sh = 0;
+        for (int q = 0; q < 4; q++) {
+            uint32_t lps = h264_range_lps[tid][q];
+            w |= lps << (8 * q);
+            sh |= (uint32_t)(8 - ilog2_(lps)) << (3 * q);
+        }
+        rtab[tid] = make_uint2(w, sh);
+    }
+    if (tid == 0)
+        carry_q = 0, carry_P = 0;
+    int prev_hi = -1; // limbs [0, prev_hi] are initialised (uniform over the CTA)
+    bool overflow = false;
+    const int ntiles = (nb + CP_TB - 1) / CP_TB;
+    for (int tile = 0; tile < ntiles; tile++) {
+        const int lo = tile * CP_TB, n_load = imin_(CP_TB + CP_K, nb - lo);
+        __syncthreads();
+        for (int i = tid; i < n_load; i += CP_THREADS)
+            meta_s[i] = mg[lo + i];
+        __syncthreads();
+        auto M = [&](int i) -> uint32_t { return i - lo < n_load ? meta_s[i - lo] : mg[i]; };
+        // ---- chunk starts; entry CP_THREADS = first chunk start of the tiles that follow (or nb) ----
+        for (int c = tid; c <= CP_THREADS; c += CP_THREADS) {
+            const int lo_c = lo + c * CP_K;
+            int st = -1;
+            if (tile == 0 && c == 0)
+                st = 0;
+            else if (lo_c < nb) {
+                const int hi_c = imin_(nb, lo_c + CP_K);
+                for (int i = lo_c; i < hi_c; i++)
+                    if (cabac_meta_is_lps(meta_s[i - lo])) {
+                        st = i + 1 < nb ? i + 1 : -1;
+                        break;
+                    }
+                if (c == CP_THREADS && st < 0) // rare: no LPS bin in the look-ahead stretch
+                    for (int i = hi_c; i < nb; i++)
+                        if (cabac_meta_is_lps(mg[i])) {
+                            st = i + 1;
+                            break;
+                        }
+            }
+            if (c == CP_THREADS && (st < 0 || st > nb))
+                st = nb;
+            start_s[c] = st;
+        }
+        __syncthreads();
+        const int st = start_s[tid];
+        const bool valid = st >= 0;
+        int en = nb;
+        if (valid) {
+            int c = tid + 1;
+            while (start_s[c] < 0)
+                c++;
+            en = start_s[c];
+        }
+        const bool last_tile = start_s[CP_THREADS] >= nb;
+        if (!__syncthreads_or(valid))
+            continue;
+        // ---- pass 1: the four hypotheses ----
+        uint32_t lps4_0 = 0, shw_0 = 0; // table row of the LPS bin in front of the chunk
+        {
+            ChunkMap m = chunkmap_identity();
+            if (valid) {
+                uint32_t r[4] = {510, 510, 510, 510};
+                if (st > 0) {
+                    const uint2 t0 = rtab[(M(st - 1) >> 3) & 63];
+                    lps4_0 = t0.x, shw_0 = t0.y;
+#pragma unroll
+                    for (int h = 0; h < 4; h++)
+                        r[h] = cabac_range_after_lps(lps4_0, shw_0, h);
+                }
+                m.qmap = 0;
+                const bool closing = en < nb; // bin en - 1 is the LPS bin in front of the next chunk
+                const int stop = closing ? en - 1 : en;
+                for (int i = st; i < stop; i++) {
+                    const uint32_t mm = M(i);
+                    const uint2 t = rtab[(mm >> 3) & 63];
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        uint32_t add, pre1, sh;
+                        cabac_rstep(r[h], mm, t.x, t.y, add, pre1, sh);
+                        m.s[h] += pre1 + sh;
+                    }
+                }
+                if (closing) {
+                    const uint2 t = rtab[(M(en - 1) >> 3) & 63];
+#pragma unroll
+                    for (int h = 0; h < 4; h++) {
+                        const uint32_t q = (r[h] >> 6) & 3;
+                        m.qmap |= q << (2 * h);
+                        m.s[h] += (t.y >> (3 * q)) & 7;
+                    }
+                }
+            }
+            qmap_s[tid] = m.qmap;
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+                shift_s[h][tid] = m.s[h];
+        }
+        __syncthreads();
+        // ---- scan of the chunk maps: true hypothesis and stream position of every chunk ----
         if (warp == 0) {
-            if (it < ntiles) {
-                const uint32_t base = (uint32_t)it * CABAC_TILE;
-                const uint32_t n = nb - base < CABAC_TILE ? nb - base : CABAC_TILE;
-                uint16_t *tile = binsT[it % 3];
-                uint8_t *ptile = preT[it & 1];
-                for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-                    const uint32_t b = nx;
-                    const uint32_t nidx = base + k0 + 32 + lane;
-                    if (nidx < nb) // prefetch the next chunk (possibly the next tile's first)
-                        nx = gbins[nidx];
-                    const bool live = k0 + lane < n;
-                    const bool reg = live && !(b & (BIN_BYPASS | BIN_TERM));
-                    const uint32_t c = b & 0x3ff;
-                    const uint32_t grp = __match_any_sync(0xffffffffu, reg ? c : 1024u + lane);
-                    const int rank = __popc(grp & ((1u << lane) - 1));
-                    const int rounds = __reduce_max_sync(0xffffffffu, reg ? rank : 0);
-                    uint32_t st = 0;
-                    for (int r = 0; r <= rounds; r++) {
-                        if (reg && rank == r) {
-                            st = ctx_state[c];
-                            ctx_state[c] = (uint8_t)cabac_next_state(tab, st, (b >> 15) & 1);
-                        }
-                        __syncwarp();
-                    }
-                    if (live) {
-                        tile[k0 + lane] = (uint16_t)b;
-                        ptile[k0 + lane] = (uint8_t)st;
-                    }
-                }
+            ChunkMap loc[CP_THREADS / 32], run = chunkmap_identity();
+#pragma unroll
+            for (int j = 0; j < CP_THREADS / 32; j++) {
+                const int k = lane * (CP_THREADS / 32) + j;
+                ChunkMap m;
+                m.qmap = qmap_s[k];
+#pragma unroll
+                for (int h = 0; h < 4; h++)
+                    m.s[h] = shift_s[h][k];
+                loc[j] = run;
+                run = chunkmap_compose(run, m);
             }
-        } else if (warp == 1) {
-            const int t = it - 1;
-            if (t >= 0 && t < ntiles) {
-                const uint32_t base = (uint32_t)t * CABAC_TILE;
-                const uint32_t n = nb - base < CABAC_TILE ? nb - base : CABAC_TILE;
-                const uint16_t *tb = binsT[t % 3];
-                const uint8_t *ptile = preT[t & 1];
-                uint32_t *steps = stepT[t & 1];
-                for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-                    const uint32_t ps = ptile[k0 + lane];
-                    stage[lane] = make_uint2(tab.lpsw[(ps >> 1) & 63], cabac_stage_meta(tb[k0 + lane], ps, tab));
-                    __syncwarp();
-                    if (lane == 0) {
-                        const int cnt = n - k0 < 32 ? (int)(n - k0) : 32;
-                        uint32_t range = rc.range;
-                        if (cnt == 32) {
-#pragma unroll 8
-                            for (int k = 0; k < 32; k++) {
-                                const uint2 e = stage[k];
-                                steps[k0 + k] = cabac_range_step_flat(range, e.x, e.y);
-                            }
-                        } else {
-#pragma unroll 1
-                            for (int k = 0; k < cnt; k++) {
-                                const uint2 e = stage[k];
-                                steps[k0 + k] = cabac_range_step_flat(range, e.x, e.y);
-                            }
-                        }
-                        rc.range = range;
-                    }
-                    __syncwarp();
-                }
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                ChunkMap o = shfl_up_map(run, off);
+                if (lane >= off)
+                    run = chunkmap_compose(o, run);
             }
-        } else {
-            const int t = it - 2;
-            if (t >= 0 && t < ntiles && lane == 0 && !overflow) {
-                const uint32_t base = (uint32_t)t * CABAC_TILE;
-                const int n = nb - base < CABAC_TILE ? (int)(nb - base) : CABAC_TILE;
-                const uint32_t *steps = stepT[t & 1];
-                const int nfast = (t == ntiles - 1) ? n - 1 : n; // the slice's last step carries the flush
-                int k = 0;
-                for (; k + 4 <= nfast; k += 4) {
-                    const uint4 e = *(const uint4 *)(steps + k);
-                    cb.step_fast(e.x);
-                    cb.step_fast(e.y);
-                    cb.step_fast(e.z);
-                    cb.step_fast(e.w);
-                }
-                for (; k < nfast; k++)
-                    cb.step_fast(steps[k]);
-                if (nfast < n)
-                    cb.step(steps[n - 1]);
-                overflow = cb.pos + cb.outstanding > limit;
+            ChunkMap ex = shfl_up_map(run, 1);
+            if (lane == 0)
+                ex = chunkmap_identity();
+            const uint32_t cq = carry_q, cP = carry_P;
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < CP_THREADS / 32; j++) {
+                const int k = lane * (CP_THREADS / 32) + j;
+                const ChunkMap e = chunkmap_compose(ex, loc[j]);
+                qin_s[k] = (e.qmap >> (2 * cq)) & 3;
+                pbase_s[k] = cP + sel4(e.s, cq);
+            }
+            if (lane == 31) {
+                carry_q = (run.qmap >> (2 * cq)) & 3;
+                carry_P = cP + sel4(run.s, cq);
             }
         }
         __syncthreads();
+        // ---- initialise the limbs this tile reaches ----
+        const int hi = (int)((carry_P + 8) >> 4);
+        if ((unsigned long long)hi + 2 > eb.limb_cap)
+            overflow = true;
+        if (overflow)
+            break;
+        for (int j = prev_hi + 1 + tid; j <= hi; j += CP_THREADS)
+            limbs[j] = 0;
+        prev_hi = hi;
+        __threadfence();
+        __syncthreads();
+        // ---- pass 2: the true walk; every bin adds its value into the limbs ----
+        if (valid) {
+            uint32_t range = st > 0 ? cabac_range_after_lps(lps4_0, shw_0, qin_s[tid]) : 510u;
+            uint32_t P = pbase_s[tid];
+            auto adder = [&](unsigned long long j, uint32_t v) { atomicAdd(limbs + j, v); };
+            for (int i = st; i < en; i++) {
+                const uint32_t mm = M(i);
+                const uint2 t = rtab[(mm >> 3) & 63];
+                uint32_t add, pre1, sh;
+                cabac_rstep(range, mm, t.x, t.y, add, pre1, sh);
+                P += pre1;
+                if (add)
+                    limb_add(adder, P, add);
+                P += sh;
+            }
+        }
+        if (last_tile)
+            break;
     }
-    if (tid == 64) {
-        if (overflow) {
+    __threadfence();
+    __syncthreads();
+    // ---- carry-lookahead over the limbs (from the end of the stream to its start), stop bit, bytes ----
+    const uint32_t T_end = carry_P;
+    const uint32_t nbytes = (T_end + 2 + 7) >> 3;
+    if (!overflow && (unsigned long long)hb + nbytes + 64 > eb.rbsp_cap)
+        overflow = true;
+    if (overflow) {
+        if (tid == 0) {
             atomicExch(eb.error, 3);
             eb.rbsp_len[u] = 0;
-        } else
-            eb.rbsp_len[u] = (uint32_t)(hb + cb.pos);
+        }
+        return;
     }
+    const int NL = prev_hi + 1;
+    const uint32_t sb = T_end + 1; // stream position of the rbsp stop bit
+    if (tid == 0)
+        cin_s = 0;
+    __syncthreads();
+    for (int j0 = ((NL - 1) / CP_THREADS) * CP_THREADS; j0 >= 0; j0 -= CP_THREADS) {
+        const int j = j0 + tid;
+        const uint32_t x = j < NL ? __ldcg(limbs + j) : 0, xn = j + 1 < NL ? __ldcg(limbs + j + 1) : 0;
+        const uint32_t w = (x & 0xffff) + (xn >> 16); // <= 0xffff + 24: single-bit carries from here on
+        // lane with the higher limb index = less significant: bit 31 - lane, so carries run up an integer add
+        const uint32_t G = __brev(__ballot_sync(0xffffffffu, (w >> 16) != 0));
+        const uint32_t Pm = __brev(__ballot_sync(0xffffffffu, (w & 0xffff) == 0xffff));
+        if (lane == 0) {
+            wg_s[warp] = (uint32_t)(((unsigned long long)(G | Pm) + G) >> 32);
+            wp_s[warp] = Pm == 0xffffffffu;
+        }
+        __syncthreads();
+        uint32_t c = cin_s;
+        for (int w2 = CP_THREADS / 32 - 1; w2 > warp; w2--)
+            c = wg_s[w2] | (wp_s[w2] & c);
+        const unsigned long long sum = (unsigned long long)(G | Pm) + G + c;
+        const uint32_t C = (G | Pm) ^ G ^ (uint32_t)sum; // carry into every bit
+        uint32_t o = (w + ((C >> (31 - lane)) & 1)) & 0xffff;
+        __syncthreads();
+        if (tid == 0)
+            cin_s = (uint32_t)(sum >> 32);
+        // 9.3.4.5 flush: code-word bits below the stop bit are dropped, the stop bit is set
+        if ((uint32_t)j > (sb >> 4))
+            o = 0;
+        else if ((uint32_t)j == (sb >> 4)) {
+            const uint32_t k2 = sb & 15;
+            o = (o & ~((1u << (16 - k2)) - 1)) | (1u << (15 - k2));
+        }
+        if (2u * j < nbytes)
+            out[hb + 2 * j] = (uint8_t)(o >> 8);
+        if (2u * j + 1 < nbytes)
+            out[hb + 2 * j + 1] = (uint8_t)o;
+    }
+    if (tid == 0)
+        eb.rbsp_len[u] = hb + nbytes;
 }
 
 // ================================================================================================

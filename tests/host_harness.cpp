@@ -5,6 +5,7 @@
 // It is not linked into the product library and does not link the oracle.
 #include "../cedarx_h264_encoder_b200/csrc/entropy.cuh"
 
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -65,7 +66,7 @@ long hh_cavlc_slice(const void *mbi, const uint8_t *nnz, const int16_t *coef, in
 }
 
 long hh_cabac_slice(const void *mbi, const uint8_t *nnz, const int16_t *coef, int mbw, int mbh, int srows, int slice,
-                    int frame_i, int qp, uint64_t hdr_bits, int hdr_nbits, uint8_t *out, long cap)
+                    int frame_i, int qp, uint64_t hdr_bits, int hdr_nbits, uint8_t *out, long cap, int chunk_bins)
 {
     FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh, srows};
     const int row0 = slice * srows, row1 = row0 + srows < mbh ? row0 + srows : mbh;
@@ -111,10 +112,11 @@ long hh_cabac_slice(const void *mbi, const uint8_t *nnz, const int16_t *coef, in
         uint32_t lps4 = tab.lpsw[(pre[i] >> 1) & 63], meta = cabac_stage_meta(bins[i], pre[i], tab);
         steps[i] = rc.step(lps4, meta);
         if (cabac_range_step_flat(flat_range, lps4, meta) != steps[i] || (flat_range != rc.range && i + 1 < total))
-            return -2; // the branch-free variant the GPU uses must agree step by step
+            return -2; // the branch-free variant must agree step by step
     }
     CabacBytes c;
-    c.out = out + hb;
+    std::vector<uint8_t> serial_out(cap + 16);
+    c.out = serial_out.data();
     for (size_t i = 0; i < total; i++) {
         if ((long)(hb + c.pos + 8) > cap)
             return -1;
@@ -122,6 +124,137 @@ long hh_cabac_slice(const void *mbi, const uint8_t *nnz, const int16_t *coef, in
             c.step_fast(steps[i]);
         else
             c.step(steps[i]);
+    }
+    // ---- the parallel formulation the GPU runs (cabac_code_kernel), emulated chunk by chunk ----
+    const long nb = (long)total;
+    std::vector<uint16_t> meta(total + 1);
+    for (long i = 0; i < nb; i++)
+        meta[i] = cabac_meta(bins[i], pre[i]);
+    const int K = chunk_bins > 0 ? chunk_bins : 62;
+    const long nchunks = (nb + K - 1) / K;
+    std::vector<long> start(nchunks + 1, -1);
+    for (long k = 0; k < nchunks; k++) {
+        if (k == 0) {
+            start[0] = 0;
+            continue;
+        }
+        for (long i = k * K; i < std::min(nb, (k + 1) * K); i++)
+            if (cabac_meta_is_lps(meta[i])) {
+                start[k] = i + 1 < nb ? i + 1 : -1; // an LPS in the very last position opens no chunk
+                break;
+            }
+    }
+    start[nchunks] = nb;
+    auto next_start = [&](long k) {
+        for (long j = k + 1; j <= nchunks; j++)
+            if (start[j] >= 0)
+                return start[j];
+        return nb;
+    };
+    // pass 1: four hypotheses per chunk
+    std::vector<ChunkMap> maps(nchunks, chunkmap_identity());
+    for (long k = 0; k < nchunks; k++) {
+        if (start[k] < 0)
+            continue;
+        long st = start[k], en = next_start(k);
+        uint32_t r[4];
+        ChunkMap m;
+        m.qmap = 0;
+        for (int h = 0; h < 4; h++) {
+            m.s[h] = 0;
+            if (st == 0)
+                r[h] = 510;
+            else {
+                uint32_t ps = (meta[st - 1] >> 3) & 63;
+                r[h] = cabac_range_after_lps(tab.lpsw[ps], tab.shw[ps], h);
+            }
+        }
+        const bool closing_lps = en < nb; // bin en - 1 is the LPS bin that opens the next chunk
+        for (long i = st; i < (closing_lps ? en - 1 : en); i++) {
+            uint32_t ps = (meta[i] >> 3) & 63;
+            for (int h = 0; h < 4; h++) {
+                uint32_t add, pre1, sh;
+                cabac_rstep(r[h], meta[i], tab.lpsw[ps], tab.shw[ps], add, pre1, sh);
+                m.s[h] += pre1 + sh;
+            }
+        }
+        if (closing_lps) {
+            uint32_t ps = (meta[en - 1] >> 3) & 63;
+            if (!cabac_meta_is_lps(meta[en - 1]))
+                return -4;
+            for (int h = 0; h < 4; h++) {
+                uint32_t q = (r[h] >> 6) & 3;
+                m.qmap |= q << (2 * h);
+                m.s[h] += (tab.shw[ps] >> (3 * q)) & 7;
+            }
+        }
+        maps[k] = m;
+    }
+    // scan (sequential here): true hypothesis and stream position of every chunk
+    std::vector<uint32_t> qin(nchunks, 0);
+    std::vector<unsigned long long> pbase(nchunks, 0);
+    ChunkMap acc = chunkmap_identity();
+    for (long k = 0; k < nchunks; k++) {
+        qin[k] = acc.qmap & 3; // hypothesis 0 of the running composition: chunk 0 ignores its input
+        pbase[k] = acc.s[0];
+        acc = chunkmap_compose(acc, maps[k]);
+    }
+    const unsigned long long T_end = acc.s[0];
+    // pass 2: true walk + limb accumulation
+    std::vector<uint32_t> limbs((T_end + 8) / 16 + 3, 0);
+    auto adder = [&](unsigned long long j, uint32_t v) { limbs[j] += v; };
+    for (long k = nchunks - 1; k >= 0; k--) { // any order
+        if (start[k] < 0)
+            continue;
+        long st = start[k], en = next_start(k);
+        uint32_t range = 510;
+        if (st > 0) {
+            uint32_t ps = (meta[st - 1] >> 3) & 63;
+            range = cabac_range_after_lps(tab.lpsw[ps], tab.shw[ps], qin[k]);
+        }
+        unsigned long long P = pbase[k];
+        for (long i = st; i < en; i++) {
+            uint32_t ps = (meta[i] >> 3) & 63, add, pre1, sh;
+            cabac_rstep(range, meta[i], tab.lpsw[ps], tab.shw[ps], add, pre1, sh);
+            P += pre1;
+            if (add)
+                limb_add(adder, P, add);
+            P += sh;
+        }
+        if (P != (k + 1 < nchunks ? [&] { for (long j = k + 1; j < nchunks; j++) if (start[j] >= 0) return pbase[j]; return T_end; }() : T_end))
+            return -5;
+    }
+    // carry resolution (two-step, as the kernel does it) + stop bit
+    const long NL = (long)((T_end + 8) >> 4) + 1;
+    std::vector<uint32_t> w(NL + 1, 0);
+    for (long j = 0; j < NL; j++)
+        w[j] = (limbs[j] & 0xffff) + (limbs[j + 1] >> 16);
+    uint32_t carry = 0;
+    std::vector<uint16_t> o16(NL);
+    for (long j = NL - 1; j >= 0; j--) {
+        uint32_t v = w[j] + carry;
+        o16[j] = (uint16_t)v;
+        carry = v >> 16;
+    }
+    if (carry)
+        return -6;
+    const unsigned long long sb = T_end + 1; // stream position of the stop bit
+    const long nbytes = (long)((T_end + 2 + 7) >> 3);
+    for (long j = 0; j < NL; j++) {
+        if ((unsigned long long)j > (sb >> 4))
+            o16[j] = 0;
+        else if ((unsigned long long)j == (sb >> 4)) {
+            uint32_t k2 = (uint32_t)sb & 15;
+            o16[j] = (uint16_t)((o16[j] & ~((1u << (16 - k2)) - 1)) | (1u << (15 - k2)));
+        }
+    }
+    if (nbytes != (long)c.pos)
+        return -7;
+    for (long i = 0; i < nbytes; i++) {
+        uint8_t v = (uint8_t)(i & 1 ? o16[i >> 1] & 0xff : o16[i >> 1] >> 8);
+        if (v != serial_out[i])
+            return -8;
+        out[hb + i] = v;
     }
     return hb + (long)c.pos;
 }

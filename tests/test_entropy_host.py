@@ -43,7 +43,7 @@ def test_entropy_logic_matches_oracle(oracle, harness, kind, qp, rows, cabac):
             out = np.zeros(len(payload) * 2 + 4096, np.uint8)
             if cabac:
                 n = harness.hh_cabac_slice(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, mbw, mbh, srows, k, fi, qp,
-                                           int(bits, 2), len(bits), out.ctypes.data, out.size)
+                                           int(bits, 2), len(bits), out.ctypes.data, out.size, [62, 7, 1000][t % 3])
             else:
                 n = harness.hh_cavlc_slice(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, mbw, mbh, srows, k, fi,
                                            int(bits, 2), len(bits), out.ctypes.data, out.size)

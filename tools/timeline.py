@@ -44,7 +44,7 @@ for name, a, b in rows:
     d[0] = min(d[0], a); d[1] = max(d[1], b); d[2] += 1; d[3] += b - a
 for k, v in agg.items():
     print("%-24s first start %8.2f  last end %8.2f  n %4d  sum %9.2f" % (k, v[0], v[1], v[2], v[3]))
-side = [(float(a), float(b)) for nme, a, b in rows if nme == "cabac_kernel"]
+side = [(float(a), float(b)) for nme, a, b in rows if nme in ("cabac_kernel", "cabac_resolve_kernel", "cabac_code_kernel")]
 print("cabac (start,end) first 6:", [(round(a, 1), round(b, 1)) for a, b in side[:6]], "last 4:", [(round(a, 1), round(b, 1)) for a, b in side[-4:]])
 me = [(float(a), float(b)) for nme, a, b in rows if nme == "me_kernel"]
 print("me first 4:", [(round(a, 1), round(b, 1)) for a, b in me[:4]], "last 2:", [(round(a, 1), round(b, 1)) for a, b in me[-2:]])
