@@ -328,7 +328,7 @@ int alloc_buffers(cedar_b200_handle *h)
     r |= dmalloc(&h->eb.rbsp_len, U);
     h->eb.limb_cap = h->eb.rbsp_cap / 2 + 8;
     if (g.cabac) {
-        r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap);
+        r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap + 64); // + slack: 16-byte vector loads round outwards
         r |= dmalloc(&h->eb.limbs, (size_t)h->eb.limb_cap * U);
     }
     r |= dmalloc(&h->eb.bins_cursor, 1);
@@ -438,7 +438,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         cudaStream_t side = no_overlap ? st : h->stream_cabac[h->side_next];
         CK(cudaStreamWaitEvent(side, h->ev_post[p], 0));
         LAUNCH_ON(side, K_CRESOLVE, cabac_resolve_kernel, nl * g.nslices, RES_WARPS * 32, 0, g, s, h->K, gop_pos0, h->eb);
-        LAUNCH_ON(side, K_CCODE, cabac_code_kernel, nl * g.nslices, CP_THREADS, 0, g, s, h->eb);
+        LAUNCH_ON(side, K_CCODE, cabac_code_kernel, nl * g.nslices, CP_THREADS, CP_SMEM_BYTES, g, s, h->eb);
         if (!no_overlap) {
             h->side_used |= 1u << h->side_next;
             h->side_next = (h->side_next + 1) % cedar_b200_handle::NSIDE;
@@ -625,6 +625,12 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
         ok = cudaStreamCreateWithPriority(&h->stream_cabac[i], cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
              cudaEventCreateWithFlags(&h->ev_cabac[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
+        delete h;
+        return -ENODEV;
+    }
+    if (cudaFuncSetAttribute(cabac_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES) != cudaSuccess) {
+        fprintf(stderr, "cedar_b200: cabac_code_kernel needs %d bytes of shared memory\n", CP_SMEM_BYTES);
+        cudaGetLastError();
         delete h;
         return -ENODEV;
     }

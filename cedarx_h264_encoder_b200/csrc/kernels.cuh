@@ -1317,14 +1317,14 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
 // (distinct contexts inside a round => no conflicts).  Rewrites the bin stream in place as per-bin records
 // (cabac_meta: isLPS / bypass / terminate + pStateIdx).  This is the only stage that is serial along the
 // slice; it runs at a few cycles per bin.
-#define RES_WARPS 8
-#define RES_TILE 2048
+#define RES_WARPS 16
+#define RES_TILE 4096
 __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0,
                                                                        EntropyBufs eb)
 {
-    __shared__ uint16_t tile[RES_TILE], mtile[RES_TILE];
+    __shared__ __align__(16) uint16_t tile[RES_TILE + 8], mtile[RES_TILE + 8];
     __shared__ uint16_t trans[128];
-    __shared__ uint8_t ctx_state[464];
+    __shared__ uint8_t ctx_state[464], tag[464];
     const int f = lane_frame(s, blockIdx.x / g.nslices); // one CTA per slice
     if (f < 0)
         return;
@@ -1335,6 +1335,8 @@ __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, S
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int frame_i = ((gop_pos0 + f) % gop_len) == 0;
     uint16_t *gb = eb.bins + eb.bins_off[u];
+    // 16-byte vector loads / stores: tile k starts at the aligned address at or below gb + k * RES_TILE
+    const uint32_t mis = (uint32_t)(((uintptr_t)gb >> 1) & 7); // elements between that address and the first bin
     for (int st = tid; st < 128; st += RES_WARPS * 32) {
         int ps = st >> 1, mps = st & 1;
         int after_mps = (h264_next_state_mps[ps] << 1) | mps;
@@ -1343,52 +1345,85 @@ __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, S
     }
     for (int i = tid; i < 460; i += RES_WARPS * 32)
         ctx_state[i] = (uint8_t)cabac_init_state(i, frame_i, g.qp);
+    auto advance = [&](uint32_t c, uint32_t b) -> uint32_t { // read and advance the state of context c for bin b
+        const uint32_t st = ctx_state[c], tr = trans[st];
+        ctx_state[c] = (uint8_t)((((b >> 15) & 1) != (st & 1)) ? (tr >> 8) : (tr & 0xff));
+        return st;
+    };
     for (uint32_t base = 0; base < nb; base += RES_TILE) {
         const uint32_t n = nb - base < RES_TILE ? nb - base : RES_TILE;
+        const uint16_t *src = gb + base - mis; // 16-byte aligned
+        const uint32_t nv = (mis + n + 7) >> 3;
         __syncthreads(); // tables ready / previous tile's records stored
-        for (uint32_t i = tid; i < n; i += RES_WARPS * 32)
-            tile[i] = gb[base + i];
+        for (uint32_t v = tid; v < nv; v += RES_WARPS * 32) {
+            // the first and the last vector may reach into a neighbouring slice's bins (same pool): read-only here
+            ((uint4 *)tile)[v] = ((const uint4 *)src)[v];
+        }
         __syncthreads();
         for (uint32_t k0 = 0; k0 < n; k0 += 32) {
             const bool live = k0 + lane < n;
-            const uint32_t b = live ? tile[k0 + lane] : (uint32_t)BIN_BYPASS;
+            const uint32_t b = live ? tile[mis + k0 + lane] : (uint32_t)BIN_BYPASS;
             const bool reg = !(b & (BIN_BYPASS | BIN_TERM));
             const uint32_t c = b & 0x3ff;
             const bool mine = reg && (int)(c & (RES_WARPS - 1)) == warp;
-            if (warp == 0 && live && !reg)
-                mtile[k0 + lane] = cabac_meta((uint16_t)b, 0);
-            if (!__any_sync(0xffffffffu, mine))
+            if (warp == (int)((k0 >> 5) & (RES_WARPS - 1)) && live && !reg)
+                mtile[mis + k0 + lane] = cabac_meta((uint16_t)b, 0);
+            const uint32_t own = __ballot_sync(0xffffffffu, mine);
+            if (!own)
                 continue;
-            const uint32_t grp = __match_any_sync(0xffffffffu, mine ? c : 1024u + lane);
-            const int rank = __popc(grp & ((1u << lane) - 1));
-            const int rounds = __reduce_max_sync(0xffffffffu, mine ? rank : 0);
             uint32_t st = 0;
-            for (int r = 0; r <= rounds; r++) {
-                if (mine && rank == r) {
-                    st = ctx_state[c];
-                    const uint32_t tr = trans[st];
-                    ctx_state[c] = (uint8_t)((((b >> 15) & 1) != (st & 1)) ? (tr >> 8) : (tr & 0xff));
-                }
+            if (!(own & (own - 1))) { // a single bin of this warp's contexts
+                if (mine)
+                    st = advance(c, b);
+            } else {
+                // Bins of one context must go in order.  Every lane tags its context with its lane index; a lane that
+                // reads back another lane's tag shares the context with it: those lanes (and the tag holders) go
+                // one by one in lane order, everybody else at once.
+                if (mine)
+                    tag[c] = (uint8_t)lane;
                 __syncwarp();
+                const uint32_t holder = mine ? tag[c] : lane;
+                const uint32_t lost = __ballot_sync(0xffffffffu, holder != (uint32_t)lane);
+                uint32_t conf = 0;
+                if (lost)
+                    conf = lost | __reduce_or_sync(0xffffffffu, holder != (uint32_t)lane ? (1u << holder) : 0u);
+                if (mine && !((conf >> lane) & 1))
+                    st = advance(c, b);
+                for (uint32_t m2 = conf; m2; m2 &= m2 - 1) {
+                    if (lane == __ffs(m2) - 1)
+                        st = advance(c, b);
+                    __syncwarp();
+                }
             }
             if (mine)
-                mtile[k0 + lane] = cabac_meta((uint16_t)b, st);
+                mtile[mis + k0 + lane] = cabac_meta((uint16_t)b, st);
         }
         __syncthreads();
-        for (uint32_t i = tid; i < n; i += RES_WARPS * 32)
-            gb[base + i] = mtile[i];
+        // records back in place of the bins; the partial vectors at both ends are written element-wise
+        uint16_t *dst = gb + base - mis;
+        for (uint32_t v = tid; v < nv; v += RES_WARPS * 32) {
+            const uint32_t e0 = v * 8;
+            if (e0 >= mis && e0 + 8 <= mis + n)
+                ((uint4 *)dst)[v] = ((const uint4 *)mtile)[v];
+            else
+                for (uint32_t e = e0 > mis ? e0 : mis; e < e0 + 8 && e < mis + n; e++)
+                    dst[e] = mtile[e];
+        }
     }
 }
 
 // cabac_code_kernel: the arithmetic coder proper, all bins of the slice in parallel (entropy.cuh, "parallel
 // formulation").  Per tile of CP_THREADS chunks x CP_K bins: stage the records in shared memory; find the
 // chunk starts (right after the first LPS bin of each CP_K-bin stretch); walk every chunk for the four
-// hypotheses; scan the chunk maps (warp 0); walk again with the true start range and add every bin's value
-// into the slice's limb array (global, red.add); finally one carry-lookahead pass over the limbs writes the
-// bytes.  CP_K = 62 bins = 31 words: the strided walks are bank-conflict free.
-#define CP_THREADS 128
+// hypotheses; scan the chunk maps; walk again with the true start range, every thread collecting its values in
+// two limb registers and adding them to the slice's limb array when it moves on (few global reductions);
+// finally one carry-lookahead pass over the limbs writes the bytes.  CP_K = 62 bins = 31 words: the strided
+// walks are bank-conflict free.  16 warps per CTA: both walks are latency bound per thread.
+#define CP_THREADS 512
+#define CP_WARPS (CP_THREADS / 32)
 #define CP_K 62
 #define CP_TB (CP_THREADS * CP_K)
+#define CP_SMEM_BYTES ((CP_TB + CP_K + 16) * 2)
 __device__ __forceinline__ ChunkMap shfl_up_map(const ChunkMap &m, int off)
 {
     ChunkMap o;
@@ -1401,11 +1436,11 @@ __device__ __forceinline__ ChunkMap shfl_up_map(const ChunkMap &m, int off)
 
 __global__ void __launch_bounds__(CP_THREADS) cabac_code_kernel(Geom g, Step s, EntropyBufs eb)
 {
-    __shared__ uint16_t meta_s[CP_TB + CP_K + 2];
+    extern __shared__ __align__(16) uint16_t meta_raw[]; // [CP_TB + CP_K + 16]
     __shared__ uint2 rtab[64];
     __shared__ int start_s[CP_THREADS + 1];
-    __shared__ uint32_t qmap_s[CP_THREADS], shift_s[4][CP_THREADS], qin_s[CP_THREADS], pbase_s[CP_THREADS];
-    __shared__ uint32_t carry_q, carry_P, wg_s[CP_THREADS / 32], wp_s[CP_THREADS / 32], cin_s;
+    __shared__ uint32_t wmap_s[CP_WARPS][5];
+    __shared__ uint32_t carry_q, carry_P, wg_s[CP_WARPS], wp_s[CP_WARPS], cin_s;
     const int f = lane_frame(s, blockIdx.x / g.nslices);
     if (f < 0)
         return;
@@ -1418,6 +1453,8 @@ __global__ void __launch_bounds__(CP_THREADS) cabac_code_kernel(Geom g, Step s, 
         return;
     }
     const uint16_t *mg = eb.bins + eb.bins_off[u];
+    const int mis = (int)(((uintptr_t)mg >> 1) & 7);
+    const uint16_t *meta_s = meta_raw + mis; // meta_s[i - lo] = record of bin i
     uint32_t *limbs = eb.limbs + u * eb.limb_cap;
     uint8_t *out = eb.rbsp + u * eb.rbsp_cap;
     const int hn = eb.hdr_nbits[u], hb = (hn + 7) >> 3;
@@ -1443,8 +1480,12 @@ __global__ void __launch_bounds__(CP_THREADS) cabac_code_kernel(Geom g, Step s, 
     for (int tile = 0; tile < ntiles; tile++) {
         const int lo = tile * CP_TB, n_load = imin_(CP_TB + CP_K, nb - lo);
         __syncthreads();
-        for (int i = tid; i < n_load; i += CP_THREADS)
-            meta_s[i] = mg[lo + i];
+        {
+            const uint4 *src = (const uint4 *)(mg + lo - mis); // 16-byte aligned; may start / end in a neighbour's bins
+            const int nv = (mis + n_load + 7) >> 3;
+            for (int v = tid; v < nv; v += CP_THREADS)
+                ((uint4 *)meta_raw)[v] = src[v];
+        }
         __syncthreads();
         auto M = [&](int i) -> uint32_t { return i - lo < n_load ? meta_s[i - lo] : mg[i]; };
         // ---- chunk starts; entry CP_THREADS = first chunk start of the tiles that follow (or nb) ----
@@ -1486,82 +1527,75 @@ __global__ void __launch_bounds__(CP_THREADS) cabac_code_kernel(Geom g, Step s, 
             continue;
         // ---- pass 1: the four hypotheses ----
         uint32_t lps4_0 = 0, shw_0 = 0; // table row of the LPS bin in front of the chunk
-        {
-            ChunkMap m = chunkmap_identity();
-            if (valid) {
-                uint32_t r[4] = {510, 510, 510, 510};
-                if (st > 0) {
-                    const uint2 t0 = rtab[(M(st - 1) >> 3) & 63];
-                    lps4_0 = t0.x, shw_0 = t0.y;
-#pragma unroll
-                    for (int h = 0; h < 4; h++)
-                        r[h] = cabac_range_after_lps(lps4_0, shw_0, h);
-                }
-                m.qmap = 0;
-                const bool closing = en < nb; // bin en - 1 is the LPS bin in front of the next chunk
-                const int stop = closing ? en - 1 : en;
-                for (int i = st; i < stop; i++) {
-                    const uint32_t mm = M(i);
-                    const uint2 t = rtab[(mm >> 3) & 63];
-#pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        uint32_t add, pre1, sh;
-                        cabac_rstep(r[h], mm, t.x, t.y, add, pre1, sh);
-                        m.s[h] += pre1 + sh;
-                    }
-                }
-                if (closing) {
-                    const uint2 t = rtab[(M(en - 1) >> 3) & 63];
-#pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        const uint32_t q = (r[h] >> 6) & 3;
-                        m.qmap |= q << (2 * h);
-                        m.s[h] += (t.y >> (3 * q)) & 7;
-                    }
-                }
-            }
-            qmap_s[tid] = m.qmap;
-#pragma unroll
-            for (int h = 0; h < 4; h++)
-                shift_s[h][tid] = m.s[h];
-        }
-        __syncthreads();
-        // ---- scan of the chunk maps: true hypothesis and stream position of every chunk ----
-        if (warp == 0) {
-            ChunkMap loc[CP_THREADS / 32], run = chunkmap_identity();
-#pragma unroll
-            for (int j = 0; j < CP_THREADS / 32; j++) {
-                const int k = lane * (CP_THREADS / 32) + j;
-                ChunkMap m;
-                m.qmap = qmap_s[k];
+        ChunkMap m = chunkmap_identity();
+        if (valid) {
+            uint32_t r[4] = {510, 510, 510, 510};
+            if (st > 0) {
+                const uint2 t0 = rtab[(M(st - 1) >> 3) & 63];
+                lps4_0 = t0.x, shw_0 = t0.y;
 #pragma unroll
                 for (int h = 0; h < 4; h++)
-                    m.s[h] = shift_s[h][k];
-                loc[j] = run;
-                run = chunkmap_compose(run, m);
+                    r[h] = cabac_range_after_lps(lps4_0, shw_0, h);
             }
+            m.qmap = 0;
+            const bool closing = en < nb; // bin en - 1 is the LPS bin in front of the next chunk
+            const int stop = closing ? en - 1 : en;
+            for (int i = st; i < stop; i++) {
+                const uint32_t mm = M(i);
+                const uint2 t = rtab[(mm >> 3) & 63];
 #pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                ChunkMap o = shfl_up_map(run, off);
-                if (lane >= off)
-                    run = chunkmap_compose(o, run);
+                for (int h = 0; h < 4; h++) {
+                    uint32_t add, pre1, sh;
+                    cabac_rstep(r[h], mm, t.x, t.y, add, pre1, sh);
+                    m.s[h] += pre1 + sh;
+                }
             }
-            ChunkMap ex = shfl_up_map(run, 1);
-            if (lane == 0)
-                ex = chunkmap_identity();
-            const uint32_t cq = carry_q, cP = carry_P;
-            __syncwarp();
+            if (closing) {
+                const uint2 t = rtab[(M(en - 1) >> 3) & 63];
 #pragma unroll
-            for (int j = 0; j < CP_THREADS / 32; j++) {
-                const int k = lane * (CP_THREADS / 32) + j;
-                const ChunkMap e = chunkmap_compose(ex, loc[j]);
-                qin_s[k] = (e.qmap >> (2 * cq)) & 3;
-                pbase_s[k] = cP + sel4(e.s, cq);
+                for (int h = 0; h < 4; h++) {
+                    const uint32_t q = (r[h] >> 6) & 3;
+                    m.qmap |= q << (2 * h);
+                    m.s[h] += (t.y >> (3 * q)) & 7;
+                }
             }
-            if (lane == 31) {
-                carry_q = (run.qmap >> (2 * cq)) & 3;
-                carry_P = cP + sel4(run.s, cq);
-            }
+        }
+        // ---- scan of the chunk maps (per warp, then over the warps): true hypothesis and stream position ----
+        ChunkMap run = m;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            ChunkMap o = shfl_up_map(run, off);
+            if (lane >= off)
+                run = chunkmap_compose(o, run);
+        }
+        ChunkMap ex = shfl_up_map(run, 1); // chunks of this warp in front of this one
+        if (lane == 0)
+            ex = chunkmap_identity();
+        if (lane == 31) {
+            wmap_s[warp][0] = run.qmap;
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+                wmap_s[warp][1 + h] = run.s[h];
+        }
+        __syncthreads();
+        const uint32_t cq = carry_q, cP = carry_P;
+        ChunkMap pre = chunkmap_identity(); // warps in front of this one
+        for (int w2 = 0; w2 < warp; w2++) {
+            ChunkMap o;
+            o.qmap = wmap_s[w2][0];
+#pragma unroll
+            for (int h = 0; h < 4; h++)
+                o.s[h] = wmap_s[w2][1 + h];
+            pre = chunkmap_compose(pre, o);
+        }
+        ex = chunkmap_compose(pre, ex);
+        const uint32_t q_in = (ex.qmap >> (2 * cq)) & 3;
+        uint32_t P = cP + sel4(ex.s, cq);
+        __syncthreads();
+        if (tid == CP_THREADS - 1) {
+            const ChunkMap tot = chunkmap_compose(ex, m);
+            carry_q = (tot.qmap >> (2 * cq)) & 3;
+            carry_P = cP + sel4(tot.s, cq);
         }
         __syncthreads();
         // ---- initialise the limbs this tile reaches ----
@@ -1575,21 +1609,45 @@ __global__ void __launch_bounds__(CP_THREADS) cabac_code_kernel(Geom g, Step s, 
         prev_hi = hi;
         __threadfence();
         __syncthreads();
-        // ---- pass 2: the true walk; every bin adds its value into the limbs ----
+        // ---- pass 2: the true walk.  The thread's values collect in two limb registers (limb jc and jc + 1) ----
         if (valid) {
-            uint32_t range = st > 0 ? cabac_range_after_lps(lps4_0, shw_0, qin_s[tid]) : 510u;
-            uint32_t P = pbase_s[tid];
-            auto adder = [&](unsigned long long j, uint32_t v) { atomicAdd(limbs + j, v); };
+            uint32_t range = st > 0 ? cabac_range_after_lps(lps4_0, shw_0, q_in) : 510u;
+            uint32_t jc = P >> 4, cur = 0, nxt = 0;
+            auto adder = [&](unsigned long long j, uint32_t v) {
+                if ((uint32_t)j == jc)
+                    cur += v;
+                else
+                    nxt += v;
+            };
             for (int i = st; i < en; i++) {
                 const uint32_t mm = M(i);
                 const uint2 t = rtab[(mm >> 3) & 63];
                 uint32_t add, pre1, sh;
                 cabac_rstep(range, mm, t.x, t.y, add, pre1, sh);
                 P += pre1;
-                if (add)
+                if (add) {
+                    const uint32_t j = P >> 4;
+                    if (j != jc) { // moved on: hand the finished limb(s) over
+                        if (cur)
+                            atomicAdd(limbs + jc, cur);
+                        if (j == jc + 1)
+                            cur = nxt;
+                        else {
+                            if (nxt)
+                                atomicAdd(limbs + jc + 1, nxt);
+                            cur = 0;
+                        }
+                        nxt = 0;
+                        jc = j;
+                    }
                     limb_add(adder, P, add);
+                }
                 P += sh;
             }
+            if (cur)
+                atomicAdd(limbs + jc, cur);
+            if (nxt)
+                atomicAdd(limbs + jc + 1, nxt);
         }
         if (last_tile)
             break;
@@ -1625,15 +1683,18 @@ __global__ void __launch_bounds__(CP_THREADS) cabac_code_kernel(Geom g, Step s, 
             wp_s[warp] = Pm == 0xffffffffu;
         }
         __syncthreads();
-        uint32_t c = cin_s;
-        for (int w2 = CP_THREADS / 32 - 1; w2 > warp; w2--)
-            c = wg_s[w2] | (wp_s[w2] & c);
+        // the same trick over the warps: warp w's carry in = carry out of warps w + 1 .. (higher limbs)
+        const uint32_t G2 = __brev(__ballot_sync(0xffffffffu, lane < CP_WARPS && wg_s[lane])) >> (32 - CP_WARPS);
+        const uint32_t P2 = __brev(__ballot_sync(0xffffffffu, lane < CP_WARPS && wp_s[lane])) >> (32 - CP_WARPS);
+        const uint32_t sum2 = (G2 | P2) + G2 + cin_s; // bit k <-> warp CP_WARPS - 1 - k; bit CP_WARPS = carry out
+        const uint32_t C2 = (G2 | P2) ^ G2 ^ sum2;
+        const uint32_t c = (C2 >> (CP_WARPS - 1 - warp)) & 1;
         const unsigned long long sum = (unsigned long long)(G | Pm) + G + c;
         const uint32_t C = (G | Pm) ^ G ^ (uint32_t)sum; // carry into every bit
         uint32_t o = (w + ((C >> (31 - lane)) & 1)) & 0xffff;
         __syncthreads();
         if (tid == 0)
-            cin_s = (uint32_t)(sum >> 32);
+            cin_s = (sum2 >> CP_WARPS) & 1;
         // 9.3.4.5 flush: code-word bits below the stop bit are dropped, the stop bit is set
         if ((uint32_t)j > (sb >> 4))
             o = 0;
