@@ -412,7 +412,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
     } else {
         const int nstrip = me_strip(g.R);
         LAUNCH_ON(st, K_ME, me_kernel, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
-                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi);
+                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1]);
         LAUNCH_ON(st, K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, src, ref, unf, mbi, nnz, coef);
         LAUNCH_ON(st, K_MVP, mvp_skip_kernel, dim3((g.nmb + 127) / 128, nl), 128, 0, g, s, mbi);
     }

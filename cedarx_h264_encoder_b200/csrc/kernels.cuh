@@ -125,7 +125,8 @@ __host__ __device__ inline size_t me_smem_bytes(int R, int nstrip)
 }
 
 __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstrip, const uint8_t *__restrict__ src,
-                                                       const uint8_t *__restrict__ ref, MbInfo *__restrict__ mbi)
+                                                       const uint8_t *__restrict__ ref, MbInfo *__restrict__ mbi,
+                                                       const MbInfo *__restrict__ mbi_prev)
 {
     extern __shared__ uint32_t sm[];
     __shared__ uint32_t mb_best[ME_MAX_STRIP];
@@ -198,6 +199,32 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31, nwarps = ME_THREADS / 32;
+    // Seed the running minimum with two real candidates per macroblock -- the zero vector and the vector the
+    // co-located macroblock had in the previous frame (any value is fine: it only has to be a candidate of the
+    // search) -- so that the exhaustive loop below can drop a task as soon as the partial cost of every candidate
+    // in it exceeds the best complete cost so far.  SAD terms are non-negative, so the partial key is a lower
+    // bound of the final key: the argmin, and with it the bitstream, is unchanged.
+    for (int sd = warp; sd < 2 * nm; sd += nwarps) {
+        const int m = sd >> 1;
+        int ox = R, oy = R;
+        if (sd & 1) {
+            const MbInfo pv = mbi_prev[(size_t)blockIdx.y * g.nmb + (size_t)mby * g.mbw + mbx0 + m];
+            ox = clip3_(0, nd - 1, (pv.mv[0] >> 2) + R);
+            oy = clip3_(0, nd - 1, (pv.mv[1] >> 2) + R);
+        }
+        uint32_t a = 0;
+        if (lane < 16) {
+            const uint32_t *wp = cp + (ox & 3) * CWs + (oy + lane) * RSW + 4 * m + (ox >> 2);
+            const uint32_t *cu = cur_s + 64 * m + 4 * lane;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                a = sad4_acc(wp[k], cu[k], a);
+        }
+        a = __reduce_add_sync(0xffffffffu, a);
+        if (lane == 0)
+            atomicMin(&mb_best[m], ((a + mvcost[ox] + mvcost[oy]) << 15) | (uint32_t)(oy * nd + ox));
+    }
+    __syncthreads();
     const int ntask = ntask_full * nm + ((nitems_left + 31) >> 5);
     for (int task = warp; task < ntask; task += nwarps) {
         // task table entry: macroblock | column offset << 4 | row group << 12 (0xffffffff = idle lane)
@@ -218,8 +245,23 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
             }
             const uint32_t *wp = cp + (ox & 3) * CWs + oy0 * RSW + 4 * m + (ox >> 2);
             uint32_t acc[4] = {0, 0, 0, 0};
+            const uint32_t cx = mvcost[ox], rank0 = (uint32_t)(oy0 * nd + ox);
+            const uint32_t cy[4] = {mvcost[oy0], mvcost[oy0 + 1], mvcost[oy0 + 2], mvcost[oy0 + 3]};
+            bool dead = false;
 #pragma unroll
             for (int r = 0; r < 19; r++) {
+                if (r == 5 || r == 9 || r == 13) { // partial keys (rows 0 .. r - 1 - j of candidate j) against the best complete key
+                    uint32_t pm = 0xffffffffu;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint32_t k = ((acc[j] + cx + cy[j]) << 15) | (rank0 + (uint32_t)(j * nd));
+                        k = cy[j] >= 0x10000u ? 0xffffffffu : k;
+                        pm = k < pm ? k : pm;
+                    }
+                    dead = pm > *(volatile uint32_t *)&mb_best[m];
+                }
+                if (dead)
+                    break;
                 uint32_t w0 = wp[r * RSW], w1 = wp[r * RSW + 1], w2 = wp[r * RSW + 2], w3 = wp[r * RSW + 3];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -233,12 +275,13 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
                 }
             }
             // cost = SAD + lambda * (bits(mvx) + bits(mvy)); rows beyond the search range have an infinite cost
-            const uint32_t cx = mvcost[ox], rank0 = (uint32_t)(oy0 * nd + ox);
+            if (!dead) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                uint32_t k = ((acc[j] + cx + mvcost[oy0 + j]) << 15) | (rank0 + (uint32_t)(j * nd));
-                k = mvcost[oy0 + j] >= 0x10000u ? 0xffffffffu : k;
-                key = k < key ? k : key;
+                for (int j = 0; j < 4; j++) {
+                    uint32_t k = ((acc[j] + cx + cy[j]) << 15) | (rank0 + (uint32_t)(j * nd));
+                    k = cy[j] >= 0x10000u ? 0xffffffffu : k;
+                    key = k < key ? k : key;
+                }
             }
         }
         // the lanes of a full task share the macroblock; the left-over task mixes macroblocks
