@@ -311,6 +311,9 @@ def run_gpu(args, rank, local_rank, world):
         for name, (ms, cnt) in prof.items():
             kernels[name] = {"ms_total": round(ms, 4), "launches": cnt, "share": round(ms / tot_ms, 4),
                              "ms_total_live": round(prof_live.get(name, (0.0, 0))[0], 4)}
+        for name, (ms, cnt) in prof_live.items():  # launches that only exist in the overlapped schedule (fused kernels)
+            if name not in kernels:
+                kernels[name] = {"ms_total": None, "launches": cnt, "share": None, "ms_total_live": round(ms, 4)}
         dominant = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
         roofline = None
         if "me_kernel" in prof:
