@@ -1354,12 +1354,12 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
 // cedar.c:992-993), in two kernels; entropy.cuh derives the parallel formulation.
 //
 // cabac_resolve_kernel: context-state resolution.  The state a regular bin is coded in depends only on the
-// earlier bins of the same context, so the contexts are split over RES_WARPS warps (ctxIdx mod RES_WARPS);
-// every warp walks the slice's bins 32 at a time, __match_any_sync groups the lanes of its own bins by
-// context and round r lets the r-th bin of every group read / advance its context state in shared memory
-// (distinct contexts inside a round => no conflicts).  Rewrites the bin stream in place as per-bin records
-// (cabac_meta: isLPS / bypass / terminate + pStateIdx).  This is the only stage that is serial along the
-// slice; it runs at a few cycles per bin.
+// earlier bins of the same context, so the contexts are split over RES_WARPS warps -- per tile of RES_TILE
+// bins, in contiguous ranges of equal bin count (histogram + prefix sum), because a fixed split leaves the
+// warp that owns the hottest contexts with twice the average load.  Every warp walks the tile's bins 32 at a
+// time and advances the states of its own contexts in shared memory: bins of distinct contexts at once, bins
+// that share a context one by one in order.  Rewrites the bin stream in place as per-bin records (cabac_meta:
+// isLPS / bypass / terminate + pStateIdx).  This is the only stage that is serial along the slice.
 #define RES_WARPS 16
 #define RES_TILE 4096
 __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0,
@@ -1367,7 +1367,8 @@ __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, S
 {
     __shared__ __align__(16) uint16_t tile[RES_TILE + 8], mtile[RES_TILE + 8];
     __shared__ uint16_t trans[128];
-    __shared__ uint8_t ctx_state[464], tag[464];
+    __shared__ uint8_t ctx_state[464], owner[480];
+    __shared__ uint32_t hist[480], cmask[464];
     const int f = lane_frame(s, blockIdx.x / g.nslices); // one CTA per slice
     if (f < 0)
         return;
@@ -1386,13 +1387,10 @@ __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, S
         int after_lps = (h264_next_state_lps[ps] << 1) | (ps == 0 ? mps ^ 1 : mps);
         trans[st] = (uint16_t)(after_mps | (after_lps << 8));
     }
-    for (int i = tid; i < 460; i += RES_WARPS * 32)
+    for (int i = tid; i < 460; i += RES_WARPS * 32) {
         ctx_state[i] = (uint8_t)cabac_init_state(i, frame_i, g.qp);
-    auto advance = [&](uint32_t c, uint32_t b) -> uint32_t { // read and advance the state of context c for bin b
-        const uint32_t st = ctx_state[c], tr = trans[st];
-        ctx_state[c] = (uint8_t)((((b >> 15) & 1) != (st & 1)) ? (tr >> 8) : (tr & 0xff));
-        return st;
-    };
+        cmask[i] = 0;
+    }
     for (uint32_t base = 0; base < nb; base += RES_TILE) {
         const uint32_t n = nb - base < RES_TILE ? nb - base : RES_TILE;
         const uint16_t *src = gb + base - mis; // 16-byte aligned
@@ -1402,44 +1400,76 @@ __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, S
             // the first and the last vector may reach into a neighbouring slice's bins (same pool): read-only here
             ((uint4 *)tile)[v] = ((const uint4 *)src)[v];
         }
+        for (int i = tid; i < 480; i += RES_WARPS * 32)
+            hist[i] = 0;
+        __syncthreads();
+        // ---- balance: contexts -> warps in contiguous ranges holding about n / RES_WARPS regular bins each ----
+        for (uint32_t i = tid; i < n; i += RES_WARPS * 32) {
+            const uint32_t b = tile[mis + i];
+            if (!(b & (BIN_BYPASS | BIN_TERM)))
+                atomicAdd(&hist[b & 0x3ff], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t loc[15], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                loc[k] = sum;
+                sum += hist[lane * 15 + k];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += y;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), before = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 15; k++) {
+                uint32_t w = total ? ((before + loc[k]) * RES_WARPS) / total : 0;
+                owner[lane * 15 + k] = (uint8_t)(w < RES_WARPS ? w : RES_WARPS - 1);
+            }
+        }
         __syncthreads();
         for (uint32_t k0 = 0; k0 < n; k0 += 32) {
             const bool live = k0 + lane < n;
             const uint32_t b = live ? tile[mis + k0 + lane] : (uint32_t)BIN_BYPASS;
             const bool reg = !(b & (BIN_BYPASS | BIN_TERM));
             const uint32_t c = b & 0x3ff;
-            const bool mine = reg && (int)(c & (RES_WARPS - 1)) == warp;
+            const bool mine = reg && owner[c] == warp;
             if (warp == (int)((k0 >> 5) & (RES_WARPS - 1)) && live && !reg)
                 mtile[mis + k0 + lane] = cabac_meta((uint16_t)b, 0);
             const uint32_t own = __ballot_sync(0xffffffffu, mine);
             if (!own)
                 continue;
-            uint32_t st = 0;
-            if (!(own & (own - 1))) { // a single bin of this warp's contexts
+            // Bins of one context must go in order: the lowest lane of every context present in this group of 32
+            // (its "leader") walks all of that context's bins with the state in a register -- one table look-up
+            // per bin on the dependent chain -- and writes their records; leaders of different contexts run side
+            // by side.  cmask[c] collects the lanes of context c (shared-memory atomic OR) and is left at zero.
+            const uint32_t bitsmask = __ballot_sync(0xffffffffu, (b >> 15) & 1);
+            uint32_t msk = mine ? 1u << lane : 0u;
+            if (own & (own - 1)) {
                 if (mine)
-                    st = advance(c, b);
-            } else {
-                // Bins of one context must go in order.  Every lane tags its context with its lane index; a lane that
-                // reads back another lane's tag shares the context with it: those lanes (and the tag holders) go
-                // one by one in lane order, everybody else at once.
-                if (mine)
-                    tag[c] = (uint8_t)lane;
+                    atomicOr(&cmask[c], 1u << lane);
                 __syncwarp();
-                const uint32_t holder = mine ? tag[c] : lane;
-                const uint32_t lost = __ballot_sync(0xffffffffu, holder != (uint32_t)lane);
-                uint32_t conf = 0;
-                if (lost)
-                    conf = lost | __reduce_or_sync(0xffffffffu, holder != (uint32_t)lane ? (1u << holder) : 0u);
-                if (mine && !((conf >> lane) & 1))
-                    st = advance(c, b);
-                for (uint32_t m2 = conf; m2; m2 &= m2 - 1) {
-                    if (lane == __ffs(m2) - 1)
-                        st = advance(c, b);
-                    __syncwarp();
-                }
+                if (mine)
+                    msk = cmask[c];
+                __syncwarp();
             }
-            if (mine)
-                mtile[mis + k0 + lane] = cabac_meta((uint16_t)b, st);
+            if (mine && (__ffs(msk) - 1) == lane) {
+                if (own & (own - 1))
+                    cmask[c] = 0;
+                uint32_t st = ctx_state[c];
+                for (uint32_t m2 = msk; m2; m2 &= m2 - 1) {
+                    const int j = __ffs(m2) - 1;
+                    const uint32_t bit = (bitsmask >> j) & 1, tr = trans[st];
+                    mtile[mis + k0 + j] = (uint16_t)((bit ^ (st & 1)) | ((st >> 1) << 3));
+                    st = (bit != (st & 1)) ? (tr >> 8) : (tr & 0xff);
+                }
+                ctx_state[c] = (uint8_t)st;
+            }
+            __syncwarp(); // the leaders' stores (states, cleared masks) before the next group's atomics and loads
         }
         __syncthreads();
         // records back in place of the bins; the partial vectors at both ends are written element-wise
