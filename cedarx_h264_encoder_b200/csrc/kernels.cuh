@@ -1354,20 +1354,29 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
 // cedar.c:992-993), in two kernels; entropy.cuh derives the parallel formulation.
 //
 // cabac_resolve_kernel: context-state resolution.  The state a regular bin is coded in depends only on the
-// earlier bins of the same context, so the contexts are split over RES_WARPS warps -- per tile of RES_TILE
-// bins, in contiguous ranges of equal bin count (histogram + prefix sum), because a fixed split leaves the
-// warp that owns the hottest contexts with twice the average load.  Every warp walks the tile's bins 32 at a
-// time and advances the states of its own contexts in shared memory: bins of distinct contexts at once, bins
-// that share a context one by one in order.  Rewrites the bin stream in place as per-bin records (cabac_meta:
-// isLPS / bypass / terminate + pStateIdx).  This is the only stage that is serial along the slice.
+// earlier bins of the same context.  Per tile of RES_TILE bins:
+//   1. histogram of the contexts; the contexts are split over the RES_WARPS warps in contiguous ranges of equal
+//      bin count (prefix sum) -- a fixed split leaves the warp with the hottest contexts at twice the load;
+//   2. stable partition of the tile's regular bins by owning warp (per 32 bins: four ballots give every lane the
+//      mask of lanes of its class, counts per class and group are prefix-summed), so that every warp gets a
+//      dense, ordered queue of its own bins;
+//   3. every warp walks its queue 32 bins at a time: the lowest lane of every context present (its "leader")
+//      advances that context's state over all of its bins with the state in a register -- one table look-up per
+//      bin on the dependent chain -- and leaders of different contexts run side by side.
+// Rewrites the bin stream in place as per-bin records (cabac_meta: isLPS / bypass / terminate + pStateIdx).
+// This is the only stage that is serial along the slice: its critical path is the hottest context's chain.
 #define RES_WARPS 16
 #define RES_TILE 4096
+#define RES_GROUPS (RES_TILE / 32)
 __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0,
                                                                        EntropyBufs eb)
 {
     __shared__ __align__(16) uint16_t tile[RES_TILE + 8], mtile[RES_TILE + 8];
+    __shared__ uint32_t queue[RES_TILE];                 // ctx | bit << 9 | index in tile << 10, grouped by owning warp
+    __shared__ uint16_t cnt[RES_WARPS][RES_GROUPS];      // bins of class k in group G -> exclusive prefix over G
+    __shared__ uint32_t coff[RES_WARPS + 1];             // queue range of every class
     __shared__ uint16_t trans[128];
-    __shared__ uint8_t ctx_state[464], owner[480];
+    __shared__ uint8_t ctx_state[464], owner[480], pre_s[RES_WARPS][32];
     __shared__ uint32_t hist[480], cmask[464];
     const int f = lane_frame(s, blockIdx.x / g.nslices); // one CTA per slice
     if (f < 0)
@@ -1377,6 +1386,7 @@ __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, S
     if (nb == 0)
         return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t lt = (1u << lane) - 1;
     const int frame_i = ((gop_pos0 + f) % gop_len) == 0;
     uint16_t *gb = eb.bins + eb.bins_off[u];
     // 16-byte vector loads / stores: tile k starts at the aligned address at or below gb + k * RES_TILE
@@ -1402,8 +1412,10 @@ __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, S
         }
         for (int i = tid; i < 480; i += RES_WARPS * 32)
             hist[i] = 0;
+        for (int i = tid; i < RES_WARPS * RES_GROUPS / 2; i += RES_WARPS * 32)
+            ((uint32_t *)cnt)[i] = 0;
         __syncthreads();
-        // ---- balance: contexts -> warps in contiguous ranges holding about n / RES_WARPS regular bins each ----
+        // ---- 1. balance: contexts -> warps in contiguous ranges holding about n / RES_WARPS regular bins each ----
         for (uint32_t i = tid; i < n; i += RES_WARPS * 32) {
             const uint32_t b = tile[mis + i];
             if (!(b & (BIN_BYPASS | BIN_TERM)))
@@ -1432,44 +1444,100 @@ __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, S
             }
         }
         __syncthreads();
-        for (uint32_t k0 = 0; k0 < n; k0 += 32) {
-            const bool live = k0 + lane < n;
-            const uint32_t b = live ? tile[mis + k0 + lane] : (uint32_t)BIN_BYPASS;
+        // ---- 2. stable partition by owner: warp w ranks the bins of groups [w * 8, w * 8 + 8) ----
+        uint32_t ent[RES_GROUPS / RES_WARPS]; // queue entry | rank << 22 | class << 27; 0xffffffff = not a regular bin
+#pragma unroll
+        for (int gi = 0; gi < RES_GROUPS / RES_WARPS; gi++) {
+            const uint32_t G = warp * (RES_GROUPS / RES_WARPS) + gi, i = G * 32 + lane;
+            const bool live = i < n;
+            const uint32_t b = live ? tile[mis + i] : (uint32_t)BIN_BYPASS;
             const bool reg = !(b & (BIN_BYPASS | BIN_TERM));
-            const uint32_t c = b & 0x3ff;
-            const bool mine = reg && owner[c] == warp;
-            if (warp == (int)((k0 >> 5) & (RES_WARPS - 1)) && live && !reg)
-                mtile[mis + k0 + lane] = cabac_meta((uint16_t)b, 0);
-            const uint32_t own = __ballot_sync(0xffffffffu, mine);
-            if (!own)
-                continue;
-            // Bins of one context must go in order: the lowest lane of every context present in this group of 32
-            // (its "leader") walks all of that context's bins with the state in a register -- one table look-up
-            // per bin on the dependent chain -- and writes their records; leaders of different contexts run side
-            // by side.  cmask[c] collects the lanes of context c (shared-memory atomic OR) and is left at zero.
-            const uint32_t bitsmask = __ballot_sync(0xffffffffu, (b >> 15) & 1);
-            uint32_t msk = mine ? 1u << lane : 0u;
-            if (own & (own - 1)) {
-                if (mine)
-                    atomicOr(&cmask[c], 1u << lane);
-                __syncwarp();
-                if (mine)
-                    msk = cmask[c];
-                __syncwarp();
+            const uint32_t c = b & 0x3ff, k = reg ? owner[c] : 0;
+            if (live && !reg)
+                mtile[mis + i] = cabac_meta((uint16_t)b, 0);
+            uint32_t m = __ballot_sync(0xffffffffu, reg);
+#pragma unroll
+            for (int bit = 0; bit < 4; bit++) {
+                const uint32_t bb = __ballot_sync(0xffffffffu, (k >> bit) & 1);
+                m &= ((k >> bit) & 1) ? bb : ~bb;
             }
-            if (mine && (__ffs(msk) - 1) == lane) {
-                if (own & (own - 1))
-                    cmask[c] = 0;
+            const uint32_t rank = __popc(m & lt);
+            ent[gi] = 0xffffffffu;
+            if (reg) {
+                if (rank == 0)
+                    cnt[k][G] = (uint16_t)__popc(m);
+                ent[gi] = c | (((b >> 15) & 1) << 9) | (i << 10) | (rank << 22) | (k << 27);
+            }
+        }
+        __syncthreads();
+        { // exclusive prefix of cnt[warp][*] over the groups (4 per lane), class totals
+            uint32_t v[RES_GROUPS / 32], sum = 0;
+#pragma unroll
+            for (int k = 0; k < RES_GROUPS / 32; k++) {
+                v[k] = sum;
+                sum += cnt[warp][lane * (RES_GROUPS / 32) + k];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += y;
+            }
+#pragma unroll
+            for (int k = 0; k < RES_GROUPS / 32; k++)
+                cnt[warp][lane * (RES_GROUPS / 32) + k] = (uint16_t)(incl - sum + v[k]);
+            if (lane == 31)
+                coff[warp + 1] = incl; // class total for now
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t run = 0;
+            coff[0] = 0;
+            for (int k = 1; k <= RES_WARPS; k++) {
+                run += coff[k];
+                coff[k] = run;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int gi = 0; gi < RES_GROUPS / RES_WARPS; gi++) {
+            const uint32_t e = ent[gi];
+            if (e != 0xffffffffu) {
+                const uint32_t k = e >> 27, G = warp * (RES_GROUPS / RES_WARPS) + gi;
+                queue[coff[k] + cnt[k][G] + ((e >> 22) & 31)] = e & 0x3fffffu;
+            }
+        }
+        __syncthreads();
+        // ---- 3. every warp advances the states of its own contexts over its queue ----
+        const uint32_t q0 = coff[warp], q1 = coff[warp + 1];
+        for (uint32_t k0 = q0; k0 < q1; k0 += 32) {
+            const bool live = k0 + lane < q1;
+            const uint32_t e = live ? queue[k0 + lane] : 0;
+            const uint32_t c = e & 0x1ff;
+            const uint32_t bitsmask = __ballot_sync(0xffffffffu, (e >> 9) & 1);
+            if (live)
+                atomicOr(&cmask[c], 1u << lane);
+            __syncwarp();
+            const uint32_t msk = live ? cmask[c] : 0;
+            __syncwarp();
+            if (live && (__ffs(msk) - 1) == lane) { // leader of context c in this batch
+                cmask[c] = 0;
                 uint32_t st = ctx_state[c];
                 for (uint32_t m2 = msk; m2; m2 &= m2 - 1) {
                     const int j = __ffs(m2) - 1;
-                    const uint32_t bit = (bitsmask >> j) & 1, tr = trans[st];
-                    mtile[mis + k0 + j] = (uint16_t)((bit ^ (st & 1)) | ((st >> 1) << 3));
-                    st = (bit != (st & 1)) ? (tr >> 8) : (tr & 0xff);
+                    const uint32_t tr = trans[st];
+                    pre_s[warp][j] = (uint8_t)st;
+                    st = (((bitsmask >> j) & 1) != (st & 1)) ? (tr >> 8) : (tr & 0xff);
                 }
                 ctx_state[c] = (uint8_t)st;
             }
-            __syncwarp(); // the leaders' stores (states, cleared masks) before the next group's atomics and loads
+            __syncwarp();
+            if (live) {
+                const uint32_t st = pre_s[warp][lane];
+                mtile[mis + (e >> 10)] = (uint16_t)((((e >> 9) & 1) ^ (st & 1)) | ((st >> 1) << 3));
+            }
+            __syncwarp();
         }
         __syncthreads();
         // records back in place of the bins; the partial vectors at both ends are written element-wise
