@@ -76,7 +76,18 @@ static int emit_nal(uint8_t *out, int cap, int ref_idc, int type, const struct h
     return n;
 }
 
-int cedar_hdr_sps(int profile, int level, int width_mb, int height_mb, uint8_t *out, int cap)
+int cedar_hdr_min_level(int mbs)
+{
+    static const int max_fs[][2] = {{99, 10},   {396, 11},  {792, 21},   {1620, 22},  {3600, 31},  {5120, 32},
+                                    {8192, 40}, {8704, 42}, {22080, 50}, {36864, 51}, {139264, 60}};
+    for (unsigned i = 0; i < sizeof(max_fs) / sizeof(max_fs[0]); i++)
+        if (mbs <= max_fs[i][0])
+            return max_fs[i][1];
+    return 62;
+}
+
+int cedar_hdr_sps(int profile, int level, int width_mb, int height_mb, int crop_right, int crop_bottom, uint8_t *out,
+                  int cap)
 {
     struct hbits b;
     memset(&b, 0, sizeof(b));
@@ -92,7 +103,14 @@ int cedar_hdr_sps(int profile, int level, int width_mb, int height_mb, uint8_t *
     hb_ue(&b, (uint32_t)(height_mb - 1)); /* :916 */
     hb_put(&b, 1, 1);                 /* :919 frame_mbs_only_flag */
     hb_put(&b, 0, 1);                 /* :922 direct_8x8_inference_flag */
-    hb_put(&b, 0, 1);                 /* :931 frame_cropping_flag (crop is always 0: :756-761) */
+    if (crop_right || crop_bottom) {  /* :924-929, dead in the reference (:756-761); the `sps_crop` extension */
+        hb_put(&b, 1, 1);             /* frame_cropping_flag */
+        hb_ue(&b, 0);                 /* frame_crop_left_offset */
+        hb_ue(&b, (uint32_t)crop_right);
+        hb_ue(&b, 0);                 /* frame_crop_top_offset */
+        hb_ue(&b, (uint32_t)crop_bottom);
+    } else
+        hb_put(&b, 0, 1);             /* :931 frame_cropping_flag (crop is always 0: :756-761) */
     hb_put(&b, 0, 1);                 /* :934 vui_parameters_present_flag */
     hb_trailing(&b);                  /* :936 */
     return emit_nal(out, cap, 3, 7, &b);

@@ -530,8 +530,10 @@ const char *cedar_b200_version(void) { return "cedar_b200 0.1 (sm_100a)"; }
 
 int cedar_b200_write_sps(const struct cedar_b200_config *cfg, uint8_t *out, int cap)
 {
-    return cedar_hdr_sps(cfg->profile, cfg->level, (int)ALIGN_UP(cfg->dst_width, 16) >> 4,
-                         (int)ALIGN_UP(cfg->dst_height, 16) >> 4, out, cap);
+    const int wmb = (int)ALIGN_UP(cfg->dst_width, 16) >> 4, hmb = (int)ALIGN_UP(cfg->dst_height, 16) >> 4;
+    return cedar_hdr_sps(cfg->profile, cfg->auto_level ? cedar_hdr_min_level(wmb * hmb) : cfg->level, wmb, hmb,
+                         cfg->sps_crop ? (wmb * 16 - cfg->src_width) / 2 : 0,
+                         cfg->sps_crop ? (hmb * 16 - cfg->src_height) / 2 : 0, out, cap);
 }
 int cedar_b200_write_pps(const struct cedar_b200_config *cfg, uint8_t *out, int cap)
 {
@@ -650,8 +652,8 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
         return r;
     }
     // SPS + PPS, emitted once before the first frame (cedar.c:1058-1061)
-    int n1 = cedar_b200_write_sps(cfg, h->prefix, 32);
-    int n2 = cedar_b200_write_pps(cfg, h->prefix + n1, 32);
+    int n1 = cedar_b200_write_sps(cfg, h->prefix, 40);
+    int n2 = cedar_b200_write_pps(cfg, h->prefix + n1, 24);
     h->prefix_len = n1 + n2;
     io->input_luma = h->h_in_luma;
     io->input_luma_size = h->in_luma_size;

@@ -52,6 +52,10 @@ struct cedar_b200_config {
     int slice_rows;          /* macroblock rows per slice; 0 = one slice per picture as the reference writes it
                               * (first_mb_in_slice always 0, cedar.c:992-993).  N > 0: every N rows start a new slice
                               * NAL, coded by its own (parallel) entropy coder at some cost in bits. */
+    int sps_crop;            /* non-zero: signal src_width x src_height with frame cropping in the SPS (1920x1080 instead
+                              * of the coded 1920x1088).  The reference never does: cedar.c:756-761 makes :924-931 dead. */
+    int auto_level;          /* non-zero: level_idc = lowest level whose MaxFS fits the picture (4K: 5.1) instead of the
+                              * configured `level`, which the reference writes unchecked (cedar.c:900). */
 };
 
 /*

@@ -128,7 +128,19 @@ int gm_write_sps(const gm_config *cfg, uint8_t *out, int cap)
     bw_init(&b, rb, sizeof(rb));
     bw_put(&b, (uint32_t)cfg->profile, 8);
     bw_put(&b, 0, 8); /* constraints */
-    bw_put(&b, (uint32_t)cfg->level, 8);
+    {
+        /* auto_level extension: lowest level whose MaxFS (table A-1) holds the picture; cedar.c:900 writes cfg->level */
+        static const int max_fs[][2] = {{99, 10},   {396, 11},  {792, 21},   {1620, 22},  {3600, 31},  {5120, 32},
+                                        {8192, 40}, {8704, 42}, {22080, 50}, {36864, 51}, {139264, 60}};
+        int level = cfg->level;
+        if (cfg->auto_level) {
+            level = 62;
+            for (int i = 10; i >= 0; i--)
+                if (w_mb * h_mb <= max_fs[i][0])
+                    level = max_fs[i][1];
+        }
+        bw_put(&b, (uint32_t)level, 8);
+    }
     bw_ue(&b, 0); /* seq_parameter_set_id */
     bw_ue(&b, 0); /* log2_max_frame_num_minus4 */
     bw_ue(&b, 2); /* pic_order_cnt_type */
@@ -138,7 +150,15 @@ int gm_write_sps(const gm_config *cfg, uint8_t *out, int cap)
     bw_ue(&b, (uint32_t)(h_mb - 1));
     bw_put(&b, 1, 1); /* frame_mbs_only_flag */
     bw_put(&b, 0, 1); /* direct_8x8_inference_flag */
-    bw_put(&b, 0, 1); /* frame_cropping_flag: crop is always 0 (cedar.c:756-761 makes :924-931 dead) */
+    if (cfg->sps_crop && (w_mb * 16 > cfg->src_width || h_mb * 16 > cfg->src_height)) {
+        /* sps_crop extension, field order of cedar.c:924-929; offsets in crop units of two luma samples */
+        bw_put(&b, 1, 1);
+        bw_ue(&b, 0);
+        bw_ue(&b, (uint32_t)((w_mb * 16 - cfg->src_width) / 2));
+        bw_ue(&b, 0);
+        bw_ue(&b, (uint32_t)((h_mb * 16 - cfg->src_height) / 2));
+    } else
+        bw_put(&b, 0, 1); /* frame_cropping_flag: crop is always 0 (cedar.c:756-761 makes :924-931 dead) */
     bw_put(&b, 0, 1); /* vui_parameters_present_flag */
     bw_trailing_cedar(&b);
     if (cap < 5 + 2 * (int)(b.nbits >> 3))

@@ -46,6 +46,8 @@ typedef struct gm_config {
     int relax_gop;     /* extension: accept keyframe_interval >= 32 (cedar.c:784-789 rejects) */
     int intra4x4;      /* extension: enable Intra4x4 macroblocks in I frames */
     int slice_rows;    /* extension: macroblock rows per slice; 0 = one slice per picture (cedar.c:992-993) */
+    int sps_crop;      /* extension: frame cropping to src_width x src_height in the SPS (dead in the reference) */
+    int auto_level;    /* extension: level_idc from the picture size instead of cfg->level */
 } gm_config;
 
 /* Per-macroblock record: every syntax element the entropy coder needs. */

@@ -14,7 +14,8 @@ LIB = os.path.join(ORACLE_DIR, "liboracle_h264.so")
 class GmConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "src_width", "src_height", "src_format", "dst_width", "dst_height", "profile", "level", "qp",
-        "keyframe_interval", "entropy_coding_mode", "me_range", "relax_gop", "intra4x4", "slice_rows")]
+        "keyframe_interval", "entropy_coding_mode", "me_range", "relax_gop", "intra4x4", "slice_rows", "sps_crop",
+        "auto_level")]
 
 
 class GmMb(C.Structure):
@@ -70,10 +71,10 @@ def align16(x):
 
 
 def make_config(width, height, qp=24, gop=25, cabac=1, fmt=0, me_range=16, profile=77, level=41, intra4x4=0,
-                dst_width=None, dst_height=None, relax_gop=1, slice_rows=0):
+                dst_width=None, dst_height=None, relax_gop=1, slice_rows=0, sps_crop=0, auto_level=0):
     return GmConfig(width, height, fmt, align16(width) if dst_width is None else dst_width,
                     align16(height) if dst_height is None else dst_height, profile, level, qp, gop, cabac,
-                    me_range, relax_gop, intra4x4, slice_rows)
+                    me_range, relax_gop, intra4x4, slice_rows, sps_crop, auto_level)
 
 
 def synth_frame(width, height, t, fmt=0):

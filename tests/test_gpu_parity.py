@@ -213,3 +213,18 @@ def test_slices_full_size_decode_and_bitrate_cost(cabac):
             for p in range(3):
                 assert np.array_equal(dec[-1][p], last_recon[p])
     assert total[0] < total[4] < 1.10 * total[0], total
+
+
+def test_sps_crop_and_auto_level_stream_matches_oracle(oracle):
+    w, h = 100, 50
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=25, gop=2, cabac=1, me_range=8, sps_crop=1, auto_level=1))
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=2, cabac=1, me_range=8, sps_crop=1, auto_level=1)) as enc:
+        stream = b""
+        for t in range(3):
+            y, c = content("synth", w, h, t)
+            got = enc.encode(y, c)
+            assert got == gold.encode(y, c), "frame %d" % t
+            stream += got
+    gold.close()
+    dec = avdec.decode(stream)
+    assert len(dec) == 3 and dec[0][0].shape == (h, w)

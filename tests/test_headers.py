@@ -68,3 +68,51 @@ def test_first_frame_carries_sps_pps_once(oracle):
         y, c = oracle.synth_frame(64, 48, t)
         types.append([n[0] for n in avdec.split_nals(enc.encode(y, c))])
     assert types == [[7, 8, 5], [1], [5], [1], [5]]
+
+
+def _spec_sps(profile, level, wmb, hmb, crop_right, crop_bottom):
+    """SPS written straight from the syntax table of H.264 7.3.2.1.1 (independent of both writers)."""
+    bits = ""
+
+    def u(v, n):
+        nonlocal bits
+        bits += format(v, "0%db" % n)
+
+    def ue(v):
+        nonlocal bits
+        s = format(v + 1, "b")
+        bits += "0" * (len(s) - 1) + s
+
+    u(profile, 8); u(0, 8); u(level, 8)
+    ue(0); ue(0); ue(2); ue(1); u(0, 1); ue(wmb - 1); ue(hmb - 1); u(1, 1); u(0, 1)
+    if crop_right or crop_bottom:
+        u(1, 1); ue(0); ue(crop_right); ue(0); ue(crop_bottom)
+    else:
+        u(0, 1)
+    u(0, 1)
+    bits += "1"                       # rbsp_stop_one_bit
+    extra = len(bits) % 8 == 0        # cedar.c:883-890 quirk: stop bit in the last position is followed by a whole 0x00
+    bits += "0" * (-len(bits) % 8)
+    body = int(bits, 2).to_bytes(len(bits) // 8, "big") + (b"\x00" if extra else b"")
+    out, zeros = bytearray(b"\x00\x00\x00\x01\x67"), 0
+    for b in body:
+        if zeros >= 2 and b <= 3:
+            out.append(3)
+            zeros = 0
+        out.append(b)
+        zeros = zeros + 1 if b == 0 else 0
+    return bytes(out)
+
+
+@pytest.mark.parametrize("w,h", [(1920, 1080), (854, 480), (100, 50), (3840, 2160), (1280, 720), (64, 48)])
+def test_sps_crop_and_auto_level_extensions(oracle, product_lib, w, h):
+    """sps_crop / auto_level: off by default (reference bytes), on = cropping syntax in the field
+    order of the reference's dead branch (cedar.c:924-929) with offsets in crop units, level from table A-1."""
+    from cedarx_h264_encoder_b200 import api
+    wmb, hmb = (w + 15) // 16, (h + 15) // 16
+    levels = {(1920, 1080): 40, (854, 480): 22, (100, 50): 10, (3840, 2160): 51, (1280, 720): 31, (64, 48): 10}
+    plain = _spec_sps(77, 41, wmb, hmb, 0, 0)
+    assert api.write_sps(api.make_config(w, h)) == oracle.write_sps(oracle.make_config(w, h)) == plain
+    want = _spec_sps(77, levels[(w, h)], wmb, hmb, (wmb * 16 - w) // 2, (hmb * 16 - h) // 2)
+    assert api.write_sps(api.make_config(w, h, sps_crop=1, auto_level=1)) == want
+    assert oracle.write_sps(oracle.make_config(w, h, sps_crop=1, auto_level=1)) == want

@@ -149,3 +149,16 @@ def test_slice_rows_zero_and_full_height_are_the_reference_layout(oracle):
     b, _, _ = oracle_encode_clip(clip, 64, 48, qp=24, gop=2, cabac=1, me_range=8, slice_rows=3)
     c, _, _ = oracle_encode_clip(clip, 64, 48, qp=24, gop=2, cabac=1, me_range=8, slice_rows=99)
     assert a == b == c
+
+
+@needs_decoder
+def test_sps_crop_makes_the_decoder_output_the_source_size(oracle):
+    w, h, n = 100, 50, 3
+    clip = make_clip("synth", w, h, n)
+    stream, _, recs = oracle_encode_clip(clip, w, h, keep_recon=True, qp=24, gop=2, cabac=1, me_range=8, sps_crop=1,
+                                         auto_level=1)
+    dec = avdec.decode(stream)
+    assert len(dec) == n
+    for r, d in zip(recs, dec):
+        assert d[0].shape == (h, w) and d[1].shape == (h // 2, w // 2)
+        assert np.array_equal(r[0][:h, :w], d[0]) and np.array_equal(r[1][:h // 2, :w // 2], d[1])
