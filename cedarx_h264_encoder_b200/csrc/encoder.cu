@@ -26,11 +26,11 @@ using namespace cedar;
 namespace {
 
 enum KernelId {
-    K_INGEST, K_ME, K_INTER, K_MVP, K_INTRA, K_BS, K_DEBLOCK, K_SSE, K_ESIZE, K_ESCAN, K_EZERO, K_EWRITE,
+    K_INGEST, K_ME, K_INTER, K_INTRA, K_BS, K_DEBLOCK, K_SSE, K_ESIZE, K_ESCAN, K_EZERO, K_EWRITE,
     K_CRESOLVE, K_CCODE, K_EPBCOUNT, K_EPBSCAN, K_PACKSCAN, K_EPBWRITE, K_COUNT
 };
 const char *kKernelNames[K_COUNT] = {
-    "ingest_kernel", "me_kernel", "inter_kernel", "mvp_skip_kernel", "intra_kernel", "bs_kernel", "deblock_kernel",
+    "ingest_kernel", "me_kernel", "inter_kernel", "intra_kernel", "bs_kernel", "deblock_kernel",
     "sse_kernel", "entropy_size_kernel", "entropy_scan_kernel", "rbsp_zero_kernel", "entropy_write_kernel",
     "cabac_resolve_kernel", "cabac_code_kernel", "epb_count_kernel", "epb_scan_kernel", "pack_scan_kernel", "epb_write_kernel"};
 
@@ -414,9 +414,9 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         LAUNCH_ON(st, K_ME, me_kernel, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
                   me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1]);
         LAUNCH_ON(st, K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, src, ref, unf, mbi, nnz, coef);
-        LAUNCH_ON(st, K_MVP, mvp_skip_kernel, dim3((g.nmb + 127) / 128, nl), 128, 0, g, s, mbi);
     }
-    LAUNCH_ON(st, K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, mbi, nnz, bs);
+    // boundary strengths; on inter steps the same launch runs median MV prediction / the skip decision (K2)
+    LAUNCH_ON(st, K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, mbi, nnz, bs, !frame_i);
     LAUNCH_ON(st, K_DEBLOCK, deblock_kernel, dim3((g.mbh + DB_ROWS - 1) / DB_ROWS, nl, 2), (DB_ROWS + 2) * 32, 0, g, s, unf,
               rec, bs, fl_y, fl_c);
     CK(cudaEventRecord(h->ev_main[p], st));

@@ -492,17 +492,11 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
 }
 
 // ================================================================================================
-// K2 median MV prediction, mvd and the P_Skip decision.  One thread per macroblock; runs after all
-// MVs of the frame are final (they never change here), so it is order independent.
+// K2 median MV prediction, mvd and the P_Skip decision.  One thread per macroblock (called from bs_kernel); runs
+// after all MVs of the frame are final (they never change here), so it is order independent.
 // ================================================================================================
-__global__ void mvp_skip_kernel(Geom g, Step s, MbInfo *__restrict__ mbi)
+__device__ __forceinline__ void mvp_skip_mb(const Geom &g, MbInfo *frame, int mb)
 {
-    if (lane_frame(s, blockIdx.y) < 0)
-        return;
-    int mb = blockIdx.x * blockDim.x + threadIdx.x;
-    if (mb >= g.nmb)
-        return;
-    MbInfo *frame = mbi + (size_t)blockIdx.y * g.nmb;
     MbInfo m = frame[mb];
     if (m.type != MB_P16x16 && m.type != MB_PSKIP)
         return;
@@ -520,6 +514,7 @@ __global__ void mvp_skip_kernel(Geom g, Step s, MbInfo *__restrict__ mbi)
     frame[mb].mvd[1] = mvdy;
     frame[mb].type = type;
 }
+
 
 // ================================================================================================
 // K4 intra macroblocks of I frames: Intra16x16 (V/H/DC/Plane) + chroma (DC/H/V/Plane), mode by SAD,
@@ -733,8 +728,10 @@ __global__ void __launch_bounds__(32) intra_kernel(Geom g, Step s, const uint8_t
 // before the current one waits on the row above.
 // Bound: dependency latency (mbw + 2 * mbh steps per frame).
 // ================================================================================================
-__global__ void bs_kernel(Geom g, Step s, const MbInfo *__restrict__ mbi, const uint8_t *__restrict__ nnz,
-                          uint8_t *__restrict__ bs)
+// with_mvp: the thread of edge (dir 0, e 0) also runs K2 (mvp_skip_mb) for its macroblock, which saves a launch on the
+// critical chain.  K2 only rewrites type P16x16 -> PSKIP and mvd, neither of which a boundary strength depends on.
+__global__ void bs_kernel(Geom g, Step s, MbInfo *mbi, const uint8_t *__restrict__ nnz, uint8_t *__restrict__ bs,
+                          int with_mvp)
 {
     if (lane_frame(s, blockIdx.y) < 0)
         return;
@@ -768,6 +765,8 @@ __global__ void bs_kernel(Geom g, Step s, const MbInfo *__restrict__ mbi, const 
         }
     }
     ((uint32_t *)bs)[((size_t)blockIdx.y * g.nmb + mb) * 8 + dir * 4 + e] = out;
+    if (with_mvp && dir == 0 && e == 0)
+        mvp_skip_mb(g, mbi + (size_t)blockIdx.y * g.nmb, mb);
 }
 
 // Shared-memory mailbox between a filtering warp and its two helper warps.
