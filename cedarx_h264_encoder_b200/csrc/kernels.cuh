@@ -393,15 +393,33 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
         const uint8_t *sp = src + fo + (size_t)py * g.W + px;
         const uint8_t *rp = ref + fo;
         int d[16];
+        const int rx = px + dx, ry = py + dy;
+        if (rx >= 0 && rx + 7 < g.W && ry >= 0 && ry + 3 < g.H) {
+            // interior: each 4-sample row of the prediction is two aligned words and a funnel shift
 #pragma unroll
-        for (int y = 0; y < 4; y++) {
-            uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.W);
-            const uint8_t *rr = rp + (size_t)clip3_(0, g.H - 1, py + y + dy) * g.W;
+            for (int y = 0; y < 4; y++) {
+                const uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.W);
+                const uintptr_t a = (uintptr_t)(rp + (size_t)(ry + y) * g.W + rx);
+                const uint32_t *aw = (const uint32_t *)(a & ~(uintptr_t)3);
+                const uint32_t pv = __funnelshift_r(aw[0], aw[1], (uint32_t)(a & 3) * 8);
 #pragma unroll
-            for (int x = 0; x < 4; x++) {
-                int p = rr[clip3_(0, g.W - 1, px + x + dx)];
-                pred[y * 4 + x] = p;
-                d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
+                for (int x = 0; x < 4; x++) {
+                    const int p = (int)((pv >> (8 * x)) & 0xff);
+                    pred[y * 4 + x] = p;
+                    d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+                uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.W);
+                const uint8_t *rr = rp + (size_t)clip3_(0, g.H - 1, py + y + dy) * g.W;
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    int p = rr[clip3_(0, g.W - 1, px + x + dx)];
+                    pred[y * 4 + x] = p;
+                    d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
+                }
             }
         }
         fdct4x4(d, w);
@@ -417,16 +435,36 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
         int mvx = me.mv[0], mvy = me.mv[1];
         int xi = mvx >> 3, yi = mvy >> 3, xf = mvx & 7, yf = mvy & 7;
         int d[16];
+        // the 5 x 5 reference samples the bilinear filter of this 4 x 4 block touches, one 64-bit window per row
+        unsigned long long prow[5];
+        const int cx0 = px + xi, cy0 = py + yi;
+        if (cx0 >= 0 && cx0 + 7 < g.CW && cy0 >= 0 && cy0 + 4 < g.CH) {
+#pragma unroll
+            for (int y = 0; y < 5; y++) {
+                const uintptr_t a = (uintptr_t)(rp + (size_t)(cy0 + y) * g.CW + cx0);
+                const uint32_t *aw = (const uint32_t *)(a & ~(uintptr_t)3);
+                prow[y] = (((unsigned long long)aw[1] << 32) | aw[0]) >> ((a & 3) * 8);
+            }
+        } else {
+#pragma unroll
+            for (int y = 0; y < 5; y++) {
+                const uint8_t *rr = rp + (size_t)clip3_(0, g.CH - 1, cy0 + y) * g.CW;
+                unsigned long long v = 0;
+#pragma unroll
+                for (int x = 0; x < 5; x++)
+                    v |= (unsigned long long)rr[clip3_(0, g.CW - 1, cx0 + x)] << (8 * x);
+                prow[y] = v;
+            }
+        }
+        const int w00 = (8 - xf) * (8 - yf), w01 = xf * (8 - yf), w10 = (8 - xf) * yf, w11 = xf * yf;
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.CW);
-            const uint8_t *r0 = rp + (size_t)clip3_(0, g.CH - 1, py + y + yi) * g.CW;
-            const uint8_t *r1 = rp + (size_t)clip3_(0, g.CH - 1, py + y + yi + 1) * g.CW;
+            const uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.CW);
 #pragma unroll
             for (int x = 0; x < 4; x++) {
-                int xa = clip3_(0, g.CW - 1, px + x + xi), xb = clip3_(0, g.CW - 1, px + x + xi + 1);
-                int A = r0[xa], B = r0[xb], C = r1[xa], D = r1[xb];
-                int p = ((8 - xf) * (8 - yf) * A + xf * (8 - yf) * B + (8 - xf) * yf * C + xf * yf * D + 32) >> 6;
+                const int A = (int)((prow[y] >> (8 * x)) & 0xff), B = (int)((prow[y] >> (8 * x + 8)) & 0xff);
+                const int C = (int)((prow[y + 1] >> (8 * x)) & 0xff), D = (int)((prow[y + 1] >> (8 * x + 8)) & 0xff);
+                const int p = (w00 * A + w01 * B + w10 * C + w11 * D + 32) >> 6;
                 pred[y * 4 + x] = p;
                 d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
             }
