@@ -408,7 +408,8 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         CK(cudaStreamWaitEvent(st, h->ev_post[p ^ 1], 0));
     CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 3 * flag_n, st));
     if (frame_i) {
-        LAUNCH_ON(st, K_INTRA, intra_kernel, dim3(g.mbh, nl), 32, 0, g, s, src, unf, mbi, nnz, coef, fl_intra);
+        LAUNCH_ON(st, K_INTRA, intra_kernel, dim3((g.mbh + INTRA_ROWS - 1) / INTRA_ROWS, nl), INTRA_ROWS * 32, 0, g, s, src, unf,
+                  mbi, nnz, coef, fl_intra);
     } else {
         const int nstrip = me_strip(g.R);
         LAUNCH_ON(st, K_ME, me_kernel, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,

@@ -558,17 +558,30 @@ __device__ __forceinline__ void mvp_skip_mb(const Geom &g, MbInfo *frame, int mb
 // K4 intra macroblocks of I frames: Intra16x16 (V/H/DC/Plane) + chroma (DC/H/V/Plane), mode by SAD,
 // transform / quant / recon.  Neighbours are the UNFILTERED reconstruction, so macroblock (x, y)
 // depends on (x-1, y) and on row y-1 up to x: one warp walks one macroblock row and publishes its
-// progress in flags[row]; the row below spins on it (wavefront).  Lanes as in K3.
-// Bound: dependency latency (mbw + mbh steps per frame) -- many lanes run side by side.
+// progress; the row below spins on it (wavefront).  INTRA_ROWS consecutive rows share a CTA: between them the
+// progress counter is a shared-memory word (a hop of a few hundred cycles; the pixels themselves go through L2),
+// only every INTRA_ROWS-th row synchronises through flags[row] in global memory (a hop of ~10^4 cycles).  Lanes as
+// in K3.  Bound: dependency latency (mbw + mbh steps per frame) -- many lanes run side by side.
 // ================================================================================================
-__global__ void __launch_bounds__(32) intra_kernel(Geom g, Step s, const uint8_t *__restrict__ src,
-                                                   uint8_t *unf, MbInfo *__restrict__ mbi,
-                                                   uint8_t *__restrict__ nnz, int16_t *__restrict__ coef, int *flags)
+#define INTRA_ROWS 8
+__global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, const uint8_t *__restrict__ src,
+                                                                uint8_t *unf, MbInfo *__restrict__ mbi,
+                                                                uint8_t *__restrict__ nnz, int16_t *__restrict__ coef,
+                                                                int *flags)
 {
     if (lane_frame(s, blockIdx.y) < 0)
         return;
-    __shared__ uint8_t topY[20], leftY[16], topC[2][12], leftC[2][8];
-    const int lane = threadIdx.x, row = blockIdx.x;
+    __shared__ uint8_t topY_s[INTRA_ROWS][20], leftY_s[INTRA_ROWS][16], topC_s[INTRA_ROWS][2][12], leftC_s[INTRA_ROWS][2][8];
+    __shared__ volatile int progress[INTRA_ROWS]; // macroblocks finished by each row of this CTA
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, row = blockIdx.x * INTRA_ROWS + wrp;
+    if (threadIdx.x < INTRA_ROWS)
+        progress[threadIdx.x] = 0;
+    __syncthreads();
+    if (row >= g.mbh)
+        return;
+    uint8_t *topY = topY_s[wrp], *leftY = leftY_s[wrp];
+    uint8_t(*topC)[12] = topC_s[wrp];
+    uint8_t(*leftC)[8] = leftC_s[wrp];
     const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
     int *fl = flags + (size_t)blockIdx.y * g.mbh;
     const bool luma = lane < 16, chroma = lane >= 16 && lane < 24;
@@ -592,8 +605,13 @@ __global__ void __launch_bounds__(32) intra_kernel(Geom g, Step s, const uint8_t
         }
         if (has_top) {
             if (lane == 0) {
-                while (ld_acquire(fl + row - 1) < mbx + 1)
-                    ;
+                if (wrp > 0) { // the row above lives in this CTA
+                    while (progress[wrp - 1] < mbx + 1)
+                        __nanosleep(20);
+                    __threadfence_block();
+                } else
+                    while (ld_acquire(fl + row - 1) < mbx + 1)
+                        ;
             }
             __syncwarp();
             const uint8_t *ty = unf + fo + (size_t)(row * 16 - 1) * g.W + mbx * 16 - 1;
@@ -748,8 +766,14 @@ __global__ void __launch_bounds__(32) intra_kernel(Geom g, Step s, const uint8_t
             mbi[rec] = m;
         }
         __syncwarp();
-        if (lane == 0)
-            st_release(fl + row, mbx + 1);
+        if (lane == 0) {
+            if (wrp == INTRA_ROWS - 1 || row == g.mbh - 1)
+                st_release(fl + row, mbx + 1); // read by the first row of the next CTA
+            else {
+                __threadfence(); // the pixels (global stores, read back through L2 by the row below) before the counter
+                progress[wrp] = mbx + 1;
+            }
+        }
     }
 }
 
