@@ -295,7 +295,7 @@ int alloc_buffers(cedar_b200_handle *h)
     const size_t U = (size_t)F * S; // slice NALs
     const size_t slice_mbs = (size_t)g.srows * g.mbw;
     h->eb.rbsp_cap = (unsigned)ALIGN_UP(slice_mbs * (F > 1 ? (g.qp < 20 ? 1024 : 400) : 1024) + 4096, 256);
-    size_t per_frame_out = (F > 1 ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) + 4096 : (size_t)h->bytestream_size) + 8 * S;
+    size_t per_frame_out = (F > 1 ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) + 4096 : (size_t)h->bytestream_size) + 8 * S + 64;
     h->out_cap = per_frame_out * F;
     size_t bins_per_mb = F > 1 ? (g.qp < 12 ? 8192 : (g.qp < 20 ? 2048 : 640)) : 16384;
     if (const char *e = getenv("CEDAR_B200_BINS_PER_MB"))
@@ -466,14 +466,17 @@ int finish_stream(cedar_b200_handle *h, int nframes, int gop_pos0, bool with_par
     const int nunits = nframes * h->S; // slice NALs
     LAUNCH(K_EPBCOUNT, epb_count_kernel, dim3((cpf + 255) / 256, nunits), 256, 0, nunits, h->eb.rbsp, h->eb.rbsp_cap,
            h->eb.rbsp_len, h->d_chunk_cnt, cpf);
-    LAUNCH(K_EPBSCAN, epb_scan_kernel, nunits, 1024, 0, nunits, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_bytes);
-    unsigned prefix = with_param_sets ? (unsigned)h->prefix_len : 0;
-    LAUNCH(K_PACKSCAN, pack_scan_kernel, 1, 1024, 0, nunits, h->S, h->d_nal_bytes, prefix, h->d_nal_off, h->d_frame_bytes,
+    ParamSets ps;
+    memset(&ps, 0, sizeof(ps));
+    memcpy(ps.bytes, h->prefix, (size_t)h->prefix_len);
+    ps.len = h->prefix_len;
+    ps.mode = h->cfg.repeat_headers ? 2 : (with_param_sets ? 1 : 0); // cedar.c:1058-1061: once, before stream frame 0
+    LAUNCH(K_EPBSCAN, epb_scan_kernel, nunits, 1024, 0, nunits, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_bytes, ps, h->S,
+           h->K, gop_pos0);
+    LAUNCH(K_PACKSCAN, pack_scan_kernel, 1, 1024, 0, nunits, h->S, h->d_nal_bytes, 0u, h->d_nal_off, h->d_frame_bytes,
            h->d_total, (unsigned long long)h->out_cap, h->eb.error);
     LAUNCH(K_EPBWRITE, epb_write_kernel, dim3((cpf + 255) / 256, nunits), 256, 0, nunits, h->S, h->K, gop_pos0, h->eb.rbsp,
-           h->eb.rbsp_cap, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_off, h->d_total, h->d_out);
-    if (prefix)
-        CK(cudaMemcpyAsync(h->d_out, h->prefix, prefix, cudaMemcpyHostToDevice, h->stream));
+           h->eb.rbsp_cap, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_off, h->d_total, h->d_out, ps);
     return 0;
 }
 

@@ -1921,6 +1921,19 @@ __global__ void __launch_bounds__(CP_THREADS) cabac_code_kernel(Geom g, Step s, 
 // ================================================================================================
 #define EPB_CHUNK 64
 
+// SPS + PPS bytes (host written) and which slice NALs they precede: mode 0 none, 1 the first NAL of this call
+// (stream frame 0, cedar.c:1058-1061), 2 the first slice of every IDR picture (repeat_headers extension).
+struct ParamSets {
+    uint8_t bytes[64];
+    int len, mode;
+};
+__device__ __forceinline__ bool has_param_sets(const ParamSets &ps, int u, int nslices, int gop_len, int first_frame_index)
+{
+    if (u % nslices)
+        return false;
+    return (ps.mode == 1 && u == 0) || (ps.mode == 2 && ((first_frame_index + u / nslices) % gop_len) == 0);
+}
+
 __device__ __forceinline__ unsigned zero_run_before(const uint8_t *p, long i)
 {
     unsigned run = 0;
@@ -1954,7 +1967,8 @@ __global__ void epb_count_kernel(int nframes, const uint8_t *__restrict__ rbsp, 
 // One CTA per frame: exclusive scan of its chunk counts (in place) and the frame's NAL size.
 __global__ void __launch_bounds__(1024) epb_scan_kernel(int nframes, const uint32_t *__restrict__ rbsp_len,
                                                         uint32_t *chunk_cnt, unsigned chunks_per_frame,
-                                                        uint32_t *__restrict__ nal_bytes)
+                                                        uint32_t *__restrict__ nal_bytes, ParamSets ps, int nslices,
+                                                        int gop_len, int first_frame_index)
 {
     int f = blockIdx.x;
     __shared__ uint32_t warp_sum[32];
@@ -1997,7 +2011,9 @@ __global__ void __launch_bounds__(1024) epb_scan_kernel(int nframes, const uint3
         __syncthreads();
     }
     if (tid == 0)
-        nal_bytes[f] = rbsp_len[f] ? 5 + rbsp_len[f] + carry_s : 0; // start code + NAL header + payload
+        nal_bytes[f] = rbsp_len[f] ? 5 + rbsp_len[f] + carry_s + // start code + NAL header + payload (+ SPS, PPS in front)
+                                         (has_param_sets(ps, f, nslices, gop_len, first_frame_index) ? ps.len : 0)
+                                   : 0;
 }
 
 // Single CTA: exclusive scan of the per-frame NAL sizes -> offsets in the packed stream.
@@ -2065,7 +2081,7 @@ __global__ void epb_write_kernel(int nframes /* units */, int nslices, int gop_l
                                  const uint8_t *__restrict__ rbsp, unsigned rbsp_cap,
                                  const uint32_t *__restrict__ rbsp_len, const uint32_t *__restrict__ chunk_off,
                                  unsigned chunks_per_frame, const unsigned long long *__restrict__ nal_off,
-                                 const unsigned long long *__restrict__ total, uint8_t *__restrict__ out)
+                                 const unsigned long long *__restrict__ total, uint8_t *__restrict__ out, ParamSets ps)
 {
     int f = blockIdx.y;
     unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2076,6 +2092,12 @@ __global__ void epb_write_kernel(int nframes /* units */, int nslices, int gop_l
     if (n == 0)
         return;
     uint8_t *o = out + nal_off[f];
+    if (has_param_sets(ps, f, nslices, gop_len, first_frame_index)) {
+        if (ch == 0)
+            for (int i = 0; i < ps.len; i++)
+                o[i] = ps.bytes[i];
+        o += ps.len;
+    }
     if (ch == 0) {
         // cedar.c:868-881 start code + NAL header: IDR ref_idc 3 type 5, P ref_idc 2 type 1 (:987-990)
         int frame_i = ((first_frame_index + f / nslices) % gop_len) == 0;

@@ -56,6 +56,9 @@ struct cedar_b200_config {
                               * of the coded 1920x1088).  The reference never does: cedar.c:756-761 makes :924-931 dead. */
     int auto_level;          /* non-zero: level_idc = lowest level whose MaxFS fits the picture (4K: 5.1) instead of the
                               * configured `level`, which the reference writes unchecked (cedar.c:900). */
+    int repeat_headers;      /* non-zero: SPS + PPS in front of every IDR picture, so that every closed GOP (e.g. one
+                              * GPU's share of a GOP-parallel encode) decodes on its own; the reference writes them
+                              * once, before the first frame (cedar.c:1058-1061). */
 };
 
 /*

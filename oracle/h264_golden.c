@@ -1958,7 +1958,7 @@ int gm_encode_frame(gm_encoder *e, const uint8_t *luma, const uint8_t *chroma, u
     int n = 0, r;
     ingest(e, luma, chroma);
 
-    if (!e->frame_count) { /* cedar.c:1058-1061 */
+    if (!e->frame_count || (e->cfg.repeat_headers && frame_i)) { /* cedar.c:1058-1061: once; extension: every IDR */
         if ((r = gm_write_sps(&e->cfg, out + n, out_cap - n)) < 0)
             return r;
         n += r;

@@ -228,3 +228,26 @@ def test_sps_crop_and_auto_level_stream_matches_oracle(oracle):
     gold.close()
     dec = avdec.decode(stream)
     assert len(dec) == 3 and dec[0][0].shape == (h, w)
+
+
+@pytest.mark.parametrize("rows", [0, 2])
+def test_repeat_headers_makes_every_gop_decodable_on_its_own(oracle, rows):
+    """repeat_headers: SPS + PPS before every IDR (frame mode == clip mode == oracle); a later GOP, cut out of the
+    stream, decodes by itself -- what a rank of a GOP-parallel encode produces with first_frame_index != 0."""
+    w, h, n, gop = 96, 80, 9, 3
+    clip = make_clip("synth", w, h, n)
+    want, sizes, recs = oracle_encode_clip(clip, w, h, keep_recon=True, qp=24, gop=gop, cabac=1, me_range=8,
+                                           slice_rows=rows, repeat_headers=1)
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=gop, cabac=1, me_range=8, max_clip_frames=n, slice_rows=rows,
+                                    repeat_headers=1)) as enc:
+        got, gsz = enc.encode_clip(clip)
+        assert got == want and gsz.tolist() == sizes
+        tail, _ = enc.encode_clip(clip[3:], first_frame_index=3)
+    assert tail == want[sum(sizes[:3]):]
+    dec = avdec.decode(tail)
+    assert len(dec) == 6
+    for p in range(3):
+        assert np.array_equal(dec[-1][p], recs[-1][p])
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=gop, cabac=1, me_range=8, slice_rows=rows, repeat_headers=1)) as enc:
+        frames = b"".join(enc.encode(*split_frame(clip[t], w, h, 0)) for t in range(n))
+    assert frames == want
