@@ -227,6 +227,15 @@ def run_gpu(args, rank, local_rank, world):
     data, sizes = enc.clip_download(n)
     stream_bytes = int(len(data))
     sse = enc.sse_y(n)
+    # CABAC bins of the clip (debug read 6: one count per slice NAL), for the per-bin cost of the two coder kernels
+    import numpy as np
+    nbins = 0
+    if cabac:
+        mbh_ = (h + 15) // 16
+        nsl = 1 if not args.slice_rows or args.slice_rows >= mbh_ else -(-mbh_ // args.slice_rows)
+        bins = np.zeros(n * nsl, np.uint32)
+        enc.L.cedar_b200_debug_read(enc.h, 6, bins.ctypes.data, bins.nbytes)
+        nbins = int(bins.sum())
 
     # -------- end to end through the C ABI with host buffers (`e2e`) --------
     for _ in range(min(args.warmup, 1)):
@@ -347,6 +356,16 @@ def run_gpu(args, rank, local_rank, world):
                 hbm[name] = {"bound": "hbm", "achieved": round(gbs, 2), "peak": hbm_peak, "unit": "GB/s",
                              "frac": round(gbs / hbm_peak, 5), "traffic": None, "peak_source": hbm_src}
         mse = float(sse.sum()) / (n * W16 * H16)
+        cabac_stats = None
+        if nbins and clocks and clocks.get("sm_mhz"):
+            lanes = int(enc.cfg.gops_in_flight) or min(16, -(-n // gop))  # CTAs of a launch = lanes x slices, side by side
+            per_cta_bins = nbins / float(lanes * nsl)
+            cabac_stats = {"bins_per_clip": nbins, "bins_per_frame": round(nbins / n, 1),
+                           "note": "one CTA per slice NAL; cycles per bin = summed launch time x SM clock / bins one CTA codes per "
+                                   "clip; resolve is serial along one context's bins, code is parallel over all bins"}
+            for k in ("cabac_resolve_kernel", "cabac_code_kernel"):
+                if k in prof:
+                    cabac_stats[k + "_cycles_per_bin"] = round(prof[k][0] * 1e-3 * clocks["sm_mhz"] * 1e6 / per_cta_bins, 2)
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -365,6 +384,7 @@ def run_gpu(args, rank, local_rank, world):
             "roofline_hbm_kernels": hbm,
             "kernels": kernels,
             "slice_parallel": slice_report,
+            "cabac": cabac_stats,
             "quality": {"y_psnr_db": round(10 * math.log10(255.0 ** 2 / mse), 3) if mse > 0 else None,
                         "kbit_per_frame": round(stream_bytes * 8 / 1000.0 / n, 2)},
         }

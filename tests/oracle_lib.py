@@ -32,7 +32,8 @@ _lib = None
 
 
 def build(force=False):
-    src = [os.path.join(ORACLE_DIR, f) for f in ("h264_golden.c", "h264_golden.h", "h264_tables.h")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("h264_golden.c", "h264_golden.h", "h264_tables.h", "h264_decoder.c",
+                                                 "h264_decoder.h")]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in src):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liboracle_h264.so", "golden_enc"])
     return LIB
@@ -60,6 +61,15 @@ def lib():
         L.gm_slice_header_bits.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
         L.gm_slice_header_bits64.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64),
                                              C.POINTER(C.c_int)]
+        L.gd_open.restype = C.c_void_p
+        L.gd_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.gd_error.argtypes = [C.c_void_p]
+        L.gd_error.restype = C.c_char_p
+        for f in ("gd_frames", "gd_width", "gd_height", "gd_crop_right", "gd_crop_bottom", "gd_close"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.gd_close.restype = None
+        L.gd_frame.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.gd_frame.restype = C.c_void_p
         L.gm_synth_frame.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         assert C.sizeof(GmMb) == MB_DTYPE.itemsize, (C.sizeof(GmMb), MB_DTYPE.itemsize)
         _lib = L
@@ -166,3 +176,26 @@ def slice_header_bits(frame_i, frame_p_count, cabac, first_mb=0):
     bits, n = C.c_uint32(), C.c_int()
     lib().gm_slice_header_bits(frame_i, frame_p_count, cabac, C.byref(bits), C.byref(n))
     return format(bits.value, "0%db" % n.value)
+
+
+def golden_decode(stream: bytes, crop=True):
+    """The golden model's own decoder (oracle/h264_decoder.c): list of (Y, U, V) planes, like tests/avdec.decode."""
+    L = lib()
+    d = L.gd_open()
+    buf = np.frombuffer(stream, np.uint8)
+    n = L.gd_decode(d, buf.ctypes.data, buf.size)
+    if n < 0:
+        msg = L.gd_error(d).decode()
+        L.gd_close(d)
+        raise ValueError("golden decoder: " + msg)
+    W, H = L.gd_width(d), L.gd_height(d)
+    w, h = (W - L.gd_crop_right(d), H - L.gd_crop_bottom(d)) if crop else (W, H)
+    out = []
+    for i in range(n):
+        planes = []
+        for p, (pw, ph, cw, ch) in enumerate(((W, H, w, h), (W // 2, H // 2, w // 2, h // 2), (W // 2, H // 2, w // 2, h // 2))):
+            a = np.ctypeslib.as_array(C.cast(L.gd_frame(d, i, p), C.POINTER(C.c_uint8)), shape=(ph, pw))
+            planes.append(a[:ch, :cw].copy())
+        out.append(tuple(planes))
+    L.gd_close(d)
+    return out

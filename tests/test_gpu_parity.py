@@ -251,3 +251,21 @@ def test_repeat_headers_makes_every_gop_decodable_on_its_own(oracle, rows):
     with cx.Encoder(api.make_config(w, h, qp=24, gop=gop, cabac=1, me_range=8, slice_rows=rows, repeat_headers=1)) as enc:
         frames = b"".join(enc.encode(*split_frame(clip[t], w, h, 0)) for t in range(n))
     assert frames == want
+
+
+@pytest.mark.parametrize("cabac,rows", [(1, 0), (0, 0), (1, 3)])
+def test_gpu_stream_through_the_golden_decoder(oracle, cabac, rows):
+    """The CUDA encoder's stream, decoded by the golden model's decoder (no libavcodec), equals the CUDA encoder's own
+    reconstruction."""
+    w, h, n = 176, 144, 5
+    clip = make_clip("synth", w, h, n)
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=3, cabac=cabac, slice_rows=rows)) as enc:
+        stream, recs = b"", []
+        for t in range(n):
+            stream += enc.encode(*split_frame(clip[t], w, h, 0))
+            recs.append(enc.debug_planes(2))
+    dec = oracle.golden_decode(stream)
+    assert len(dec) == n
+    for r, d in zip(recs, dec):
+        for p in range(3):
+            assert np.array_equal(r[p], d[p])
