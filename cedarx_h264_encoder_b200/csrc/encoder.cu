@@ -102,6 +102,7 @@ struct cedar_b200_handle {
     uint8_t *d_raw, *d_src[2], *d_unf, *d_rec[2];
     MbInfo *d_mbi[2];
     uint8_t *d_nnz[2];
+    uint8_t *d_i4[2]; // Intra4x4 prediction modes, [L][nmb][16]
     int16_t *d_coef[2];
     int *d_flags; // [3][L][mbh]
     uint8_t *d_bs; // [L][nmb][32] boundary strengths
@@ -315,6 +316,7 @@ int alloc_buffers(cedar_b200_handle *h)
     for (int p = 0; p < 2; p++) {
         r |= dmalloc(&h->d_mbi[p], (size_t)g.nmb * L);
         r |= dmalloc(&h->d_nnz[p], (size_t)g.nmb * L * NNZ_STRIDE);
+        r |= dmalloc(&h->d_i4[p], (size_t)g.nmb * L * 16);
         r |= dmalloc(&h->d_coef[p], (size_t)g.nmb * L * COEF_STRIDE);
     }
     r |= dmalloc(&h->d_flags, (size_t)3 * L * g.mbh);
@@ -357,7 +359,7 @@ int alloc_buffers(cedar_b200_handle *h)
 void free_buffers(cedar_b200_handle *h)
 {
     void *dev[] = {h->d_raw, h->d_src[0], h->d_src[1], h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi[0], h->d_mbi[1],
-                   h->d_nnz[0], h->d_nnz[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_bs,
+                   h->d_nnz[0], h->d_nnz[1], h->d_i4[0], h->d_i4[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_bs,
                    h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp, h->eb.rbsp_len,
                    h->eb.bins, h->eb.limbs, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
                    h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes, h->d_out};
@@ -409,7 +411,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
     CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 3 * flag_n, st));
     if (frame_i) {
         LAUNCH_ON(st, K_INTRA, intra_kernel, dim3((g.mbh + INTRA_ROWS - 1) / INTRA_ROWS, nl), INTRA_ROWS * 32, 0, g, s, src, unf,
-                  mbi, nnz, coef, fl_intra);
+                  mbi, nnz, coef, fl_intra, h->d_i4[p]);
     } else {
         const int nstrip = me_strip(g.R);
         LAUNCH_ON(st, K_ME, me_kernel, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
@@ -426,12 +428,14 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
     CK(cudaStreamWaitEvent(post, h->ev_main[p], 0));
     LAUNCH_ON(post, K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, src, rec, h->d_sse);
     dim3 egrid((g.nmb + g.nslices + 127) / 128, nl);
-    LAUNCH_ON(post, K_ESIZE, entropy_size_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, h->eb);
+    EntropyBufs eb = h->eb;
+    eb.i4 = h->d_i4[p];
+    LAUNCH_ON(post, K_ESIZE, entropy_size_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, eb);
     LAUNCH_ON(post, K_ESCAN, entropy_scan_kernel, dim3(1, nl), 1024, 0, g, s, h->eb);
     if (!g.cabac)
         LAUNCH_ON(post, K_EZERO, rbsp_zero_kernel, dim3(8, nl, g.nslices), 256, 0, s, h->eb.rbsp, h->eb.rbsp_cap,
                   h->eb.rbsp_len);
-    LAUNCH_ON(post, K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, h->eb);
+    LAUNCH_ON(post, K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, eb);
     CK(cudaEventRecord(h->ev_post[p], post));
     h->post_valid[p] = true;
     if (g.cabac) {
@@ -594,6 +598,7 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     g.cabac = cfg->entropy_coding_mode == CEDAR_B200_ENTROPY_CABAC;
     g.srows = cfg->slice_rows > 0 && cfg->slice_rows < g.mbh ? cfg->slice_rows : g.mbh;
     g.nslices = (g.mbh + g.srows - 1) / g.srows;
+    g.intra4x4 = cfg->intra4x4 != 0;
     h->S = g.nslices;
     g.frame_bytes = (unsigned long long)g.W * g.H * 3 / 2;
     h->K = cfg->keyframe_interval;
@@ -858,6 +863,7 @@ long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_
     case 3: src = h->d_mbi[h->last_par], n = sizeof(MbInfo) * g.nmb; break;
     case 4: src = h->d_nnz[h->last_par], n = (size_t)NNZ_STRIDE * g.nmb; break;
     case 5: src = h->d_coef[h->last_par], n = sizeof(int16_t) * COEF_STRIDE * g.nmb; break;
+    case 7: src = h->d_i4[h->last_par], n = (size_t)16 * g.nmb; break;
     case 6: src = h->eb.bins_len, n = sizeof(uint32_t) * (h->last_nframes > 0 ? h->last_nframes : 1) * h->S; break;
     default: return -EINVAL;
     }

@@ -17,6 +17,7 @@ struct FrameSyntax {
     const int16_t *coef;  // [nmb][COEF_STRIDE]
     int mbw, mbh;
     int srows; // macroblock rows per slice (== mbh: one slice per picture, the reference's layout)
+    const uint8_t *i4; // [nmb][16] Intra4x4PredMode per luma4x4BlkIdx (only read for MB_I4x4 macroblocks; may be null)
 };
 
 // Slices are whole macroblock rows, so the left neighbour is always in the same slice; the row above is
@@ -84,6 +85,38 @@ HD int nnz_top(const FrameSyntax &fs, int mbx, int mby, int kind, int blk)
     if (!top_avail(fs, mby))
         return -1;
     return (cur - (size_t)fs.mbw * NNZ_STRIDE)[base + 2 + bx];
+}
+
+// Intra4x4PredMode of the 4x4 block left of / above block blk for the prediction of the mode (8.3.1.1 with
+// constrained_intra_pred_flag = 0): -1 = not available, 2 (DC) when the neighbouring macroblock is not Intra4x4.
+HD int i4_neighbour_mode(const FrameSyntax &fs, int mbx, int mby, int blk, int left)
+{
+    int mb = mby * fs.mbw + mbx, bx = blk_x(blk), by = blk_y(blk), nb;
+    if (left) {
+        if (bx > 0)
+            nb = xy2blk(bx - 1, by);
+        else {
+            if (mbx == 0)
+                return -1;
+            mb -= 1;
+            nb = xy2blk(3, by);
+        }
+    } else {
+        if (by > 0)
+            nb = xy2blk(bx, by - 1);
+        else {
+            if (!top_avail(fs, mby))
+                return -1;
+            mb -= fs.mbw;
+            nb = xy2blk(bx, 3);
+        }
+    }
+    return fs.mbi[mb].type == MB_I4x4 ? fs.i4[(size_t)mb * 16 + nb] : 2;
+}
+HD int i4_pred_mode(const FrameSyntax &fs, int mbx, int mby, int blk)
+{
+    int a = i4_neighbour_mode(fs, mbx, mby, blk, 1), b = i4_neighbour_mode(fs, mbx, mby, blk, 0);
+    return (a < 0 || b < 0) ? 2 : imin_(a, b);
 }
 
 // =============================================================================================
@@ -297,6 +330,22 @@ template <class S> HD void cavlc_mb(S &s, const FrameSyntax &fs, int mb_index, i
         if (cbpl)
             for (int b = 0; b < 16; b++)
                 cavlc_block(s, coef + b * 16 + 1, 15, cavlc_nc(fs, mbx, mby, 0, b));
+    } else if (mb.type == MB_I4x4) {
+        put_ue(s, frame_i ? 0u : 5u); // I_NxN
+        for (int b = 0; b < 16; b++) {
+            int pm = i4_pred_mode(fs, mbx, mby, b), mode = fs.i4[(size_t)mb_index * 16 + b];
+            if (mode == pm)
+                s.put(1, 1); // prev_intra4x4_pred_mode_flag
+            else
+                s.put((uint32_t)(mode < pm ? mode : mode - 1), 4); // flag 0 + rem_intra4x4_pred_mode
+        }
+        put_ue(s, mb.chroma_mode);
+        put_ue(s, h264_cbp_to_codenum_intra[mb.cbp]);
+        if (mb.cbp)
+            put_se(s, 0); // mb_qp_delta
+        for (int b = 0; b < 16; b++)
+            if (cbpl & (1 << (b >> 2)))
+                cavlc_block(s, coef + b * 16, 16, cavlc_nc(fs, mbx, mby, 0, b));
     } else {
         put_ue(s, 0); // P_L0_16x16
         put_se(s, mb.mvd[0]);
@@ -477,6 +526,23 @@ template <class S> HD void cabac_mb(S &s, const FrameSyntax &fs, int mb_index, i
         }
         s.bin(c4, mb.i16_mode >> 1);
         s.bin(c5, mb.i16_mode & 1);
+    } else if (mb.type == MB_I4x4) {
+        if (frame_i)
+            s.bin(3 + (A && A->type != MB_I4x4) + (B && B->type != MB_I4x4), 0); // I_NxN
+        else {
+            s.bin(14, 1);
+            s.bin(17, 0);
+        }
+        for (int b = 0; b < 16; b++) {
+            int pm = i4_pred_mode(fs, mbx, mby, b), mode = fs.i4[(size_t)mb_index * 16 + b];
+            s.bin(68, mode == pm);
+            if (mode != pm) {
+                int rem = mode < pm ? mode : mode - 1;
+                s.bin(69, rem & 1);
+                s.bin(69, (rem >> 1) & 1);
+                s.bin(69, (rem >> 2) & 1);
+            }
+        }
     } else {
         s.bin(14, 0);
         s.bin(15, 0);

@@ -48,6 +48,7 @@ struct Geom {
     int R, lambda;      // ME radius and SAD lambda
     int cabac;
     int srows, nslices; // macroblock rows per slice (mbh = the reference's one slice per picture), slices per picture
+    int intra4x4;       // extension: Intra4x4 macroblocks in I frames (off: Intra16x16 only)
     unsigned long long frame_bytes; // W*H*3/2 : one planar frame (Y, U, V)
 };
 
@@ -380,6 +381,68 @@ HD void pred16_block(int mode, const uint8_t *top, const uint8_t *left, int has_
         for (int i = 0; i < 16; i++)
             pred[i] = clip255_((a + b * (bx + (i & 3) - 7) + c * (by + (i >> 2) - 7) + 16) >> 5);
     }
+}
+
+// One sample (x, y) of an Intra4x4 prediction (H.264 8.3.1.2): t[0..7] = A..H (above, above-right), l[0..3] = I..L
+// (left), m = M (above-left).  Modes: 0 V, 1 H, 2 DC, 3 DDL, 4 DDR, 5 VR, 6 HD, 7 VL, 8 HU.
+HD int pred4x4_pixel(int mode, int x, int y, const uint8_t *t, const uint8_t *l, int m, int has_top, int has_left)
+{
+#define PT_(i) ((i) < 0 ? m : (int)t[i])
+#define PL_(i) ((i) < 0 ? m : (int)l[i])
+    switch (mode) {
+    case 0: return t[x];
+    case 1: return l[y];
+    case 2: {
+        int s = 0;
+        if (has_top)
+            s += t[0] + t[1] + t[2] + t[3];
+        if (has_left)
+            s += l[0] + l[1] + l[2] + l[3];
+        return (has_top && has_left) ? (s + 4) >> 3 : ((has_top || has_left) ? (s + 2) >> 2 : 128);
+    }
+    case 3: return (x == 3 && y == 3) ? (t[6] + 3 * t[7] + 2) >> 2 : (t[x + y] + 2 * t[x + y + 1] + t[x + y + 2] + 2) >> 2;
+    case 4:
+        if (x > y)
+            return (PT_(x - y - 2) + 2 * PT_(x - y - 1) + PT_(x - y) + 2) >> 2;
+        if (x < y)
+            return (PL_(y - x - 2) + 2 * PL_(y - x - 1) + PL_(y - x) + 2) >> 2;
+        return (t[0] + 2 * m + l[0] + 2) >> 2;
+    case 5: {
+        int z = 2 * x - y;
+        if (z >= 0 && !(z & 1))
+            return (PT_(x - (y >> 1) - 1) + PT_(x - (y >> 1)) + 1) >> 1;
+        if (z >= 0)
+            return (PT_(x - (y >> 1) - 2) + 2 * PT_(x - (y >> 1) - 1) + PT_(x - (y >> 1)) + 2) >> 2;
+        if (z == -1)
+            return (l[0] + 2 * m + t[0] + 2) >> 2;
+        return (PL_(y - 1) + 2 * PL_(y - 2) + PL_(y - 3) + 2) >> 2;
+    }
+    case 6: {
+        int z = 2 * y - x;
+        if (z >= 0 && !(z & 1))
+            return (PL_(y - (x >> 1) - 1) + PL_(y - (x >> 1)) + 1) >> 1;
+        if (z >= 0)
+            return (PL_(y - (x >> 1) - 2) + 2 * PL_(y - (x >> 1) - 1) + PL_(y - (x >> 1)) + 2) >> 2;
+        if (z == -1)
+            return (l[0] + 2 * m + t[0] + 2) >> 2;
+        return (PT_(x - 1) + 2 * PT_(x - 2) + PT_(x - 3) + 2) >> 2;
+    }
+    case 7:
+        return !(y & 1) ? (t[x + (y >> 1)] + t[x + (y >> 1) + 1] + 1) >> 1
+                        : (t[x + (y >> 1)] + 2 * t[x + (y >> 1) + 1] + t[x + (y >> 1) + 2] + 2) >> 2;
+    default: {
+        int z = x + 2 * y;
+        if (z > 5)
+            return l[3];
+        if (z == 5)
+            return (l[2] + 3 * l[3] + 2) >> 2;
+        if (!(z & 1))
+            return (l[y + (x >> 1)] + l[y + (x >> 1) + 1] + 1) >> 1;
+        return (l[y + (x >> 1)] + 2 * l[y + (x >> 1) + 1] + l[y + (x >> 1) + 2] + 2) >> 2;
+    }
+    }
+#undef PT_
+#undef PL_
 }
 
 // Chroma 8x8: mode 0 DC, 1 H, 2 V, 3 Plane.

@@ -564,13 +564,139 @@ __device__ __forceinline__ void mvp_skip_mb(const Geom &g, MbInfo *frame, int mb
 // in K3.  Bound: dependency latency (mbw + mbh steps per frame) -- many lanes run side by side.
 // ================================================================================================
 #define INTRA_ROWS 8
+
+// Per-warp shared state of the Intra4x4 trial (intra4x4 extension).
+struct __align__(16) I4Work {
+    uint8_t patch[17][24]; // row 0: samples above (col 3 above-left, 4..19 above, 20..23 above-right); rows 1..16: col 3 =
+                           // left neighbours, cols 4..19 = the macroblock as it is reconstructed block by block
+    uint8_t nb[16];        // neighbours of the current block: 0..7 above / above-right, 8..11 left, 12 above-left
+    uint8_t mode[16], nnzb[16]; // per luma4x4BlkIdx
+    uint8_t left_mode[16]; // modes of the macroblock to the left
+    uint8_t left_is_i4;
+};
+
+// Tries to code the macroblock's luma as Intra4x4 (oracle: try_intra4x4): block by block, mode = argmin over the
+// available modes of (SAD + lambda * modebits) << 4 | mode (modebits 1 for the predicted mode, 4 otherwise); the block
+// is reconstructed at once because the next blocks predict from it.  Gives up as soon as the accumulated cost reaches
+// cost16.  Warp-collective: lane = sample (x, y) of the current block in both half-warps, the halves evaluate two
+// modes at a time; transforms run across the 16 lanes with shuffles.  top_kind: -1 no macroblock above, 0 it is not
+// Intra4x4, 1 its modes are at top_modes.
+__device__ __forceinline__ bool intra4x4_trial(const Geom &g, I4Work &w, int lane, const uint32_t *sv, bool has_topmb,
+                                               bool has_leftmb, bool has_trmb, int top_kind, const uint8_t *top_modes,
+                                               uint32_t cost16, int16_t *cf, int &cbp_out)
+{
+    const uint8_t izz[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};
+    const int r = lane & 15, x = r & 3, y = r >> 2, half = lane & 16, qp = g.qp;
+    const int qbits = 15 + qp / 6, f = (1 << qbits) / 3, cls = pos_class(r);
+    uint32_t cost4 = 0;
+    int cbp = 0;
+    for (int b = 0; b < 16; b++) {
+        const int bx = blk_x(b), by = blk_y(b);
+        const bool ht = by > 0 || has_topmb, hl = bx > 0 || has_leftmb, htl = ht && hl;
+        const bool htr = by == 0 ? (has_topmb && (bx < 3 || has_trmb)) : (bx < 3 && xy2blk(bx + 1, by - 1) < b);
+        if (lane < 8)
+            w.nb[lane] = ht ? w.patch[by * 4][4 + bx * 4 + ((lane < 4 || htr) ? lane : 3)] : 0;
+        else if (lane < 12)
+            w.nb[lane] = hl ? w.patch[1 + by * 4 + (lane - 8)][3 + bx * 4] : 0;
+        else if (lane == 12)
+            w.nb[12] = htl ? w.patch[by * 4][3 + bx * 4] : 0;
+        __syncwarp();
+        int ma, mb2; // modes of the blocks to the left / above, for the predicted mode
+        if (bx > 0)
+            ma = w.mode[xy2blk(bx - 1, by)];
+        else
+            ma = !has_leftmb ? -1 : (w.left_is_i4 ? (int)w.left_mode[xy2blk(3, by)] : 2);
+        if (by > 0)
+            mb2 = w.mode[xy2blk(bx, by - 1)];
+        else
+            mb2 = top_kind < 0 ? -1 : (top_kind == 0 ? 2 : (int)__ldcg(top_modes + xy2blk(bx, 3)));
+        const int pm = (ma < 0 || mb2 < 0) ? 2 : imin_(ma, mb2);
+        // source sample (x, y) of block b: lane b holds the block's four rows
+        const uint32_t r0 = __shfl_sync(0xffffffffu, sv[0], b), r1 = __shfl_sync(0xffffffffu, sv[1], b);
+        const uint32_t r2 = __shfl_sync(0xffffffffu, sv[2], b), r3 = __shfl_sync(0xffffffffu, sv[3], b);
+        const int sp = (int)(((y & 2 ? (y & 1 ? r3 : r2) : (y & 1 ? r1 : r0)) >> (8 * x)) & 0xff);
+        const int m = w.nb[12];
+        uint32_t best = 0xffffffffu;
+#pragma unroll 1
+        for (int i = 0; i < 5; i++) {
+            const int mode = 2 * i + (half >> 4);
+            const bool need_top = mode == 0 || mode == 3 || mode == 7 || (mode >= 4 && mode <= 6);
+            const bool need_left = mode == 1 || mode == 8 || (mode >= 4 && mode <= 6);
+            const bool valid = mode <= 8 && (!need_top || ht) && (!need_left || hl) && (!(mode >= 4 && mode <= 6) || htl);
+            int ad = 0;
+            if (valid)
+                ad = iabs_(sp - pred4x4_pixel(mode, x, y, w.nb, w.nb + 8, m, ht, hl));
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1)
+                ad += __shfl_xor_sync(0xffffffffu, ad, o);
+            const uint32_t key = valid ? (((uint32_t)ad + (uint32_t)(g.lambda * (mode == pm ? 1 : 4))) << 4) | (uint32_t)mode : 0xffffffffu;
+            best = key < best ? key : best;
+        }
+        {
+            const uint32_t o = __shfl_xor_sync(0xffffffffu, best, 16);
+            best = o < best ? o : best;
+        }
+        cost4 += best >> 4;
+        if (cost4 >= cost16)
+            return false;
+        const int mode_b = (int)(best & 15);
+        // ---- reconstruct the block: residual, 4x4 transform, quantisation, and back ----
+        const int pv = pred4x4_pixel(mode_b, x, y, w.nb, w.nb + 8, m, ht, hl);
+        int v = sp - pv;
+        {
+            const int rb = lane & ~3; // forward transform, rows
+            const int a = __shfl_sync(0xffffffffu, v, rb), b1 = __shfl_sync(0xffffffffu, v, rb + 1);
+            const int c = __shfl_sync(0xffffffffu, v, rb + 2), e = __shfl_sync(0xffffffffu, v, rb + 3);
+            const int s03 = a + e, d03 = a - e, s12 = b1 + c, d12 = b1 - c;
+            v = x == 0 ? s03 + s12 : (x == 1 ? 2 * d03 + d12 : (x == 2 ? s03 - s12 : d03 - 2 * d12));
+        }
+        {
+            const int cbase = half + x; // columns
+            const int a = __shfl_sync(0xffffffffu, v, cbase), b1 = __shfl_sync(0xffffffffu, v, cbase + 4);
+            const int c = __shfl_sync(0xffffffffu, v, cbase + 8), e = __shfl_sync(0xffffffffu, v, cbase + 12);
+            const int s03 = a + e, d03 = a - e, s12 = b1 + c, d12 = b1 - c;
+            v = y == 0 ? s03 + s12 : (y == 1 ? 2 * d03 + d12 : (y == 2 ? s03 - s12 : d03 - 2 * d12));
+        }
+        const int z = quant1(v, h264_quant_mf[qp % 6][cls], f, qbits);
+        const int n = __popc(__ballot_sync(0xffffffffu, z != 0) & 0xffffu);
+        if (lane < 16)
+            cf[b * 16 + izz[r]] = (int16_t)z;
+        v = n ? dequant_ac(z, qp, cls) : 0;
+        {
+            const int rb = lane & ~3; // inverse transform, rows
+            const int d0 = __shfl_sync(0xffffffffu, v, rb), d1 = __shfl_sync(0xffffffffu, v, rb + 1);
+            const int d2 = __shfl_sync(0xffffffffu, v, rb + 2), d3 = __shfl_sync(0xffffffffu, v, rb + 3);
+            const int e0 = d0 + d2, e1 = d0 - d2, e2 = (d1 >> 1) - d3, e3 = d1 + (d3 >> 1);
+            v = x == 0 ? e0 + e3 : (x == 1 ? e1 + e2 : (x == 2 ? e1 - e2 : e0 - e3));
+        }
+        {
+            const int cbase = half + x; // columns
+            const int d0 = __shfl_sync(0xffffffffu, v, cbase), d1 = __shfl_sync(0xffffffffu, v, cbase + 4);
+            const int d2 = __shfl_sync(0xffffffffu, v, cbase + 8), d3 = __shfl_sync(0xffffffffu, v, cbase + 12);
+            const int e0 = d0 + d2, e1 = d0 - d2, e2 = (d1 >> 1) - d3, e3 = d1 + (d3 >> 1);
+            v = ((y == 0 ? e0 + e3 : (y == 1 ? e1 + e2 : (y == 2 ? e1 - e2 : e0 - e3))) + 32) >> 6;
+        }
+        if (lane < 16)
+            w.patch[1 + by * 4 + y][4 + bx * 4 + x] = (uint8_t)clip255_(pv + v);
+        if (lane == 0) {
+            w.mode[b] = (uint8_t)mode_b;
+            w.nnzb[b] = (uint8_t)n;
+        }
+        if (n)
+            cbp |= 1 << (b >> 2);
+        __syncwarp();
+    }
+    cbp_out = cbp;
+    return true;
+}
 __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, const uint8_t *__restrict__ src,
                                                                 uint8_t *unf, MbInfo *__restrict__ mbi,
                                                                 uint8_t *__restrict__ nnz, int16_t *__restrict__ coef,
-                                                                int *flags)
+                                                                int *flags, uint8_t *i4)
 {
     if (lane_frame(s, blockIdx.y) < 0)
         return;
+    __shared__ I4Work i4w_s[INTRA_ROWS];
     __shared__ uint8_t topY_s[INTRA_ROWS][20], leftY_s[INTRA_ROWS][16], topC_s[INTRA_ROWS][2][12], leftC_s[INTRA_ROWS][2][8];
     __shared__ volatile int progress[INTRA_ROWS]; // macroblocks finished by each row of this CTA
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, row = blockIdx.x * INTRA_ROWS + wrp;
@@ -582,6 +708,9 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
     uint8_t *topY = topY_s[wrp], *leftY = leftY_s[wrp];
     uint8_t(*topC)[12] = topC_s[wrp];
     uint8_t(*leftC)[8] = leftC_s[wrp];
+    I4Work &i4w = i4w_s[wrp];
+    if (lane == 0)
+        i4w.left_is_i4 = 0;
     const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
     int *fl = flags + (size_t)blockIdx.y * g.mbh;
     const bool luma = lane < 16, chroma = lane >= 16 && lane < 24;
@@ -605,18 +734,22 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
         }
         if (has_top) {
             if (lane == 0) {
+                // Intra4x4 predicts from the macroblock above and to the right as well
+                const int need = g.intra4x4 ? imin_(mbx + 2, g.mbw) : mbx + 1;
                 if (wrp > 0) { // the row above lives in this CTA
-                    while (progress[wrp - 1] < mbx + 1)
+                    while (progress[wrp - 1] < need)
                         __nanosleep(20);
                     __threadfence_block();
                 } else
-                    while (ld_acquire(fl + row - 1) < mbx + 1)
+                    while (ld_acquire(fl + row - 1) < need)
                         ;
             }
             __syncwarp();
             const uint8_t *ty = unf + fo + (size_t)(row * 16 - 1) * g.W + mbx * 16 - 1;
             if (lane < 17 && (lane > 0 || has_left))
                 topY[lane] = __ldcg(ty + lane);
+            if (g.intra4x4 && lane >= 17 && lane < 21 && mbx + 1 < g.mbw)
+                i4w.patch[0][20 + lane - 17] = __ldcg(ty + lane); // above-right
             if (lane < 9 || (lane >= 16 && lane < 25)) {
                 int pl = lane >> 4, i = lane & 15;
                 const uint8_t *tc = unf + fo + (size_t)g.W * g.H + (size_t)pl * g.CW * g.CH +
@@ -655,13 +788,29 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
             best = key < best ? key : best;
         }
         const int mode = (int)(best & 3);
+        // ---- intra4x4 extension: try Intra4x4 against the best Intra16x16 cost (luma only; chroma is unchanged) ----
+        bool use_i4 = false;
+        int cbp4 = 0;
+        if (g.intra4x4) {
+            if (lane < 17)
+                i4w.patch[0][3 + lane] = (has_top && (lane > 0 || has_left)) ? topY[lane] : 0;
+            if (lane < 16)
+                i4w.patch[1 + lane][3] = has_left ? leftY[lane] : 0;
+            __syncwarp();
+            int top_kind = -1;
+            if (has_top)
+                top_kind = __ldcg((const uint8_t *)(mbi + rec - g.mbw)) == MB_I4x4; // MbInfo::type is the first byte
+            use_i4 = intra4x4_trial(g, i4w, lane, sv, has_top, has_left, mbx + 1 < g.mbw, top_kind, i4 + (rec - g.mbw) * 16,
+                                    __shfl_sync(0xffffffffu, best, 0) >> 2, coef + rec * COEF_STRIDE, cbp4);
+        }
+        const bool luma16 = luma && !use_i4; // lanes that code an Intra16x16 luma block
         int pred[16], d[16], w[16];
         int16_t lev[16];
         int nz = 0;
 #pragma unroll
         for (int i = 0; i < 16; i++)
             pred[i] = 0, w[i] = 0, lev[i] = 0;
-        if (luma || chroma) {
+        if (luma16 || chroma) {
             if (luma)
                 pred16_block(mode, tp, lp, has_top, has_left, bx, by, pred);
             else
@@ -683,7 +832,7 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
 #pragma unroll
         for (int p = 0; p < 16; p++)
             ydc = (lane == p) ? Y[p] : ydc;
-        int zdc16 = luma ? quant1(ydc, h264_quant_mf[qp % 6][0], 4 * f, qbits + 2) : 0; // raster position = lane
+        int zdc16 = luma16 ? quant1(ydc, h264_quant_mf[qp % 6][0], 4 * f, qbits + 2) : 0; // raster position = lane
         unsigned m_dc16 = __ballot_sync(0xffffffffu, zdc16 != 0);
 #pragma unroll
         for (int p = 0; p < 16; p++)
@@ -696,13 +845,22 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
             for (int p = 0; p < 16; p++)
                 fdc = (mypos == p) ? Y[p] : fdc;
         }
-        unsigned m_ac = __ballot_sync(0xffffffffu, luma && nz > 0);
+        unsigned m_ac = __ballot_sync(0xffffffffu, luma16 && nz > 0);
         const int any_ac = m_ac != 0;
         ChromaOut co = chroma_dc_path(w, nz, chroma, lane, qpc, 1);
 
         // ---- reconstruction ----
         int recv[16];
-        if (luma || chroma) {
+        if (luma && use_i4) { // the Intra4x4 reconstruction is in the trial's patch
+            uint8_t *op = unf + blk_off;
+#pragma unroll
+            for (int y = 0; y < 4; y++) {
+                const uint32_t v = *(const uint32_t *)&i4w.patch[1 + by + y][4 + bx];
+                *(uint32_t *)(op + (size_t)y * stride) = v;
+                recv[y * 4 + 3] = (int)(v >> 24);
+            }
+        }
+        if (luma16 || chroma) {
             int dd[16], r[16];
 #pragma unroll
             for (int i = 0; i < 16; i++)
@@ -739,10 +897,17 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
         // ---- syntax records ----
         int16_t *cf = coef + rec * COEF_STRIDE;
         uint8_t *nn = nnz + rec * NNZ_STRIDE;
-        if (luma) {
+        if (luma && use_i4) { // the levels were stored by the trial
+            nn[lane] = i4w.nnzb[lane];
+            cf[16 * 16 + izz[lane]] = 0;
+            i4[rec * 16 + lane] = i4w.mode[lane];
+            i4w.left_mode[lane] = i4w.mode[lane];
+        } else if (luma) {
             store_levels(cf + lane * 16, lev);
             nn[lane] = (uint8_t)(any_ac ? nz : 0);
             cf[16 * 16 + izz[lane]] = (int16_t)zdc16;
+            if (g.intra4x4)
+                i4[rec * 16 + lane] = 0;
         } else if (chroma) {
             store_levels(cf + (18 + c * 4 + cb) * 16, lev);
             nn[NNZ_CB + c * 4 + cb] = (uint8_t)nz;
@@ -757,10 +922,11 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
         int cmode = __shfl_sync(0xffffffffu, mode, 16);
         if (lane == 0) {
             MbInfo m;
-            m.type = MB_I16x16;
-            m.i16_mode = (uint8_t)mode;
+            m.type = use_i4 ? MB_I4x4 : MB_I16x16;
+            m.i16_mode = (uint8_t)(use_i4 ? 0 : mode);
             m.chroma_mode = (uint8_t)cmode;
-            m.cbp = (uint8_t)((any_ac ? 15 : 0) | (co.cbpc << 4));
+            m.cbp = (uint8_t)((use_i4 ? cbp4 : (any_ac ? 15 : 0)) | (co.cbpc << 4));
+            i4w.left_is_i4 = (uint8_t)use_i4;
             m.mv[0] = m.mv[1] = m.mvd[0] = m.mvd[1] = 0;
             m.pad = 0;
             mbi[rec] = m;
@@ -1246,10 +1412,11 @@ struct EntropyBufs {
     uint32_t *limbs;         // [U][limb_cap] code-word limbs of the CABAC coder (16 stream bits per 32-bit word)
     unsigned long long limb_cap;
     int *error;              // sticky overflow flag
+    const uint8_t *i4;       // [L][nmb][16] Intra4x4 prediction modes of the step being coded (intra4x4 extension)
 };
 
 __device__ __forceinline__ FrameSyntax lane_syntax(const Geom &g, int lane, const MbInfo *mbi, const uint8_t *nnz,
-                                                   const int16_t *coef)
+                                                   const int16_t *coef, const uint8_t *i4 = nullptr)
 {
     FrameSyntax fs;
     fs.mbi = mbi + (size_t)lane * g.nmb;
@@ -1258,6 +1425,7 @@ __device__ __forceinline__ FrameSyntax lane_syntax(const Geom &g, int lane, cons
     fs.mbw = g.mbw;
     fs.mbh = g.mbh;
     fs.srows = g.srows;
+    fs.i4 = i4 ? i4 + (size_t)lane * g.nmb * 16 : nullptr;
     return fs;
 }
 
@@ -1270,7 +1438,7 @@ __global__ void entropy_size_kernel(Geom g, Step s, int frame_i, const MbInfo *_
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nitems)
         return;
-    FrameSyntax fs = lane_syntax(g, blockIdx.y, mbi, nnz, coef);
+    FrameSyntax fs = lane_syntax(g, blockIdx.y, mbi, nnz, coef, eb.i4);
     const SliceItem it = slice_item(fs, i);
     unsigned n;
     if (g.cabac) {
@@ -1377,7 +1545,7 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nitems)
         return;
-    FrameSyntax fs = lane_syntax(g, blockIdx.y, mbi, nnz, coef);
+    FrameSyntax fs = lane_syntax(g, blockIdx.y, mbi, nnz, coef, eb.i4);
     const SliceItem it = slice_item(fs, i);
     const uint32_t *offs = eb.mb_off + (size_t)blockIdx.y * (nitems + 1);
     const uint32_t off = offs[i] - offs[it.slice * slice_items_per(fs)]; // relative to the slice's first item

@@ -59,6 +59,8 @@ struct cedar_b200_config {
     int repeat_headers;      /* non-zero: SPS + PPS in front of every IDR picture, so that every closed GOP (e.g. one
                               * GPU's share of a GOP-parallel encode) decodes on its own; the reference writes them
                               * once, before the first frame (cedar.c:1058-1061). */
+    int intra4x4;            /* non-zero: I frames may use Intra4x4 macroblocks (nine prediction modes per 4x4 block)
+                              * where their SAD-based cost beats the best Intra16x16 mode. */
 };
 
 /*
@@ -134,7 +136,8 @@ long long cedar_b200_launch_count(cedar_b200_handle *h);
 /* Debug / parity-test access to intermediates of the last encode_frame call (lane 0):
  * what = 0 source planes, 1 unfiltered recon, 2 deblocked recon (Y then U then V, coded size),
  *        3 macroblock info records, 4 nnz records, 5 coefficient levels,
- *        6 CABAC bins per frame of the last call (uint32 each).  Returns bytes copied. */
+ *        6 CABAC bins per slice NAL of the last call (uint32 each), 7 Intra4x4 prediction modes (16 bytes per
+ *        macroblock).  Returns bytes copied. */
 long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_t cap);
 
 /* Header writer on its own (host C; restates kernel/cedar.c:868-1030) for byte-identity tests. */

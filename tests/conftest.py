@@ -41,7 +41,8 @@ def harness():
     H.hh_cavlc_slice.restype = C.c_long
     H.hh_cabac_slice.restype = C.c_long
     H.hh_epb.restype = C.c_long
-    H.hh_cavlc_slice.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_uint64, C.c_int, C.c_void_p, C.c_long]
-    H.hh_cabac_slice.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_uint64, C.c_int, C.c_void_p, C.c_long, C.c_int]
+    H.hh_cavlc_slice.argtypes = [C.c_void_p] * 3 + [C.c_int] * 5 + [C.c_uint64, C.c_int, C.c_void_p, C.c_long, C.c_void_p]
+    H.hh_cabac_slice.argtypes = [C.c_void_p] * 3 + [C.c_int] * 6 + [C.c_uint64, C.c_int, C.c_void_p, C.c_long, C.c_int,
+                                 C.c_void_p]
     H.hh_epb.argtypes = [C.c_void_p, C.c_long, C.c_void_p, C.c_long]
     return H

@@ -17,9 +17,9 @@ extern "C" {
 // count / prefix-sum / scatter passes.  Returns RBSP length in bytes (header bits + slice data + trailing
 // bits, byte aligned).
 long hh_cavlc_slice(const void *mbi, const uint8_t *nnz, const int16_t *coef, int mbw, int mbh, int srows, int slice,
-                    int frame_i, uint64_t hdr_bits, int hdr_nbits, uint8_t *out, long cap)
+                    int frame_i, uint64_t hdr_bits, int hdr_nbits, uint8_t *out, long cap, const uint8_t *i4)
 {
-    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh, srows};
+    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh, srows, i4};
     const int per = slice_items_per(fs), nitems = mbw * mbh + (mbh + srows - 1) / srows;
     const int j0 = slice * per, j1 = per * (slice + 1) < nitems ? per * (slice + 1) : nitems;
     std::vector<unsigned long long> off(j1 - j0 + 1);
@@ -66,9 +66,10 @@ long hh_cavlc_slice(const void *mbi, const uint8_t *nnz, const int16_t *coef, in
 }
 
 long hh_cabac_slice(const void *mbi, const uint8_t *nnz, const int16_t *coef, int mbw, int mbh, int srows, int slice,
-                    int frame_i, int qp, uint64_t hdr_bits, int hdr_nbits, uint8_t *out, long cap, int chunk_bins)
+                    int frame_i, int qp, uint64_t hdr_bits, int hdr_nbits, uint8_t *out, long cap, int chunk_bins,
+                    const uint8_t *i4)
 {
-    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh, srows};
+    FrameSyntax fs{(const MbInfo *)mbi, nnz, coef, mbw, mbh, srows, i4};
     const int row0 = slice * srows, row1 = row0 + srows < mbh ? row0 + srows : mbh;
     const int mb0 = row0 * mbw, nmb = (row1 - row0) * mbw;
     std::vector<size_t> off(nmb + 1);

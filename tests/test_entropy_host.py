@@ -19,34 +19,35 @@ def to_product_layout(mbs):
     nnz = np.zeros((n, 32), np.uint8)
     nnz[:, :27] = mbs["nnz"]
     coef = np.ascontiguousarray(mbs["coef"]).reshape(n, 26 * 16)
-    return mbi, nnz, coef
+    return mbi, nnz, coef, np.ascontiguousarray(mbs["i4_mode"])
 
 
 @pytest.mark.parametrize("cabac", [0, 1])
-@pytest.mark.parametrize("kind,qp,rows", [("synth", 24, 0), ("noise", 1, 0), ("noise", 12, 0), ("noise", 40, 0), ("static", 36, 0),
-                                          ("synth", 24, 1), ("static", 36, 3), ("noise", 30, 2)])
-def test_entropy_logic_matches_oracle(oracle, harness, kind, qp, rows, cabac):
+@pytest.mark.parametrize("kind,qp,rows,i4", [("synth", 24, 0, 0), ("noise", 1, 0, 0), ("noise", 12, 0, 0), ("noise", 40, 0, 0),
+                                             ("static", 36, 0, 0), ("synth", 24, 1, 0), ("static", 36, 3, 0), ("noise", 30, 2, 0),
+                                             ("synth", 24, 0, 1), ("noise", 12, 2, 1), ("shift", 36, 0, 1)])
+def test_entropy_logic_matches_oracle(oracle, harness, kind, qp, rows, i4, cabac):
     """rows = slice_rows: every slice NAL of the picture goes through the product logic on its own."""
     w, h, gop = 96, 80, 3
     mbw, mbh = w // 16, h // 16
     srows = rows if rows else mbh
     nslices = -(-mbh // srows)
-    enc = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, slice_rows=rows))
+    enc = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, slice_rows=rows, intra4x4=i4))
     for t in range(5):
         y, c = content(kind, w, h, t)
         payloads = [nal[5:] for ty, nal in avdec.split_nals(enc.encode(y, c)) if ty in (1, 5)]
         assert len(payloads) == nslices
-        mbi, nnz, coef = to_product_layout(enc.mbs())
+        mbi, nnz, coef, i4m = to_product_layout(enc.mbs())
         fi = int(enc.frame_is_i())
         for k, payload in enumerate(payloads):
             bits = oracle.slice_header_bits(fi, t % gop, cabac, k * srows * mbw)
             out = np.zeros(len(payload) * 2 + 4096, np.uint8)
             if cabac:
                 n = harness.hh_cabac_slice(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, mbw, mbh, srows, k, fi, qp,
-                                           int(bits, 2), len(bits), out.ctypes.data, out.size, [62, 7, 1000][t % 3])
+                                           int(bits, 2), len(bits), out.ctypes.data, out.size, [62, 7, 1000][t % 3], i4m.ctypes.data)
             else:
                 n = harness.hh_cavlc_slice(mbi.ctypes.data, nnz.ctypes.data, coef.ctypes.data, mbw, mbh, srows, k, fi,
-                                           int(bits, 2), len(bits), out.ctypes.data, out.size)
+                                           int(bits, 2), len(bits), out.ctypes.data, out.size, i4m.ctypes.data)
             assert n > 0
             esc = np.zeros(n * 2 + 16, np.uint8)
             m = harness.hh_epb(out.ctypes.data, n, esc.ctypes.data, esc.size)

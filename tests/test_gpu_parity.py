@@ -269,3 +269,51 @@ def test_gpu_stream_through_the_golden_decoder(oracle, cabac, rows):
     for r, d in zip(recs, dec):
         for p in range(3):
             assert np.array_equal(r[p], d[p])
+
+
+# ---- intra4x4 extension (SURVEY 8f rank 2, I frames) -----------------------------------------------------------------
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("kind,qp,rows", [("synth", 24, 0), ("noise", 12, 0), ("shift", 36, 0), ("synth", 30, 2), ("flat", 20, 0),
+                                          ("noise", 1, 3)])
+def test_intra4x4_every_stage_matches_oracle(oracle, kind, qp, rows, cabac):
+    w, h, gop, n = 96, 80, 2, 4
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, intra4x4=1, slice_rows=rows))
+    with cx.Encoder(api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, intra4x4=1, slice_rows=rows)) as enc:
+        for t in range(n):
+            y, c = content(kind, w, h, t)
+            want, got = gold.encode(y, c), enc.encode(y, c)
+            mbs = gold.mbs()
+            mbi, nnz, coef = enc.debug_syntax()
+            for k in ("type", "i16_mode", "chroma_mode", "cbp", "mv", "mvd"):
+                assert np.array_equal(mbs[k], mbi[k]), "mb.%s frame %d" % (k, t)
+            if gold.frame_is_i():
+                i4 = mbs["type"] == 3
+                assert np.array_equal(mbs["i4_mode"][i4], enc.debug_i4_modes()[i4]), "Intra4x4 modes frame %d" % t
+            assert np.array_equal(mbs["nnz"], nnz[:, :27]), "nnz frame %d" % t
+            assert np.array_equal(mbs["coef"], coef), "levels frame %d" % t
+            for p, (a, b) in enumerate(zip(gold.recon(), enc.debug_planes(2))):
+                assert np.array_equal(a, b), "recon plane %d frame %d" % (p, t)
+            assert got == want, "bytestream frame %d" % t
+    gold.close()
+
+
+def test_intra4x4_clip_and_full_size(oracle):
+    """clip mode == oracle at a small size; at 1080p the stream decodes (libavcodec) to the encoder's reconstruction and
+    some macroblocks actually are Intra4x4."""
+    w, h, n, gop = 96, 80, 7, 3
+    clip = make_clip("synth", w, h, n)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=24, gop=gop, cabac=1, me_range=8, intra4x4=1)
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=gop, cabac=1, me_range=8, max_clip_frames=n, intra4x4=1)) as enc:
+        got, gsz = enc.encode_clip(clip)
+    assert got == want and gsz.tolist() == sizes
+    w, h = 1920, 1088
+    clip = synth.synth_clip(w, h, [0, 1], 0).numpy()
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=60, cabac=1, intra4x4=1)) as enc:
+        stream = enc.encode(*split_frame(clip[0], w, h, 0))
+        ntype = (enc.debug_syntax()[0]["type"] == 3).sum()
+        stream += enc.encode(*split_frame(clip[1], w, h, 0))
+        last = enc.debug_planes(2)
+    assert ntype > 0
+    dec = avdec.decode(stream)
+    for p in range(3):
+        assert np.array_equal(dec[-1][p], last[p])
