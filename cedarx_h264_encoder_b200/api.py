@@ -24,7 +24,7 @@ class CedarConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "src_width", "src_height", "src_format", "dst_width", "dst_height", "profile", "level", "qp",
         "keyframe_interval", "thumbnail", "thumbnail_downscale", "entropy_coding_mode",
-        "me_range", "relax_gop", "device", "gops_in_flight", "max_clip_frames", "slice_rows", "sps_crop", "auto_level", "repeat_headers", "intra4x4")]
+        "me_range", "relax_gop", "device", "gops_in_flight", "max_clip_frames", "slice_rows", "sps_crop", "auto_level", "repeat_headers", "intra4x4", "p_intra")]
 
 
 class CedarIO(C.Structure):
@@ -97,11 +97,11 @@ def align16(x):
 
 def make_config(width, height, qp=24, gop=25, cabac=1, fmt=FORMAT_NV12, me_range=16, profile=77, level=41,
                 dst_width=None, dst_height=None, relax_gop=1, device=0, gops_in_flight=0, max_clip_frames=0,
-                slice_rows=0, sps_crop=0, auto_level=0, repeat_headers=0, intra4x4=0):
+                slice_rows=0, sps_crop=0, auto_level=0, repeat_headers=0, intra4x4=0, p_intra=0):
     """Defaults are the reference's hard-coded ones (userspace/h264enc.c:53-66)."""
     return CedarConfig(width, height, fmt, align16(width) if dst_width is None else dst_width,
                        align16(height) if dst_height is None else dst_height, profile, level, qp, gop, 0, 0,
-                       cabac, me_range, relax_gop, device, gops_in_flight, max_clip_frames, slice_rows, sps_crop, auto_level, repeat_headers, intra4x4)
+                       cabac, me_range, relax_gop, device, gops_in_flight, max_clip_frames, slice_rows, sps_crop, auto_level, repeat_headers, intra4x4, p_intra)
 
 
 def write_sps(cfg):

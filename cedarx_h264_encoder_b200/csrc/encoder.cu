@@ -26,11 +26,11 @@ using namespace cedar;
 namespace {
 
 enum KernelId {
-    K_INGEST, K_ME, K_INTER, K_INTRA, K_BS, K_DEBLOCK, K_SSE, K_ESIZE, K_ESCAN, K_EZERO, K_EWRITE,
+    K_INGEST, K_ME, K_INTER, K_PINTRA, K_INTRA, K_BS, K_DEBLOCK, K_SSE, K_ESIZE, K_ESCAN, K_EZERO, K_EWRITE,
     K_CRESOLVE, K_CCODE, K_EPBCOUNT, K_EPBSCAN, K_PACKSCAN, K_EPBWRITE, K_COUNT
 };
 const char *kKernelNames[K_COUNT] = {
-    "ingest_kernel", "me_kernel", "inter_kernel", "intra_kernel", "bs_kernel", "deblock_kernel",
+    "ingest_kernel", "me_kernel", "inter_kernel", "pintra_decide_kernel", "intra_kernel", "bs_kernel", "deblock_kernel",
     "sse_kernel", "entropy_size_kernel", "entropy_scan_kernel", "rbsp_zero_kernel", "entropy_write_kernel",
     "cabac_resolve_kernel", "cabac_code_kernel", "epb_count_kernel", "epb_scan_kernel", "pack_scan_kernel", "epb_write_kernel"};
 
@@ -103,6 +103,8 @@ struct cedar_b200_handle {
     MbInfo *d_mbi[2];
     uint8_t *d_nnz[2];
     uint8_t *d_i4[2]; // Intra4x4 prediction modes, [L][nmb][16]
+    uint8_t *d_pwant; // p_intra: macroblocks of the current P step to re-code as intra, [L][nmb]
+    int *d_pcount;    // p_intra: how many per lane
     int16_t *d_coef[2];
     int *d_flags; // [3][L][mbh]
     uint8_t *d_bs; // [L][nmb][32] boundary strengths
@@ -320,6 +322,8 @@ int alloc_buffers(cedar_b200_handle *h)
         r |= dmalloc(&h->d_coef[p], (size_t)g.nmb * L * COEF_STRIDE);
     }
     r |= dmalloc(&h->d_flags, (size_t)3 * L * g.mbh);
+    r |= dmalloc(&h->d_pwant, (size_t)g.nmb * L);
+    r |= dmalloc(&h->d_pcount, (size_t)L);
     r |= dmalloc(&h->d_bs, (size_t)g.nmb * L * 32);
     r |= dmalloc(&h->d_sse, F);
     r |= dmalloc(&h->eb.mb_size, (size_t)L * (g.nmb + S + 1));
@@ -359,7 +363,7 @@ int alloc_buffers(cedar_b200_handle *h)
 void free_buffers(cedar_b200_handle *h)
 {
     void *dev[] = {h->d_raw, h->d_src[0], h->d_src[1], h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi[0], h->d_mbi[1],
-                   h->d_nnz[0], h->d_nnz[1], h->d_i4[0], h->d_i4[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_bs,
+                   h->d_nnz[0], h->d_nnz[1], h->d_i4[0], h->d_i4[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_pwant, h->d_pcount, h->d_bs,
                    h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp, h->eb.rbsp_len,
                    h->eb.bins, h->eb.limbs, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
                    h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes, h->d_out};
@@ -411,12 +415,19 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
     CK(cudaMemsetAsync(h->d_flags, 0, sizeof(int) * 3 * flag_n, st));
     if (frame_i) {
         LAUNCH_ON(st, K_INTRA, intra_kernel, dim3((g.mbh + INTRA_ROWS - 1) / INTRA_ROWS, nl), INTRA_ROWS * 32, 0, g, s, src, unf,
-                  mbi, nnz, coef, fl_intra, h->d_i4[p]);
+                  mbi, nnz, coef, fl_intra, h->d_i4[p], nullptr, nullptr);
     } else {
         const int nstrip = me_strip(g.R);
         LAUNCH_ON(st, K_ME, me_kernel, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
                   me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1]);
         LAUNCH_ON(st, K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, src, ref, unf, mbi, nnz, coef);
+        if (g.p_intra) { // decide (parallel), then re-code the chosen macroblocks as intra in wavefront order
+            CK(cudaMemsetAsync(h->d_pcount, 0, sizeof(int) * h->L, st));
+            LAUNCH_ON(st, K_PINTRA, pintra_decide_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, src, unf, mbi, h->d_pwant,
+                      h->d_pcount);
+            LAUNCH_ON(st, K_INTRA, intra_kernel, dim3((g.mbh + INTRA_ROWS - 1) / INTRA_ROWS, nl), INTRA_ROWS * 32, 0, g, s, src, unf,
+                      mbi, nnz, coef, fl_intra, h->d_i4[p], h->d_pwant, h->d_pcount);
+        }
     }
     // boundary strengths; on inter steps the same launch runs median MV prediction / the skip decision (K2)
     LAUNCH_ON(st, K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, mbi, nnz, bs, !frame_i);
@@ -599,6 +610,7 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     g.srows = cfg->slice_rows > 0 && cfg->slice_rows < g.mbh ? cfg->slice_rows : g.mbh;
     g.nslices = (g.mbh + g.srows - 1) / g.srows;
     g.intra4x4 = cfg->intra4x4 != 0;
+    g.p_intra = cfg->p_intra != 0;
     h->S = g.nslices;
     g.frame_bytes = (unsigned long long)g.W * g.H * 3 / 2;
     h->K = cfg->keyframe_interval;

@@ -49,6 +49,7 @@ struct Geom {
     int cabac;
     int srows, nslices; // macroblock rows per slice (mbh = the reference's one slice per picture), slices per picture
     int intra4x4;       // extension: Intra4x4 macroblocks in I frames (off: Intra16x16 only)
+    int p_intra;        // extension: Intra16x16 macroblocks inside P frames where they beat the motion search
     unsigned long long frame_bytes; // W*H*3/2 : one planar frame (Y, U, V)
 };
 

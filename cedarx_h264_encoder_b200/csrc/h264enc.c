@@ -9,7 +9,7 @@
  * (:195), progress line "\rFrame %5d: %5dbytes" (:194), stop at the first short read, exit 0 (:200).
  * The ioctl/mmap calls on /dev/cedar_dev become the C ABI of include/cedar_b200.h.
  * Optional trailing flags (extensions): --qp N --gop N --cavlc --nv16 --me-range N --slice-rows N --crop --auto-level
- * --repeat-headers --intra4x4 --device N --stats
+ * --repeat-headers --intra4x4 --p-intra --device N --stats
  */
 #define _GNU_SOURCE
 #define _FILE_OFFSET_BITS 64
@@ -101,6 +101,8 @@ int main(int argc, char **argv)
             config.repeat_headers = 1;
         else if (!strcmp(argv[i], "--intra4x4"))
             config.intra4x4 = 1;
+        else if (!strcmp(argv[i], "--p-intra"))
+            config.p_intra = 1;
         else if (!strcmp(argv[i], "--cavlc"))
             config.entropy_coding_mode = CEDAR_B200_ENTROPY_CAVLC;
         else if (!strcmp(argv[i], "--nv16"))

@@ -563,6 +563,62 @@ __device__ __forceinline__ void mvp_skip_mb(const Geom &g, MbInfo *frame, int mb
 // only every INTRA_ROWS-th row synchronises through flags[row] in global memory (a hop of ~10^4 cycles).  Lanes as
 // in K3.  Bound: dependency latency (mbw + mbh steps per frame) -- many lanes run side by side.
 // ================================================================================================
+// p_intra extension, decision (oracle: p_intra_decide): one warp per macroblock, all macroblocks in parallel.  Best
+// Intra16x16 SAD against the neighbours as they are after the all-inter reconstruction of the picture (inter_kernel),
+// chosen when sad16 + 8 * lambda < the motion search's best cost (MbInfo::pad).  The chosen macroblocks are then
+// re-coded by intra_kernel in wavefront order.
+__global__ void __launch_bounds__(128) pintra_decide_kernel(Geom g, Step s, const uint8_t *__restrict__ src,
+                                                           const uint8_t *__restrict__ unf, const MbInfo *__restrict__ mbi,
+                                                           uint8_t *__restrict__ want, int *__restrict__ count)
+{
+    if (lane_frame(s, blockIdx.y) < 0)
+        return;
+    __shared__ uint8_t top_s[4][20], left_s[4][16];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, mb = blockIdx.x * 4 + wrp;
+    if (mb >= g.nmb)
+        return;
+    const int mbx = mb % g.mbw, mby = mb / g.mbw, has_top = (mby % g.srows) != 0, has_left = mbx > 0;
+    const size_t fo = (size_t)blockIdx.y * g.frame_bytes, rec = (size_t)blockIdx.y * g.nmb + mb;
+    const uint8_t *dst = unf + fo + (size_t)(mby * 16) * g.W + mbx * 16;
+    uint8_t *top = top_s[wrp], *left = left_s[wrp];
+    if (lane < 17)
+        top[lane] = (has_top && (lane > 0 || has_left)) ? dst[-g.W - 1 + lane] : 0;
+    if (lane >= 16)
+        left[lane - 16] = has_left ? dst[(size_t)(lane - 16) * g.W - 1] : 0;
+    __syncwarp();
+    const bool luma = lane < 16;
+    const int bx = blk_x(lane & 15) * 4, by = blk_y(lane & 15) * 4;
+    uint32_t sv[4] = {0, 0, 0, 0};
+    if (luma)
+#pragma unroll
+        for (int y = 0; y < 4; y++)
+            sv[y] = *(const uint32_t *)(src + fo + (size_t)(mby * 16 + by + y) * g.W + mbx * 16 + bx);
+    uint32_t best = 0xffffffffu;
+#pragma unroll 1
+    for (int mode = 0; mode < 4; mode++) {
+        const bool avail = !((mode == 0 && !has_top) || (mode == 1 && !has_left) || (mode == 3 && !(has_top && has_left)));
+        int sad = 0;
+        if (avail && luma) {
+            int p[16];
+            pred16_block(mode, top, left, has_top, has_left, bx, by, p);
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                sad += iabs_((int)((sv[i >> 2] >> (8 * (i & 3))) & 0xff) - p[i]);
+        }
+#pragma unroll
+        for (int o = 8; o >= 1; o >>= 1)
+            sad += __shfl_xor_sync(0xffffffffu, sad, o);
+        if (avail && (uint32_t)sad < best)
+            best = (uint32_t)sad;
+    }
+    if (lane == 0) {
+        const bool w = best + 8u * (uint32_t)g.lambda < mbi[rec].pad;
+        want[rec] = (uint8_t)w;
+        if (w)
+            atomicAdd(count + blockIdx.y, 1);
+    }
+}
+
 #define INTRA_ROWS 8
 
 // Per-warp shared state of the Intra4x4 trial (intra4x4 extension).
@@ -692,9 +748,13 @@ __device__ __forceinline__ bool intra4x4_trial(const Geom &g, I4Work &w, int lan
 __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, const uint8_t *__restrict__ src,
                                                                 uint8_t *unf, MbInfo *__restrict__ mbi,
                                                                 uint8_t *__restrict__ nnz, int16_t *__restrict__ coef,
-                                                                int *flags, uint8_t *i4)
+                                                                int *flags, uint8_t *i4, const uint8_t *pwant,
+                                                                const int *pcount)
 {
-    if (lane_frame(s, blockIdx.y) < 0)
+    // pwant != null: P frame of the p_intra extension -- only the macroblocks marked by pintra_decide_kernel are coded
+    // (as Intra16x16, over their inter version); the wavefront still runs over all of them because a marked macroblock
+    // predicts from whatever its neighbours ended up as.
+    if (lane_frame(s, blockIdx.y) < 0 || (pwant && pcount[blockIdx.y] == 0))
         return;
     __shared__ I4Work i4w_s[INTRA_ROWS];
     __shared__ uint8_t topY_s[INTRA_ROWS][20], leftY_s[INTRA_ROWS][16], topC_s[INTRA_ROWS][2][12], leftC_s[INTRA_ROWS][2][8];
@@ -721,9 +781,32 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
     const int stride = luma ? g.W : g.CW, mbsz = luma ? 16 : 8;
     const uint8_t izz[16] = {0, 1, 5, 6, 2, 4, 7, 12, 3, 8, 11, 13, 9, 10, 14, 15};
 
+    const bool try_i4 = g.intra4x4 && !pwant;
     for (int mbx = 0; mbx < g.mbw; mbx++) {
         const int has_top = (row % g.srows) != 0, has_left = mbx > 0; // the row above may belong to another slice
         const size_t rec = (size_t)blockIdx.y * g.nmb + (size_t)row * g.mbw + mbx;
+        if (pwant) {
+            if (!pwant[rec]) { // stays inter: nothing to do but to let the row below pass
+                if (lane == 0) {
+                    if (wrp == INTRA_ROWS - 1 || row == g.mbh - 1)
+                        st_release(fl + row, mbx + 1);
+                    else {
+                        __threadfence();
+                        progress[wrp] = mbx + 1;
+                    }
+                }
+                continue;
+            }
+            if (has_left) { // the left neighbour may be an inter macroblock: its column comes from the picture, not from this warp
+                const uint8_t *ly = unf + fo + (size_t)(row * 16) * g.W + mbx * 16 - 1;
+                if (lane < 16)
+                    leftY[lane] = __ldcg(ly + (size_t)lane * g.W);
+                else {
+                    const int pl = (lane - 16) >> 3, i = lane & 7;
+                    leftC[pl][i] = __ldcg(unf + fo + (size_t)g.W * g.H + (size_t)pl * g.CW * g.CH + (size_t)(row * 8 + i) * g.CW + mbx * 8 - 1);
+                }
+            }
+        }
         // source block (independent of the wavefront)
         uint32_t sv[4] = {0, 0, 0, 0};
         const size_t blk_off = plane_off + (size_t)(row * mbsz + by) * stride + mbx * mbsz + bx;
@@ -735,7 +818,7 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
         if (has_top) {
             if (lane == 0) {
                 // Intra4x4 predicts from the macroblock above and to the right as well
-                const int need = g.intra4x4 ? imin_(mbx + 2, g.mbw) : mbx + 1;
+                const int need = try_i4 ? imin_(mbx + 2, g.mbw) : mbx + 1;
                 if (wrp > 0) { // the row above lives in this CTA
                     while (progress[wrp - 1] < need)
                         __nanosleep(20);
@@ -748,7 +831,7 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
             const uint8_t *ty = unf + fo + (size_t)(row * 16 - 1) * g.W + mbx * 16 - 1;
             if (lane < 17 && (lane > 0 || has_left))
                 topY[lane] = __ldcg(ty + lane);
-            if (g.intra4x4 && lane >= 17 && lane < 21 && mbx + 1 < g.mbw)
+            if (try_i4 && lane >= 17 && lane < 21 && mbx + 1 < g.mbw)
                 i4w.patch[0][20 + lane - 17] = __ldcg(ty + lane); // above-right
             if (lane < 9 || (lane >= 16 && lane < 25)) {
                 int pl = lane >> 4, i = lane & 15;
@@ -791,7 +874,7 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
         // ---- intra4x4 extension: try Intra4x4 against the best Intra16x16 cost (luma only; chroma is unchanged) ----
         bool use_i4 = false;
         int cbp4 = 0;
-        if (g.intra4x4) {
+        if (try_i4) {
             if (lane < 17)
                 i4w.patch[0][3 + lane] = (has_top && (lane > 0 || has_left)) ? topY[lane] : 0;
             if (lane < 16)

@@ -61,6 +61,8 @@ struct cedar_b200_config {
                               * once, before the first frame (cedar.c:1058-1061). */
     int intra4x4;            /* non-zero: I frames may use Intra4x4 macroblocks (nine prediction modes per 4x4 block)
                               * where their SAD-based cost beats the best Intra16x16 mode. */
+    int p_intra;             /* non-zero: macroblocks of P frames are coded as Intra16x16 where that beats the motion
+                              * search (scene changes, uncovered content). */
 };
 
 /*

@@ -301,6 +301,8 @@ struct gm_encoder {
     int cur;                        /* reference_current index (ping-pong, cedar.c:1198-1201) */
     gm_mb *mbs;
     uint8_t *refpad; /* edge-extended reference luma for the motion search */
+    uint32_t *inter_cost; /* p_intra: best motion-search cost (SAD + lambda * mv bits) per macroblock */
+    uint8_t *want_intra;  /* p_intra: decision per macroblock */
     uint8_t *rbsp;
     size_t rbsp_cap;
     int last_frame_i;
@@ -357,6 +359,8 @@ int gm_open(const gm_config *cfg, gm_encoder **out)
     int err = frame_alloc(&e->src, e->W, e->H) | frame_alloc(&e->rec[0], e->W, e->H) |
               frame_alloc(&e->rec[1], e->W, e->H) | frame_alloc(&e->unf, e->W, e->H);
     e->mbs = (gm_mb *)calloc((size_t)e->mbw * e->mbh, sizeof(gm_mb));
+    e->inter_cost = (uint32_t *)calloc((size_t)e->mbw * e->mbh, sizeof(uint32_t));
+    e->want_intra = (uint8_t *)calloc((size_t)e->mbw * e->mbh, 1);
     e->rbsp_cap = (size_t)e->mbw * e->mbh * 2048 + 4096;
     e->rbsp = (uint8_t *)malloc(e->rbsp_cap);
     if (err || !e->mbs || !e->rbsp) {
@@ -377,6 +381,8 @@ void gm_close(gm_encoder *e)
     frame_free(&e->unf);
     free(e->mbs);
     free(e->refpad);
+    free(e->inter_cost);
+    free(e->want_intra);
     free(e->rbsp);
     free(e);
 }
@@ -897,7 +903,7 @@ static int try_intra4x4(gm_encoder *e, int mbx, int mby, uint32_t cost16)
     return 1;
 }
 
-static void encode_mb_intra(gm_encoder *e, int mbx, int mby)
+static void encode_mb_intra(gm_encoder *e, int mbx, int mby, int allow_i4)
 {
     int W = e->W, CW = W / 2, qp = e->qp;
     gm_mb *mb = &e->mbs[mby * e->mbw + mbx];
@@ -936,7 +942,7 @@ static void encode_mb_intra(gm_encoder *e, int mbx, int mby)
         }
     }
     mb->i16_mode = (uint8_t)(best & 3);
-    int use_i4 = e->cfg.intra4x4 && try_intra4x4(e, mbx, mby, best >> 2);
+    int use_i4 = allow_i4 && e->cfg.intra4x4 && try_intra4x4(e, mbx, mby, best >> 2);
     if (use_i4) {
         mb->i16_mode = 0;
     } else {
@@ -1092,7 +1098,7 @@ static void pad_reference(gm_encoder *e, const frame_t *ref)
     }
 }
 
-static void motion_search(gm_encoder *e, const frame_t *ref, int mbx, int mby, int *bdx, int *bdy)
+static uint32_t motion_search(gm_encoder *e, const frame_t *ref, int mbx, int mby, int *bdx, int *bdy)
 {
     (void)ref;
     int W = e->W, R = e->cfg.me_range, lam = me_lambda(e->qp), P = R + 16, PW = W + 2 * P;
@@ -1115,7 +1121,39 @@ static void motion_search(gm_encoder *e, const frame_t *ref, int mbx, int mby, i
                 *bdy = dy;
             }
         }
+    return best >> 15; /* cost of the winner */
 }
+
+/* p_intra extension: intra macroblocks inside P frames.  Decision per macroblock, order
+ * independent: best Intra16x16 SAD against the neighbours as they are after the ALL-INTER reconstruction of the frame
+ * (pass A), chosen when sad16 + 8 * lambda < the motion search's best cost.  The chosen macroblocks are then re-coded
+ * as Intra16x16 in raster order with their true neighbours (pass C, encode_mb_intra). */
+static int p_intra_decide(gm_encoder *e, int mbx, int mby, uint32_t inter_cost)
+{
+    int W = e->W, has_top = top_avail(e, mby), has_left = mbx > 0;
+    const uint8_t *src = e->src.p[0] + (size_t)(mby * 16) * W + mbx * 16;
+    const uint8_t *dst = e->unf.p[0] + (size_t)(mby * 16) * W + mbx * 16;
+    uint8_t top[16] = {0}, left[16] = {0}, pred[256];
+    int tl = 0;
+    if (has_top)
+        memcpy(top, dst - W, 16);
+    if (has_left)
+        for (int y = 0; y < 16; y++)
+            left[y] = dst[y * W - 1];
+    if (has_top && has_left)
+        tl = dst[-W - 1];
+    uint32_t best = 0xffffffffu;
+    for (int mode = 0; mode < 4; mode++) {
+        if ((mode == 0 && !has_top) || (mode == 1 && !has_left) || (mode == 3 && !(has_top && has_left)))
+            continue;
+        pred16x16(mode, top, left, tl, has_top, has_left, pred);
+        uint32_t sad = (uint32_t)sad_block(src, W, pred, 16, 16, 16);
+        if (sad < best)
+            best = sad;
+    }
+    return best + 8u * (uint32_t)me_lambda(e->qp) < inter_cost;
+}
+
 
 /* ------------------------------------------------------------------------------------------
  * K3 inter macroblock: integer luma MC, bilinear chroma MC (xFrac,yFrac in {0,4}),
@@ -1971,15 +2009,24 @@ int gm_encode_frame(gm_encoder *e, const uint8_t *luma, const uint8_t *chroma, u
     if (frame_i) {
         for (int mby = 0; mby < e->mbh; mby++)
             for (int mbx = 0; mbx < e->mbw; mbx++)
-                encode_mb_intra(e, mbx, mby);
+                encode_mb_intra(e, mbx, mby, 1);
     } else {
         pad_reference(e, ref);
         for (int mby = 0; mby < e->mbh; mby++)
             for (int mbx = 0; mbx < e->mbw; mbx++) {
                 int dx = 0, dy = 0;
-                motion_search(e, ref, mbx, mby, &dx, &dy);
+                uint32_t cost = motion_search(e, ref, mbx, mby, &dx, &dy);
                 encode_mb_inter(e, ref, mbx, mby, dx, dy);
+                if (e->cfg.p_intra)
+                    e->inter_cost[mby * e->mbw + mbx] = cost;
             }
+        if (e->cfg.p_intra) {
+            for (int i = 0; i < e->mbw * e->mbh; i++)
+                e->want_intra[i] = (uint8_t)p_intra_decide(e, i % e->mbw, i / e->mbw, e->inter_cost[i]);
+            for (int i = 0; i < e->mbw * e->mbh; i++)
+                if (e->want_intra[i])
+                    encode_mb_intra(e, i % e->mbw, i / e->mbw, 0);
+        }
         mvp_and_skip(e);
     }
     for (int p = 0; p < 3; p++)

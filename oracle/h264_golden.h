@@ -49,6 +49,7 @@ typedef struct gm_config {
     int sps_crop;      /* extension: frame cropping to src_width x src_height in the SPS (dead in the reference) */
     int auto_level;    /* extension: level_idc from the picture size instead of cfg->level */
     int repeat_headers; /* extension: SPS + PPS before every IDR picture (cedar.c:1058-1061 writes them once) */
+    int p_intra;       /* extension: Intra16x16 macroblocks inside P frames where they beat the motion search */
 } gm_config;
 
 /* Per-macroblock record: every syntax element the entropy coder needs. */

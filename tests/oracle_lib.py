@@ -15,7 +15,7 @@ class GmConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "src_width", "src_height", "src_format", "dst_width", "dst_height", "profile", "level", "qp",
         "keyframe_interval", "entropy_coding_mode", "me_range", "relax_gop", "intra4x4", "slice_rows", "sps_crop",
-        "auto_level", "repeat_headers")]
+        "auto_level", "repeat_headers", "p_intra")]
 
 
 class GmMb(C.Structure):
@@ -81,10 +81,10 @@ def align16(x):
 
 
 def make_config(width, height, qp=24, gop=25, cabac=1, fmt=0, me_range=16, profile=77, level=41, intra4x4=0,
-                dst_width=None, dst_height=None, relax_gop=1, slice_rows=0, sps_crop=0, auto_level=0, repeat_headers=0):
+                dst_width=None, dst_height=None, relax_gop=1, slice_rows=0, sps_crop=0, auto_level=0, repeat_headers=0, p_intra=0):
     return GmConfig(width, height, fmt, align16(width) if dst_width is None else dst_width,
                     align16(height) if dst_height is None else dst_height, profile, level, qp, gop, cabac,
-                    me_range, relax_gop, intra4x4, slice_rows, sps_crop, auto_level, repeat_headers)
+                    me_range, relax_gop, intra4x4, slice_rows, sps_crop, auto_level, repeat_headers, p_intra)
 
 
 def synth_frame(width, height, t, fmt=0):

@@ -317,3 +317,46 @@ def test_intra4x4_clip_and_full_size(oracle):
     dec = avdec.decode(stream)
     for p in range(3):
         assert np.array_equal(dec[-1][p], last[p])
+
+
+# ---- p_intra extension (intra macroblocks inside P frames) -----------------------------------------
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("kind,qp,rows", [("noise", 30, 0), ("noise", 12, 3), ("synth", 24, 0), ("shift", 36, 2), ("static", 30, 0)])
+def test_p_intra_every_stage_matches_oracle(oracle, kind, qp, rows, cabac):
+    w, h, gop, n = 96, 80, 4, 5
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, p_intra=1, slice_rows=rows))
+    intra_in_p = 0
+    with cx.Encoder(api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, p_intra=1, slice_rows=rows)) as enc:
+        for t in range(n):
+            y, c = content(kind, w, h, t)
+            want, got = gold.encode(y, c), enc.encode(y, c)
+            mbs = gold.mbs()
+            mbi, nnz, coef = enc.debug_syntax()
+            for k in ("type", "i16_mode", "chroma_mode", "cbp", "mv", "mvd"):
+                assert np.array_equal(mbs[k], mbi[k]), "mb.%s frame %d" % (k, t)
+            assert np.array_equal(mbs["nnz"], nnz[:, :27]), "nnz frame %d" % t
+            assert np.array_equal(mbs["coef"], coef), "levels frame %d" % t
+            for p, (a, b) in enumerate(zip(gold.recon(), enc.debug_planes(2))):
+                assert np.array_equal(a, b), "recon plane %d frame %d" % (p, t)
+            assert got == want, "bytestream frame %d" % t
+            if not gold.frame_is_i():
+                intra_in_p += int((mbs["type"] == 0).sum())
+    gold.close()
+    if kind == "noise":
+        assert intra_in_p > 0, "the noise clip should exercise intra macroblocks in P frames"
+
+
+def test_p_intra_clip_mode_and_decoders(oracle, monkeypatch):
+    monkeypatch.setenv("CEDAR_B200_BINS_PER_MB", "4096")  # random-noise pictures need more than the clip-mode default
+    w, h, n, gop = 96, 80, 9, 4
+    clip = make_clip("noise", w, h, n)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=28, gop=gop, cabac=1, me_range=8, p_intra=1)
+    with cx.Encoder(api.make_config(w, h, qp=28, gop=gop, cabac=1, me_range=8, max_clip_frames=n, p_intra=1,
+                                    gops_in_flight=2)) as enc:
+        got, gsz = enc.encode_clip(clip)
+    assert got == want and gsz.tolist() == sizes
+    a, b = avdec.decode(got), oracle.golden_decode(got)
+    assert len(a) == len(b) == n
+    for x, y in zip(a, b):
+        for p in range(3):
+            assert np.array_equal(x[p], y[p])

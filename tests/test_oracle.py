@@ -200,3 +200,19 @@ def test_golden_decoder_rejects_what_it_does_not_cover(oracle):
     stream, _, _ = oracle_encode_clip(clip, 64, 48, qp=24, gop=2, cabac=0, me_range=8)
     with pytest.raises(ValueError):
         oracle.golden_decode(stream[stream.index(b"\x00\x00\x00\x01\x65"):])  # slice before SPS / PPS
+
+
+@needs_decoder
+@pytest.mark.parametrize("cabac", [0, 1])
+@pytest.mark.parametrize("kind,qp,rows", [("noise", 30, 0), ("noise", 12, 3), ("shift", 36, 2)])
+def test_p_intra_option_decodes_bit_exactly(oracle, kind, qp, rows, cabac):
+    """p_intra extension: Intra16x16 macroblocks inside P slices (mb_type 5 + ..., intra prediction from inter
+    neighbours, mixed-edge deblocking) -- libavcodec and the golden decoder both reproduce the reconstruction."""
+    clip = make_clip(kind, 96, 80, 5)
+    stream, _, recs = oracle_encode_clip(clip, 96, 80, keep_recon=True, qp=qp, gop=4, cabac=cabac, me_range=8, slice_rows=rows,
+                                         p_intra=1)
+    for dec in (avdec.decode(stream), oracle.golden_decode(stream)):
+        assert len(dec) == 5
+        for r, d in zip(recs, dec):
+            for p in range(3):
+                assert np.array_equal(r[p], d[p])
