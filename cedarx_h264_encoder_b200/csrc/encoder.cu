@@ -107,6 +107,7 @@ struct cedar_b200_handle {
     int *d_pcount;    // p_intra: how many per lane
     int16_t *d_coef[2];
     int *d_flags; // [3][L][mbh]
+    uint32_t *d_me_tabs; // me_kernel's cost / task tables (me_build_tables)
     uint8_t *d_bs; // [L][nmb][32] boundary strengths
     unsigned long long *d_sse;
     EntropyBufs eb;
@@ -322,6 +323,7 @@ int alloc_buffers(cedar_b200_handle *h)
         r |= dmalloc(&h->d_coef[p], (size_t)g.nmb * L * COEF_STRIDE);
     }
     r |= dmalloc(&h->d_flags, (size_t)3 * L * g.mbh);
+    r |= dmalloc(&h->d_me_tabs, me_table_words(g.R, me_strip(g.R)));
     r |= dmalloc(&h->d_pwant, (size_t)g.nmb * L);
     r |= dmalloc(&h->d_pcount, (size_t)L);
     r |= dmalloc(&h->d_bs, (size_t)g.nmb * L * 32);
@@ -353,6 +355,11 @@ int alloc_buffers(cedar_b200_handle *h)
     h->eb.hdr_bits = h->d_hdr_bits;
     h->eb.hdr_nbits = h->d_hdr_nbits;
     CK(cudaMemset(h->eb.error, 0, sizeof(int)));
+    {
+        std::vector<uint32_t> tabs(me_table_words(g.R, me_strip(g.R)));
+        me_build_tables(g.R, me_strip(g.R), g.lambda, tabs.data());
+        CK(cudaMemcpy(h->d_me_tabs, tabs.data(), tabs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     CK(cudaMemset(h->d_mbi[0], 0, sizeof(MbInfo) * g.nmb * L));
     CK(cudaMemset(h->d_mbi[1], 0, sizeof(MbInfo) * g.nmb * L));
     CK(cudaMemset(h->d_rec[0], 0, g.frame_bytes * L));
@@ -363,7 +370,7 @@ int alloc_buffers(cedar_b200_handle *h)
 void free_buffers(cedar_b200_handle *h)
 {
     void *dev[] = {h->d_raw, h->d_src[0], h->d_src[1], h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi[0], h->d_mbi[1],
-                   h->d_nnz[0], h->d_nnz[1], h->d_i4[0], h->d_i4[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_pwant, h->d_pcount, h->d_bs,
+                   h->d_nnz[0], h->d_nnz[1], h->d_i4[0], h->d_i4[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_me_tabs, h->d_pwant, h->d_pcount, h->d_bs,
                    h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp, h->eb.rbsp_len,
                    h->eb.bins, h->eb.limbs, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
                    h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes, h->d_out};
@@ -419,7 +426,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
     } else {
         const int nstrip = me_strip(g.R);
         LAUNCH_ON(st, K_ME, me_kernel, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
-                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1]);
+                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs);
         LAUNCH_ON(st, K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, src, ref, unf, mbi, nnz, coef);
         if (g.p_intra) { // decide (parallel), then re-code the chosen macroblocks as intra in wavefront order
             CK(cudaMemsetAsync(h->d_pcount, 0, sizeof(int) * h->L, st));

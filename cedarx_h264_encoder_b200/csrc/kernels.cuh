@@ -119,6 +119,34 @@ __host__ __device__ inline int me_item_words(int R, int nstrip) // left-over col
     int nd = 2 * R + 1;
     return (((nd & 31) * ((nd + 3) >> 2) * nstrip) + 31) & ~31;
 }
+// Host side of me_kernel's tables: [0, 136) lambda * bits(offset - R) (>= 0x10000 beyond the range: padded row groups),
+// [136, 136 + 528) task table entries macroblock | column offset << 4 | row group << 12, then the left-over items.
+inline size_t me_table_words(int R, int nstrip) { return 136 + ME_MAX_STRIP * 4 * 33 + me_item_words(R, nstrip); }
+inline void me_build_tables(int R, int nstrip, int lambda, uint32_t *t)
+{
+    const int nd = 2 * R + 1, nfull = nd >> 5, nleft = nd & 31, ndyg = (nd + 3) >> 2, ntask_full = nfull * ndyg;
+    for (int i = 0; i < 136; i++) {
+        int d = i - R, a = d < 0 ? -d : d, bits = 1;
+        if (a) {
+            int lg = 0;
+            while ((a >> lg) > 1)
+                lg++;
+            bits = 7 + 2 * lg;
+        }
+        t[i] = i < nd ? (uint32_t)(lambda * bits) : 0x10000u;
+    }
+    uint32_t *task = t + 136, *item = task + ME_MAX_STRIP * 4 * 33;
+    for (int i = 0; i < ntask_full * nstrip; i++) {
+        int m = i / ntask_full, k = i - m * ntask_full;
+        task[i] = (uint32_t)m | ((uint32_t)((k / ndyg) * 32) << 4) | ((uint32_t)(k % ndyg) << 12);
+    }
+    const int per_mb = nleft * ndyg;
+    for (int i = 0; i < me_item_words(R, nstrip); i++) {
+        int m = per_mb ? i / per_mb : 0, jj = i - m * per_mb;
+        item[i] = (per_mb && m < nstrip) ? (uint32_t)m | ((uint32_t)(nfull * 32 + jj / ndyg) << 4) | ((uint32_t)(jj % ndyg) << 12)
+                                         : 0xffffffffu;
+    }
+}
 __host__ __device__ inline size_t me_smem_bytes(int R, int nstrip)
 {
     return (size_t)(64 * nstrip + 4 * me_copy_words(R, nstrip) + me_item_words(R, nstrip)) * 4;
@@ -126,7 +154,8 @@ __host__ __device__ inline size_t me_smem_bytes(int R, int nstrip)
 
 __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstrip, const uint8_t *__restrict__ src,
                                                        const uint8_t *__restrict__ ref, MbInfo *__restrict__ mbi,
-                                                       const MbInfo *__restrict__ mbi_prev)
+                                                       const MbInfo *__restrict__ mbi_prev,
+                                                       const uint32_t *__restrict__ tabs)
 {
     extern __shared__ uint32_t sm[];
     __shared__ uint32_t mb_best[ME_MAX_STRIP];
@@ -145,21 +174,18 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
     uint32_t *cur_s = sm, *cp = sm + 64 * nstrip, *item_tab = cp + 4 * CWs;
     const int tid = threadIdx.x;
 
-    // Tables that take every division and every bit-length computation out of the task loop.
+    // Tables that take every division and every bit-length computation out of the task loop; they only depend on the
+    // configuration, so the host builds them once (me_build_tables) and a CTA copies what its strip needs.  Both
+    // tables are macroblock-major, so a strip of fewer than nstrip macroblocks uses a prefix.
     const int nfull = nd >> 5, nleft = nd & 31, ndyg = (nd + 3) >> 2;
     const int ntask_full = nfull * ndyg;               // per macroblock: 32 columns x one row group
     const int nitems_left = nleft * ndyg * nm;         // left-over columns of all macroblocks, one item per lane
     for (int i = tid; i < 136; i += ME_THREADS)
-        mvcost[i] = i < nd ? (uint32_t)(g.lambda * mv_bits(i - R)) : 0x10000u;
-    for (int i = tid; i < ntask_full * nm; i += ME_THREADS) {
-        int m = i / ntask_full, t = i - m * ntask_full;
-        task_tab[i] = (uint32_t)m | ((uint32_t)((t / ndyg) * 32) << 4) | ((uint32_t)(t % ndyg) << 12);
-    }
-    for (int i = tid; i < ((nitems_left + 31) & ~31); i += ME_THREADS) {
-        int per_mb = nleft * ndyg, m = i / (per_mb > 0 ? per_mb : 1), jj = i - m * per_mb;
-        item_tab[i] = i < nitems_left ? (uint32_t)m | ((uint32_t)(nfull * 32 + jj / ndyg) << 4) | ((uint32_t)(jj % ndyg) << 12)
-                                      : 0xffffffffu;
-    }
+        mvcost[i] = tabs[i];
+    for (int i = tid; i < ntask_full * nm; i += ME_THREADS)
+        task_tab[i] = tabs[136 + i];
+    for (int i = tid; i < ((nitems_left + 31) & ~31); i += ME_THREADS)
+        item_tab[i] = i < nitems_left ? tabs[136 + ME_MAX_STRIP * 4 * 33 + i] : 0xffffffffu;
     if (tid < ME_MAX_STRIP)
         mb_best[tid] = 0xffffffffu;
     for (int i = tid; i < 64 * nm; i += ME_THREADS) { // current blocks: [mb][row][4 words]
@@ -172,27 +198,31 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
     {
         const int warp_ = tid >> 5, lane_ = tid & 31;
         const bool interior_x = x0 - R >= 0 && x0 - R + 4 * RSW + 4 <= g.W && !((x0 - R) & 3);
+        auto fetch = [&](const uint8_t *row, int k) -> uint32_t { // window word k of a row, edge clamped
+            const int fx = x0 - R + 4 * k;
+            if (interior_x)
+                return *(const uint32_t *)(row + fx);
+            uint32_t v = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                v |= (uint32_t)row[clip3_(0, g.W - 1, fx + i)] << (8 * i);
+            return v;
+        };
         for (int r = warp_; r < WR; r += ME_THREADS / 32) {
             const uint8_t *row = refY + (size_t)clip3_(0, g.H - 1, y0 - R + r) * g.W;
-            for (int k = lane_; k < RSW; k += 32) {
-                const int fx = x0 - R + 4 * k;
-                uint32_t lo, hi;
-                if (interior_x) {
-                    lo = *(const uint32_t *)(row + fx);
-                    hi = *(const uint32_t *)(row + fx + 4);
-                } else {
-                    lo = hi = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        lo |= (uint32_t)row[clip3_(0, g.W - 1, fx + i)] << (8 * i);
-                        hi |= (uint32_t)row[clip3_(0, g.W - 1, fx + 4 + i)] << (8 * i);
-                    }
+            for (int k0 = 0; k0 < RSW; k0 += 32) {
+                const int k = k0 + lane_;
+                const uint32_t lo = k <= RSW ? fetch(row, k) : 0u;
+                uint32_t hi = __shfl_down_sync(0xffffffffu, lo, 1); // the next word is the neighbouring lane's
+                if (lane_ == 31 && k < RSW)
+                    hi = fetch(row, k + 1);
+                if (k < RSW) {
+                    uint32_t *d = cp + r * RSW + k;
+                    d[0] = lo;
+                    d[CWs] = __byte_perm(lo, hi, 0x4321);
+                    d[2 * CWs] = __byte_perm(lo, hi, 0x5432);
+                    d[3 * CWs] = __byte_perm(lo, hi, 0x6543);
                 }
-                uint32_t *d = cp + r * RSW + k;
-                d[0] = lo;
-                d[CWs] = __byte_perm(lo, hi, 0x4321);
-                d[2 * CWs] = __byte_perm(lo, hi, 0x5432);
-                d[3 * CWs] = __byte_perm(lo, hi, 0x6543);
             }
         }
     }
