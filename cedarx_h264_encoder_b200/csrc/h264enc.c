@@ -9,7 +9,9 @@
  * (:195), progress line "\rFrame %5d: %5dbytes" (:194), stop at the first short read, exit 0 (:200).
  * The ioctl/mmap calls on /dev/cedar_dev become the C ABI of include/cedar_b200.h.
  * Optional trailing flags (extensions): --qp N --gop N --cavlc --nv16 --me-range N --slice-rows N --crop --auto-level
- * --repeat-headers --intra4x4 --p-intra --device N --stats
+ * --repeat-headers --intra4x4 --p-intra --batch-gops N --device N --stats
+ * --batch-gops N: read N GOPs at a time and encode them GOP-parallel (clip mode of the C ABI); the bytes written, one
+ * write() per frame, are identical to the frame-at-a-time default, only later.
  */
 #define _GNU_SOURCE
 #define _FILE_OFFSET_BITS 64
@@ -59,7 +61,7 @@ static int read_frame(int fd, void *buffer, int size) /* userspace/h264enc.c:119
 int main(int argc, char **argv)
 {
     uint32_t frame_count = 0;
-    int width, height, fd_in, fd_out, luma_size, chroma_size, ret, stats = 0;
+    int width, height, fd_in, fd_out, luma_size, chroma_size, ret, stats = 0, batch_gops = 0;
     struct cedar_b200_config config;
     double sse_total = 0, bytes_total = 0;
 
@@ -107,6 +109,8 @@ int main(int argc, char **argv)
             config.entropy_coding_mode = CEDAR_B200_ENTROPY_CAVLC;
         else if (!strcmp(argv[i], "--nv16"))
             config.src_format = CEDAR_B200_FORMAT_NV16;
+        else if (!strcmp(argv[i], "--batch-gops") && i + 1 < argc)
+            batch_gops = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--stats"))
             stats = 1;
         else {
@@ -130,6 +134,8 @@ int main(int argc, char **argv)
         return -1;
     }
 
+    if (batch_gops > 0)
+        config.max_clip_frames = batch_gops * config.keyframe_interval;
     ret = ve_config(&config);
     if (ret)
         return ret;
@@ -137,7 +143,46 @@ int main(int argc, char **argv)
     luma_size = width * height;
     chroma_size = config.src_format == CEDAR_B200_FORMAT_NV16 ? luma_size : luma_size / 2;
 
-    while (1) {
+    while (batch_gops > 0) { /* GOP-parallel: whole batches through the clip calls of the C ABI */
+        size_t frame_bytes = 0;
+        uint8_t *in = (uint8_t *)cedar_b200_clip_input(enc, &frame_bytes);
+        const uint8_t *out = NULL;
+        int n = 0, cap = config.max_clip_frames;
+        int *sizes = (int *)malloc(sizeof(int) * (size_t)cap);
+        double *sse = (double *)malloc(sizeof(double) * (size_t)cap);
+        while (n < cap && read_frame(fd_in, in + (size_t)n * frame_bytes, (int)frame_bytes) == (int)frame_bytes)
+            n++;
+        if (n > 0) {
+            long long total = -1;
+            ret = cedar_b200_clip_upload(enc, n);
+            if (!ret)
+                ret = cedar_b200_clip_encode(enc, n, (int)frame_count);
+            if (!ret)
+                total = cedar_b200_clip_download(enc, &out, sizes);
+            if (ret || total < 0)
+                fprintf(stderr, "%s(): %d: clip encode failed: %s\n", __func__, frame_count, strerror(ret ? -ret : (int)-total));
+            else {
+                if (stats)
+                    cedar_b200_stats(enc, sse, n);
+                for (int i = 0; i < n; i++) {
+                    printf("\rFrame %5d: %5dbytes", frame_count, sizes[i]);
+                    if (write(fd_out, out, (size_t)sizes[i]) != sizes[i])
+                        fprintf(stderr, "%s(): short write\n", __func__);
+                    out += sizes[i];
+                    if (stats) {
+                        sse_total += sse[i];
+                        bytes_total += sizes[i];
+                    }
+                    frame_count++;
+                }
+            }
+        }
+        free(sizes);
+        free(sse);
+        if (n < cap)
+            break;
+    }
+    while (batch_gops <= 0) {
         ret = read_frame(fd_in, io.input_luma, luma_size);
         if (ret != luma_size)
             break;
