@@ -425,8 +425,15 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
                   mbi, nnz, coef, fl_intra, h->d_i4[p], nullptr, nullptr);
     } else {
         const int nstrip = me_strip(g.R);
-        LAUNCH_ON(st, K_ME, me_kernel, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
-                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs);
+        // the 1080p (R = 16) and 4K (R = 64) geometries have compiled-in row strides
+        switch (me_row_words(g.R, nstrip)) {
+        case 27: LAUNCH_ON(st, K_ME, me_kernel<27>, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
+                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
+        case 43: LAUNCH_ON(st, K_ME, me_kernel<43>, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
+                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
+        default: LAUNCH_ON(st, K_ME, me_kernel<0>, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
+                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
+        }
         LAUNCH_ON(st, K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, src, ref, unf, mbi, nnz, coef);
         if (g.p_intra) { // decide (parallel), then re-code the chosen macroblocks as intra in wavefront order
             CK(cudaMemsetAsync(h->d_pcount, 0, sizeof(int) * h->L, st));
@@ -665,8 +672,10 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
         delete h;
         return -ENODEV;
     }
-    if (cudaFuncSetAttribute(me_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)me_smem_bytes(g.R, me_strip(g.R))) != cudaSuccess) {
+    const int me_smem = (int)me_smem_bytes(g.R, me_strip(g.R));
+    if (cudaFuncSetAttribute(me_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(me_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(me_kernel<43>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess) {
         fprintf(stderr, "cedar_b200: search range %d needs more shared memory than the device offers\n", g.R);
         cudaGetLastError();
         delete h;
