@@ -397,6 +397,30 @@ __device__ __forceinline__ void store_levels(int16_t *dst, const int16_t *lev)
     ((uint4 *)dst)[1] = b;
 }
 
+// Quantiser constants of one lane's 4x4 block of an inter macroblock (luma lanes: QP, chroma lanes: QPc), so that luma
+// and chroma lanes run the transform / quantisation / reconstruction as one instruction stream.  Same arithmetic as
+// quant_block / dequant_ac (h264_core.cuh).
+struct LaneQuant {
+    int mf[3], ls[3]; // by position class
+    int f, qbits, mul, rnd, sr;
+};
+__device__ __forceinline__ LaneQuant lane_quant_inter(int q)
+{
+    LaneQuant k;
+    const int m = q % 6, e = q / 6;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        k.mf[c] = h264_quant_mf[m][c];
+        k.ls[c] = 16 * h264_dequant_v[m][c];
+    }
+    k.qbits = 15 + e;
+    k.f = (1 << k.qbits) / 6;
+    k.mul = e >= 4 ? 1 << (e - 4) : 1; // dequant_ac: (c * ls) * 2^(e - 4), or (c * ls + 2^(3 - e)) >> (4 - e)
+    k.rnd = e >= 4 ? 0 : 1 << (3 - e);
+    k.sr = e >= 4 ? 0 : 4 - e;
+    return k;
+}
+
 // ================================================================================================
 // K3 inter macroblock: integer luma MC, bilinear chroma MC (xFrac, yFrac in {0, 4}), 4x4 transform,
 // quantisation, CBP, dequantisation, inverse transform, reconstruction (before deblocking).
@@ -422,19 +446,18 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
     const bool luma = lane < 16, chroma = lane >= 16 && lane < 24;
     const int qp = g.qp, qpc = g.qpc;
 
-    int pred[16], w[16];
+    int pred[16], w[16], d[16];
     int16_t lev[16];
     int nz = 0;
     size_t out_off = 0;
     int out_stride = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++)
-        w[i] = 0, lev[i] = 0, pred[i] = 0;
+        d[i] = 0, pred[i] = 0;
     if (luma) {
         int px = mbx * 16 + blk_x(lane) * 4, py = mby * 16 + blk_y(lane) * 4;
         const uint8_t *sp = src + fo + (size_t)py * g.W + px;
         const uint8_t *rp = ref + fo;
-        int d[16];
         const int rx = px + dx, ry = py + dy;
         if (rx >= 0 && rx + 7 < g.W && ry >= 0 && ry + 3 < g.H) {
             // interior: each 4-sample row of the prediction is two aligned words and a funnel shift
@@ -464,8 +487,6 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
                 }
             }
         }
-        fdct4x4(d, w);
-        nz = quant_block(w, qp, 0, 0, lev);
         out_off = fo + (size_t)py * g.W + px;
         out_stride = g.W;
     } else if (chroma) {
@@ -476,7 +497,6 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
         const uint8_t *rp = ref + po;
         int mvx = me.mv[0], mvy = me.mv[1];
         int xi = mvx >> 3, yi = mvy >> 3, xf = mvx & 7, yf = mvy & 7;
-        int d[16];
         // the 5 x 5 reference samples the bilinear filter of this 4 x 4 block touches, one 64-bit window per row
         unsigned long long prow[5];
         const int cx0 = px + xi, cy0 = py + yi;
@@ -511,28 +531,36 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
                 d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
             }
         }
-        fdct4x4(d, w);
-        nz = quant_block(w, qpc, 0, 1, lev);
         out_off = po + (size_t)py * g.CW + px;
         out_stride = g.CW;
+    }
+    // transform and quantisation, luma and chroma lanes together (idle lanes carry zeros); the chroma DC goes its own way
+    const LaneQuant lq = lane_quant_inter(luma ? qp : qpc);
+    fdct4x4(d, w);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const int r = h264_zigzag4x4[i];
+        int z = quant1(w[r], lq.mf[pos_class(r)], lq.f, lq.qbits);
+        if (i == 0 && chroma)
+            z = 0;
+        lev[i] = (int16_t)z;
+        nz += z != 0;
     }
     ChromaOut co = chroma_dc_path(w, nz, chroma, lane, qpc, 0);
     unsigned m_l = __ballot_sync(0xffffffffu, luma && nz > 0);
     int cbpl = ((m_l & 0x000f) ? 1 : 0) | ((m_l & 0x00f0) ? 2 : 0) | ((m_l & 0x0f00) ? 4 : 0) | ((m_l & 0xf000) ? 8 : 0);
 
     if (luma || chroma) {
-        int d[16], r[16];
+        int r[16];
+        // levels that are not coded (chroma AC without cbp 2) do not reach the reconstruction
+        const bool coded = luma ? nz != 0 : co.cbpc == 2;
 #pragma unroll
-        for (int i = 0; i < 16; i++)
-            d[i] = 0;
-        if (luma) {
-            if (nz)
-                dequant_block(lev, qp, 0, d);
-        } else {
-            if (co.cbpc == 2)
-                dequant_block(lev, qpc, 1, d);
-            d[0] = co.cbpc ? co.dcq : 0;
+        for (int i = 0; i < 16; i++) {
+            const int rr = h264_zigzag4x4[i];
+            d[rr] = coded ? ((int)lev[i] * lq.ls[pos_class(rr)] * lq.mul + lq.rnd) >> lq.sr : 0;
         }
+        if (chroma)
+            d[0] = co.cbpc ? co.dcq : 0;
         idct4x4(d, r);
         uint8_t *op = unf + out_off;
 #pragma unroll
