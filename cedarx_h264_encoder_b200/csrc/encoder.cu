@@ -424,15 +424,14 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         LAUNCH_ON(st, K_INTRA, intra_kernel, dim3((g.mbh + INTRA_ROWS - 1) / INTRA_ROWS, nl), INTRA_ROWS * 32, 0, g, s, src, unf,
                   mbi, nnz, coef, fl_intra, h->d_i4[p], nullptr, nullptr);
     } else {
-        const int nstrip = me_strip(g.R);
+        const MeShape ms = me_shape(g.R);
+        const dim3 me_grid((g.mbw + ms.nstrip - 1) / ms.nstrip, g.mbh, nl);
+        const size_t me_smem = me_smem_bytes(g.R, ms.nstrip);
         // the 1080p (R = 16) and 4K (R = 64) geometries have compiled-in row strides
-        switch (me_row_words(g.R, nstrip)) {
-        case 27: LAUNCH_ON(st, K_ME, me_kernel<27>, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
-                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
-        case 43: LAUNCH_ON(st, K_ME, me_kernel<43>, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
-                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
-        default: LAUNCH_ON(st, K_ME, me_kernel<0>, dim3(((g.mbw + nstrip - 1) / nstrip) * g.mbh, nl), ME_THREADS,
-                  me_smem_bytes(g.R, nstrip), g, s, nstrip, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
+        switch (ms.RSW) {
+        case 27: LAUNCH_ON(st, K_ME, me_kernel<27>, me_grid, ME_THREADS, me_smem, g, s, ms, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
+        case 43: LAUNCH_ON(st, K_ME, me_kernel<43>, me_grid, ME_THREADS, me_smem, g, s, ms, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
+        default: LAUNCH_ON(st, K_ME, me_kernel<0>, me_grid, ME_THREADS, me_smem, g, s, ms, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
         }
         LAUNCH_ON(st, K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, src, ref, unf, mbi, nnz, coef);
         if (g.p_intra) { // decide (parallel), then re-code the chosen macroblocks as intra in wavefront order

@@ -4,7 +4,7 @@
 // there are no tensor-core instructions here: integer SIMD-video (VABSDIFF4) for motion search,
 // HBM / L2 streaming and dependency-ordered wavefronts for everything else.
 //
-// Many closed GOPs ("lanes") are encoded in lock step: blockIdx.y = lane, lane l holds stream
+// Many closed GOPs ("lanes") are encoded in lock step: blockIdx.y = lane (me_kernel: blockIdx.z), lane l holds stream
 // frame step.frame0 + l * step.lane_stride.
 #pragma once
 #include "entropy.cuh"
@@ -162,10 +162,28 @@ __host__ __device__ inline size_t me_smem_bytes(int R, int nstrip)
     return (size_t)(64 * nstrip + 4 * me_copy_words(R, nstrip) + me_item_words(R, nstrip)) * 4;
 }
 
+// Everything about the search geometry that only depends on the configuration, computed once on the host: the kernel's
+// prologue runs once per warp and 200 k warps per launch make every division in it count.
+struct MeShape {
+    int nstrip, RSW, CWs, WR, nd, nfull, nleft, ndyg;
+};
+inline MeShape me_shape(int R)
+{
+    MeShape m;
+    m.nstrip = me_strip(R);
+    m.RSW = me_row_words(R, m.nstrip);
+    m.CWs = me_copy_words(R, m.nstrip);
+    m.WR = me_window_rows(R);
+    m.nd = 2 * R + 1;
+    m.nfull = m.nd >> 5, m.nleft = m.nd & 31, m.ndyg = (m.nd + 3) >> 2;
+    return m;
+}
+
+// Grid: (strips per macroblock row, macroblock rows, lanes).
 // kRSW: words per window row as a compile-time constant (the offsets of the unrolled search loop become immediates:
 // 14 % fewer instructions), 0 = any geometry.
 template <int kRSW>
-__global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstrip, const uint8_t *__restrict__ src,
+__global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape ms, const uint8_t *__restrict__ src,
                                                        const uint8_t *__restrict__ ref, MbInfo *__restrict__ mbi,
                                                        const MbInfo *__restrict__ mbi_prev,
                                                        const uint32_t *__restrict__ tabs)
@@ -174,24 +192,23 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
     __shared__ uint32_t mb_best[ME_MAX_STRIP];
     __shared__ uint32_t mvcost[136];      // lambda * bits(offset - R)
     __shared__ uint32_t task_tab[ME_MAX_STRIP * 4 * 33];
-    if (lane_frame(s, blockIdx.y) < 0)
+    if (lane_frame(s, blockIdx.z) < 0)
         return;
-    const int R = g.R, nd = 2 * R + 1;
-    const int WR = me_window_rows(R), RSW = kRSW ? kRSW : me_row_words(R, nstrip), CWs = me_copy_words(R, nstrip);
-    const int strips_per_row = (g.mbw + nstrip - 1) / nstrip;
-    const int mby = blockIdx.x / strips_per_row, mbx0 = (blockIdx.x % strips_per_row) * nstrip;
+    const int R = g.R, nd = ms.nd, nstrip = ms.nstrip;
+    const int WR = ms.WR, RSW = kRSW ? kRSW : ms.RSW, CWs = ms.CWs;
+    const int mby = blockIdx.y, mbx0 = blockIdx.x * nstrip;
     const int nm = imin_(nstrip, g.mbw - mbx0); // macroblocks in this strip
     const int x0 = mbx0 * 16, y0 = mby * 16;
-    const uint8_t *srcY = src + (size_t)blockIdx.y * g.frame_bytes;
-    const uint8_t *refY = ref + (size_t)blockIdx.y * g.frame_bytes;
+    const uint8_t *srcY = src + (size_t)blockIdx.z * g.frame_bytes;
+    const uint8_t *refY = ref + (size_t)blockIdx.z * g.frame_bytes;
     uint32_t *cur_s = sm, *cp = sm + 64 * nstrip, *item_tab = cp + 4 * CWs;
     const int tid = threadIdx.x;
 
     // Tables that take every division and every bit-length computation out of the task loop; they only depend on the
     // configuration, so the host builds them once (me_build_tables) and a CTA copies what its strip needs.  Both
     // tables are macroblock-major, so a strip of fewer than nstrip macroblocks uses a prefix.
-    const int nfull = nd >> 5, nleft = nd & 31, ndyg = (nd + 3) >> 2;
-    const int ntask_full = nfull * ndyg;               // per macroblock: 32 columns x one row group
+    const int nleft = ms.nleft, ndyg = ms.ndyg;
+    const int ntask_full = ms.nfull * ndyg;               // per macroblock: 32 columns x one row group
     const int nitems_left = nleft * ndyg * nm;         // left-over columns of all macroblocks, one item per lane
     for (int i = tid; i < 136; i += ME_THREADS)
         mvcost[i] = tabs[i];
@@ -251,7 +268,7 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
         const int m = sd >> 1;
         int ox = R, oy = R;
         if (sd & 1) {
-            const MbInfo pv = mbi_prev[(size_t)blockIdx.y * g.nmb + (size_t)mby * g.mbw + mbx0 + m];
+            const MbInfo pv = mbi_prev[(size_t)blockIdx.z * g.nmb + (size_t)mby * g.mbw + mbx0 + m];
             ox = clip3_(0, nd - 1, (pv.mv[0] >> 2) + R);
             oy = clip3_(0, nd - 1, (pv.mv[1] >> 2) + R);
         }
@@ -345,7 +362,7 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, int nstr
         mi.mv[1] = (int16_t)((rank / nd - R) * 4);
         mi.mvd[0] = mi.mvd[1] = 0;
         mi.pad = b >> 15; // best cost, for statistics
-        mbi[(size_t)blockIdx.y * g.nmb + (size_t)mby * g.mbw + mbx0 + tid] = mi;
+        mbi[(size_t)blockIdx.z * g.nmb + (size_t)mby * g.mbw + mbx0 + tid] = mi;
     }
 }
 
