@@ -95,6 +95,8 @@ __global__ void ingest_kernel(Geom g, Step s, const uint8_t *__restrict__ raw, s
 // ================================================================================================
 #define ME_THREADS 320
 #define ME_MAX_STRIP 4
+#define ME_ROWS 2 // macroblock rows per CTA: the two rows share 2R of the 16 + 2R window rows each would stage alone
+#define ME_MAX_MB (ME_MAX_STRIP * ME_ROWS)
 
 __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -109,7 +111,7 @@ __host__ __device__ inline int me_row_words(int R, int nstrip)
     int w = (16 * nstrip + 2 * R + 3) / 4 + 2;
     return w | 1; // odd: consecutive row groups of the transposed (left-over column) tasks hit different banks
 }
-__host__ __device__ inline int me_window_rows(int R) { return 16 + 2 * R + (R < 2 ? 3 : 0); } // R = 1: see me_group_row
+__host__ __device__ inline int me_window_rows(int R) { return 16 * ME_ROWS + 2 * R + (R < 2 ? 3 : 0); } // R = 1: see me_group_row
 __host__ __device__ inline int me_copy_words(int R, int nstrip)
 {
     int cw = me_window_rows(R) * me_row_words(R, nstrip);
@@ -118,10 +120,11 @@ __host__ __device__ inline int me_copy_words(int R, int nstrip)
 __host__ __device__ inline int me_item_words(int R, int nstrip) // left-over column items, padded to whole warps
 {
     int nd = 2 * R + 1;
-    return (((nd & 31) * ((nd + 3) >> 2) * nstrip) + 31) & ~31;
+    return (((nd & 31) * ((nd + 3) >> 2) * nstrip * ME_ROWS) + 31) & ~31;
 }
 // Host side of me_kernel's tables: [0, 136) lambda * bits(offset - R),
 // [136, 136 + 528) task table entries macroblock | column offset << 4 | first row offset << 12, then the left-over items.
+// Macroblock m of a CTA = column m % nstrip, row m / nstrip of its nstrip x ME_ROWS tile.
 // A task covers four consecutive row offsets; the last group of a column is moved up to end at the last offset (it
 // repeats up to three candidates of the group before it, which cannot change an argmin), so no candidate lies outside
 // the range -- except the fourth one when there are only three offsets (R = 1), which the kernel discards.
@@ -145,32 +148,34 @@ inline void me_build_tables(int R, int nstrip, int lambda, uint32_t *t)
         t[i] = (uint32_t)(lambda * bits);
     }
     uint32_t *task = t + 136, *item = task + ME_MAX_STRIP * 4 * 33;
-    for (int i = 0; i < ntask_full * nstrip; i++) {
+    const int nmb = nstrip * ME_ROWS;
+    for (int i = 0; i < ntask_full * nmb; i++) {
         int m = i / ntask_full, k = i - m * ntask_full;
         task[i] = (uint32_t)m | ((uint32_t)((k / ndyg) * 32) << 4) | ((uint32_t)me_group_row(k % ndyg, nd) << 12);
     }
     const int per_mb = nleft * ndyg;
     for (int i = 0; i < me_item_words(R, nstrip); i++) {
         int m = per_mb ? i / per_mb : 0, jj = i - m * per_mb;
-        item[i] = (per_mb && m < nstrip) ? (uint32_t)m | ((uint32_t)(nfull * 32 + jj / ndyg) << 4) |
+        item[i] = (per_mb && m < nmb) ? (uint32_t)m | ((uint32_t)(nfull * 32 + jj / ndyg) << 4) |
                                                ((uint32_t)me_group_row(jj % ndyg, nd) << 12)
                                          : 0xffffffffu;
     }
 }
 __host__ __device__ inline size_t me_smem_bytes(int R, int nstrip)
 {
-    return (size_t)(64 * nstrip + 4 * me_copy_words(R, nstrip) + me_item_words(R, nstrip)) * 4;
+    return (size_t)(64 * nstrip * ME_ROWS + 4 * me_copy_words(R, nstrip) + me_item_words(R, nstrip)) * 4;
 }
 
 // Everything about the search geometry that only depends on the configuration, computed once on the host: the kernel's
 // prologue runs once per warp and 200 k warps per launch make every division in it count.
 struct MeShape {
-    int nstrip, RSW, CWs, WR, nd, nfull, nleft, ndyg;
+    int nstrip, lstrip, RSW, CWs, WR, nd, nfull, nleft, ndyg; // lstrip = log2(nstrip)
 };
 inline MeShape me_shape(int R)
 {
     MeShape m;
     m.nstrip = me_strip(R);
+    m.lstrip = m.nstrip == 4 ? 2 : 1;
     m.RSW = me_row_words(R, m.nstrip);
     m.CWs = me_copy_words(R, m.nstrip);
     m.WR = me_window_rows(R);
@@ -179,7 +184,7 @@ inline MeShape me_shape(int R)
     return m;
 }
 
-// Grid: (strips per macroblock row, macroblock rows, lanes).
+// Grid: (strips per macroblock row, macroblock rows / ME_ROWS, lanes).
 // kRSW: words per window row as a compile-time constant (the offsets of the unrolled search loop become immediates:
 // 14 % fewer instructions), 0 = any geometry.
 template <int kRSW>
@@ -189,38 +194,43 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
                                                        const uint32_t *__restrict__ tabs)
 {
     extern __shared__ uint32_t sm[];
-    __shared__ uint32_t mb_best[ME_MAX_STRIP];
+    __shared__ uint32_t mb_best[ME_MAX_MB];
     __shared__ uint32_t mvcost[136];      // lambda * bits(offset - R)
     __shared__ uint32_t task_tab[ME_MAX_STRIP * 4 * 33];
     if (lane_frame(s, blockIdx.z) < 0)
         return;
     const int R = g.R, nd = ms.nd, nstrip = ms.nstrip;
     const int WR = ms.WR, RSW = kRSW ? kRSW : ms.RSW, CWs = ms.CWs;
-    const int mby = blockIdx.y, mbx0 = blockIdx.x * nstrip;
-    const int nm = imin_(nstrip, g.mbw - mbx0); // macroblocks in this strip
-    const int x0 = mbx0 * 16, y0 = mby * 16;
+    const int mby0 = blockIdx.y * ME_ROWS, mbx0 = blockIdx.x * nstrip, nmb = nstrip * ME_ROWS, ls = ms.lstrip;
+    const int ncols = imin_(nstrip, g.mbw - mbx0), nrows = imin_(ME_ROWS, g.mbh - mby0); // the tile may hang over the picture
+    uint32_t vmask = 0; // macroblocks of the tile that exist
+#pragma unroll
+    for (int m = 0; m < ME_MAX_MB; m++)
+        vmask |= (uint32_t)(m < nmb && (m & (nstrip - 1)) < ncols && (m >> ls) < nrows) << m;
+    const int x0 = mbx0 * 16, y0 = mby0 * 16;
     const uint8_t *srcY = src + (size_t)blockIdx.z * g.frame_bytes;
     const uint8_t *refY = ref + (size_t)blockIdx.z * g.frame_bytes;
-    uint32_t *cur_s = sm, *cp = sm + 64 * nstrip, *item_tab = cp + 4 * CWs;
+    uint32_t *cur_s = sm, *cp = sm + 64 * nmb, *item_tab = cp + 4 * CWs;
     const int tid = threadIdx.x;
 
     // Tables that take every division and every bit-length computation out of the task loop; they only depend on the
-    // configuration, so the host builds them once (me_build_tables) and a CTA copies what its strip needs.  Both
-    // tables are macroblock-major, so a strip of fewer than nstrip macroblocks uses a prefix.
+    // configuration, so the host builds them once (me_build_tables) and every CTA copies them; tasks of macroblocks
+    // beyond the picture edge are skipped (vmask).
     const int nleft = ms.nleft, ndyg = ms.ndyg;
     const int ntask_full = ms.nfull * ndyg;               // per macroblock: 32 columns x one row group
-    const int nitems_left = nleft * ndyg * nm;         // left-over columns of all macroblocks, one item per lane
+    const int nitems_left = nleft * ndyg * nmb;        // left-over columns of all macroblocks, one item per lane
     for (int i = tid; i < 136; i += ME_THREADS)
         mvcost[i] = tabs[i];
-    for (int i = tid; i < ntask_full * nm; i += ME_THREADS)
+    for (int i = tid; i < ntask_full * nmb; i += ME_THREADS)
         task_tab[i] = tabs[136 + i];
     for (int i = tid; i < ((nitems_left + 31) & ~31); i += ME_THREADS)
         item_tab[i] = i < nitems_left ? tabs[136 + ME_MAX_STRIP * 4 * 33 + i] : 0xffffffffu;
-    if (tid < ME_MAX_STRIP)
+    if (tid < ME_MAX_MB)
         mb_best[tid] = 0xffffffffu;
-    for (int i = tid; i < 64 * nm; i += ME_THREADS) { // current blocks: [mb][row][4 words]
+    for (int i = tid; i < 64 * nmb; i += ME_THREADS) { // current blocks: [mb][row][4 words]
         int m = i >> 6, row = (i >> 2) & 15, k = i & 3;
-        cur_s[i] = *(const uint32_t *)(srcY + (size_t)(y0 + row) * g.W + x0 + 16 * m + 4 * k);
+        if ((vmask >> m) & 1)
+            cur_s[i] = *(const uint32_t *)(srcY + (size_t)(y0 + 16 * (m >> ls) + row) * g.W + x0 + 16 * (m & (nstrip - 1)) + 4 * k);
     }
     // Window staging: warp = window row (round robin), lane = 32-bit word of the row.  Each lane fetches its
     // word and the next one (the second fetch hits L1) and builds the three byte-shifted copies in
@@ -264,17 +274,19 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
     // search) -- so that the exhaustive loop below can drop a task as soon as the partial cost of every candidate
     // in it exceeds the best complete cost so far.  SAD terms are non-negative, so the partial key is a lower
     // bound of the final key: the argmin, and with it the bitstream, is unchanged.
-    for (int sd = warp; sd < 2 * nm; sd += nwarps) {
-        const int m = sd >> 1;
+    for (int sd = warp; sd < 2 * nmb; sd += nwarps) {
+        const int m = sd >> 1, mc = m & (nstrip - 1), mr = m >> ls;
+        if (!((vmask >> m) & 1))
+            continue;
         int ox = R, oy = R;
         if (sd & 1) {
-            const MbInfo pv = mbi_prev[(size_t)blockIdx.z * g.nmb + (size_t)mby * g.mbw + mbx0 + m];
+            const MbInfo pv = mbi_prev[(size_t)blockIdx.z * g.nmb + (size_t)(mby0 + mr) * g.mbw + mbx0 + mc];
             ox = clip3_(0, nd - 1, (pv.mv[0] >> 2) + R);
             oy = clip3_(0, nd - 1, (pv.mv[1] >> 2) + R);
         }
         uint32_t a = 0;
         if (lane < 16) {
-            const uint32_t *wp = cp + (ox & 3) * CWs + (oy + lane) * RSW + 4 * m + (ox >> 2);
+            const uint32_t *wp = cp + (ox & 3) * CWs + (oy + 16 * mr + lane) * RSW + 4 * mc + (ox >> 2);
             const uint32_t *cu = cur_s + 64 * m + 4 * lane;
 #pragma unroll
             for (int k = 0; k < 4; k++)
@@ -285,14 +297,14 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
             atomicMin(&mb_best[m], ((a + mvcost[ox] + mvcost[oy]) << 15) | (uint32_t)(oy * nd + ox));
     }
     __syncthreads();
-    const int ntask = ntask_full * nm + ((nitems_left + 31) >> 5);
+    const int ntask = ntask_full * nmb + ((nitems_left + 31) >> 5);
     for (int task = warp; task < ntask; task += nwarps) {
         // task table entry: macroblock | column offset << 4 | first row offset << 12 (0xffffffff = idle lane)
-        const uint32_t e = task < ntask_full * nm ? task_tab[task] + ((uint32_t)lane << 4)
-                                                  : item_tab[(task - ntask_full * nm) * 32 + lane];
+        const uint32_t e = task < ntask_full * nmb ? task_tab[task] + ((uint32_t)lane << 4)
+                                                   : item_tab[(task - ntask_full * nmb) * 32 + lane];
         uint32_t key = 0xffffffffu;
         const int m = (int)(e & 15);
-        if (e != 0xffffffffu) {
+        if (e != 0xffffffffu && ((vmask >> m) & 1)) {
             const int ox = (int)((e >> 4) & 255), oy0 = (int)(e >> 12);
             uint32_t cur[64];
             {
@@ -303,7 +315,7 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
                     cur[4 * i] = v.x, cur[4 * i + 1] = v.y, cur[4 * i + 2] = v.z, cur[4 * i + 3] = v.w;
                 }
             }
-            const uint32_t *wp = cp + (ox & 3) * CWs + oy0 * RSW + 4 * m + (ox >> 2);
+            const uint32_t *wp = cp + (ox & 3) * CWs + (oy0 + 16 * (m >> ls)) * RSW + 4 * (m & (nstrip - 1)) + (ox >> 2);
             // cost = SAD + lambda * (bits(mvx) + bits(mvy)): the accumulators start at the vector cost, so a key is one
             // multiply-add (cost << 15 | raster rank; cost < 2^17)
             const uint32_t cx = mvcost[ox], rank0 = (uint32_t)(oy0 * nd + ox);
@@ -344,7 +356,7 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
                 key = min_key();
         }
         // the lanes of a full task share the macroblock; the left-over task mixes macroblocks
-        if (task < ntask_full * nm) {
+        if (task < ntask_full * nmb) {
             key = __reduce_min_sync(0xffffffffu, key);
             if (lane == 0)
                 atomicMin(&mb_best[m], key);
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
             atomicMin(&mb_best[m], key);
     }
     __syncthreads();
-    if (tid < nm) {
+    if (tid < nmb && ((vmask >> tid) & 1)) {
         const uint32_t b = mb_best[tid];
         int rank = (int)(b & 0x7fff);
         MbInfo mi;
@@ -362,7 +374,7 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
         mi.mv[1] = (int16_t)((rank / nd - R) * 4);
         mi.mvd[0] = mi.mvd[1] = 0;
         mi.pad = b >> 15; // best cost, for statistics
-        mbi[(size_t)blockIdx.z * g.nmb + (size_t)mby * g.mbw + mbx0 + tid] = mi;
+        mbi[(size_t)blockIdx.z * g.nmb + (size_t)(mby0 + (tid >> ls)) * g.mbw + mbx0 + (tid & (nstrip - 1))] = mi;
     }
 }
 
