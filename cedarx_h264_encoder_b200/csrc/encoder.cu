@@ -425,7 +425,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
                   mbi, nnz, coef, fl_intra, h->d_i4[p], nullptr, nullptr);
     } else {
         const MeShape ms = me_shape(g.R);
-        const dim3 me_grid((g.mbw + ms.nstrip - 1) / ms.nstrip, (g.mbh + ME_ROWS - 1) / ME_ROWS, nl);
+        const dim3 me_grid((g.mbw + ms.nstrip - 1) / ms.nstrip, (g.mbh + ms.nrow - 1) / ms.nrow, nl);
         const size_t me_smem = me_smem_bytes(g.R, ms.nstrip);
         // the 1080p (R = 16) and 4K (R = 64) geometries have compiled-in row strides
         switch (ms.RSW) {

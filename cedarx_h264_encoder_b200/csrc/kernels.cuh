@@ -95,8 +95,9 @@ __global__ void ingest_kernel(Geom g, Step s, const uint8_t *__restrict__ raw, s
 // ================================================================================================
 #define ME_THREADS 320
 #define ME_MAX_STRIP 4
-#define ME_ROWS 2 // macroblock rows per CTA: the two rows share 2R of the 16 + 2R window rows each would stage alone
-#define ME_MAX_MB (ME_MAX_STRIP * ME_ROWS)
+#define ME_MAX_ROWS 4 // macroblock rows per CTA (me_rows): they share 2R of the 16 + 2R window rows each would stage alone
+#define ME_MAX_MB (ME_MAX_STRIP * ME_MAX_ROWS)
+#define ME_TASK_WORDS 1088 // 32-column x 4-row tasks of one tile: R = 64, 8 macroblocks x 4 x 33; R = 32, 16 x 2 x 17
 
 __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -106,12 +107,13 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
 }
 
 __host__ __device__ inline int me_strip(int R) { return R > 32 ? 2 : ME_MAX_STRIP; }
+__host__ __device__ inline int me_rows(int R) { return R > 32 ? 2 : ME_MAX_ROWS; } // shared memory: 4 CTAs per SM at R = 16
 __host__ __device__ inline int me_row_words(int R, int nstrip)
 {
     int w = (16 * nstrip + 2 * R + 3) / 4 + 2;
     return w | 1; // odd: consecutive row groups of the transposed (left-over column) tasks hit different banks
 }
-__host__ __device__ inline int me_window_rows(int R) { return 16 * ME_ROWS + 2 * R + (R < 2 ? 3 : 0); } // R = 1: see me_group_row
+__host__ __device__ inline int me_window_rows(int R) { return 16 * me_rows(R) + 2 * R + (R < 2 ? 3 : 0); } // R = 1: see me_group_row
 __host__ __device__ inline int me_copy_words(int R, int nstrip)
 {
     int cw = me_window_rows(R) * me_row_words(R, nstrip);
@@ -120,11 +122,11 @@ __host__ __device__ inline int me_copy_words(int R, int nstrip)
 __host__ __device__ inline int me_item_words(int R, int nstrip) // left-over column items, padded to whole warps
 {
     int nd = 2 * R + 1;
-    return (((nd & 31) * ((nd + 3) >> 2) * nstrip * ME_ROWS) + 31) & ~31;
+    return (((nd & 31) * ((nd + 3) >> 2) * nstrip * me_rows(R)) + 31) & ~31;
 }
 // Host side of me_kernel's tables: [0, 136) lambda * bits(offset - R),
 // [136, 136 + 528) task table entries macroblock | column offset << 4 | first row offset << 12, then the left-over items.
-// Macroblock m of a CTA = column m % nstrip, row m / nstrip of its nstrip x ME_ROWS tile.
+// Macroblock m of a CTA = column m % nstrip, row m / nstrip of its nstrip x me_rows(R) tile.
 // A task covers four consecutive row offsets; the last group of a column is moved up to end at the last offset (it
 // repeats up to three candidates of the group before it, which cannot change an argmin), so no candidate lies outside
 // the range -- except the fourth one when there are only three offsets (R = 1), which the kernel discards.
@@ -133,7 +135,7 @@ inline int me_group_row(int group, int nd) // first row offset of a group of fou
     int oy0 = 4 * group;
     return oy0 + 4 <= nd ? oy0 : (nd >= 4 ? nd - 4 : 0);
 }
-inline size_t me_table_words(int R, int nstrip) { return 136 + ME_MAX_STRIP * 4 * 33 + me_item_words(R, nstrip); }
+inline size_t me_table_words(int R, int nstrip) { return 136 + ME_TASK_WORDS + me_item_words(R, nstrip); }
 inline void me_build_tables(int R, int nstrip, int lambda, uint32_t *t)
 {
     const int nd = 2 * R + 1, nfull = nd >> 5, nleft = nd & 31, ndyg = (nd + 3) >> 2, ntask_full = nfull * ndyg;
@@ -147,8 +149,8 @@ inline void me_build_tables(int R, int nstrip, int lambda, uint32_t *t)
         }
         t[i] = (uint32_t)(lambda * bits);
     }
-    uint32_t *task = t + 136, *item = task + ME_MAX_STRIP * 4 * 33;
-    const int nmb = nstrip * ME_ROWS;
+    uint32_t *task = t + 136, *item = task + ME_TASK_WORDS;
+    const int nmb = nstrip * me_rows(R);
     for (int i = 0; i < ntask_full * nmb; i++) {
         int m = i / ntask_full, k = i - m * ntask_full;
         task[i] = (uint32_t)m | ((uint32_t)((k / ndyg) * 32) << 4) | ((uint32_t)me_group_row(k % ndyg, nd) << 12);
@@ -163,19 +165,20 @@ inline void me_build_tables(int R, int nstrip, int lambda, uint32_t *t)
 }
 __host__ __device__ inline size_t me_smem_bytes(int R, int nstrip)
 {
-    return (size_t)(64 * nstrip * ME_ROWS + 4 * me_copy_words(R, nstrip) + me_item_words(R, nstrip)) * 4;
+    return (size_t)(64 * nstrip * me_rows(R) + 4 * me_copy_words(R, nstrip) + me_item_words(R, nstrip)) * 4;
 }
 
 // Everything about the search geometry that only depends on the configuration, computed once on the host: the kernel's
 // prologue runs once per warp and 200 k warps per launch make every division in it count.
 struct MeShape {
-    int nstrip, lstrip, RSW, CWs, WR, nd, nfull, nleft, ndyg; // lstrip = log2(nstrip)
+    int nstrip, lstrip, nrow, RSW, CWs, WR, nd, nfull, nleft, ndyg; // lstrip = log2(nstrip)
 };
 inline MeShape me_shape(int R)
 {
     MeShape m;
     m.nstrip = me_strip(R);
     m.lstrip = m.nstrip == 4 ? 2 : 1;
+    m.nrow = me_rows(R);
     m.RSW = me_row_words(R, m.nstrip);
     m.CWs = me_copy_words(R, m.nstrip);
     m.WR = me_window_rows(R);
@@ -184,7 +187,7 @@ inline MeShape me_shape(int R)
     return m;
 }
 
-// Grid: (strips per macroblock row, macroblock rows / ME_ROWS, lanes).
+// Grid: (strips per macroblock row, macroblock rows / me_rows, lanes).
 // kRSW: words per window row as a compile-time constant (the offsets of the unrolled search loop become immediates:
 // 14 % fewer instructions), 0 = any geometry.
 template <int kRSW>
@@ -196,13 +199,13 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
     extern __shared__ uint32_t sm[];
     __shared__ uint32_t mb_best[ME_MAX_MB];
     __shared__ uint32_t mvcost[136];      // lambda * bits(offset - R)
-    __shared__ uint32_t task_tab[ME_MAX_STRIP * 4 * 33];
+    __shared__ uint32_t task_tab[ME_TASK_WORDS];
     if (lane_frame(s, blockIdx.z) < 0)
         return;
     const int R = g.R, nd = ms.nd, nstrip = ms.nstrip;
     const int WR = ms.WR, RSW = kRSW ? kRSW : ms.RSW, CWs = ms.CWs;
-    const int mby0 = blockIdx.y * ME_ROWS, mbx0 = blockIdx.x * nstrip, nmb = nstrip * ME_ROWS, ls = ms.lstrip;
-    const int ncols = imin_(nstrip, g.mbw - mbx0), nrows = imin_(ME_ROWS, g.mbh - mby0); // the tile may hang over the picture
+    const int mby0 = blockIdx.y * ms.nrow, mbx0 = blockIdx.x * nstrip, nmb = nstrip * ms.nrow, ls = ms.lstrip;
+    const int ncols = imin_(nstrip, g.mbw - mbx0), nrows = imin_(ms.nrow, g.mbh - mby0); // the tile may hang over the picture
     uint32_t vmask = 0; // macroblocks of the tile that exist
 #pragma unroll
     for (int m = 0; m < ME_MAX_MB; m++)
@@ -224,7 +227,7 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
     for (int i = tid; i < ntask_full * nmb; i += ME_THREADS)
         task_tab[i] = tabs[136 + i];
     for (int i = tid; i < ((nitems_left + 31) & ~31); i += ME_THREADS)
-        item_tab[i] = i < nitems_left ? tabs[136 + ME_MAX_STRIP * 4 * 33 + i] : 0xffffffffu;
+        item_tab[i] = i < nitems_left ? tabs[136 + ME_TASK_WORDS + i] : 0xffffffffu;
     if (tid < ME_MAX_MB)
         mb_best[tid] = 0xffffffffu;
     for (int i = tid; i < 64 * nmb; i += ME_THREADS) { // current blocks: [mb][row][4 words]
