@@ -25,25 +25,30 @@ FULL_METRICS = [
 
 
 def launches(src, dst):
+    """Launch list with gpu__time_duration.sum and, optionally, smsp__inst_executed.sum per launch."""
     rows = [r for r in csv.reader(l for l in open(src) if not l.startswith("=="))]
     hdr = rows[0]
-    kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    kn, mn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
     agg = collections.OrderedDict()
     for r in rows[1:]:
         if len(r) <= mv:
             continue
-        name = r[kn].split("(")[0].split("::")[-1]
+        name = r[kn].split("(")[0].split("::")[-1].split("<")[0]
         v = float(r[mv].replace(",", ""))
-        v = {"ns": v * 1e-6, "us": v * 1e-3, "ms": v, "s": v * 1e3}.get(r[mu], v)
-        a = agg.setdefault(name, [0, 0.0])
-        a[0] += 1
-        a[1] += v
+        a = agg.setdefault(name, [0, 0.0, 0.0])
+        if r[mn] == "gpu__time_duration.sum":
+            a[0] += 1
+            a[1] += {"ns": v * 1e-6, "us": v * 1e-3, "ms": v, "s": v * 1e3}.get(r[mu], v)
+        elif r[mn] == "smsp__inst_executed.sum":
+            a[2] += v
     tot = sum(v[1] for v in agg.values())
+    toti = sum(v[2] for v in agg.values())
     with open(dst, "w") as f:
-        f.write("| kernel | launches | total ms | share | avg us |\n|---|---:|---:|---:|---:|\n")
-        for name, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write("| %s | %d | %.3f | %.3f | %.1f |\n" % (name, n, ms, ms / tot, ms / n * 1e3))
-        f.write("| **total** | %d | %.3f | 1.000 | |\n" % (sum(v[0] for v in agg.values()), tot))
+        f.write("| kernel | launches | total ms | share | avg us | M warp-instr | instr share |\n|---|---:|---:|---:|---:|---:|---:|\n")
+        for name, (n, ms, ins) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("| %s | %d | %.3f | %.3f | %.1f | %.1f | %.3f |\n" % (name, n, ms, ms / tot, ms / n * 1e3, ins / 1e6,
+                                                                         ins / toti if toti else 0.0))
+        f.write("| **total** | %d | %.3f | 1.000 | | %.1f | |\n" % (sum(v[0] for v in agg.values()), tot, toti / 1e6))
     print(open(dst).read())
 
 
