@@ -40,48 +40,55 @@ __device__ __forceinline__ void st_release(int *p, int v)
 
 // ================================================================================================
 // K0 ingest: packed NV12 / NV16 (w x h) -> planar 4:2:0 at the coded size with edge replication.
-// Replaces the ISP input stage (cedar.c:1068-1080).  One thread = 4 output bytes.  HBM bound.
+// Replaces the ISP input stage (cedar.c:1068-1080).  Grid: (words of a luma row / 256, H + 2 CH output rows, lanes);
+// one thread = 4 output bytes: one aligned word of luma, or two words of interleaved chroma de-interleaved with a
+// byte permute (NV16: the rounding average of two rows, __vavgu4); bytes only at the picture edge.  HBM bound.
 // ================================================================================================
-__global__ void ingest_kernel(Geom g, Step s, const uint8_t *__restrict__ raw, size_t raw_frame_bytes,
-                              uint8_t *__restrict__ src)
+__global__ void __launch_bounds__(256) ingest_kernel(Geom g, Step s, const uint8_t *__restrict__ raw, size_t raw_frame_bytes,
+                                                     uint8_t *__restrict__ src)
 {
-    int f = lane_frame(s, blockIdx.y);
+    const int f = lane_frame(s, blockIdx.z);
     if (f < 0)
         return;
-    size_t o = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (o >= g.frame_bytes)
-        return;
+    const int row = blockIdx.y, x = (blockIdx.x * 256 + threadIdx.x) * 4;
     const uint8_t *luma = raw + (size_t)f * raw_frame_bytes;
     const uint8_t *chroma = luma + (size_t)g.src_w * g.src_h;
-    uint8_t *dst = src + (size_t)blockIdx.y * g.frame_bytes;
-    size_t ysz = (size_t)g.W * g.H, csz = (size_t)g.CW * g.CH;
+    uint8_t *dst = src + (size_t)blockIdx.z * g.frame_bytes;
     uint32_t out = 0;
-    if (o < ysz) {
-        int y = (int)(o / g.W), x = (int)(o % g.W);
-        const uint8_t *row = luma + (size_t)imin_(y, g.src_h - 1) * g.src_w;
+    if (row < g.H) {
+        if (x >= g.W)
+            return;
+        const uint8_t *rp = luma + (size_t)imin_(row, g.src_h - 1) * g.src_w;
+        if (x + 3 < g.src_w && !((uintptr_t)(rp + x) & 3))
+            out = *(const uint32_t *)(rp + x);
+        else
 #pragma unroll
-        for (int k = 0; k < 4; k++)
-            out |= (uint32_t)row[imin_(x + k, g.src_w - 1)] << (8 * k);
+            for (int k = 0; k < 4; k++)
+                out |= (uint32_t)rp[imin_(x + k, g.src_w - 1)] << (8 * k);
+        *(uint32_t *)(dst + (size_t)row * g.W + x) = out;
     } else {
-        size_t o2 = o - ysz;
-        int c = o2 >= csz;
-        size_t o3 = o2 - (c ? csz : 0);
-        int y = (int)(o3 / g.CW), x = (int)(o3 % g.CW);
-        int sy = imin_(y, g.src_h / 2 - 1);
+        if (x >= g.CW)
+            return;
+        const int cr = row - g.H, c = cr >= g.CH, y = cr - (c ? g.CH : 0);
+        const int sy = imin_(y, g.src_h / 2 - 1), nv16 = g.src_format == 1;
+        // NV16 -> 4:2:0: rounding average of the two chroma rows
+        const uint8_t *ra = chroma + (size_t)(nv16 ? 2 * sy : sy) * g.src_w, *rb = nv16 ? ra + g.src_w : ra;
+        if (2 * x + 7 < g.src_w && !(((uintptr_t)(ra + 2 * x) | (uintptr_t)(rb + 2 * x)) & 3)) {
+            const uint32_t sel = c ? 0x7531u : 0x6420u;
+            const uint32_t *pa = (const uint32_t *)(ra + 2 * x), *pb = (const uint32_t *)(rb + 2 * x);
+            out = __byte_perm(pa[0], pa[1], sel);
+            if (nv16)
+                out = __vavgu4(out, __byte_perm(pb[0], pb[1], sel));
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            int sx = imin_(x + k, g.src_w / 2 - 1);
-            int v;
-            if (g.src_format == 1) { // NV16 -> 4:2:0: rounding average of the two chroma rows
-                int a = chroma[(size_t)(2 * sy) * g.src_w + 2 * sx + c];
-                int b = chroma[(size_t)(2 * sy + 1) * g.src_w + 2 * sx + c];
-                v = (a + b + 1) >> 1;
-            } else
-                v = chroma[(size_t)sy * g.src_w + 2 * sx + c];
-            out |= (uint32_t)v << (8 * k);
+            for (int k = 0; k < 4; k++) {
+                const int sx = imin_(x + k, g.src_w / 2 - 1);
+                const int a = ra[2 * sx + c], b = rb[2 * sx + c];
+                out |= (uint32_t)((a + b + 1) >> 1) << (8 * k);
+            }
         }
+        *(uint32_t *)(dst + (size_t)g.W * g.H + (size_t)c * g.CW * g.CH + (size_t)y * g.CW + x) = out;
     }
-    *(uint32_t *)(dst + o) = out;
 }
 
 // ================================================================================================
@@ -582,26 +589,34 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
     unsigned m_l = __ballot_sync(0xffffffffu, luma && nz > 0);
     int cbpl = ((m_l & 0x000f) ? 1 : 0) | ((m_l & 0x00f0) ? 2 : 0) | ((m_l & 0x0f00) ? 4 : 0) | ((m_l & 0xf000) ? 8 : 0);
 
+    // levels that are not coded (chroma AC without cbp 2) do not reach the reconstruction
+    const bool coded = luma ? nz != 0 : (chroma && co.cbpc == 2);
+    // most macroblocks of a well-predicted picture have no residual at all: their reconstruction is the prediction
+    const bool any_residual = __any_sync(0xffffffffu, coded || (chroma && co.cbpc != 0));
     if (luma || chroma) {
-        int r[16];
-        // levels that are not coded (chroma AC without cbp 2) do not reach the reconstruction
-        const bool coded = luma ? nz != 0 : co.cbpc == 2;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            const int rr = h264_zigzag4x4[i];
-            d[rr] = coded ? ((int)lev[i] * lq.ls[pos_class(rr)] * lq.mul + lq.rnd) >> lq.sr : 0;
-        }
-        if (chroma)
-            d[0] = co.cbpc ? co.dcq : 0;
-        idct4x4(d, r);
         uint8_t *op = unf + out_off;
+        if (any_residual) {
+            int r[16];
 #pragma unroll
-        for (int y = 0; y < 4; y++) {
-            int v[4];
+            for (int i = 0; i < 16; i++) {
+                const int rr = h264_zigzag4x4[i];
+                d[rr] = coded ? ((int)lev[i] * lq.ls[pos_class(rr)] * lq.mul + lq.rnd) >> lq.sr : 0;
+            }
+            if (chroma)
+                d[0] = co.cbpc ? co.dcq : 0;
+            idct4x4(d, r);
 #pragma unroll
-            for (int x = 0; x < 4; x++)
-                v[x] = clip255_(pred[y * 4 + x] + r[y * 4 + x]);
-            *(uint32_t *)(op + (size_t)y * out_stride) = pack4(v);
+            for (int y = 0; y < 4; y++) {
+                int v[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++)
+                    v[x] = clip255_(pred[y * 4 + x] + r[y * 4 + x]);
+                *(uint32_t *)(op + (size_t)y * out_stride) = pack4(v);
+            }
+        } else {
+#pragma unroll
+            for (int y = 0; y < 4; y++)
+                *(uint32_t *)(op + (size_t)y * out_stride) = pack4(pred + 4 * y);
         }
     }
     // syntax records
