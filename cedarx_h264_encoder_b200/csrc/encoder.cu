@@ -634,6 +634,10 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
         lanes = gops;
     while (lanes > 1 && (long)lanes * g.mbh > 148L * 16) // keep every wavefront CTA resident
         lanes--;
+    if (cfg->gops_in_flight <= 0) { // auto: equal waves (20 GOPs run as 10 + 10, not 16 + 4)
+        const int waves = (gops + lanes - 1) / lanes;
+        lanes = (gops + waves - 1) / waves;
+    }
     h->L = lanes;
     h->raw_frame_bytes = (size_t)g.src_w * g.src_h * (g.src_format == CEDAR_B200_FORMAT_NV16 ? 2 : 3) /
                          (g.src_format == CEDAR_B200_FORMAT_NV16 ? 1 : 2);
