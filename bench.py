@@ -203,7 +203,11 @@ def run_gpu(args, rank, local_rank, world):
     nhandles = args.clips_in_flight or min((2, 3), key=lambda c: schedule_cost(c, max(args.steps, 1)))
     encs, streams = [enc], [stream]
     for _ in range(max(nhandles, 1) - 1):
-        e = cx.Encoder(cfg)
+        try:
+            e = cx.Encoder(cfg)
+        except OSError as ex:  # a 4K 1200-frame clip is 15 GB of device and of pinned host memory per handle
+            print("bench.py: no memory for handle %d (%s); continuing with %d" % (len(encs) + 1, ex, len(encs)), file=sys.stderr)
+            break
         torch.from_numpy(e.clip_input(n)).copy_(staging[:n])
         encs.append(e)
         streams.append(torch.cuda.ExternalStream(e.stream_ptr(), device=torch.device("cuda", local_rank)))

@@ -260,6 +260,7 @@ template <class T> int dmalloc(T **p, size_t n)
 {
     cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
     if (e != cudaSuccess) {
+        cudaGetLastError(); // not sticky, but it would surface at the next launch check of any handle
         fprintf(stderr, "cedar_b200: cudaMalloc(%zu) failed: %s\n", n * sizeof(T), cudaGetErrorString(e));
         return -ENOMEM;
     }
@@ -269,6 +270,7 @@ template <class T> int hmalloc(T **p, size_t n)
 {
     cudaError_t e = cudaHostAlloc((void **)p, n * sizeof(T), cudaHostAllocDefault);
     if (e != cudaSuccess) {
+        cudaGetLastError();
         fprintf(stderr, "cedar_b200: cudaHostAlloc(%zu) failed: %s\n", n * sizeof(T), cudaGetErrorString(e));
         return -ENOMEM;
     }
@@ -302,6 +304,13 @@ int alloc_buffers(cedar_b200_handle *h)
     size_t per_frame_out = (F > 1 ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) + 4096 : (size_t)h->bytestream_size) + 8 * S + 64;
     h->out_cap = per_frame_out * F;
     size_t bins_per_mb = F > 1 ? (g.qp < 12 ? 8192 : (g.qp < 20 ? 2048 : 640)) : 16384;
+    // the pool is shared by all frames of a clip (bump allocation), so for long clips the per-macroblock allowance can
+    // shrink: at most 24 GB, at least 160 bins per macroblock (the 1080p benchmark clip averages 38, its I frames 145)
+    if (F > 1 && bins_per_mb * g.nmb * F * sizeof(uint16_t) > (24ull << 30)) {
+        bins_per_mb = (24ull << 30) / ((size_t)g.nmb * F * sizeof(uint16_t));
+        if (bins_per_mb < 160)
+            bins_per_mb = 160;
+    }
     if (const char *e = getenv("CEDAR_B200_BINS_PER_MB"))
         bins_per_mb = (size_t)atoll(e);
     h->eb.bins_cap = g.cabac ? (unsigned long long)(bins_per_mb * g.nmb + 8) * F + 64 : 0;
@@ -337,7 +346,8 @@ int alloc_buffers(cedar_b200_handle *h)
     h->eb.limb_cap = h->eb.rbsp_cap / 2 + 8;
     if (g.cabac) {
         r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap + 64); // + slack: 16-byte vector loads round outwards
-        r |= dmalloc(&h->eb.limbs, (size_t)h->eb.limb_cap * U);
+        // one region per side stream; frame mode finishes every frame before the next one starts: one region
+        r |= dmalloc(&h->eb.limbs, (size_t)h->eb.limb_cap * L * S * (F > 1 ? cedar_b200_handle::NSIDE : 1));
     }
     r |= dmalloc(&h->eb.bins_cursor, 1);
     r |= dmalloc(&h->eb.bins_off, U);
@@ -467,7 +477,9 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         cudaStream_t side = no_overlap ? st : h->stream_cabac[h->side_next];
         CK(cudaStreamWaitEvent(side, h->ev_post[p], 0));
         LAUNCH_ON(side, K_CRESOLVE, cabac_resolve_kernel, nl * g.nslices, RES_WARPS * 32, 0, g, s, h->K, gop_pos0, h->eb);
-        LAUNCH_ON(side, K_CCODE, cabac_code_kernel, nl * g.nslices, CP_THREADS, CP_SMEM_BYTES, g, s, h->eb);
+        EntropyBufs ebc = h->eb; // the limb scratch of this side stream (its launches are serialised)
+        ebc.limbs += (size_t)(no_overlap || h->F == 1 ? 0 : h->side_next) * h->L * g.nslices * h->eb.limb_cap;
+        LAUNCH_ON(side, K_CCODE, cabac_code_kernel, nl * g.nslices, CP_THREADS, CP_SMEM_BYTES, g, s, ebc);
         if (!no_overlap) {
             h->side_used |= 1u << h->side_next;
             h->side_next = (h->side_next + 1) % cedar_b200_handle::NSIDE;

@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(256) ingest_kernel(Geom g, Step s, const uint8
 #define ME_MAX_STRIP 4
 #define ME_MAX_ROWS 4 // macroblock rows per CTA (me_rows): they share 2R of the 16 + 2R window rows each would stage alone
 #define ME_MAX_MB (ME_MAX_STRIP * ME_MAX_ROWS)
-#define ME_TASK_WORDS 1088 // 32-column x 4-row tasks of one tile: R = 64, 8 macroblocks x 4 x 33; R = 32, 16 x 2 x 17
+#define ME_TASK_WORDS 1088 // 32-column x 4-row tasks of one tile: at most 16 macroblocks x 2 x 17 (R = 32); R = 64: 2 x 4 x 33
 
 __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
 {
@@ -114,7 +114,7 @@ __device__ __forceinline__ uint32_t sad4_acc(uint32_t a, uint32_t b, uint32_t c)
 }
 
 __host__ __device__ inline int me_strip(int R) { return R > 32 ? 2 : ME_MAX_STRIP; }
-__host__ __device__ inline int me_rows(int R) { return R > 32 ? 2 : ME_MAX_ROWS; } // shared memory: 4 CTAs per SM at R = 16
+__host__ __device__ inline int me_rows(int R) { return R > 32 ? 1 : ME_MAX_ROWS; } // shared memory: 4 CTAs per SM at R = 16, 2 at R = 64
 __host__ __device__ inline int me_row_words(int R, int nstrip)
 {
     int w = (16 * nstrip + 2 * R + 3) / 4 + 2;
@@ -346,7 +346,9 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
             for (int r = 0; r < 19; r++) {
                 // partial keys (rows 0 .. r - 1 - j of candidate j) against the best complete key.  Measured on the
                 // benchmark clip: 0.1 % of the tasks are dead after 5 window rows, 5 % after 9, 30 % after 13.
-                if (r == 9 || r == 13)
+                // With a wide range (R = 64, kRSW = 43) most candidates are far from the match and the early check pays;
+                // compile-time, because the extra branch point costs the R = 16 loop 20 % even when it is never taken.
+                if ((r == 5 && kRSW == 43) || r == 9 || r == 13)
                     dead = min_key() > *(volatile uint32_t *)&mb_best[m];
                 if (dead)
                     break;
@@ -1609,7 +1611,8 @@ struct EntropyBufs {
     unsigned long long *bins_cursor; // pool bump pointer
     unsigned long long *bins_off;    // [U]
     uint32_t *bins_len;      // [U]
-    uint32_t *limbs;         // [U][limb_cap] code-word limbs of the CABAC coder (16 stream bits per 32-bit word)
+    uint32_t *limbs;         // [coder CTAs of one launch][limb_cap] code-word limbs of the CABAC coder (16 stream bits per
+                             // 32-bit word): scratch of the launch, one region per side stream (set by the host)
     unsigned long long limb_cap;
     int *error;              // sticky overflow flag
     const uint8_t *i4;       // [L][nmb][16] Intra4x4 prediction modes of the step being coded (intra4x4 extension)
@@ -2025,7 +2028,7 @@ __global__ void __launch_bounds__(CP_THREADS) cabac_code_kernel(Geom g, Step s, 
     const uint16_t *mg = eb.bins + eb.bins_off[u];
     const int mis = (int)(((uintptr_t)mg >> 1) & 7);
     const uint16_t *meta_s = meta_raw + mis; // meta_s[i - lo] = record of bin i
-    uint32_t *limbs = eb.limbs + u * eb.limb_cap;
+    uint32_t *limbs = eb.limbs + (size_t)blockIdx.x * eb.limb_cap;
     uint8_t *out = eb.rbsp + u * eb.rbsp_cap;
     const int hn = eb.hdr_nbits[u], hb = (hn + 7) >> 3;
     if (tid == 64) { // header bits, then cabac_alignment_one_bit up to the byte boundary
