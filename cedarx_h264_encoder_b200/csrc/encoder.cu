@@ -84,6 +84,7 @@ struct cedar_b200_handle {
     cudaEvent_t ev_bins, ev_cabac[NSIDE];
     unsigned side_used; // bit i: side stream i has work the main stream has not joined yet
     int side_next;
+    int device; // every entry point selects it: the current device is per host thread, and handles are driven from threads
 
     // cedar.c:118-119 counters and the ping-pong reference (frame mode, lane 0)
     int frame_p_count, frame_count;
@@ -613,6 +614,7 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     cedar_b200_handle *h = new cedar_b200_handle();
     memset((void *)&h->cfg, 0, sizeof(h->cfg));
     h->cfg = *cfg;
+    h->device = cfg->device;
     h->t_open = std::chrono::steady_clock::now();
     Geom &g = h->g;
     g.W = cfg->dst_width;
@@ -721,6 +723,7 @@ int cedar_b200_encode_frame(cedar_b200_handle *h)
 {
     if (!h)
         return -EINVAL; // cedar.c:1039-1043: not configured
+    cudaSetDevice(h->device);
     auto t0 = std::chrono::steady_clock::now();
     const Geom &g = h->g;
     size_t luma_bytes = (size_t)g.src_w * g.src_h;
@@ -771,6 +774,7 @@ int cedar_b200_clip_upload(cedar_b200_handle *h, int nframes)
 {
     if (!h || !h->h_clip_in || nframes <= 0 || nframes > h->F)
         return -EINVAL;
+    cudaSetDevice(h->device);
     // Copies are issued in the order the encoder consumes the frames (step t needs frame t of every GOP) on a
     // dedicated stream; clip_encode's step t waits for ev_upload[t] only, so the transfer overlaps the encode.
     CK(cudaEventRecord(h->ev_encode_done, h->stream)); // do not overwrite frames a running encode still reads
@@ -793,6 +797,7 @@ int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_in
 {
     if (!h || nframes <= 0 || nframes > h->F || first_frame_index < 0 || (first_frame_index % h->K) != 0)
         return -EINVAL;
+    cudaSetDevice(h->device);
     auto t0 = std::chrono::steady_clock::now();
     int r;
     if ((r = upload_headers(h, nframes, 0)))
@@ -823,6 +828,7 @@ long long cedar_b200_clip_download(cedar_b200_handle *h, const uint8_t **out, in
 {
     if (!h || !h->h_clip_out || h->last_nframes <= 0)
         return -EINVAL;
+    cudaSetDevice(h->device);
     int n = h->last_nframes;
     CK(cudaMemcpyAsync(h->h_total, h->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(h->h_error, h->eb.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -857,6 +863,7 @@ int cedar_b200_profile_enable(cedar_b200_handle *h, int enable)
 {
     if (!h)
         return -EINVAL;
+    cudaSetDevice(h->device);
     if (!enable && h->prof)
         prof_collect(h);
     h->prof = enable != 0;
@@ -868,6 +875,7 @@ int cedar_b200_profile_read(cedar_b200_handle *h, const char **names, float *ms,
 {
     if (!h)
         return -EINVAL;
+    cudaSetDevice(h->device);
     prof_collect(h);
     int n = 0;
     for (int i = 0; i < K_COUNT && n < cap; i++) {
@@ -896,6 +904,7 @@ long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_
 {
     if (!h || !dst)
         return -EINVAL;
+    cudaSetDevice(h->device);
     const Geom &g = h->g;
     const void *src = nullptr;
     size_t n = 0;
@@ -921,6 +930,7 @@ void cedar_b200_close(cedar_b200_handle *h)
 {
     if (!h)
         return;
+    cudaSetDevice(h->device);
     prof_collect(h);
     double total_ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - h->t_open).count();
     // cedar.c:715-719 prints "Time spent: <waiting>/<total>ns" at release

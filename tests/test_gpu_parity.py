@@ -91,6 +91,36 @@ def test_clip_mode_matches_oracle(oracle, cabac, lanes):
         assert got2 == want
 
 
+def test_handles_on_their_own_threads_do_not_interfere(oracle):
+    """bench.py and INTEGRATION.md section 4 drive two or three handles per GPU, each from its own host thread: handles
+    share nothing, so every one of them must still produce the oracle's bytes (different content, entropy coder and
+    slice layout and QP per handle, several rounds, all in flight together)."""
+    import threading
+    w, h, n, gop = 96, 80, 13, 4
+    jobs = [("synth", 1, 0, 27), ("static", 0, 0, 30), ("synth", 1, 2, 22)]
+    want, encs, clips = [], [], []
+    for kind, cabac, rows, qp in jobs:
+        clip = make_clip(kind, w, h, n)
+        want.append(oracle_encode_clip(clip, w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, slice_rows=rows)[0])
+        clips.append(clip)
+        encs.append(cx.Encoder(api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, me_range=8, max_clip_frames=n,
+                                               gops_in_flight=2, slice_rows=rows)))
+    got = [[] for _ in jobs]
+
+    def work(i):
+        for _ in range(6):
+            got[i].append(encs[i].encode_clip(clips[i])[0])
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for e in encs:
+        e.close()
+    for i in range(len(jobs)):
+        assert len(got[i]) == 6 and all(g == want[i] for g in got[i]), jobs[i]
+
+
 def test_clip_mode_later_gops_carry_no_parameter_sets(oracle):
     """first_frame_index != 0: a rank that owns later GOPs emits no SPS/PPS (cedar.c:1058-1061), so
     rank streams concatenate to the single stream."""
