@@ -84,6 +84,8 @@ struct cedar_b200_handle {
     cudaEvent_t ev_bins, ev_cabac[NSIDE];
     unsigned side_used; // bit i: side stream i has work the main stream has not joined yet
     int side_next;
+    int grow;             // multiplier on the heuristic entropy-buffer bounds; clip mode raises it and re-encodes on overflow
+    int last_first_frame; // of the last clip_encode
     int device; // every entry point selects it: the current device is per host thread, and handles are driven from threads
 
     // cedar.c:118-119 counters and the ping-pong reference (frame mode, lane 0)
@@ -278,6 +280,59 @@ template <class T> int hmalloc(T **p, size_t n)
     return 0;
 }
 
+// The buffers whose size is a heuristic bound on the coded size (RBSP per slice NAL, CABAC bin pool, limb scratch,
+// emulation-prevention chunk counters, packed output on device and host).  h->grow scales the bounds: clip mode raises
+// it and encodes again when a clip overflows them (clip_download), frame mode reports the overflow.
+void free_entropy_buffers(cedar_b200_handle *h)
+{
+    void *dev[] = {h->eb.rbsp, h->eb.bins, h->eb.limbs, h->d_chunk_cnt, h->d_out};
+    for (void *p : dev)
+        if (p)
+            cudaFree(p);
+    if (h->h_clip_out)
+        cudaFreeHost(h->h_clip_out);
+    h->eb.rbsp = nullptr, h->eb.bins = nullptr, h->eb.limbs = nullptr, h->d_chunk_cnt = nullptr, h->d_out = nullptr;
+    h->h_clip_out = nullptr;
+}
+
+int alloc_entropy_buffers(cedar_b200_handle *h)
+{
+    const Geom &g = h->g;
+    const int F = h->F, L = h->L, S = h->S;
+    const size_t U = (size_t)F * S, grow = (size_t)h->grow; // U slice NALs
+    const size_t slice_mbs = (size_t)g.srows * g.mbw;
+    int r = 0;
+    h->eb.rbsp_cap = (unsigned)ALIGN_UP(slice_mbs * (F > 1 ? (g.qp < 20 ? 1024 : 400) : 1024) * grow + 4096, 256);
+    size_t per_frame_out =
+        (F > 1 ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) * grow + 4096 : (size_t)h->bytestream_size) + 8 * S + 64;
+    h->out_cap = per_frame_out * F;
+    size_t bins_per_mb = F > 1 ? (g.qp < 12 ? 8192 : (g.qp < 20 ? 2048 : 640)) : 16384;
+    // the pool is shared by all frames of a clip (bump allocation), so for long clips the per-macroblock allowance can
+    // shrink: at most 24 GB, at least 160 bins per macroblock (the 1080p benchmark clip averages 38, its I frames 145)
+    if (F > 1 && bins_per_mb * g.nmb * F * sizeof(uint16_t) > (24ull << 30)) {
+        bins_per_mb = (24ull << 30) / ((size_t)g.nmb * F * sizeof(uint16_t));
+        if (bins_per_mb < 160)
+            bins_per_mb = 160;
+    }
+    if (const char *e = getenv("CEDAR_B200_BINS_PER_MB"))
+        bins_per_mb = (size_t)atoll(e);
+    bins_per_mb *= grow;
+    h->eb.bins_cap = g.cabac ? (unsigned long long)(bins_per_mb * g.nmb + 8) * F + 64 : 0;
+    h->eb.limb_cap = h->eb.rbsp_cap / 2 + 8;
+    h->chunks_per_frame = (h->eb.rbsp_cap + EPB_CHUNK - 1) / EPB_CHUNK;
+    if (F > 1)
+        r |= hmalloc(&h->h_clip_out, h->out_cap);
+    r |= dmalloc(&h->eb.rbsp, (size_t)h->eb.rbsp_cap * U);
+    if (g.cabac) {
+        r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap + 64); // + slack: 16-byte vector loads round outwards
+        // one region per side stream; frame mode finishes every frame before the next one starts: one region
+        r |= dmalloc(&h->eb.limbs, (size_t)h->eb.limb_cap * L * S * (F > 1 ? cedar_b200_handle::NSIDE : 1));
+    }
+    r |= dmalloc(&h->d_chunk_cnt, (size_t)h->chunks_per_frame * U);
+    r |= dmalloc(&h->d_out, h->out_cap + 64);
+    return r;
+}
+
 int alloc_buffers(cedar_b200_handle *h)
 {
     const Geom &g = h->g;
@@ -300,26 +355,8 @@ int alloc_buffers(cedar_b200_handle *h)
 
     const int S = h->S;
     const size_t U = (size_t)F * S; // slice NALs
-    const size_t slice_mbs = (size_t)g.srows * g.mbw;
-    h->eb.rbsp_cap = (unsigned)ALIGN_UP(slice_mbs * (F > 1 ? (g.qp < 20 ? 1024 : 400) : 1024) + 4096, 256);
-    size_t per_frame_out = (F > 1 ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) + 4096 : (size_t)h->bytestream_size) + 8 * S + 64;
-    h->out_cap = per_frame_out * F;
-    size_t bins_per_mb = F > 1 ? (g.qp < 12 ? 8192 : (g.qp < 20 ? 2048 : 640)) : 16384;
-    // the pool is shared by all frames of a clip (bump allocation), so for long clips the per-macroblock allowance can
-    // shrink: at most 24 GB, at least 160 bins per macroblock (the 1080p benchmark clip averages 38, its I frames 145)
-    if (F > 1 && bins_per_mb * g.nmb * F * sizeof(uint16_t) > (24ull << 30)) {
-        bins_per_mb = (24ull << 30) / ((size_t)g.nmb * F * sizeof(uint16_t));
-        if (bins_per_mb < 160)
-            bins_per_mb = 160;
-    }
-    if (const char *e = getenv("CEDAR_B200_BINS_PER_MB"))
-        bins_per_mb = (size_t)atoll(e);
-    h->eb.bins_cap = g.cabac ? (unsigned long long)(bins_per_mb * g.nmb + 8) * F + 64 : 0;
-
-    if (F > 1) {
+    if (F > 1)
         r |= hmalloc(&h->h_clip_in, h->raw_frame_bytes * F);
-        r |= hmalloc(&h->h_clip_out, h->out_cap);
-    }
     r |= dmalloc(&h->d_raw, h->raw_frame_bytes * F + 64);
     r |= dmalloc(&h->d_src[0], g.frame_bytes * L);
     r |= dmalloc(&h->d_src[1], g.frame_bytes * L);
@@ -342,25 +379,16 @@ int alloc_buffers(cedar_b200_handle *h)
     r |= dmalloc(&h->eb.mb_off, (size_t)L * (g.nmb + S + 1));
     r |= dmalloc(&h->d_hdr_bits, U);
     r |= dmalloc(&h->d_hdr_nbits, U);
-    r |= dmalloc(&h->eb.rbsp, (size_t)h->eb.rbsp_cap * U);
     r |= dmalloc(&h->eb.rbsp_len, U);
-    h->eb.limb_cap = h->eb.rbsp_cap / 2 + 8;
-    if (g.cabac) {
-        r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap + 64); // + slack: 16-byte vector loads round outwards
-        // one region per side stream; frame mode finishes every frame before the next one starts: one region
-        r |= dmalloc(&h->eb.limbs, (size_t)h->eb.limb_cap * L * S * (F > 1 ? cedar_b200_handle::NSIDE : 1));
-    }
     r |= dmalloc(&h->eb.bins_cursor, 1);
     r |= dmalloc(&h->eb.bins_off, U);
     r |= dmalloc(&h->eb.bins_len, U);
     r |= dmalloc(&h->eb.error, 1);
-    h->chunks_per_frame = (h->eb.rbsp_cap + EPB_CHUNK - 1) / EPB_CHUNK;
-    r |= dmalloc(&h->d_chunk_cnt, (size_t)h->chunks_per_frame * U);
     r |= dmalloc(&h->d_nal_bytes, U);
     r |= dmalloc(&h->d_nal_off, U);
     r |= dmalloc(&h->d_total, 1);
     r |= dmalloc(&h->d_frame_bytes, F);
-    r |= dmalloc(&h->d_out, h->out_cap + 64);
+    r |= alloc_entropy_buffers(h);
     if (r)
         return r;
     h->eb.hdr_bits = h->d_hdr_bits;
@@ -382,14 +410,15 @@ void free_buffers(cedar_b200_handle *h)
 {
     void *dev[] = {h->d_raw, h->d_src[0], h->d_src[1], h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi[0], h->d_mbi[1],
                    h->d_nnz[0], h->d_nnz[1], h->d_i4[0], h->d_i4[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_me_tabs, h->d_pwant, h->d_pcount, h->d_bs,
-                   h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp, h->eb.rbsp_len,
-                   h->eb.bins, h->eb.limbs, h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error, h->d_chunk_cnt,
-                   h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes, h->d_out};
+                   h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp_len,
+                   h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error,
+                   h->d_nal_bytes, h->d_nal_off, h->d_total, h->d_frame_bytes};
+    free_entropy_buffers(h);
     for (void *p : dev)
         if (p)
             cudaFree(p);
     void *host[] = {h->h_in_luma, h->h_in_chroma, h->h_bytestream, h->h_frame_bytes, h->h_total, h->h_sse,
-                    h->h_error, h->h_clip_in, h->h_clip_out};
+                    h->h_error, h->h_clip_in};
     for (void *p : host)
         if (p)
             cudaFreeHost(p);
@@ -656,6 +685,8 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     h->raw_frame_bytes = (size_t)g.src_w * g.src_h * (g.src_format == CEDAR_B200_FORMAT_NV16 ? 2 : 3) /
                          (g.src_format == CEDAR_B200_FORMAT_NV16 ? 1 : 2);
     h->prof = false;
+    h->grow = 1;
+    h->last_first_frame = 0;
     memset(h->prof_ms, 0, sizeof(h->prof_ms));
     memset(h->prof_n, 0, sizeof(h->prof_n));
     // Stream priorities were measured (main stream high / entropy streams low, and the reverse): within 1.5 % of
@@ -793,12 +824,9 @@ int cedar_b200_clip_upload(cedar_b200_handle *h, int nframes)
     return 0;
 }
 
-int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_index)
+// Issues the whole encode of the clip that is resident in d_raw (asynchronous).
+static int run_clip(cedar_b200_handle *h, int nframes, int first_frame_index)
 {
-    if (!h || nframes <= 0 || nframes > h->F || first_frame_index < 0 || (first_frame_index % h->K) != 0)
-        return -EINVAL;
-    cudaSetDevice(h->device);
-    auto t0 = std::chrono::steady_clock::now();
     int r;
     if ((r = upload_headers(h, nframes, 0)))
         return r;
@@ -817,9 +845,20 @@ int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_in
         }
     }
     h->upload_pending = false;
-    if ((r = finish_stream(h, nframes, 0, first_frame_index == 0)))
+    return finish_stream(h, nframes, 0, first_frame_index == 0);
+}
+
+int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_index)
+{
+    if (!h || nframes <= 0 || nframes > h->F || first_frame_index < 0 || (first_frame_index % h->K) != 0)
+        return -EINVAL;
+    cudaSetDevice(h->device);
+    auto t0 = std::chrono::steady_clock::now();
+    int r = run_clip(h, nframes, first_frame_index);
+    if (r)
         return r;
     h->last_nframes = nframes;
+    h->last_first_frame = first_frame_index;
     h->busy_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
     return 0;
 }
@@ -830,14 +869,35 @@ long long cedar_b200_clip_download(cedar_b200_handle *h, const uint8_t **out, in
         return -EINVAL;
     cudaSetDevice(h->device);
     int n = h->last_nframes;
-    CK(cudaMemcpyAsync(h->h_total, h->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_error, h->eb.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_frame_bytes, h->d_frame_bytes, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaMemcpyAsync(h->h_sse, h->d_sse, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    int r = check_error(h);
-    if (r)
-        return r;
+    for (;;) {
+        CK(cudaMemcpyAsync(h->h_total, h->d_total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_error, h->eb.error, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_frame_bytes, h->d_frame_bytes, sizeof(int) * n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_sse, h->d_sse, sizeof(unsigned long long) * n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (!*h->h_error)
+            break;
+        // The coded clip did not fit the heuristic bounds of the entropy buffers (nothing was written out of bounds:
+        // every writer checks).  The raw clip is still resident: enlarge the buffers and encode it again.
+        if (h->grow >= 256 || getenv("CEDAR_B200_NO_GROW"))
+            return check_error(h);
+        fprintf(stderr, "cedar_b200: coded clip exceeds the entropy buffer bounds (code %d): enlarging them x4 and encoding again\n",
+                *h->h_error);
+        CK(cudaMemset(h->eb.error, 0, sizeof(int)));
+        CK(cudaDeviceSynchronize());
+        h->grow *= 4;
+        free_entropy_buffers(h);
+        int r = alloc_entropy_buffers(h);
+        if (r) { // no memory for the larger buffers: back to the size that worked, and report
+            h->grow /= 4;
+            free_entropy_buffers(h);
+            if (alloc_entropy_buffers(h))
+                fprintf(stderr, "cedar_b200: could not restore the entropy buffers; the handle is unusable\n");
+            return r;
+        }
+        if ((r = run_clip(h, n, h->last_first_frame)))
+            return r;
+    }
     size_t total = (size_t)*h->h_total;
     if (total == 0 || total > h->out_cap)
         return -ENOMEM;

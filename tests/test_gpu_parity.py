@@ -137,10 +137,27 @@ def test_clip_mode_later_gops_carry_no_parameter_sets(oracle):
 
 def test_overflow_is_reported_not_silent(monkeypatch):
     monkeypatch.setenv("CEDAR_B200_BINS_PER_MB", "8")
+    monkeypatch.setenv("CEDAR_B200_NO_GROW", "1")
     clip = make_clip("noise", 64, 48, 2)
     with cx.Encoder(api.make_config(64, 48, qp=10, gop=25, cabac=1, me_range=8, max_clip_frames=2)) as enc:
         with pytest.raises(OSError):
             enc.encode_clip(clip)
+
+
+@pytest.mark.parametrize("cabac", [0, 1])
+def test_clip_that_overflows_the_heuristic_bounds_is_encoded_again_with_larger_buffers(oracle, monkeypatch, cabac):
+    """The entropy buffers of clip mode are sized by a per-macroblock heuristic.  Noise at a low QP exceeds it: the
+    library enlarges the buffers and encodes the resident clip again; the caller sees the oracle's bytes, not an error."""
+    if cabac:
+        monkeypatch.setenv("CEDAR_B200_BINS_PER_MB", "64")
+    w, h, n, gop = 96, 80, 9, 4
+    clip = make_clip("noise", w, h, n)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=21, gop=gop, cabac=cabac, me_range=8)
+    with cx.Encoder(api.make_config(w, h, qp=21, gop=gop, cabac=cabac, me_range=8, max_clip_frames=n)) as enc:
+        got, gsz = enc.encode_clip(clip)
+        assert got == want and gsz.tolist() == sizes
+        got2, _ = enc.encode_clip(clip)  # the enlarged buffers stay
+        assert got2 == want
 
 
 @pytest.mark.parametrize("name,w,h,fmt,gop,n,me", [("720p", 1280, 720, 0, 30, 31, 16), ("1080p", 1920, 1088, 0, 60, 61, 16),
