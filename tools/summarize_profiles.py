@@ -33,7 +33,7 @@ def launches(src, dst):
     for r in rows[1:]:
         if len(r) <= mv:
             continue
-        name = r[kn].split("(")[0].split("::")[-1].split("<")[0]
+        name = r[kn].split("(")[0].split("::")[-1].split("<")[0].replace("void ", "")
         v = float(r[mv].replace(",", ""))
         a = agg.setdefault(name, [0, 0.0, 0.0])
         if r[mn] == "gpu__time_duration.sum":
@@ -58,7 +58,7 @@ def full(rep, dst):
     hdr, units = rows[0], rows[1]
     res = []
     for r in rows[2:]:
-        d = {"kernel": r[hdr.index("Kernel Name")].split("(")[0].split("::")[-1]}
+        d = {"kernel": r[hdr.index("Kernel Name")].split("(")[0].split("::")[-1].replace("void ", "").rstrip("<")}
         for m in FULL_METRICS:
             if m in hdr:
                 d[m] = r[hdr.index(m)]
