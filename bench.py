@@ -373,7 +373,7 @@ def run_gpu(args, rank, local_rank, world):
             roofline = {"kernel": "me_kernel", "bound": "int-simd (VABSDIFF4 issue rate; neither hbm nor tensor)",
                         "achieved": ach / 1e12, "peak": simd_peak / 1e12, "unit": "T VABSDIFF4 lane-instr/s",
                         "frac": ach / simd_peak,
-                        "traffic": {"dram_bytes_per_launch": 44.92e6, "algorithmic_bytes_per_launch": 2.0 * W16 * H16 * 10,
+                        "traffic": {"dram_bytes_per_launch": 43.36e6, "algorithmic_bytes_per_launch": 2.0 * W16 * H16 * 10,
                                     "source": "ncu --set full, profiles/r01_ncu_full_summary.json (1080p, 10 GOPs in flight)"}
                         if args.workload == DEFAULT_WORKLOAD and world == 1 else None,
                         "peak_source": "measured on this pool with tools/vabsdiff_bench.cu (63.8 /SM/clk)",
