@@ -449,7 +449,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         CK(cudaStreamWaitEvent(pre, h->ev_post[p], 0)); // step - 2 has finished with src[p] (and main with it)
     if (wait_upload)
         CK(cudaStreamWaitEvent(pre, h->ev_upload[t], 0));
-    LAUNCH_ON(pre, K_INGEST, ingest_kernel, dim3((unsigned)((g.W / 4 + 255) / 256), (unsigned)(g.H + 2 * g.CH), nl), 256, 0, g, s, h->d_raw,
+    LAUNCH_ON(pre, K_INGEST, ingest_kernel, dim3((unsigned)((g.W / 16 + 127) / 128), (unsigned)(g.H + 2 * g.CH), nl), 128, 0, g, s, h->d_raw,
               h->raw_frame_bytes, src);
     CK(cudaEventRecord(h->ev_ingest[p], pre));
 

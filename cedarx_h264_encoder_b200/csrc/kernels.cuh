@@ -40,32 +40,61 @@ __device__ __forceinline__ void st_release(int *p, int v)
 
 // ================================================================================================
 // K0 ingest: packed NV12 / NV16 (w x h) -> planar 4:2:0 at the coded size with edge replication.
-// Replaces the ISP input stage (cedar.c:1068-1080).  Grid: (words of a luma row / 256, H + 2 CH output rows, lanes);
-// one thread = 4 output bytes: one aligned word of luma, or two words of interleaved chroma de-interleaved with a
-// byte permute (NV16: the rounding average of two rows, __vavgu4); bytes only at the picture edge.  HBM bound.
+// Replaces the ISP input stage (cedar.c:1068-1080).  Grid: (16-byte groups of a luma row / 128, H + 2 CH output rows,
+// lanes); one thread = 16 output bytes: one aligned 16-byte vector of luma, or two vectors of interleaved chroma
+// de-interleaved with byte permutes (NV16: the rounding average of two rows, __vavgu4); words and bytes only at the
+// picture edge or when the source is not 16-byte aligned.  HBM bound.
 // ================================================================================================
-__global__ void __launch_bounds__(256) ingest_kernel(Geom g, Step s, const uint8_t *__restrict__ raw, size_t raw_frame_bytes,
+__device__ __forceinline__ uint32_t ingest_luma_word(const uint8_t *rp, int x, int src_w)
+{
+    if (x + 3 < src_w && !((uintptr_t)(rp + x) & 3))
+        return *(const uint32_t *)(rp + x);
+    uint32_t out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        out |= (uint32_t)rp[imin_(x + k, src_w - 1)] << (8 * k);
+    return out;
+}
+__device__ __forceinline__ uint32_t ingest_chroma_word(const uint8_t *ra, const uint8_t *rb, int x, int c, int src_w, int nv16)
+{
+    uint32_t out = 0;
+    if (2 * x + 7 < src_w && !(((uintptr_t)(ra + 2 * x) | (uintptr_t)(rb + 2 * x)) & 3)) {
+        const uint32_t sel = c ? 0x7531u : 0x6420u;
+        const uint32_t *pa = (const uint32_t *)(ra + 2 * x), *pb = (const uint32_t *)(rb + 2 * x);
+        out = __byte_perm(pa[0], pa[1], sel);
+        if (nv16)
+            out = __vavgu4(out, __byte_perm(pb[0], pb[1], sel));
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int sx = imin_(x + k, src_w / 2 - 1);
+            const int a = ra[2 * sx + c], b = rb[2 * sx + c];
+            out |= (uint32_t)((a + b + 1) >> 1) << (8 * k);
+        }
+    }
+    return out;
+}
+__global__ void __launch_bounds__(128) ingest_kernel(Geom g, Step s, const uint8_t *__restrict__ raw, size_t raw_frame_bytes,
                                                      uint8_t *__restrict__ src)
 {
     const int f = lane_frame(s, blockIdx.z);
     if (f < 0)
         return;
-    const int row = blockIdx.y, x = (blockIdx.x * 256 + threadIdx.x) * 4;
+    const int row = blockIdx.y, x = (blockIdx.x * 128 + threadIdx.x) * 16;
     const uint8_t *luma = raw + (size_t)f * raw_frame_bytes;
     const uint8_t *chroma = luma + (size_t)g.src_w * g.src_h;
     uint8_t *dst = src + (size_t)blockIdx.z * g.frame_bytes;
-    uint32_t out = 0;
+    uint4 out;
     if (row < g.H) {
         if (x >= g.W)
             return;
         const uint8_t *rp = luma + (size_t)imin_(row, g.src_h - 1) * g.src_w;
-        if (x + 3 < g.src_w && !((uintptr_t)(rp + x) & 3))
-            out = *(const uint32_t *)(rp + x);
+        if (x + 15 < g.src_w && !((uintptr_t)(rp + x) & 15))
+            out = *(const uint4 *)(rp + x);
         else
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                out |= (uint32_t)rp[imin_(x + k, g.src_w - 1)] << (8 * k);
-        *(uint32_t *)(dst + (size_t)row * g.W + x) = out;
+            out = make_uint4(ingest_luma_word(rp, x, g.src_w), ingest_luma_word(rp, x + 4, g.src_w),
+                             ingest_luma_word(rp, x + 8, g.src_w), ingest_luma_word(rp, x + 12, g.src_w));
+        *(uint4 *)(dst + (size_t)row * g.W + x) = out; // W is a multiple of 16
     } else {
         if (x >= g.CW)
             return;
@@ -73,21 +102,26 @@ __global__ void __launch_bounds__(256) ingest_kernel(Geom g, Step s, const uint8
         const int sy = imin_(y, g.src_h / 2 - 1), nv16 = g.src_format == 1;
         // NV16 -> 4:2:0: rounding average of the two chroma rows
         const uint8_t *ra = chroma + (size_t)(nv16 ? 2 * sy : sy) * g.src_w, *rb = nv16 ? ra + g.src_w : ra;
-        if (2 * x + 7 < g.src_w && !(((uintptr_t)(ra + 2 * x) | (uintptr_t)(rb + 2 * x)) & 3)) {
+        uint8_t *o = dst + (size_t)g.W * g.H + (size_t)c * g.CW * g.CH + (size_t)y * g.CW + x;
+        if (x + 15 < g.CW && 2 * x + 31 < g.src_w && !(((uintptr_t)(ra + 2 * x) | (uintptr_t)(rb + 2 * x) | (uintptr_t)o) & 15)) {
             const uint32_t sel = c ? 0x7531u : 0x6420u;
-            const uint32_t *pa = (const uint32_t *)(ra + 2 * x), *pb = (const uint32_t *)(rb + 2 * x);
-            out = __byte_perm(pa[0], pa[1], sel);
-            if (nv16)
-                out = __vavgu4(out, __byte_perm(pb[0], pb[1], sel));
+            const uint4 a0 = ((const uint4 *)(ra + 2 * x))[0], a1 = ((const uint4 *)(ra + 2 * x))[1];
+            out = make_uint4(__byte_perm(a0.x, a0.y, sel), __byte_perm(a0.z, a0.w, sel), __byte_perm(a1.x, a1.y, sel),
+                             __byte_perm(a1.z, a1.w, sel));
+            if (nv16) {
+                const uint4 b0 = ((const uint4 *)(rb + 2 * x))[0], b1 = ((const uint4 *)(rb + 2 * x))[1];
+                out.x = __vavgu4(out.x, __byte_perm(b0.x, b0.y, sel));
+                out.y = __vavgu4(out.y, __byte_perm(b0.z, b0.w, sel));
+                out.z = __vavgu4(out.z, __byte_perm(b1.x, b1.y, sel));
+                out.w = __vavgu4(out.w, __byte_perm(b1.z, b1.w, sel));
+            }
+            *(uint4 *)o = out; // (CW is a multiple of 8 only: rows of some sizes start 8-byte aligned and take the word path)
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int sx = imin_(x + k, g.src_w / 2 - 1);
-                const int a = ra[2 * sx + c], b = rb[2 * sx + c];
-                out |= (uint32_t)((a + b + 1) >> 1) << (8 * k);
-            }
+            for (int k = 0; k < 4; k++)
+                if (x + 4 * k < g.CW)
+                    *(uint32_t *)(o + 4 * k) = ingest_chroma_word(ra, rb, x + 4 * k, c, g.src_w, nv16);
         }
-        *(uint32_t *)(dst + (size_t)g.W * g.H + (size_t)c * g.CW * g.CH + (size_t)y * g.CW + x) = out;
     }
 }
 
