@@ -152,7 +152,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": args.workload, "width": w, "height": h, "frames": nframes, "gop": gop, "qp": qp,
                    "me_range": me, "entropy": "cabac" if cabac else "cavlc", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "per_core": value / cores, "kind": "port", "sample": sample,
                          "note": "reference has no CPU macroblock encoder (Cedar VE silicon); this is the C golden "
                                  "model of the same algorithm, GOP-parallel across processes"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -436,7 +436,7 @@ def run_gpu(args, rank, local_rank, world):
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             fps, total, wall = cpu_sample(args.workload, args.cpu_frames, cores)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "per_core": fps / cores, "kind": "port",
                                     "sample": "%d cores x first %d frames of distinct GOPs (%.1f s wall)" % (
                                         cores, args.cpu_frames, wall)}
         else:
