@@ -127,11 +127,11 @@ __global__ void __launch_bounds__(128) ingest_kernel(Geom g, Step s, const uint8
 
 // ================================================================================================
 // K1 integer motion estimation: exhaustive +-R SAD search against the previous deblocked
-// reconstruction (edge clamped).  One CTA per horizontal strip of `nstrip` macroblocks that share one
-// search window.  The window is staged in shared memory four times, byte-shifted by 0..3, so that every
+// reconstruction (edge clamped).  One CTA per tile of nstrip x me_rows macroblocks (4 x 4 at R <= 32) that share
+// one search window.  The window is staged in shared memory four times, byte-shifted by 0..3, so that every
 // candidate reads aligned 32-bit words; a warp task = 32 column offsets x 4 consecutive row offsets of one
-// macroblock: each thread keeps that macroblock's 16x16 block in 64 registers and issues 256
-// VABSDIFF4-with-accumulate for 76 shared loads.  argmin over key = cost << 15 | raster rank
+// macroblock: each thread streams that macroblock's 16x16 block through registers and issues 256
+// VABSDIFF4-with-accumulate for 76 window loads.  argmin over key = cost << 15 | raster rank
 // (order independent => deterministic).  Bound: integer SIMD-video issue rate.
 // ================================================================================================
 #define ME_THREADS 320
