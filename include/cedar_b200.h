@@ -80,6 +80,9 @@ struct cedar_b200_io {
     int bytestream_size;   /* worst-case frame; the reference's fixed 1 MiB (cedar.c:663) is too small for 4K */
 };
 
+/* One handle = one stream of work on one GPU (the reference: one opener of /dev/cedar_dev, kernel/cedar.c:457-474).
+ * A handle is not thread-safe, but different handles share nothing and every call selects its handle's device, so
+ * handles may be driven from different host threads -- two or three per GPU keep the GPU full. */
 typedef struct cedar_b200_handle cedar_b200_handle;
 
 /* open("/dev/cedar_dev") + ioctl(CEDAR_IOCTL_CONFIG) + 3x mmap (userspace/h264enc.c:149,68,76-106;
@@ -114,7 +117,9 @@ int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_in
 
 /* Device -> host copy of the packed stream.  *out receives a pointer to pinned host memory valid
  * until the next clip call; frame_bytes (may be NULL) receives nframes per-frame byte counts.
- * Returns total bytes or a negative errno. */
+ * Returns total bytes or a negative errno.  The entropy buffers of clip mode are sized by a heuristic bound
+ * per macroblock; if the coded clip exceeds it, this call enlarges them and encodes the (still resident)
+ * clip again before it returns -- the caller sees the bytes, and a note on stderr. */
 long long cedar_b200_clip_download(cedar_b200_handle *h, const uint8_t **out, int *frame_bytes);
 
 /* Statistics of the last encode_frame / clip_encode: sum of squared luma error per frame
