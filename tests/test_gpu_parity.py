@@ -66,10 +66,14 @@ def test_frame_mode_shapes_and_formats(oracle, w, h, fmt, me):
     gold.close()
 
 
-def test_me_range_64(oracle):
+@pytest.mark.parametrize("me", [64, 1, 2, 3, 20, 32, 33, 47])
+def test_me_ranges(oracle, me):
+    """Every search-tile geometry of me_kernel: 4 x 4 macroblocks up to R = 32 (compiled-in row stride at 16, generic
+    otherwise), 2 x 1 above (R = 33 shares the row stride of R = 16, R = 64 has its own instantiation), and the ranges
+    with fewer than four row offsets per column."""
     w, h = 208, 160
-    gold = oracle.Encoder(oracle.make_config(w, h, qp=25, gop=25, cabac=0, me_range=64))
-    with cx.Encoder(api.make_config(w, h, qp=25, gop=25, cabac=0, me_range=64)) as enc:
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=25, gop=25, cabac=0, me_range=me))
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=25, cabac=0, me_range=me)) as enc:
         for t in range(2):
             y, c = content("shift", w, h, 3 * t)
             assert enc.encode(y, c) == gold.encode(y, c)
