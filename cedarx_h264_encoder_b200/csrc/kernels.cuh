@@ -292,7 +292,32 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
                 v |= (uint32_t)row[clip3_(0, g.W - 1, fx + i)] << (8 * i);
             return v;
         };
-        for (int r = warp_; r < WR; r += ME_THREADS / 32) {
+        // Interior tiles whose window starts on a 16-byte boundary (R = 16: all of them) and is at most 32 words wide:
+        // eight lanes per row, four rows per warp pass, one 16-byte load per lane -- a third of the instructions of the
+        // word-per-lane loop below.  The four rows of a pass land in different banks (RSW is odd).
+        const int nq = (RSW + 4) >> 2; // 16-byte groups that hold window words 0 .. RSW
+        const bool vec = interior_x && !((x0 - R) & 15) && RSW < 32 && x0 - R + 16 * nq <= g.W;
+        if (vec) {
+            const int sub = lane_ >> 3, q = lane_ & 7;
+            for (int r4 = 4 * warp_; r4 < WR; r4 += 4 * (ME_THREADS / 32)) {
+                const int r = r4 + sub;
+                const bool on = r < WR && q < nq;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (on)
+                    v = *(const uint4 *)(refY + (size_t)clip3_(0, g.H - 1, y0 - R + r) * g.W + (x0 - R) + 16 * q);
+                const uint32_t w[5] = {v.x, v.y, v.z, v.w, __shfl_down_sync(0xffffffffu, v.x, 1)};
+                uint32_t *d = cp + r * RSW + 4 * q;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (on && 4 * q + i < RSW) {
+                        d[i] = w[i];
+                        d[i + CWs] = __byte_perm(w[i], w[i + 1], 0x4321);
+                        d[i + 2 * CWs] = __byte_perm(w[i], w[i + 1], 0x5432);
+                        d[i + 3 * CWs] = __byte_perm(w[i], w[i + 1], 0x6543);
+                    }
+            }
+        }
+        for (int r = vec ? WR : warp_; r < WR; r += ME_THREADS / 32) {
             const uint8_t *row = refY + (size_t)clip3_(0, g.H - 1, y0 - R + r) * g.W;
             for (int k0 = 0; k0 < RSW; k0 += 32) {
                 const int k = k0 + lane_;
