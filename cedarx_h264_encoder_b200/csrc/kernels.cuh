@@ -343,26 +343,26 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
     // search) -- so that the exhaustive loop below can drop a task as soon as the partial cost of every candidate
     // in it exceeds the best complete cost so far.  SAD terms are non-negative, so the partial key is a lower
     // bound of the final key: the argmin, and with it the bitstream, is unchanged.
-    for (int sd = warp; sd < 2 * nmb; sd += nwarps) {
-        const int m = sd >> 1, mc = m & (nstrip - 1), mr = m >> ls;
+    // one warp pass per macroblock: lanes 0..15 take the rows of the zero-vector seed, lanes 16..31 those of the
+    // co-located one
+    for (int m = warp; m < nmb; m += nwarps) {
+        const int mc = m & (nstrip - 1), mr = m >> ls, half = lane >> 4, l16 = lane & 15;
         if (!((vmask >> m) & 1))
             continue;
         int ox = R, oy = R;
-        if (sd & 1) {
+        if (half) {
             const MbInfo pv = mbi_prev[(size_t)blockIdx.z * g.nmb + (size_t)(mby0 + mr) * g.mbw + mbx0 + mc];
             ox = clip3_(0, nd - 1, (pv.mv[0] >> 2) + R);
             oy = clip3_(0, nd - 1, (pv.mv[1] >> 2) + R);
         }
         uint32_t a = 0;
-        if (lane < 16) {
-            const uint32_t *wp = cp + (ox & 3) * CWs + (oy + 16 * mr + lane) * RSW + 4 * mc + (ox >> 2);
-            const uint32_t *cu = cur_s + 64 * m + 4 * lane;
+        const uint32_t *wp = cp + (ox & 3) * CWs + (oy + 16 * mr + l16) * RSW + 4 * mc + (ox >> 2);
+        const uint32_t *cu = cur_s + 64 * m + 4 * l16;
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                a = sad4_acc(wp[k], cu[k], a);
-        }
-        a = __reduce_add_sync(0xffffffffu, a);
-        if (lane == 0)
+        for (int k = 0; k < 4; k++)
+            a = sad4_acc(wp[k], cu[k], a);
+        a = __reduce_add_sync(half ? 0xffff0000u : 0x0000ffffu, a);
+        if (l16 == 0)
             atomicMin(&mb_best[m], ((a + mvcost[ox] + mvcost[oy]) << 15) | (uint32_t)(oy * nd + ox));
     }
     __syncthreads();
