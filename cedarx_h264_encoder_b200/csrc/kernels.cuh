@@ -542,7 +542,6 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
     const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
     const size_t rec = (size_t)blockIdx.y * g.nmb + mb;
     const MbInfo me = mbi[rec];
-    const int dx = me.mv[0] >> 2, dy = me.mv[1] >> 2;
     const bool luma = lane < 16, chroma = lane >= 16 && lane < 24;
     const int qp = g.qp, qpc = g.qpc;
 
@@ -554,85 +553,71 @@ __global__ void __launch_bounds__(128) inter_kernel(Geom g, Step s, const uint8_
 #pragma unroll
     for (int i = 0; i < 16; i++)
         d[i] = 0, pred[i] = 0;
-    if (luma) {
-        int px = mbx * 16 + blk_x(lane) * 4, py = mby * 16 + blk_y(lane) * 4;
-        const uint8_t *sp = src + fo + (size_t)py * g.W + px;
-        const uint8_t *rp = ref + fo;
-        const int rx = px + dx, ry = py + dy;
-        if (rx >= 0 && rx + 7 < g.W && ry >= 0 && ry + 3 < g.H) {
-            // interior: each 4-sample row of the prediction is two aligned words and a funnel shift
-#pragma unroll
-            for (int y = 0; y < 4; y++) {
-                const uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.W);
-                const uintptr_t a = (uintptr_t)(rp + (size_t)(ry + y) * g.W + rx);
-                const uint32_t *aw = (const uint32_t *)(a & ~(uintptr_t)3);
-                const uint32_t pv = __funnelshift_r(aw[0], aw[1], (uint32_t)(a & 3) * 8);
-#pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    const int p = (int)((pv >> (8 * x)) & 0xff);
-                    pred[y * 4 + x] = p;
-                    d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int y = 0; y < 4; y++) {
-                uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.W);
-                const uint8_t *rr = rp + (size_t)clip3_(0, g.H - 1, py + y + dy) * g.W;
-#pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    int p = rr[clip3_(0, g.W - 1, px + x + dx)];
-                    pred[y * 4 + x] = p;
-                    d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
-                }
-            }
-        }
-        out_off = fo + (size_t)py * g.W + px;
-        out_stride = g.W;
-    } else if (chroma) {
-        int c = (lane - 16) >> 2, cb = lane & 3;
-        int px = mbx * 8 + (cb & 1) * 4, py = mby * 8 + (cb >> 1) * 4;
-        size_t po = fo + (size_t)g.W * g.H + (size_t)c * g.CW * g.CH;
-        const uint8_t *sp = src + po + (size_t)py * g.CW + px;
+    if (luma || chroma) {
+        // One prediction fetch for luma and chroma lanes: every lane describes its 4x4 block by plane offset, plane size
+        // and vector (luma: integer-pel, no fraction; chroma: mv / 8 with a fraction of 0 or 4 eighths, because the luma
+        // vectors are integer-pel) and reads the 5 x 5 reference samples the bilinear filter can touch, per row as two
+        // words: samples 0..3 (wa) and 1..4 (wb).
+        const int c = (lane - 16) >> 2, cb = lane & 3;
+        const size_t po = luma ? fo : fo + (size_t)g.W * g.H + (size_t)c * g.CW * g.CH;
+        const int pw_ = luma ? g.W : g.CW, ph_ = luma ? g.H : g.CH;
+        const int px = luma ? mbx * 16 + blk_x(lane) * 4 : mbx * 8 + (cb & 1) * 4;
+        const int py = luma ? mby * 16 + blk_y(lane) * 4 : mby * 8 + (cb >> 1) * 4;
+        const int mvx = me.mv[0], mvy = me.mv[1];
+        const int rx = px + (luma ? mvx >> 2 : mvx >> 3), ry = py + (luma ? mvy >> 2 : mvy >> 3);
+        const int xf = luma ? 0 : mvx & 7, yf = luma ? 0 : mvy & 7;
+        const uint8_t *sp = src + po + (size_t)py * pw_ + px;
         const uint8_t *rp = ref + po;
-        int mvx = me.mv[0], mvy = me.mv[1];
-        int xi = mvx >> 3, yi = mvy >> 3, xf = mvx & 7, yf = mvy & 7;
-        // the 5 x 5 reference samples the bilinear filter of this 4 x 4 block touches, one 64-bit window per row
-        unsigned long long prow[5];
-        const int cx0 = px + xi, cy0 = py + yi;
-        if (cx0 >= 0 && cx0 + 7 < g.CW && cy0 >= 0 && cy0 + 4 < g.CH) {
+        uint32_t wa[5], wb[5];
+        if (rx >= 0 && rx + 7 < pw_ && ry >= 0 && ry + 4 < ph_) {
 #pragma unroll
             for (int y = 0; y < 5; y++) {
-                const uintptr_t a = (uintptr_t)(rp + (size_t)(cy0 + y) * g.CW + cx0);
+                const uintptr_t a = (uintptr_t)(rp + (size_t)(ry + y) * pw_ + rx);
                 const uint32_t *aw = (const uint32_t *)(a & ~(uintptr_t)3);
-                prow[y] = (((unsigned long long)aw[1] << 32) | aw[0]) >> ((a & 3) * 8);
+                const uint32_t lo = aw[0], hi = aw[1], sh = (uint32_t)(a & 3) * 8;
+                wa[y] = __funnelshift_r(lo, hi, sh);
+                wb[y] = __funnelshift_rc(lo, hi, sh + 8); // clamped: a shift of 32 is the high word
             }
         } else {
 #pragma unroll
             for (int y = 0; y < 5; y++) {
-                const uint8_t *rr = rp + (size_t)clip3_(0, g.CH - 1, cy0 + y) * g.CW;
-                unsigned long long v = 0;
+                const uint8_t *rr = rp + (size_t)clip3_(0, ph_ - 1, ry + y) * pw_;
+                uint32_t s5[5];
 #pragma unroll
                 for (int x = 0; x < 5; x++)
-                    v |= (unsigned long long)rr[clip3_(0, g.CW - 1, cx0 + x)] << (8 * x);
-                prow[y] = v;
+                    s5[x] = rr[clip3_(0, pw_ - 1, rx + x)];
+                wa[y] = s5[0] | (s5[1] << 8) | (s5[2] << 16) | (s5[3] << 24);
+                wb[y] = s5[1] | (s5[2] << 8) | (s5[3] << 16) | (s5[4] << 24);
             }
         }
-        const int w00 = (8 - xf) * (8 - yf), w01 = xf * (8 - yf), w10 = (8 - xf) * yf, w11 = xf * yf;
+        // ((8-xf)(8-yf) A + xf (8-yf) B + (8-xf) yf C + xf yf D + 32) >> 6 with xf, yf in {0, 4} is A, a rounding
+        // average of two samples, or (A + B + C + D + 2) >> 2: four samples at a time on packed bytes.
 #pragma unroll
         for (int y = 0; y < 4; y++) {
-            const uint32_t sv = *(const uint32_t *)(sp + (size_t)y * g.CW);
+            const uint32_t sv = *(const uint32_t *)(sp + (size_t)y * pw_);
+            uint32_t pw;
+            if (xf == 0 && yf == 0)
+                pw = wa[y];
+            else if (yf == 0)
+                pw = __vavgu4(wa[y], wb[y]);
+            else if (xf == 0)
+                pw = __vavgu4(wa[y], wa[y + 1]);
+            else {
+                const uint32_t m = 0x00ff00ffu;
+                const uint32_t ev = (wa[y] & m) + (wb[y] & m) + (wa[y + 1] & m) + (wb[y + 1] & m) + 0x00020002u;
+                const uint32_t od =
+                    ((wa[y] >> 8) & m) + ((wb[y] >> 8) & m) + ((wa[y + 1] >> 8) & m) + ((wb[y + 1] >> 8) & m) + 0x00020002u;
+                pw = ((ev >> 2) & m) | (((od >> 2) & m) << 8);
+            }
 #pragma unroll
             for (int x = 0; x < 4; x++) {
-                const int A = (int)((prow[y] >> (8 * x)) & 0xff), B = (int)((prow[y] >> (8 * x + 8)) & 0xff);
-                const int C = (int)((prow[y + 1] >> (8 * x)) & 0xff), D = (int)((prow[y + 1] >> (8 * x + 8)) & 0xff);
-                const int p = (w00 * A + w01 * B + w10 * C + w11 * D + 32) >> 6;
+                const int p = (int)((pw >> (8 * x)) & 0xff);
                 pred[y * 4 + x] = p;
                 d[y * 4 + x] = (int)((sv >> (8 * x)) & 0xff) - p;
             }
         }
-        out_off = po + (size_t)py * g.CW + px;
-        out_stride = g.CW;
+        out_off = po + (size_t)py * pw_ + px;
+        out_stride = pw_;
     }
     // transform and quantisation, luma and chroma lanes together (idle lanes carry zeros); the chroma DC goes its own way
     const LaneQuant lq = lane_quant_inter(luma ? qp : qpc);
