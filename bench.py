@@ -101,34 +101,61 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     (w, h, fmt, gop, qp, me, cabac, first, n) = args
+    import hashlib
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     enc = O.Encoder(O.make_config(w, h, qp=qp, gop=gop, cabac=cabac, fmt=fmt, me_range=me))
     frames = [O.synth_frame(w, h, first + i, fmt) for i in range(n)]
     t0 = time.perf_counter()
-    nbytes = 0
-    for y, c in frames:
-        nbytes += len(enc.encode(y, c))
+    out = [enc.encode(y, c) for y, c in frames]
     dt = time.perf_counter() - t0
     enc.close()
-    return n, dt, nbytes
+    # A fresh encoder writes SPS + PPS in front of its first frame (kernel/cedar.c:1058-1061); inside a stream only
+    # frame 0 carries them, so for the comparison with the GPU stream they are dropped from later GOPs.
+    if first != 0 and out:
+        out[0] = out[0][out[0].index(b"\x00\x00\x00\x01\x65"):]
+    blob = b"".join(out)
+    return n, dt, len(blob), first, hashlib.sha256(blob).hexdigest()
 
 
 def cpu_sample(workload, frames_per_core, cores):
-    """Every core encodes the first `frames_per_core` frames of a different GOP of the workload."""
+    """Every core encodes the first `frames_per_core` frames of a different GOP of the workload.
+    Returns (frames/s, frames, wall seconds, [(first frame, frames, bytes, sha256 of those frames' bytes)])."""
     import multiprocessing as mp
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_lib as O
     O.build()
     w, h, fmt, nframes, gop, qp, me, cabac = WORKLOADS[workload]
-    jobs = [(w, h, fmt, gop, qp, me, cabac, (i * gop) % max(nframes, 1), frames_per_core) for i in range(cores)]
+    jobs = []
+    for i in range(cores):
+        first = (i * gop) % max(nframes, 1)
+        jobs.append((w, h, fmt, gop, qp, me, cabac, first, min(frames_per_core, nframes - first)))
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(cores) as pool:
         res = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
-    return total / slowest, total, wall
+    return total / slowest, total, wall, [(r[3], r[0], r[2], r[4]) for r in res]
+
+
+def parity_block(gops, data, sizes):
+    """Golden-model GOPs (cpu_sample) against the same frames cut out of the stream the timed handles produced."""
+    import hashlib
+    import numpy as np
+    offs = np.concatenate([[0], np.cumsum(np.asarray(sizes, dtype=np.int64))])
+    seen, bad = set(), []
+    for first, n, nbytes, sha in gops:
+        if first in seen or first + n > len(sizes):
+            continue
+        seen.add(first)
+        got = bytes(data[int(offs[first]):int(offs[first + n])])
+        if len(got) != nbytes or hashlib.sha256(got).hexdigest() != sha:
+            bad.append(first)
+    return {"gops_checked": len(seen), "frames_checked": sum(n for f, n, _, _ in {g[0]: g for g in gops}.values()),
+            "equal": not bad, "mismatching_gops_first_frame": bad,
+            "how": "SHA-256 of the golden model's bytes for each sampled GOP == SHA-256 of the same frames of the stream "
+                   "downloaded from the timed handle"}
 
 
 def run_reference(args, rank, world):
@@ -141,7 +168,7 @@ def run_reference(args, rank, world):
         cpu_sample(args.workload, 1, cores)
     vals, t_all = [], 0.0
     for _ in range(args.steps):
-        fps, total, wall = cpu_sample(args.workload, fpc, cores)
+        fps, total, wall, _ = cpu_sample(args.workload, fpc, cores)
         vals.append(fps)
         t_all += wall
     value = sum(vals) / len(vals)
@@ -273,7 +300,12 @@ def run_gpu(args, rank, local_rank, world):
     # the same steps through one handle alone (one clip in flight): the latency-bound figure
     ms_single = timed(encs[:1], streams[:1], args.steps, lambda e: e.clip_encode(n, 0)) if len(encs) > 1 else ms_dev
     data, sizes = enc.clip_download(n)
+    data = data.copy()  # the view is only valid until the next clip call on this handle
     stream_bytes = int(len(data))
+    import hashlib
+    stream_sha = hashlib.sha256(data.tobytes()).hexdigest()
+    # every handle encoded the same clip in the timed region: their streams must be the same bytes
+    handles_identical = all(hashlib.sha256(e.clip_download(n)[0].tobytes()).hexdigest() == stream_sha for e in encs[1:])
     sse = enc.sse_y(n)
     # CABAC bins of the clip (debug read 6: one count per slice NAL), for the per-bin cost of the two coder kernels
     import numpy as np
@@ -340,6 +372,7 @@ def run_gpu(args, rank, local_rank, world):
                                  "bitrate_cost_pct": round(100.0 * (len(d2) - stream_bytes) / stream_bytes, 3),
                                  "y_psnr_delta_db": round(10 * math.log10(float(sse.sum()) / float(sse2.sum())), 4)})
             enc2.close()
+    parity_ok = handles_identical
     if rank == 0:
         peaks = {}
         try:
@@ -435,10 +468,13 @@ def run_gpu(args, rank, local_rank, world):
         }
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
-            fps, total, wall = cpu_sample(args.workload, args.cpu_frames, cores)
+            fps, total, wall, gops = cpu_sample(args.workload, args.cpu_frames, cores)
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "per_core": fps / cores, "kind": "port",
                                     "sample": "%d cores x first %d frames of distinct GOPs (%.1f s wall)" % (
                                         cores, args.cpu_frames, wall)}
+            line["parity"] = parity_block(gops, data, sizes)
+            line["parity"]["handles_identical"] = handles_identical
+            parity_ok = parity_ok and line["parity"]["equal"]
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
@@ -447,6 +483,9 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not parity_ok:
+        print("bench.py: PARITY FAILURE -- the timed stream differs from the golden model (see \"parity\")", file=sys.stderr)
+        return 3
     return 0
 
 

@@ -196,6 +196,52 @@ def test_full_size_properties(name, w, h, fmt, gop, n, me):
     assert psnr > 34.0, psnr
 
 
+def _assert_every_stage_equal(gold, enc, t):
+    for p, (a, b) in enumerate(zip(gold.source(), enc.debug_planes(0))):
+        assert np.array_equal(a, b), "ingest plane %d frame %d" % (p, t)
+    mbs = gold.mbs()
+    mbi, nnz, coef = enc.debug_syntax()
+    for k in ("type", "i16_mode", "chroma_mode", "cbp", "mv", "mvd"):
+        assert np.array_equal(mbs[k], mbi[k]), "mb.%s frame %d" % (k, t)
+    assert np.array_equal(mbs["nnz"], nnz[:, :27]), "nnz frame %d" % t
+    assert np.array_equal(mbs["coef"], coef), "levels frame %d" % t
+    for p, (a, b) in enumerate(zip(gold.recon_unfiltered(), enc.debug_planes(1))):
+        assert np.array_equal(a, b), "recon before deblocking plane %d frame %d" % (p, t)
+    for p, (a, b) in enumerate(zip(gold.recon(), enc.debug_planes(2))):
+        assert np.array_equal(a, b), "recon after deblocking plane %d frame %d" % (p, t)
+    assert gold.sse_y() == enc.sse_y(1)[0]
+
+
+@pytest.mark.parametrize("name,w,h,fmt,n,me", [("720p", 1280, 720, 0, 3, 16), ("1080p", 1920, 1088, 0, 3, 16),
+                                               ("1080p-nv16", 1920, 1088, 1, 3, 16), ("2160p-me64", 3840, 2160, 0, 2, 64)])
+def test_full_size_every_stage_matches_oracle(oracle, name, w, h, fmt, n, me):
+    """BASELINE.json's shapes against the golden model itself (not only against properties): motion vectors, levels,
+    reconstruction before and after deblocking, SSE and bytes of 1 I + (n - 1) P frames, at the search geometry the
+    benchmark runs (4 x 4 macroblock tiles with the compiled-in row stride at R = 16, 2 x 1 tiles at R = 64)."""
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=25, gop=60, cabac=1, fmt=fmt, me_range=me))
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=60, cabac=1, fmt=fmt, me_range=me)) as enc:
+        for t in range(n):
+            y, c = content("synth", w, h, t, fmt)
+            want, got = gold.encode(y, c), enc.encode(y, c)
+            _assert_every_stage_equal(gold, enc, t)
+            assert got == want, "bytestream frame %d" % t
+    gold.close()
+
+
+@pytest.mark.parametrize("cabac", [1, 0])
+def test_1080p_clip_mode_ten_gops_in_flight_matches_oracle(oracle, cabac):
+    """The benchmark's geometry -- 1920x1088, ten closed GOPs in lock step -- against the golden model, byte for byte:
+    30 frames as 10 GOPs of 1 I + 2 P, and the per-frame sizes."""
+    w, h, gop, n = 1920, 1088, 3, 30
+    clip = synth.synth_clip(w, h, list(range(n)), 0).numpy()
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=25, gop=gop, cabac=cabac, me_range=16)
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=cabac, me_range=16, max_clip_frames=n,
+                                    gops_in_flight=10)) as enc:
+        got, gsz = enc.encode_clip(clip)
+    assert gsz.tolist() == sizes
+    assert got == want
+
+
 def test_gpu_stream_decodes_bit_exactly_small(oracle):
     w, h, n = 176, 144, 6
     clip = make_clip("synth", w, h, n)
