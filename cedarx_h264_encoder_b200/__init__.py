@@ -6,9 +6,9 @@ host-side mirror used by the tests and the benchmark: ctypes over that C ABI, no
 There is no CPU fallback: importing works anywhere, but every encode call needs the built
 library and a CUDA device and raises loudly otherwise.
 """
-from .api import (CedarConfig, CedarIO, Encoder, LibraryMissing, build_library, library_path, load_library,
+from .api import (CedarConfig, CedarIO, Encoder, Pipe, LibraryMissing, build_library, library_path, load_library,
                   write_pps, write_sps, slice_header_bits, FORMAT_NV12, FORMAT_NV16, ENTROPY_CAVLC, ENTROPY_CABAC)
 
-__all__ = ["CedarConfig", "CedarIO", "Encoder", "LibraryMissing", "build_library", "library_path", "load_library",
+__all__ = ["CedarConfig", "CedarIO", "Encoder", "Pipe", "LibraryMissing", "build_library", "library_path", "load_library",
            "write_pps", "write_sps", "slice_header_bits", "FORMAT_NV12", "FORMAT_NV16", "ENTROPY_CAVLC",
            "ENTROPY_CABAC"]

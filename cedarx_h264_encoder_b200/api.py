@@ -7,6 +7,10 @@ import ctypes as C
 import os
 import subprocess
 
+# The serial CABAC stages of successive frames overlap on side streams, which need their own hardware queues; the variable
+# only counts before CUDA initialises in the process, and the library leaves its host's environment alone.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
@@ -24,7 +28,7 @@ class CedarConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "src_width", "src_height", "src_format", "dst_width", "dst_height", "profile", "level", "qp",
         "keyframe_interval", "thumbnail", "thumbnail_downscale", "entropy_coding_mode",
-        "me_range", "relax_gop", "device", "gops_in_flight", "max_clip_frames", "slice_rows", "sps_crop", "auto_level", "repeat_headers", "intra4x4", "p_intra")]
+        "me_range", "relax_gop", "device", "gops_in_flight", "max_clip_frames", "slice_rows", "sps_crop", "auto_level", "repeat_headers", "intra4x4", "p_intra", "queue_gops")]
 
 
 class CedarIO(C.Structure):
@@ -63,8 +67,21 @@ def load_library():
     H = C.c_void_p
     L.cedar_b200_open.argtypes = [C.POINTER(CedarConfig), C.POINTER(CedarIO), C.POINTER(H)]
     L.cedar_b200_encode_frame.argtypes = [H]
+    L.cedar_b200_flush.argtypes = [H]
     L.cedar_b200_close.argtypes = [H]
     L.cedar_b200_close.restype = None
+    L.cedar_b200_pipe_open.argtypes = [C.POINTER(CedarConfig), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    L.cedar_b200_pipe_workers.argtypes = [H]
+    L.cedar_b200_pipe_acquire.argtypes = [H, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+    L.cedar_b200_pipe_acquire.restype = C.c_void_p
+    L.cedar_b200_pipe_submit.argtypes = [H, C.c_int]
+    L.cedar_b200_pipe_finish.argtypes = [H]
+    L.cedar_b200_pipe_next.argtypes = [H, C.POINTER(C.c_void_p), C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.c_int),
+                                       C.POINTER(C.POINTER(C.c_double)), C.c_int]
+    L.cedar_b200_pipe_next.restype = C.c_longlong
+    L.cedar_b200_pipe_release.argtypes = [H]
+    L.cedar_b200_pipe_close.argtypes = [H]
+    L.cedar_b200_pipe_close.restype = None
     L.cedar_b200_clip_input.argtypes = [H, C.POINTER(C.c_size_t)]
     L.cedar_b200_clip_input.restype = C.c_void_p
     L.cedar_b200_clip_upload.argtypes = [H, C.c_int]
@@ -97,11 +114,11 @@ def align16(x):
 
 def make_config(width, height, qp=24, gop=25, cabac=1, fmt=FORMAT_NV12, me_range=16, profile=77, level=41,
                 dst_width=None, dst_height=None, relax_gop=1, device=0, gops_in_flight=0, max_clip_frames=0,
-                slice_rows=0, sps_crop=0, auto_level=0, repeat_headers=0, intra4x4=0, p_intra=0):
+                slice_rows=0, sps_crop=0, auto_level=0, repeat_headers=0, intra4x4=0, p_intra=0, queue_gops=0):
     """Defaults are the reference's hard-coded ones (userspace/h264enc.c:53-66)."""
     return CedarConfig(width, height, fmt, align16(width) if dst_width is None else dst_width,
                        align16(height) if dst_height is None else dst_height, profile, level, qp, gop, 0, 0,
-                       cabac, me_range, relax_gop, device, gops_in_flight, max_clip_frames, slice_rows, sps_crop, auto_level, repeat_headers, intra4x4, p_intra)
+                       cabac, me_range, relax_gop, device, gops_in_flight, max_clip_frames, slice_rows, sps_crop, auto_level, repeat_headers, intra4x4, p_intra, queue_gops)
 
 
 def write_sps(cfg):
@@ -152,6 +169,13 @@ class Encoder:
         n = self.L.cedar_b200_encode_frame(self.h)
         if n < 0:
             raise OSError(-n, "cedar_b200_encode_frame failed: %s" % os.strerror(-n))
+        return self._bs[:n].tobytes()
+
+    def flush(self) -> bytes:
+        """Queued mode (queue_gops): the next outstanding frame, b"" when drained."""
+        n = self.L.cedar_b200_flush(self.h)
+        if n < 0:
+            raise OSError(-n, "cedar_b200_flush failed: %s" % os.strerror(-n))
         return self._bs[:n].tobytes()
 
     # ---- clip mode (GOP-parallel) ----
@@ -253,3 +277,78 @@ class Encoder:
             self.close()
         except Exception:
             pass
+
+
+class Pipe:
+    """cedar_b200_pipe_*: ordered pipeline over several handles / GPUs (csrc/pipeline.cpp)."""
+
+    def __init__(self, cfg: CedarConfig, devices=None, handles_per_device=0, gops_per_batch=0):
+        self.L = load_library()
+        self.p = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices) if devices else None
+        r = self.L.cedar_b200_pipe_open(C.byref(cfg), devs, len(devices) if devices else 0, handles_per_device, gops_per_batch,
+                                        C.byref(self.p))
+        if r:
+            self.p = C.c_void_p()
+            raise OSError(-r, "cedar_b200_pipe_open failed: %s" % os.strerror(-r))
+
+    def workers(self):
+        return self.L.cedar_b200_pipe_workers(self.p)
+
+    def acquire(self):
+        """numpy view [capacity_frames, frame_bytes] of the staging buffer of the next batch."""
+        fb, cap = C.c_size_t(), C.c_int()
+        ptr = self.L.cedar_b200_pipe_acquire(self.p, C.byref(fb), C.byref(cap))
+        if not ptr:
+            raise RuntimeError("pipe_acquire: a batch is already being filled, or the stream is finished")
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(cap.value, fb.value))
+
+    def submit(self, nframes):
+        r = self.L.cedar_b200_pipe_submit(self.p, nframes)
+        if r:
+            raise OSError(-r, "cedar_b200_pipe_submit failed: %s" % os.strerror(-r))
+
+    def finish(self):
+        self.L.cedar_b200_pipe_finish(self.p)
+
+    def next(self, wait=True):
+        """(bytes, sizes, sse) of the next batch in submission order; None when nothing is outstanding."""
+        out, sizes, sse, n = C.c_void_p(), C.POINTER(C.c_int)(), C.POINTER(C.c_double)(), C.c_int()
+        total = self.L.cedar_b200_pipe_next(self.p, C.byref(out), C.byref(sizes), C.byref(n), C.byref(sse), int(wait))
+        if total == 0:
+            return None
+        if total < 0:
+            raise OSError(-total, "cedar_b200_pipe_next: %s" % os.strerror(-total))
+        res = C.string_at(out, total), [sizes[i] for i in range(n.value)], [sse[i] for i in range(n.value)]
+        self.L.cedar_b200_pipe_release(self.p)  # everything is copied: the batch's worker may go on
+        return res
+
+    def encode(self, frames):
+        """frames: uint8 [n, frame_bytes].  Single-threaded driver: keeps every worker busy, returns (bytes, sizes)."""
+        n, done, out, sizes, inflight = len(frames), 0, [], [], 0
+        W = self.workers()
+        while done < n or inflight:
+            while done < n and inflight < W:
+                buf = self.acquire()
+                k = min(len(buf), n - done)
+                buf[:k] = frames[done:done + k]
+                self.submit(k)
+                done += k
+                inflight += 1
+            got = self.next(True)
+            inflight -= 1
+            out.append(got[0])
+            sizes += got[1]
+        self.finish()
+        return b"".join(out), sizes
+
+    def close(self):
+        if self.p:
+            self.L.cedar_b200_pipe_close(self.p)
+            self.p = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

@@ -62,6 +62,7 @@ struct cedar_b200_handle {
     Geom g;
     int K;                 // keyframe_interval
     int F;                 // clip capacity in frames (>= 1)
+    bool clip_mode;        // max_clip_frames > 0: the clip calls are usable and the buffers are sized for whole clips
     int L;                 // lanes (GOPs in flight)
     int S;                 // slices per picture (1 = the reference's layout)
     size_t raw_frame_bytes;
@@ -125,6 +126,18 @@ struct cedar_b200_handle {
     int prefix_len;
 
     int last_nframes, last_cur, last_par;
+    bool sse_valid; // h_sse holds the statistics of the last encode
+    // Queued mode of the per-frame call (cfg.queue_gops): this handle is only a front -- io buffers and counters -- over a
+    // pipeline of worker handles (pipeline.cpp); none of the device members above exist.
+    cedar_b200_pipe *pipe;
+    uint8_t *q_staging;        // batch being filled (pipe_acquire)
+    size_t q_frame_bytes;
+    int q_cap, q_fill;         // frames per batch, frames in the batch being filled
+    long long q_in, q_out;     // frames accepted / returned so far
+    std::vector<uint8_t> q_bytes; // coded bytes of the batch being handed out, one frame per call
+    std::vector<int> q_sizes;
+    std::vector<double> q_sse;
+    size_t q_pos, q_off;
     long long launches;
     bool prof;
     bool serialize; // profile mode 2: no stream overlap, so that per-kernel event times are standalone times
@@ -302,14 +315,23 @@ int alloc_entropy_buffers(cedar_b200_handle *h)
     const size_t U = (size_t)F * S, grow = (size_t)h->grow; // U slice NALs
     const size_t slice_mbs = (size_t)g.srows * g.mbw;
     int r = 0;
-    h->eb.rbsp_cap = (unsigned)ALIGN_UP(slice_mbs * (F > 1 ? (g.qp < 20 ? 1024 : 400) : 1024) * grow + 4096, 256);
+    const bool clip = h->clip_mode;
+    // all bounds in 64 bits: the x4 regrow of clip mode reaches 8 GB per slice at 4K before anything else gives up
+    const size_t rbsp_cap = ALIGN_UP(slice_mbs * (clip ? (g.qp < 20 ? 1024 : 400) : 1024) * grow + 4096, 256);
     size_t per_frame_out =
-        (F > 1 ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) * grow + 4096 : (size_t)h->bytestream_size) + 8 * S + 64;
+        (clip ? (size_t)g.nmb * (g.qp < 20 ? 512 : 96) * grow + 4096 : (size_t)h->bytestream_size) + 8 * S + 64;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    if (rbsp_cap > 0xFFFFFF00ull || rbsp_cap * U > total_b || per_frame_out * F > total_b) {
+        fprintf(stderr, "cedar_b200: entropy buffers of %zu bytes per slice x %zu slices do not fit the device\n", rbsp_cap, U);
+        return -ENOMEM;
+    }
+    h->eb.rbsp_cap = (unsigned)rbsp_cap;
     h->out_cap = per_frame_out * F;
-    size_t bins_per_mb = F > 1 ? (g.qp < 12 ? 8192 : (g.qp < 20 ? 2048 : 640)) : 16384;
+    size_t bins_per_mb = clip ? (g.qp < 12 ? 8192 : (g.qp < 20 ? 2048 : 640)) : 16384;
     // the pool is shared by all frames of a clip (bump allocation), so for long clips the per-macroblock allowance can
     // shrink: at most 24 GB, at least 160 bins per macroblock (the 1080p benchmark clip averages 38, its I frames 145)
-    if (F > 1 && bins_per_mb * g.nmb * F * sizeof(uint16_t) > (24ull << 30)) {
+    if (clip && bins_per_mb * g.nmb * F * sizeof(uint16_t) > (24ull << 30)) {
         bins_per_mb = (24ull << 30) / ((size_t)g.nmb * F * sizeof(uint16_t));
         if (bins_per_mb < 160)
             bins_per_mb = 160;
@@ -320,13 +342,13 @@ int alloc_entropy_buffers(cedar_b200_handle *h)
     h->eb.bins_cap = g.cabac ? (unsigned long long)(bins_per_mb * g.nmb + 8) * F + 64 : 0;
     h->eb.limb_cap = h->eb.rbsp_cap / 2 + 8;
     h->chunks_per_frame = (h->eb.rbsp_cap + EPB_CHUNK - 1) / EPB_CHUNK;
-    if (F > 1)
+    if (clip)
         r |= hmalloc(&h->h_clip_out, h->out_cap);
     r |= dmalloc(&h->eb.rbsp, (size_t)h->eb.rbsp_cap * U);
     if (g.cabac) {
         r |= dmalloc(&h->eb.bins, (size_t)h->eb.bins_cap + 64); // + slack: 16-byte vector loads round outwards
         // one region per side stream; frame mode finishes every frame before the next one starts: one region
-        r |= dmalloc(&h->eb.limbs, (size_t)h->eb.limb_cap * L * S * (F > 1 ? cedar_b200_handle::NSIDE : 1));
+        r |= dmalloc(&h->eb.limbs, (size_t)h->eb.limb_cap * L * S * (clip ? cedar_b200_handle::NSIDE : 1));
     }
     r |= dmalloc(&h->d_chunk_cnt, (size_t)h->chunks_per_frame * U);
     r |= dmalloc(&h->d_out, h->out_cap + 64);
@@ -355,7 +377,7 @@ int alloc_buffers(cedar_b200_handle *h)
 
     const int S = h->S;
     const size_t U = (size_t)F * S; // slice NALs
-    if (F > 1)
+    if (h->clip_mode)
         r |= hmalloc(&h->h_clip_in, h->raw_frame_bytes * F);
     r |= dmalloc(&h->d_raw, h->raw_frame_bytes * F + 64);
     r |= dmalloc(&h->d_src[0], g.frame_bytes * L);
@@ -377,8 +399,8 @@ int alloc_buffers(cedar_b200_handle *h)
     r |= dmalloc(&h->d_sse, F);
     r |= dmalloc(&h->eb.mb_size, (size_t)L * (g.nmb + S + 1));
     r |= dmalloc(&h->eb.mb_off, (size_t)L * (g.nmb + S + 1));
-    r |= dmalloc(&h->d_hdr_bits, U);
-    r |= dmalloc(&h->d_hdr_nbits, U);
+    r |= dmalloc(&h->d_hdr_bits, (size_t)(F > h->K ? F : h->K) * S);
+    r |= dmalloc(&h->d_hdr_nbits, (size_t)(F > h->K ? F : h->K) * S);
     r |= dmalloc(&h->eb.rbsp_len, U);
     r |= dmalloc(&h->eb.bins_cursor, 1);
     r |= dmalloc(&h->eb.bins_off, U);
@@ -508,7 +530,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         CK(cudaStreamWaitEvent(side, h->ev_post[p], 0));
         LAUNCH_ON(side, K_CRESOLVE, cabac_resolve_kernel, nl * g.nslices, RES_WARPS * 32, 0, g, s, h->K, gop_pos0, h->eb);
         EntropyBufs ebc = h->eb; // the limb scratch of this side stream (its launches are serialised)
-        ebc.limbs += (size_t)(no_overlap || h->F == 1 ? 0 : h->side_next) * h->L * g.nslices * h->eb.limb_cap;
+        ebc.limbs += (size_t)(no_overlap || !h->clip_mode ? 0 : h->side_next) * h->L * g.nslices * h->eb.limb_cap;
         LAUNCH_ON(side, K_CCODE, cabac_code_kernel, nl * g.nslices, CP_THREADS, CP_SMEM_BYTES, g, s, ebc);
         if (!no_overlap) {
             h->side_used |= 1u << h->side_next;
@@ -523,7 +545,6 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
 // Serial CABAC stage (all frames at once), emulation prevention and packing of `nframes` frames.
 int finish_stream(cedar_b200_handle *h, int nframes, int gop_pos0, bool with_param_sets)
 {
-    const Geom &g = h->g;
     CK(cudaEventRecord(h->ev_post_done, h->stream_post));
     CK(cudaStreamWaitEvent(h->stream, h->ev_post_done, 0));
     for (int i = 0; i < cedar_b200_handle::NSIDE; i++)
@@ -534,8 +555,9 @@ int finish_stream(cedar_b200_handle *h, int nframes, int gop_pos0, bool with_par
     h->side_used = 0;
     unsigned cpf = h->chunks_per_frame;
     const int nunits = nframes * h->S; // slice NALs
-    LAUNCH(K_EPBCOUNT, epb_count_kernel, dim3((cpf + 255) / 256, nunits), 256, 0, nunits, h->eb.rbsp, h->eb.rbsp_cap,
-           h->eb.rbsp_len, h->d_chunk_cnt, cpf);
+    const unsigned cblocks = (cpf + 255) / 256; // grid.x = units x chunk blocks (gridDim.y would cap the units at 65535)
+    LAUNCH(K_EPBCOUNT, epb_count_kernel, (unsigned)nunits * cblocks, 256, 0, nunits, h->eb.rbsp, h->eb.rbsp_cap,
+           h->eb.rbsp_len, h->d_chunk_cnt, cpf, cblocks);
     ParamSets ps;
     memset(&ps, 0, sizeof(ps));
     memcpy(ps.bytes, h->prefix, (size_t)h->prefix_len);
@@ -545,18 +567,22 @@ int finish_stream(cedar_b200_handle *h, int nframes, int gop_pos0, bool with_par
            h->K, gop_pos0);
     LAUNCH(K_PACKSCAN, pack_scan_kernel, 1, 1024, 0, nunits, h->S, h->d_nal_bytes, 0u, h->d_nal_off, h->d_frame_bytes,
            h->d_total, (unsigned long long)h->out_cap, h->eb.error);
-    LAUNCH(K_EPBWRITE, epb_write_kernel, dim3((cpf + 255) / 256, nunits), 256, 0, nunits, h->S, h->K, gop_pos0, h->eb.rbsp,
-           h->eb.rbsp_cap, h->eb.rbsp_len, h->d_chunk_cnt, cpf, h->d_nal_off, h->d_total, h->d_out, ps);
+    LAUNCH(K_EPBWRITE, epb_write_kernel, (unsigned)nunits * cblocks, 256, 0, nunits, h->S, h->K, gop_pos0, h->eb.rbsp,
+           h->eb.rbsp_cap, h->eb.rbsp_len, h->d_chunk_cnt, cpf, cblocks, h->d_nal_off, h->d_total, h->d_out, ps);
     return 0;
 }
 
-int upload_headers(cedar_b200_handle *h, int nframes, int gop_pos0)
+// Slice-header bits of every unit a clip (or a frame-mode call) can address, written once at open(): the bits depend
+// only on the frame's position in its GOP and on the slice (cedar.c:984-1030: slice type, frame_num = frame_p_count & 15),
+// clips start at a GOP boundary, so entry (f, k) serves frame f of any clip, and frame mode points the entropy passes at
+// the row of its current frame_p_count.
+int build_header_table(cedar_b200_handle *h)
 {
-    const int S = h->S;
-    std::vector<unsigned long long> bits((size_t)nframes * S);
-    std::vector<int> nbits((size_t)nframes * S);
-    for (int f = 0; f < nframes; f++) {
-        int p = (gop_pos0 + f) % h->K;
+    const int S = h->S, rows = h->F > h->K ? h->F : h->K;
+    std::vector<unsigned long long> bits((size_t)rows * S);
+    std::vector<int> nbits((size_t)rows * S);
+    for (int f = 0; f < rows; f++) {
+        int p = f % h->K;
         for (int k = 0; k < S; k++) { // first_mb_in_slice = first macroblock of the slice's first row (0: cedar.c:992-993)
             uint64_t b = 0;
             int r = cedar_hdr_slice_mb(p == 0, p, h->g.cabac, k * h->g.srows * h->g.mbw, &b, &nbits[(size_t)f * S + k]);
@@ -565,10 +591,8 @@ int upload_headers(cedar_b200_handle *h, int nframes, int gop_pos0)
             bits[(size_t)f * S + k] = b;
         }
     }
-    CK(cudaMemcpyAsync(h->d_hdr_bits, bits.data(), sizeof(unsigned long long) * bits.size(), cudaMemcpyHostToDevice,
-                       h->stream));
-    CK(cudaMemcpyAsync(h->d_hdr_nbits, nbits.data(), sizeof(int) * nbits.size(), cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream)); // the vectors go out of scope
+    CK(cudaMemcpy(h->d_hdr_bits, bits.data(), sizeof(unsigned long long) * bits.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d_hdr_nbits, nbits.data(), sizeof(int) * nbits.size(), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -622,6 +646,65 @@ int cedar_b200_slice_header_mb(int frame_i, int frame_p_count, int cabac, int fi
     return cedar_hdr_slice_mb(frame_i, frame_p_count, cabac, first_mb, bits, nbits);
 }
 
+// Everything a handle owns, in the order cedar_b200_close releases it; also the unwinding of a failed open()
+// (members are zero until they are created: the handle is value-initialised).
+static void destroy_handle(cedar_b200_handle *h)
+{
+    if (h->pipe)
+        cedar_b200_pipe_close(h->pipe);
+    for (cudaEvent_t e : h->ev_pool)
+        cudaEventDestroy(e);
+    free_buffers(h);
+    cudaEvent_t evs[] = {h->ev_bins, h->ev_begin, h->ev_post_done, h->ev_encode_done, h->ev_ingest[0], h->ev_ingest[1],
+                         h->ev_main[0], h->ev_main[1], h->ev_post[0], h->ev_post[1]};
+    for (cudaEvent_t e : evs)
+        if (e)
+            cudaEventDestroy(e);
+    for (auto &e : h->ev_upload)
+        if (e)
+            cudaEventDestroy(e);
+    for (int i = 0; i < cedar_b200_handle::NSIDE; i++) {
+        if (h->ev_cabac[i])
+            cudaEventDestroy(h->ev_cabac[i]);
+        if (h->stream_cabac[i])
+            cudaStreamDestroy(h->stream_cabac[i]);
+    }
+    cudaStream_t sts[] = {h->stream_copy, h->stream_pre, h->stream_post, h->stream};
+    for (cudaStream_t st : sts)
+        if (st)
+            cudaStreamDestroy(st);
+    delete h;
+}
+
+// Queued mode (cfg.queue_gops): the handle is a front over a pipeline of worker handles (pipeline.cpp).
+static int open_queued(const struct cedar_b200_config *cfg, struct cedar_b200_io *io, cedar_b200_handle *h)
+{
+    cedar_b200_config wc = *cfg;
+    wc.queue_gops = 0;
+    int r = cedar_b200_pipe_open(&wc, nullptr, 0, 2, cfg->queue_gops, &h->pipe);
+    if (r)
+        return r;
+    const Geom &g = h->g;
+    h->in_luma_size = (int)ALIGN_UP((size_t)g.src_w * g.src_h, 4096);
+    size_t chroma_bytes = (size_t)g.src_w * g.src_h / (g.src_format == CEDAR_B200_FORMAT_NV16 ? 1 : 2);
+    h->in_chroma_size = (int)ALIGN_UP(chroma_bytes, 4096);
+    h->bytestream_size = (int)ALIGN_UP((size_t)g.nmb * 1536 + 4096, 4096);
+    r |= hmalloc(&h->h_in_luma, h->in_luma_size);
+    r |= hmalloc(&h->h_in_chroma, h->in_chroma_size);
+    r |= hmalloc(&h->h_bytestream, h->bytestream_size);
+    r |= hmalloc(&h->h_sse, 1);
+    if (r)
+        return r;
+    h->q_cap = cfg->queue_gops * h->K;
+    io->input_luma = h->h_in_luma;
+    io->input_luma_size = h->in_luma_size;
+    io->input_chroma = h->h_in_chroma;
+    io->input_chroma_size = h->in_chroma_size;
+    io->bytestream = h->h_bytestream;
+    io->bytestream_size = h->bytestream_size;
+    return 0;
+}
+
 int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *io, cedar_b200_handle **out)
 {
     if (!cfg || !io || !out)
@@ -629,19 +712,18 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     int r = validate(cfg);
     if (r)
         return r;
-    // The serial CABAC stages of successive steps run concurrently on side streams; with the default of
-    // 8 hardware connections streams share queues and serialise.  Only effective before CUDA initialises
-    // in this process (a host that initialises CUDA earlier should export it itself).
-    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    // The serial CABAC stages of successive steps run concurrently on side streams; with the default of 8 hardware
+    // connections streams share queues and serialise.  CUDA_DEVICE_MAX_CONNECTIONS=32 must be in the environment before
+    // CUDA initialises in the host process: the CLI and bench.py export it themselves; a library does not touch its
+    // host's environment.
     int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev) {
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device >= ndev || cfg->device < 0) {
         fprintf(stderr, "cedar_b200: no usable CUDA device (this encoder has no CPU fallback).\n");
         return -ENODEV;
     }
     if (cudaSetDevice(cfg->device) != cudaSuccess)
         return -ENODEV;
     cedar_b200_handle *h = new cedar_b200_handle();
-    memset((void *)&h->cfg, 0, sizeof(h->cfg));
     h->cfg = *cfg;
     h->device = cfg->device;
     h->t_open = std::chrono::steady_clock::now();
@@ -670,7 +752,20 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     h->S = g.nslices;
     g.frame_bytes = (unsigned long long)g.W * g.H * 3 / 2;
     h->K = cfg->keyframe_interval;
-    h->F = cfg->max_clip_frames > 0 ? cfg->max_clip_frames : 1;
+    h->clip_mode = cfg->max_clip_frames > 0;
+    h->F = h->clip_mode ? cfg->max_clip_frames : 1;
+    h->raw_frame_bytes = (size_t)g.src_w * g.src_h * (g.src_format == CEDAR_B200_FORMAT_NV16 ? 2 : 3) /
+                         (g.src_format == CEDAR_B200_FORMAT_NV16 ? 1 : 2);
+    h->grow = 1;
+    if (cfg->queue_gops > 0) {
+        r = open_queued(cfg, io, h);
+        if (r) {
+            destroy_handle(h);
+            return r;
+        }
+        *out = h;
+        return 0;
+    }
     int gops = (h->F + h->K - 1) / h->K;
     int lanes = cfg->gops_in_flight > 0 ? cfg->gops_in_flight : 16;
     if (lanes > gops)
@@ -682,42 +777,28 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
         lanes = (gops + waves - 1) / waves;
     }
     h->L = lanes;
-    h->raw_frame_bytes = (size_t)g.src_w * g.src_h * (g.src_format == CEDAR_B200_FORMAT_NV16 ? 2 : 3) /
-                         (g.src_format == CEDAR_B200_FORMAT_NV16 ? 1 : 2);
-    h->prof = false;
-    h->grow = 1;
-    h->last_first_frame = 0;
-    memset(h->prof_ms, 0, sizeof(h->prof_ms));
-    memset(h->prof_n, 0, sizeof(h->prof_n));
     // Stream priorities were measured (main stream high / entropy streams low, and the reverse): within 1.5 % of
     // plain default priorities, which are the fastest (80.1 ms per 1080p clip against 81.4), so none are set.
-    const int prio_lo = 0, prio_hi = 0;
-    bool ok = cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-              cudaEventCreateWithFlags(&h->ev_bins, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithPriority(&h->stream_pre, cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
-         cudaStreamCreateWithPriority(&h->stream_post, cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
-         cudaEventCreateWithFlags(&h->ev_begin, cudaEventDisableTiming) == cudaSuccess &&
-         cudaEventCreateWithFlags(&h->ev_post_done, cudaEventDisableTiming) == cudaSuccess;
+    auto mkstream = [](cudaStream_t *st) { return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking) == cudaSuccess; };
+    auto mkevent = [](cudaEvent_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+    bool ok = mkstream(&h->stream) && mkstream(&h->stream_pre) && mkstream(&h->stream_post) && mkstream(&h->stream_copy) &&
+              mkevent(&h->ev_bins) && mkevent(&h->ev_begin) && mkevent(&h->ev_post_done) && mkevent(&h->ev_encode_done);
     for (int i = 0; ok && i < 2; i++)
-        ok = cudaEventCreateWithFlags(&h->ev_ingest[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->ev_main[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->ev_post[i], cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking) == cudaSuccess &&
-         cudaEventCreateWithFlags(&h->ev_encode_done, cudaEventDisableTiming) == cudaSuccess;
-    h->ev_upload.resize(h->F > 1 ? h->K : 0);
+        ok = mkevent(&h->ev_ingest[i]) && mkevent(&h->ev_main[i]) && mkevent(&h->ev_post[i]);
+    h->ev_upload.assign(h->clip_mode ? h->K : 0, nullptr);
     for (auto &e : h->ev_upload)
-        ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && mkevent(&e);
     for (int i = 0; ok && i < cedar_b200_handle::NSIDE; i++)
-        ok = cudaStreamCreateWithPriority(&h->stream_cabac[i], cudaStreamNonBlocking, prio_lo) == cudaSuccess &&
-             cudaEventCreateWithFlags(&h->ev_cabac[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = mkstream(&h->stream_cabac[i]) && mkevent(&h->ev_cabac[i]);
     if (!ok) {
-        delete h;
+        fprintf(stderr, "cedar_b200: could not create streams / events: %s\n", cudaGetErrorString(cudaGetLastError()));
+        destroy_handle(h);
         return -ENODEV;
     }
     if (cudaFuncSetAttribute(cabac_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES) != cudaSuccess) {
         fprintf(stderr, "cedar_b200: cabac_code_kernel needs %d bytes of shared memory\n", CP_SMEM_BYTES);
         cudaGetLastError();
-        delete h;
+        destroy_handle(h);
         return -ENODEV;
     }
     const int me_smem = (int)me_smem_bytes(g.R, me_strip(g.R));
@@ -726,19 +807,21 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
         cudaFuncSetAttribute(me_kernel<43>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess) {
         fprintf(stderr, "cedar_b200: search range %d needs more shared memory than the device offers\n", g.R);
         cudaGetLastError();
-        delete h;
+        destroy_handle(h);
         return -EINVAL;
     }
     r = alloc_buffers(h);
+    if (!r)
+        r = build_header_table(h);
+    // SPS + PPS, emitted once before the first frame (cedar.c:1058-1061)
+    int n1 = r ? 0 : cedar_b200_write_sps(cfg, h->prefix, 40);
+    int n2 = r || n1 < 0 ? 0 : cedar_b200_write_pps(cfg, h->prefix + n1, 24);
+    if (!r && (n1 < 0 || n2 < 0))
+        r = -EINVAL;
     if (r) {
-        free_buffers(h);
-        cudaStreamDestroy(h->stream);
-        delete h;
+        destroy_handle(h);
         return r;
     }
-    // SPS + PPS, emitted once before the first frame (cedar.c:1058-1061)
-    int n1 = cedar_b200_write_sps(cfg, h->prefix, 40);
-    int n2 = cedar_b200_write_pps(cfg, h->prefix + n1, 24);
     h->prefix_len = n1 + n2;
     io->input_luma = h->h_in_luma;
     io->input_luma_size = h->in_luma_size;
@@ -750,10 +833,101 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     return 0;
 }
 
+// Queued mode: frame t goes into the batch being filled; a full batch is handed to the pipeline (asynchronous); the call
+// returns the bytes of frame t - 2 * batch (0 before that): while batch j fills, batch j - 1 is being encoded and batch
+// j - 2 is handed out, so the producer never waits unless the GPU is the slower side.
+static int queued_take_frame(cedar_b200_handle *h)
+{
+    if (h->q_pos >= h->q_sizes.size()) { // next finished batch, copied out so that its worker is free again at once
+        const uint8_t *out = nullptr;
+        const int *sizes = nullptr;
+        const double *sse = nullptr;
+        int n = 0;
+        long long total = cedar_b200_pipe_next(h->pipe, &out, &sizes, &n, &sse, 1);
+        if (total <= 0)
+            return (int)total;
+        h->q_bytes.assign(out, out + total);
+        h->q_sizes.assign(sizes, sizes + n);
+        h->q_sse.assign(sse, sse + n);
+        h->q_pos = 0, h->q_off = 0;
+        cedar_b200_pipe_release(h->pipe);
+    }
+    const int sz = h->q_sizes[h->q_pos];
+    if (sz > h->bytestream_size)
+        return -ENOMEM;
+    memcpy(h->h_bytestream, h->q_bytes.data() + h->q_off, (size_t)sz);
+    h->h_sse[0] = (unsigned long long)h->q_sse[h->q_pos]; // cedar_b200_stats: the frame just handed out
+    h->last_nframes = 1;
+    h->sse_valid = true;
+    h->q_off += (size_t)sz;
+    h->q_pos++;
+    h->q_out++;
+    return sz;
+}
+
+static int queued_encode_frame(cedar_b200_handle *h)
+{
+    const size_t luma_bytes = (size_t)h->g.src_w * h->g.src_h;
+    int ret = 0;
+    if (h->q_in >= 2LL * h->q_cap) { // before the slot of batch j is acquired: batch j - 2 frees its worker
+        ret = queued_take_frame(h);
+        if (ret < 0)
+            return ret;
+    }
+    if (!h->q_staging) {
+        int cap = 0;
+        h->q_staging = (uint8_t *)cedar_b200_pipe_acquire(h->pipe, &h->q_frame_bytes, &cap);
+        if (!h->q_staging || cap != h->q_cap || h->q_frame_bytes != h->raw_frame_bytes)
+            return -EIO;
+        h->q_fill = 0;
+    }
+    uint8_t *dst = h->q_staging + (size_t)h->q_fill * h->q_frame_bytes;
+    memcpy(dst, h->h_in_luma, luma_bytes);
+    memcpy(dst + luma_bytes, h->h_in_chroma, h->raw_frame_bytes - luma_bytes);
+    h->q_in++;
+    if (++h->q_fill == h->q_cap) {
+        int r = cedar_b200_pipe_submit(h->pipe, h->q_fill);
+        h->q_staging = nullptr;
+        if (r)
+            return r;
+    }
+    // cedar.c:1193-1196
+    h->frame_p_count++;
+    if (h->frame_p_count == h->K)
+        h->frame_p_count = 0;
+    h->frame_count++;
+    return ret;
+}
+
+int cedar_b200_flush(cedar_b200_handle *h)
+{
+    if (!h)
+        return -EINVAL;
+    if (!h->pipe)
+        return 0;
+    auto t0 = std::chrono::steady_clock::now();
+    if (h->q_staging) { // the partial last batch
+        int r = cedar_b200_pipe_submit(h->pipe, h->q_fill);
+        h->q_staging = nullptr;
+        if (r)
+            return r;
+    }
+    cedar_b200_pipe_finish(h->pipe);
+    int ret = h->q_out < h->q_in ? queued_take_frame(h) : 0;
+    h->busy_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
+    return ret;
+}
+
 int cedar_b200_encode_frame(cedar_b200_handle *h)
 {
     if (!h)
         return -EINVAL; // cedar.c:1039-1043: not configured
+    if (h->pipe) {
+        auto tq = std::chrono::steady_clock::now();
+        int rq = queued_encode_frame(h);
+        h->busy_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tq).count();
+        return rq;
+    }
     cudaSetDevice(h->device);
     auto t0 = std::chrono::steady_clock::now();
     const Geom &g = h->g;
@@ -762,8 +936,8 @@ int cedar_b200_encode_frame(cedar_b200_handle *h)
     CK(cudaMemcpyAsync(h->d_raw + luma_bytes, h->h_in_chroma, h->raw_frame_bytes - luma_bytes, cudaMemcpyHostToDevice,
                        h->stream));
     int r;
-    if ((r = upload_headers(h, 1, h->frame_p_count)))
-        return r;
+    h->eb.hdr_bits = h->d_hdr_bits + (size_t)h->frame_p_count * h->S; // the header row of this GOP position
+    h->eb.hdr_nbits = h->d_hdr_nbits + (size_t)h->frame_p_count * h->S;
     if ((r = begin_stream(h, 1)))
         return r;
     Step s = {1, 0, 1, 1};
@@ -783,6 +957,7 @@ int cedar_b200_encode_frame(cedar_b200_handle *h)
     CK(cudaMemcpyAsync(h->h_bytestream, h->d_out, total, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->last_nframes = 1;
+    h->sse_valid = true;
     // cedar.c:1193-1196 (the reference swap of :1198-1201 is the `t & 1` buffer choice in encode_step)
     h->frame_p_count++;
     if (h->frame_p_count == h->K)
@@ -828,8 +1003,8 @@ int cedar_b200_clip_upload(cedar_b200_handle *h, int nframes)
 static int run_clip(cedar_b200_handle *h, int nframes, int first_frame_index)
 {
     int r;
-    if ((r = upload_headers(h, nframes, 0)))
-        return r;
+    h->eb.hdr_bits = h->d_hdr_bits;
+    h->eb.hdr_nbits = h->d_hdr_nbits;
     if ((r = begin_stream(h, nframes)))
         return r;
     const int K = h->K, gops = (nframes + K - 1) / K;
@@ -850,7 +1025,7 @@ static int run_clip(cedar_b200_handle *h, int nframes, int first_frame_index)
 
 int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_index)
 {
-    if (!h || nframes <= 0 || nframes > h->F || first_frame_index < 0 || (first_frame_index % h->K) != 0)
+    if (!h || !h->clip_mode || nframes <= 0 || nframes > h->F || first_frame_index < 0 || (first_frame_index % h->K) != 0)
         return -EINVAL;
     cudaSetDevice(h->device);
     auto t0 = std::chrono::steady_clock::now();
@@ -858,6 +1033,7 @@ int cedar_b200_clip_encode(cedar_b200_handle *h, int nframes, int first_frame_in
     if (r)
         return r;
     h->last_nframes = nframes;
+    h->sse_valid = false;
     h->last_first_frame = first_frame_index;
     h->busy_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count();
     return 0;
@@ -898,6 +1074,7 @@ long long cedar_b200_clip_download(cedar_b200_handle *h, const uint8_t **out, in
         if ((r = run_clip(h, n, h->last_first_frame)))
             return r;
     }
+    h->sse_valid = true;
     size_t total = (size_t)*h->h_total;
     if (total == 0 || total > h->out_cap)
         return -ENOMEM;
@@ -912,8 +1089,14 @@ long long cedar_b200_clip_download(cedar_b200_handle *h, const uint8_t **out, in
 
 int cedar_b200_stats(cedar_b200_handle *h, double *sse_y, int nframes)
 {
-    if (!h || !sse_y || nframes > h->last_nframes)
+    if (!h || !sse_y || nframes <= 0 || nframes > h->last_nframes)
         return -EINVAL;
+    if (!h->sse_valid) { // clip_encode without clip_download so far: fetch the statistics of that encode
+        cudaSetDevice(h->device);
+        CK(cudaMemcpyAsync(h->h_sse, h->d_sse, sizeof(unsigned long long) * h->last_nframes, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        h->sse_valid = true;
+    }
     for (int i = 0; i < nframes; i++)
         sse_y[i] = (double)h->h_sse[i];
     return 0;
@@ -921,7 +1104,7 @@ int cedar_b200_stats(cedar_b200_handle *h, double *sse_y, int nframes)
 
 int cedar_b200_profile_enable(cedar_b200_handle *h, int enable)
 {
-    if (!h)
+    if (!h || h->pipe)
         return -EINVAL;
     cudaSetDevice(h->device);
     if (!enable && h->prof)
@@ -933,7 +1116,7 @@ int cedar_b200_profile_enable(cedar_b200_handle *h, int enable)
 
 int cedar_b200_profile_read(cedar_b200_handle *h, const char **names, float *ms, int *launches, int cap, int reset)
 {
-    if (!h)
+    if (!h || h->pipe)
         return -EINVAL;
     cudaSetDevice(h->device);
     prof_collect(h);
@@ -962,7 +1145,7 @@ void *cedar_b200_stream(cedar_b200_handle *h) { return h ? (void *)h->stream : n
 
 long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_t cap)
 {
-    if (!h || !dst)
+    if (!h || !dst || h->pipe)
         return -EINVAL;
     cudaSetDevice(h->device);
     const Geom &g = h->g;
@@ -991,33 +1174,12 @@ void cedar_b200_close(cedar_b200_handle *h)
     if (!h)
         return;
     cudaSetDevice(h->device);
-    prof_collect(h);
+    if (!h->pipe)
+        prof_collect(h);
     double total_ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - h->t_open).count();
     // cedar.c:715-719 prints "Time spent: <waiting>/<total>ns" at release
     fprintf(stderr, "cedar_b200: Time spent: %.0f/%.0fns\n", h->busy_ns, total_ns);
-    for (cudaEvent_t e : h->ev_pool)
-        cudaEventDestroy(e);
-    free_buffers(h);
-    cudaEventDestroy(h->ev_bins);
-    cudaEventDestroy(h->ev_begin);
-    cudaEventDestroy(h->ev_post_done);
-    cudaEventDestroy(h->ev_encode_done);
-    for (auto &e : h->ev_upload)
-        cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++) {
-        cudaEventDestroy(h->ev_ingest[i]);
-        cudaEventDestroy(h->ev_main[i]);
-        cudaEventDestroy(h->ev_post[i]);
-    }
-    cudaStreamDestroy(h->stream_copy);
-    cudaStreamDestroy(h->stream_pre);
-    cudaStreamDestroy(h->stream_post);
-    for (int i = 0; i < cedar_b200_handle::NSIDE; i++) {
-        cudaEventDestroy(h->ev_cabac[i]);
-        cudaStreamDestroy(h->stream_cabac[i]);
-    }
-    cudaStreamDestroy(h->stream);
-    delete h;
+    destroy_handle(h);
 }
 
 } // extern "C"

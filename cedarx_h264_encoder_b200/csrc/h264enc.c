@@ -6,12 +6,18 @@
  * Same positional arguments, same defaults (NV12, dst = ALIGN16, profile 77, level 41, QP 24,
  * keyframe interval 25, CABAC -- userspace/h264enc.c:50-66), same I/O pattern: read w*h luma then
  * w*h/2 interleaved chroma per frame (:178-187), one write() of the returned byte count per frame
- * (:195), progress line "\rFrame %5d: %5dbytes" (:194), stop at the first short read, exit 0 (:200).
- * The ioctl/mmap calls on /dev/cedar_dev become the C ABI of include/cedar_b200.h.
+ * (:195), progress line "\rFrame %5d: %5dbytes" (:194), the three buffer lines (:86,100,113), stop at
+ * the first short read, exit 0 (:200).  The ioctl/mmap calls on /dev/cedar_dev become the C ABI of
+ * include/cedar_b200.h.
+ *
  * Optional trailing flags (extensions): --qp N --gop N --cavlc --nv16 --me-range N --slice-rows N --crop --auto-level
- * --repeat-headers --intra4x4 --p-intra --batch-gops N --device N --stats
- * --batch-gops N: read N GOPs at a time and encode them GOP-parallel (clip mode of the C ABI); the bytes written, one
- * write() per frame, are identical to the frame-at-a-time default, only later.
+ * --repeat-headers --intra4x4 --p-intra --device N --stats, and the GOP-parallel modes, all of which write exactly the
+ * bytes of the frame-at-a-time default, one write() per frame, only later:
+ *   --queue-gops N   the reference's loop unchanged (fill buffers, encode_frame, write ret bytes) on a queued handle:
+ *                    encode_frame returns frame t - 2N GOPs while batches of N GOPs are encoded behind it; flush drains
+ *   --batch-gops N   a reader thread fills batches of N GOPs while earlier batches are encoded and written
+ *                    (cedar_b200_pipe_*); --handles M encoder handles per GPU (default 2)
+ *   --gpus N         the same across GPUs 0..N-1 of this box (batch b -> worker b mod (N*M)); --devices a,b,c picks them
  */
 #define _GNU_SOURCE
 #define _FILE_OFFSET_BITS 64
@@ -19,6 +25,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -39,13 +46,17 @@ static int ve_config(struct cedar_b200_config *config) /* userspace/h264enc.c:47
         fprintf(stderr, "%s(): cedar_b200_open failed: %s\n", __func__, strerror(-ret));
         return ret;
     }
-    printf("Input Y: %dbytes at %p\n", io.input_luma_size, io.input_luma);
-    printf("Input C: %dbytes at %p\n", io.input_chroma_size, io.input_chroma);
-    printf("Bytestream: %dbytes at %p\n", io.bytestream_size, io.bytestream);
+    /* the reference prints "<size>bytes at 0x<dma address> -> <mapping>" (:86,100,113); the buffers are pinned host
+     * memory and have no bus address: 0 is printed in its place */
+    printf("Input Y: %dbytes at 0x%08X -> %p\n", io.input_luma_size, 0u, io.input_luma);
+    printf("Input C: %dbytes at 0x%08X -> %p\n", io.input_chroma_size, 0u, io.input_chroma);
+    printf("Bytestream: %dbytes at 0x%08X -> %p\n", io.bytestream_size, 0u, io.bytestream);
     return 0;
 }
 
-static int read_frame(int fd, void *buffer, int size) /* userspace/h264enc.c:119-132 */
+/* userspace/h264enc.c:119-132.  The reference only stops on end of file (len == 0) and would spin on a read error
+ * (len < 0 is added to total); here an error ends the stream like end of file does. */
+static int read_frame(int fd, void *buffer, int size)
 {
     int total = 0, len;
 
@@ -58,12 +69,89 @@ static int read_frame(int fd, void *buffer, int size) /* userspace/h264enc.c:119
     return total;
 }
 
+static double sse_total, bytes_total;
+static uint32_t frame_count;
+
+static void emit_frame(int fd_out, const void *data, int bytes, int stats, double sse)
+{
+    printf("\rFrame %5d: %5dbytes", frame_count, bytes);
+    if (write(fd_out, data, (size_t)bytes) != bytes)
+        fprintf(stderr, "%s(): short write\n", __func__);
+    if (stats) {
+        sse_total += sse;
+        bytes_total += bytes;
+    }
+    frame_count++;
+}
+
+/* ---- --batch-gops / --gpus: reader thread -> pipeline workers -> writer (this thread) ---- */
+struct reader_ctx {
+    cedar_b200_pipe *pipe;
+    int fd_in;
+};
+
+static void *reader_main(void *arg)
+{
+    struct reader_ctx *rc = (struct reader_ctx *)arg;
+    for (;;) {
+        size_t frame_bytes = 0;
+        int cap = 0, n = 0;
+        uint8_t *in = (uint8_t *)cedar_b200_pipe_acquire(rc->pipe, &frame_bytes, &cap);
+        if (!in)
+            break;
+        while (n < cap && read_frame(rc->fd_in, in + (size_t)n * frame_bytes, (int)frame_bytes) == (int)frame_bytes)
+            n++;
+        if (cedar_b200_pipe_submit(rc->pipe, n) || n < cap)
+            break;
+    }
+    cedar_b200_pipe_finish(rc->pipe);
+    return NULL;
+}
+
+static int run_pipeline(struct cedar_b200_config *config, const int *devices, int ndevices, int handles, int batch_gops,
+                        int fd_in, int fd_out, int stats)
+{
+    cedar_b200_pipe *pipe = NULL;
+    struct reader_ctx rc;
+    pthread_t reader;
+    int ret = cedar_b200_pipe_open(config, devices, ndevices, handles, batch_gops, &pipe);
+    if (ret) {
+        fprintf(stderr, "%s(): cedar_b200_pipe_open failed: %s\n", __func__, strerror(-ret));
+        return ret;
+    }
+    rc.pipe = pipe;
+    rc.fd_in = fd_in;
+    if (pthread_create(&reader, NULL, reader_main, &rc)) {
+        cedar_b200_pipe_close(pipe);
+        return -EAGAIN;
+    }
+    for (;;) {
+        const uint8_t *out = NULL;
+        const int *sizes = NULL;
+        const double *sse = NULL;
+        int n = 0;
+        long long total = cedar_b200_pipe_next(pipe, &out, &sizes, &n, &sse, 1);
+        if (total == 0)
+            break;
+        if (total < 0) {
+            fprintf(stderr, "%s(): %d: batch encode failed: %s\n", __func__, frame_count, strerror((int)-total));
+            continue;
+        }
+        for (int i = 0; i < n; i++) {
+            emit_frame(fd_out, out, sizes[i], stats, sse[i]);
+            out += sizes[i];
+        }
+    }
+    pthread_join(reader, NULL);
+    cedar_b200_pipe_close(pipe);
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
-    uint32_t frame_count = 0;
-    int width, height, fd_in, fd_out, luma_size, chroma_size, ret, stats = 0, batch_gops = 0;
+    int width, height, fd_in, fd_out, luma_size, chroma_size, ret, stats = 0, batch_gops = 0, queue_gops = 0;
+    int devices[64], ndevices = 0, handles = 0, one_device = -1;
     struct cedar_b200_config config;
-    double sse_total = 0, bytes_total = 0;
 
     if (argc < 5 || (argc > 5 && strncmp(argv[5], "--", 2))) {
         printf("Usage: %s <infile> <width> <height> <outfile>\n", argv[0]);
@@ -94,7 +182,24 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--slice-rows") && i + 1 < argc)
             config.slice_rows = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--device") && i + 1 < argc)
-            config.device = atoi(argv[++i]);
+            one_device = config.device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) {
+            int n = atoi(argv[++i]);
+            if (n < 1 || n > 64) {
+                fprintf(stderr, "%s: --gpus %d out of range\n", argv[0], n);
+                return -1;
+            }
+            for (ndevices = 0; ndevices < n; ndevices++)
+                devices[ndevices] = ndevices;
+        } else if (!strcmp(argv[i], "--devices") && i + 1 < argc) {
+            char *s = argv[++i];
+            for (ndevices = 0; *s && ndevices < 64; ndevices++) {
+                devices[ndevices] = (int)strtol(s, &s, 10);
+                if (*s == ',')
+                    s++;
+            }
+        } else if (!strcmp(argv[i], "--handles") && i + 1 < argc)
+            handles = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--crop"))
             config.sps_crop = 1;
         else if (!strcmp(argv[i], "--auto-level"))
@@ -111,6 +216,8 @@ int main(int argc, char **argv)
             config.src_format = CEDAR_B200_FORMAT_NV16;
         else if (!strcmp(argv[i], "--batch-gops") && i + 1 < argc)
             batch_gops = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--queue-gops") && i + 1 < argc)
+            queue_gops = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--stats"))
             stats = 1;
         else {
@@ -118,6 +225,15 @@ int main(int argc, char **argv)
             return -1;
         }
     }
+    if (batch_gops < 0 || queue_gops < 0 || handles < 0 || (batch_gops && queue_gops)) {
+        fprintf(stderr, "%s: invalid --batch-gops / --queue-gops / --handles\n", argv[0]);
+        return -1;
+    }
+    if (ndevices > 0 && !batch_gops)
+        batch_gops = 4; /* several GPUs only make sense GOP-parallel */
+    /* the serial CABAC stages of successive frames overlap on side streams: they need their own hardware queues, and
+     * the variable only counts before CUDA initialises in this process */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
 
     if (strcmp(argv[1], "-")) {
         fd_in = open(argv[1], O_RDONLY);
@@ -134,76 +250,47 @@ int main(int argc, char **argv)
         return -1;
     }
 
-    if (batch_gops > 0)
-        config.max_clip_frames = batch_gops * config.keyframe_interval;
-    ret = ve_config(&config);
-    if (ret)
-        return ret;
-
     luma_size = width * height;
     chroma_size = config.src_format == CEDAR_B200_FORMAT_NV16 ? luma_size : luma_size / 2;
 
-    while (batch_gops > 0) { /* GOP-parallel: whole batches through the clip calls of the C ABI */
-        size_t frame_bytes = 0;
-        uint8_t *in = (uint8_t *)cedar_b200_clip_input(enc, &frame_bytes);
-        const uint8_t *out = NULL;
-        int n = 0, cap = config.max_clip_frames;
-        int *sizes = (int *)malloc(sizeof(int) * (size_t)cap);
-        double *sse = (double *)malloc(sizeof(double) * (size_t)cap);
-        while (n < cap && read_frame(fd_in, in + (size_t)n * frame_bytes, (int)frame_bytes) == (int)frame_bytes)
-            n++;
-        if (n > 0) {
-            long long total = -1;
-            ret = cedar_b200_clip_upload(enc, n);
-            if (!ret)
-                ret = cedar_b200_clip_encode(enc, n, (int)frame_count);
-            if (!ret)
-                total = cedar_b200_clip_download(enc, &out, sizes);
-            if (ret || total < 0)
-                fprintf(stderr, "%s(): %d: clip encode failed: %s\n", __func__, frame_count, strerror(ret ? -ret : (int)-total));
-            else {
+    if (batch_gops > 0) { /* GOP-parallel: reader thread, pipeline workers (per GPU, per handle), ordered writes */
+        if (ndevices == 0 && one_device >= 0)
+            devices[ndevices++] = one_device;
+        ret = run_pipeline(&config, ndevices ? devices : NULL, ndevices, handles, batch_gops, fd_in, fd_out, stats);
+        if (ret)
+            return ret;
+    } else {
+        config.queue_gops = queue_gops;
+        ret = ve_config(&config);
+        if (ret)
+            return ret;
+        while (1) { /* userspace/h264enc.c:181-198, unchanged in shape */
+            ret = read_frame(fd_in, io.input_luma, luma_size);
+            if (ret != luma_size)
+                break;
+            ret = read_frame(fd_in, io.input_chroma, chroma_size);
+            if (ret != chroma_size)
+                break;
+
+            ret = cedar_b200_encode_frame(enc);
+            if (ret < 0)
+                fprintf(stderr, "%s(): %d: cedar_b200_encode_frame failed: %s\n", __func__, frame_count, strerror(-ret));
+            else if (ret > 0 || !queue_gops) {
+                double sse = 0;
                 if (stats)
-                    cedar_b200_stats(enc, sse, n);
-                for (int i = 0; i < n; i++) {
-                    printf("\rFrame %5d: %5dbytes", frame_count, sizes[i]);
-                    if (write(fd_out, out, (size_t)sizes[i]) != sizes[i])
-                        fprintf(stderr, "%s(): short write\n", __func__);
-                    out += sizes[i];
-                    if (stats) {
-                        sse_total += sse[i];
-                        bytes_total += sizes[i];
-                    }
-                    frame_count++;
-                }
+                    cedar_b200_stats(enc, &sse, 1);
+                emit_frame(fd_out, io.bytestream, ret, stats, sse);
             }
         }
-        free(sizes);
-        free(sse);
-        if (n < cap)
-            break;
-    }
-    while (batch_gops <= 0) {
-        ret = read_frame(fd_in, io.input_luma, luma_size);
-        if (ret != luma_size)
-            break;
-        ret = read_frame(fd_in, io.input_chroma, chroma_size);
-        if (ret != chroma_size)
-            break;
-
-        ret = cedar_b200_encode_frame(enc);
-        if (ret < 0)
-            fprintf(stderr, "%s(): %d: cedar_b200_encode_frame failed: %s\n", __func__, frame_count, strerror(-ret));
-        else {
-            printf("\rFrame %5d: %5dbytes", frame_count, ret);
-            if (write(fd_out, io.bytestream, (size_t)ret) != ret)
-                fprintf(stderr, "%s(): short write\n", __func__);
-            if (stats) {
-                double sse = 0;
-                cedar_b200_stats(enc, &sse, 1);
-                sse_total += sse;
-                bytes_total += ret;
+        while (queue_gops && (ret = cedar_b200_flush(enc)) != 0) { /* queued handle: the frames still in flight */
+            double sse = 0;
+            if (ret < 0) {
+                fprintf(stderr, "%s(): %d: cedar_b200_flush failed: %s\n", __func__, frame_count, strerror(-ret));
+                break;
             }
-            frame_count++;
+            if (stats)
+                cedar_b200_stats(enc, &sse, 1);
+            emit_frame(fd_out, io.bytestream, ret, stats, sse);
         }
     }
     printf("\n");
@@ -212,6 +299,7 @@ int main(int argc, char **argv)
         fprintf(stderr, "frames %u, %.2f kbit/frame, Y-PSNR %.2f dB\n", frame_count,
                 bytes_total * 8.0 / 1000.0 / frame_count, mse > 0 ? 10.0 * log10(255.0 * 255.0 / mse) : 99.0);
     }
-    cedar_b200_close(enc);
+    if (enc)
+        cedar_b200_close(enc);
     return 0;
 }

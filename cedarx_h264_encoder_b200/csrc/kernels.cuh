@@ -2359,10 +2359,10 @@ __device__ __forceinline__ unsigned zero_run_before(const uint8_t *p, long i)
 
 __global__ void epb_count_kernel(int nframes, const uint8_t *__restrict__ rbsp, unsigned rbsp_cap,
                                  const uint32_t *__restrict__ rbsp_len, uint32_t *__restrict__ chunk_cnt,
-                                 unsigned chunks_per_frame)
+                                 unsigned chunks_per_frame, unsigned cblocks)
 {
-    int f = blockIdx.y;
-    unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = (int)(blockIdx.x / cblocks);
+    unsigned ch = (blockIdx.x % cblocks) * blockDim.x + threadIdx.x;
     if (f >= nframes || ch >= chunks_per_frame)
         return;
     const uint8_t *p = rbsp + (size_t)f * rbsp_cap;
@@ -2495,11 +2495,11 @@ __global__ void __launch_bounds__(1024) pack_scan_kernel(int nunits, int nslices
 __global__ void epb_write_kernel(int nframes /* units */, int nslices, int gop_len, int first_frame_index,
                                  const uint8_t *__restrict__ rbsp, unsigned rbsp_cap,
                                  const uint32_t *__restrict__ rbsp_len, const uint32_t *__restrict__ chunk_off,
-                                 unsigned chunks_per_frame, const unsigned long long *__restrict__ nal_off,
+                                 unsigned chunks_per_frame, unsigned cblocks, const unsigned long long *__restrict__ nal_off,
                                  const unsigned long long *__restrict__ total, uint8_t *__restrict__ out, ParamSets ps)
 {
-    int f = blockIdx.y;
-    unsigned ch = blockIdx.x * blockDim.x + threadIdx.x;
+    int f = (int)(blockIdx.x / cblocks);
+    unsigned ch = (blockIdx.x % cblocks) * blockDim.x + threadIdx.x;
     if (f >= nframes || ch >= chunks_per_frame || *total == 0)
         return;
     const uint8_t *p = rbsp + (size_t)f * rbsp_cap;

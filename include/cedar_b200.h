@@ -63,6 +63,13 @@ struct cedar_b200_config {
                               * where their SAD-based cost beats the best Intra16x16 mode. */
     int p_intra;             /* non-zero: macroblocks of P frames are coded as Intra16x16 where that beats the motion
                               * search (scene changes, uncovered content). */
+    int queue_gops;          /* non-zero: QUEUED mode of the per-frame call.  encode_frame() keeps the
+                              * reference's call pattern -- fill the input buffers, call, write `ret` bytes
+                              * (userspace/h264enc.c:181-198) -- but the frames are encoded GOP-parallel in batches of
+                              * queue_gops closed GOPs: the call returns 0 while the first two batches fill, afterwards
+                              * the bytes of frame t - 2 * queue_gops * keyframe_interval, and cedar_b200_flush() drains
+                              * the rest, one frame per call.  The concatenated output is byte-identical to the
+                              * synchronous mode. */
 };
 
 /*
@@ -93,6 +100,11 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
  * io->input_luma / io->input_chroma; returns the number of bytes now valid at io->bytestream
  * (SPS+PPS precede the first frame only, cedar.c:1058-1061) or a negative errno. */
 int cedar_b200_encode_frame(cedar_b200_handle *h);
+
+/* Queued mode only (cfg.queue_gops != 0): after the last encode_frame() call, every call returns the bytes of the next
+ * outstanding frame in io->bytestream (display order), 0 when the stream is drained, or a negative errno.  In the
+ * synchronous mode it returns 0: nothing is ever outstanding. */
+int cedar_b200_flush(cedar_b200_handle *h);
 
 /* close(fd) -> cedar_slashdev_release (kernel/cedar.c:706-730): frees everything and prints the
  * busy/total time line the reference prints. */
@@ -153,6 +165,41 @@ int cedar_b200_write_pps(const struct cedar_b200_config *cfg, uint8_t *out, int 
 int cedar_b200_slice_header(int frame_i, int frame_p_count, int cabac, uint32_t *bits, int *nbits);
 /* Slice header of a slice that starts at macroblock first_mb (slice_rows extension); up to 64 bits. */
 int cedar_b200_slice_header_mb(int frame_i, int frame_p_count, int cabac, int first_mb, uint64_t *bits, int *nbits);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ordered pipeline over several handles and GPUs (csrc/pipeline.cpp): the north star's "GOP-parallel across the GPUs of
+ * one box, per-GPU bytestreams concatenated on the host".  Batches of gops_per_batch closed GOPs; batch b is encoded by
+ * worker b % W, W = ndevices * handles_per_device, every worker being one handle on one device with its own host
+ * thread.  The batches come back in submission order and concatenate to exactly the stream one handle -- or the
+ * frame-at-a-time call -- produces: SPS + PPS only in front of stream frame 0 (kernel/cedar.c:1058-1061), an IDR
+ * picture at every multiple of keyframe_interval (:1047-1050, :1193-1196).
+ * One producer thread (acquire, fill, submit, ..., finish) and one consumer thread (next, ...), which may be the same
+ * thread as long as it does not acquire more than W batches ahead of what it has consumed.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct cedar_b200_pipe cedar_b200_pipe;
+
+/* devices == NULL or ndevices == 0: cfg->device only.  handles_per_device == 0: 2.  gops_per_batch == 0: 4.
+ * cfg->max_clip_frames and cfg->device are overridden per worker.  Returns 0 or a negative errno. */
+int cedar_b200_pipe_open(const struct cedar_b200_config *cfg, const int *devices, int ndevices, int handles_per_device,
+                         int gops_per_batch, cedar_b200_pipe **p);
+int cedar_b200_pipe_workers(cedar_b200_pipe *p);
+/* Pinned host staging of the next batch: capacity_frames packed frames of frame_bytes each (luma then chroma, as the
+ * reference's read loop consumes them, userspace/h264enc.c:181-187).  Blocks until the worker that will encode the
+ * batch is free (its previous batch consumed).  NULL when a batch is already being filled or after finish. */
+void *cedar_b200_pipe_acquire(cedar_b200_pipe *p, size_t *frame_bytes, int *capacity_frames);
+/* Hands the acquired batch, holding nframes frames, to its worker (asynchronous).  Only the last batch of a stream may
+ * hold fewer than capacity_frames; nframes == 0 gives the buffer back and ends the stream. */
+int cedar_b200_pipe_submit(cedar_b200_pipe *p, int nframes);
+/* No more batches will be submitted: pipe_next returns 0 once everything submitted has been consumed. */
+int cedar_b200_pipe_finish(cedar_b200_pipe *p);
+/* The next batch in submission order: total bytes (> 0), the packed stream in *out, per-frame byte counts, frame count
+ * and per-frame luma SSE (pointers valid until the next pipe_next / pipe_release call).  wait != 0 blocks until that
+ * batch is encoded; otherwise -EAGAIN.  0: nothing outstanding.  Negative errno: that batch failed. */
+long long cedar_b200_pipe_next(cedar_b200_pipe *p, const uint8_t **out, const int **frame_sizes, int *nframes,
+                               const double **sse_y, int wait);
+/* The consumer is done with the batch the last pipe_next returned (implied by the next pipe_next call). */
+int cedar_b200_pipe_release(cedar_b200_pipe *p);
+void cedar_b200_pipe_close(cedar_b200_pipe *p);
 
 const char *cedar_b200_version(void);
 

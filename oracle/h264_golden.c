@@ -401,6 +401,7 @@ const uint8_t *gm_recon_unfiltered(const gm_encoder *e, int plane) { return e->u
 const uint8_t *gm_source(const gm_encoder *e, int plane) { return e->src.p[plane]; }
 int gm_last_frame_type(const gm_encoder *e) { return e->last_frame_i; }
 double gm_last_sse_y(const gm_encoder *e) { return e->last_sse_y; }
+void gm_set_frame_p_count(gm_encoder *e, int frame_p_count) { e->frame_p_count = frame_p_count; }
 
 /* ------------------------------------------------------------------------------------------
  * K0 ingest: packed w x h NV12/NV16 -> planar 4:2:0 at the coded size, edge replicated.

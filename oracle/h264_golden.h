@@ -86,6 +86,10 @@ const uint8_t *gm_recon(const gm_encoder *e, int plane);       /* after deblocki
 const uint8_t *gm_recon_unfiltered(const gm_encoder *e, int plane);
 const uint8_t *gm_source(const gm_encoder *e, int plane);      /* ingested (padded, planar) */
 int gm_last_frame_type(const gm_encoder *e);                   /* 1 = I, 0 = P */
+/* Position of the next frame inside its GOP (cedar.c:118 frame_p_count; 0 = the next frame is an IDR picture).  For
+ * callers that own the GOP counter themselves: oracle/refsim's model of the video engine is told the picture type per
+ * frame by the reference driver's PARA0 write (cedar.c:1160-1163). */
+void gm_set_frame_p_count(gm_encoder *e, int frame_p_count);
 double gm_last_sse_y(const gm_encoder *e);
 
 /* Header writer on its own (for byte-identity tests against Appendix A vectors). */

@@ -35,7 +35,13 @@ def test_cli_fails_loudly_without_gpu(product_lib, tmp_path):
 @pytest.mark.skipif(not torch.cuda.is_available(), reason="no CUDA device")
 @pytest.mark.parametrize("flags,cfg", [([], dict(qp=24, gop=25, cabac=1)),
                                        (["--cavlc", "--qp", "30", "--gop", "4"], dict(qp=30, gop=4, cabac=0)),
-                                       (["--gop", "2", "--batch-gops", "2", "--slice-rows", "2"], dict(qp=24, gop=2, cabac=1, slice_rows=2))])
+                                       (["--gop", "2", "--batch-gops", "2", "--slice-rows", "2"], dict(qp=24, gop=2, cabac=1, slice_rows=2)),
+                                       (["--gop", "2", "--batch-gops", "1", "--handles", "3"], dict(qp=24, gop=2, cabac=1)),
+                                       (["--gop", "1", "--batch-gops", "1", "--handles", "1"], dict(qp=24, gop=1, cabac=1)),
+                                       (["--gop", "2", "--queue-gops", "1"], dict(qp=24, gop=2, cabac=1)),
+                                       (["--gop", "3", "--queue-gops", "4", "--cavlc"], dict(qp=24, gop=3, cabac=0)),
+                                       (["--gop", "2", "--gpus", "1", "--batch-gops", "1"], dict(qp=24, gop=2, cabac=1)),
+                                       (["--gop", "2", "--devices", "0,0"], dict(qp=24, gop=2, cabac=1))])
 def test_cli_pipe_equals_golden_model(product_lib, tmp_path, flags, cfg):
     """raw nv12 on stdin -> Annex-B file, reference defaults; trailing garbage (short frame) is ignored
     exactly like the reference's read loop (userspace/h264enc.c:183-187)."""

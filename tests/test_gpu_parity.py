@@ -457,3 +457,95 @@ def test_p_intra_clip_mode_and_decoders(oracle, monkeypatch):
     for x, y in zip(a, b):
         for p in range(3):
             assert np.array_equal(x[p], y[p])
+
+
+# ---- queued per-frame mode and the multi-handle / multi-GPU pipeline (SURVEY 8b "queued mode", 8e) -----------------------
+@pytest.mark.parametrize("cabac,n", [(1, 20), (0, 12), (1, 5), (1, 13)])
+def test_queued_frame_mode_equals_oracle(oracle, cabac, n):
+    """queue_gops = 2 with GOP 3: batches of 6 frames; encode_frame returns nothing for the first 12 calls, then frame
+    t - 12; flush drains.  Frame by frame the bytes are the synchronous mode's, i.e. the golden model's."""
+    w, h, gop = 96, 80, 3
+    clip = make_clip("synth", w, h, n)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=24, gop=gop, cabac=cabac, me_range=8)
+    frames = []
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=gop, cabac=cabac, me_range=8, queue_gops=2)) as enc:
+        for t in range(n):
+            got = enc.encode(*split_frame(clip[t], w, h, 0))
+            assert (len(got) == 0) == (t < 12), t
+            if got:
+                frames.append(got)
+        while True:
+            got = enc.flush()
+            if not got:
+                break
+            frames.append(got)
+        assert enc.flush() == b""
+    assert [len(f) for f in frames] == sizes
+    assert b"".join(frames) == want
+
+
+@pytest.mark.parametrize("handles,batch,n", [(1, 1, 14), (2, 2, 20), (3, 1, 14), (2, 4, 7)])
+def test_pipeline_equals_oracle(oracle, handles, batch, n):
+    """Batches of whole GOPs round robin over several handles: the batches concatenate to the single stream (SPS/PPS only
+    in front of frame 0, cedar.c:1058-1061), including a short last batch."""
+    w, h, gop = 96, 80, 3
+    clip = make_clip("synth", w, h, n)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=24, gop=gop, cabac=1, me_range=8)
+    with cx.Pipe(api.make_config(w, h, qp=24, gop=gop, cabac=1, me_range=8), None, handles, batch) as pipe:
+        assert pipe.workers() == handles
+        got, gsz = pipe.encode(clip)
+    assert gsz == sizes and got == want
+
+
+def test_pipeline_across_devices_equals_single_stream(oracle):
+    """GOP-parallel across the GPUs of the box (every visible device; with one GPU the same device twice): batch b on
+    worker b mod W, merged on the host == the golden model's single stream == one handle's stream (BASELINE.md gate 4)."""
+    w, h, gop, n = 176, 144, 4, 40
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    clip = make_clip("synth", w, h, n)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=25, gop=gop, cabac=1, me_range=16)
+    with cx.Pipe(api.make_config(w, h, qp=25, gop=gop, cabac=1), devices, 1, 1) as pipe:
+        assert pipe.workers() == len(devices)
+        got, gsz = pipe.encode(clip)
+    assert gsz == sizes and got == want
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1, max_clip_frames=n)) as enc:
+        one, _ = enc.encode_clip(clip)
+    assert one == got
+
+
+def test_pipeline_1080p_two_handles_equals_frame_mode():
+    w, h, gop, n = 1920, 1088, 4, 16
+    clip = synth.synth_clip(w, h, list(range(n)), 0).numpy()
+    with cx.Pipe(api.make_config(w, h, qp=25, gop=gop, cabac=1), None, 2, 1) as pipe:
+        got, gsz = pipe.encode(clip)
+    with cx.Encoder(api.make_config(w, h, qp=25, gop=gop, cabac=1)) as enc:
+        frames = [enc.encode(*split_frame(clip[t], w, h, 0)) for t in range(n)]
+    assert [len(f) for f in frames] == gsz and b"".join(frames) == got
+
+
+def test_stats_after_clip_encode_without_download(oracle):
+    """cedar_b200_stats right after clip_encode (no clip_download in between) returns that encode's SSE."""
+    w, h, n, gop = 96, 80, 5, 3
+    clip = make_clip("synth", w, h, n)
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=24, gop=gop, me_range=8))
+    want = []
+    for t in range(n):
+        gold.encode(*split_frame(clip[t], w, h, 0))
+        want.append(gold.sse_y())
+    gold.close()
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=gop, me_range=8, max_clip_frames=n)) as enc:
+        enc.clip_input(n)[:] = clip
+        enc.clip_upload(n)
+        enc.clip_encode(n, 0)
+        assert enc.sse_y(n).tolist() == want
+
+
+def test_clip_mode_with_a_capacity_of_one_frame(oracle):
+    """max_clip_frames = 1 is clip mode (it used to be mistaken for 'clip mode off')."""
+    w, h = 64, 48
+    clip = make_clip("synth", w, h, 1)
+    want, sizes, _ = oracle_encode_clip(clip, w, h, qp=24, gop=1, me_range=8)
+    with cx.Encoder(api.make_config(w, h, qp=24, gop=1, me_range=8, max_clip_frames=1)) as enc:
+        got, gsz = enc.encode_clip(clip)
+    assert got == want

@@ -1,6 +1,11 @@
 #!/usr/bin/env python3
-"""CLI end to end (SURVEY 8d ii): a synthetic 1080p clip in a file, through cedarx_h264_encoder_b200/h264enc, frame at a
-time (the reference's flow) and GOP-parallel (--batch-gops); prints frames/s of both and checks the outputs are equal."""
+"""CLI end to end (SURVEY 8d ii): a synthetic 1080p clip in a file (page cache), through cedarx_h264_encoder_b200/h264enc:
+frame at a time (the reference's synchronous flow), --queue-gops (the same loop on a queued handle), --batch-gops (reader
+thread + pipeline workers + ordered writer) and --gpus N when the box has several GPUs.  Prints one JSON line with
+frames/s of each (process start, pinned allocations and file I/O included) and checks that all outputs are identical.
+
+    python tools/cli_throughput.py [frames] [out.json]"""
+import json
 import os
 import subprocess
 import sys
@@ -8,6 +13,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import torch  # noqa: E402
 from cedarx_h264_encoder_b200 import synth  # noqa: E402
 
 w, h, n, gop = 1920, 1080, int(sys.argv[1]) if len(sys.argv) > 1 else 600, 60
@@ -16,14 +22,28 @@ with open(raw, "wb") as f:
     for i in range(0, n, 20):
         f.write(synth.synth_clip(w, h, list(range(i, min(n, i + 20))), 0, device="cuda").cpu().numpy().tobytes())
 cli = os.path.join(ROOT, "cedarx_h264_encoder_b200", "h264enc")
-res = {}
-for name, extra in (("frame_at_a_time", []), ("batch_gops_10", ["--batch-gops", "10"])):
+modes = [("frame_at_a_time", []), ("queue_gops_2", ["--queue-gops", "2"]), ("batch_gops_2_handles_2", ["--batch-gops", "2"]),
+         ("batch_gops_5_handles_2", ["--batch-gops", "5"]), ("batch_gops_2_handles_3", ["--batch-gops", "2", "--handles", "3"])]
+ngpu = torch.cuda.device_count()
+if ngpu > 1:
+    modes.append(("gpus_%d_batch_gops_2" % ngpu, ["--gpus", str(ngpu), "--batch-gops", "2"]))
+res, outs = {}, {}
+for name, extra in modes:
     out = "/tmp/out_%s.264" % name
-    t = time.time()
-    subprocess.run([cli, raw, str(w), str(h), out, "--qp", "25", "--gop", str(gop)] + extra, check=True,
-                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    dt = time.time() - t
-    res[name] = (n / dt, open(out, "rb").read())
-    print("%-16s %7.1f frames/s (%.2f s wall, process start and file I/O included)" % (name, n / dt, dt))
-assert res["frame_at_a_time"][1] == res["batch_gops_10"][1], "outputs differ"
-print("outputs identical: %d bytes" % len(res["batch_gops_10"][1]))
+    best = None
+    for rep in range(2):  # second run: input in the page cache, driver warm
+        t = time.time()
+        subprocess.run([cli, raw, str(w), str(h), out, "--qp", "25", "--gop", str(gop)] + extra, check=True,
+                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        dt = time.time() - t
+        best = dt if best is None else min(best, dt)
+    res[name] = {"frames_per_s": round(n / best, 1), "wall_s": round(best, 3)}
+    outs[name] = open(out, "rb").read()
+    print("%-26s %8.1f frames/s (%.2f s wall)" % (name, n / best, best), file=sys.stderr)
+same = all(v == outs["frame_at_a_time"] for v in outs.values())
+line = {"tool": "cli_throughput", "clip": "%dx%d nv12, %d frames, GOP %d, QP 25, from a file" % (w, h, n, gop), "gpus": ngpu,
+        "modes": res, "outputs_identical": same, "bytes": len(outs["frame_at_a_time"])}
+print(json.dumps(line))
+if len(sys.argv) > 2:
+    json.dump(line, open(sys.argv[2], "w"), indent=1)
+assert same, "outputs differ"
