@@ -189,6 +189,98 @@ def run_reference(args, rank, world):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------------
+# Secondary measurements (other BASELINE.json configs, strong scaling): the same timing rules as the headline
+# ------------------------------------------------------------------------------------------------
+def measure_share(torch, cx, api, synth, spec, frame_ids, local_rank, steps, warmup, nhandles, sync, max_over_ranks,
+                  first_frame_index=0, repeat_content=1):
+    """Encodes this rank's frames of a clip (`frame_ids`, whole GOPs, already in encode order) `steps` times on `nhandles`
+    handles.  Returns device-resident and end-to-end milliseconds (max over ranks), per-GOP SHA-256s, stream bytes, SSE.
+    repeat_content > 1: the share is `repeat_content` clips of len(frame_ids) frames with the same content (a clip too
+    long to keep resident is encoded wave after wave from the same resident frames)."""
+    import hashlib
+    import threading
+    w, h, fmt, _, gop, qp, me, cabac = spec
+    n = len(frame_ids)
+    if n == 0:  # a rank without work still takes part in the barriers
+        sync(), sync()
+        ms_dev = max_over_ranks(0.0)
+        sync(), sync()
+        ms_e2e = max_over_ranks(0.0)
+        return {"handles": 0, "frames": 0, "ms_dev": ms_dev, "ms_e2e": ms_e2e, "gop_sha": [], "bytes": 0, "sse": 0.0, "h2d": 0, "d2h": 0}
+    cfg = api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, fmt=fmt, me_range=me, device=local_rank, max_clip_frames=n)
+    encs = []
+    for _ in range(max(1, nhandles)):
+        try:
+            encs.append(cx.Encoder(cfg))
+        except OSError:
+            if not encs:
+                raise
+            break
+    staging = torch.from_numpy(encs[0].clip_input(n))
+    for i in range(0, n, 20):
+        part = synth.synth_clip(w, h, frame_ids[i:i + 20], fmt, device="cuda")
+        staging[i:i + len(part)].copy_(part)
+    torch.cuda.synchronize()
+    for e in encs[1:]:
+        torch.from_numpy(e.clip_input(n)).copy_(staging[:n])
+    strs = [torch.cuda.ExternalStream(e.stream_ptr(), device=torch.device("cuda", local_rank)) for e in encs]
+
+    def run(total_steps, body):
+        errs = []
+
+        def work(i):
+            try:
+                for _ in range(i, total_steps, len(encs)):
+                    body(encs[i])
+            except Exception as ex:
+                errs.append(ex)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(encs))]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def timed(total_steps, body):
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in strs]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in strs]
+        sync()
+        for e, st in zip(ev0, strs):
+            e.record(st)
+        run(total_steps, body)
+        for e, st in zip(ev1, strs):
+            e.record(st)
+        sync()
+        return max_over_ranks(max(a.elapsed_time(b) for a in ev0 for b in ev1))
+
+    def e2e_step(e):
+        e.clip_upload(n)
+        e.clip_encode(n, first_frame_index)
+        e.clip_download(n)
+    for e in encs:
+        e.clip_upload(n)
+    run(max(warmup, 1) * len(encs), lambda e: e.clip_encode(n, first_frame_index))
+    ms_dev = timed(steps * repeat_content, lambda e: e.clip_encode(n, first_frame_index))
+    run(len(encs), e2e_step)
+    ms_e2e = timed(steps * repeat_content, e2e_step)
+    data, sizes = encs[0].clip_download(n)
+    data = data.tobytes()
+    sse = float(encs[0].sse_y(n).sum())
+    shas, off = [], 0
+    for g0 in range(0, n, gop):
+        nb = int(sizes[g0:g0 + gop].sum())
+        shas.append((int(frame_ids[g0]), hashlib.sha256(data[off:off + nb]).hexdigest()))
+        off += nb
+    fb = encs[0].frame_bytes
+    for e in encs:
+        e.close()
+    return {"frames": n, "ms_dev": ms_dev, "ms_e2e": ms_e2e, "gop_sha": shas, "bytes": len(data), "sse": sse,
+            "h2d": n * fb, "d2h": len(data) + 4 * n + 16, "handles": len(encs)}
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -373,6 +465,86 @@ def run_gpu(args, rank, local_rank, world):
                                  "y_psnr_delta_db": round(10 * math.log10(float(sse.sum()) / float(sse2.sum())), 4)})
             enc2.close()
     parity_ok = handles_identical
+    parity_extra_ok = True
+    # -------- GOP-parallel merge check on hardware (SURVEY 8e invariant, BASELINE.md gate 4) --------
+    # Every rank hashes each closed GOP of the stream its timed handle produced; rank 0 gathers them, checks that every
+    # GOP of the N x 600-frame clip is there exactly once, and re-encodes spot GOPs owned by OTHER ranks on its own GPU
+    # (with their first_frame_index): same bytes => the rank streams concatenate to the stream one GPU produces.
+    my_gops = partition.gops_for_rank(total_frames, gop, rank, world)
+    offs = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
+    gop_sha = {}
+    for i, g in enumerate(my_gops):
+        nf = len(partition.frames_of_gop(total_frames, gop, g))
+        gop_sha[g] = hashlib.sha256(data[int(offs[i * gop]):int(offs[i * gop + nf])].tobytes()).hexdigest()
+    merged = None
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, gop_sha)
+        if rank == 0:
+            allg = {}
+            for d in gathered:
+                allg.update(d)
+            spots = [g for g in (1, partition.num_gops(total_frames, gop) - 1) if g % world != 0]
+            spot_ok = []
+            for g in spots:
+                ids = partition.frames_of_gop(total_frames, gop, g)
+                staging[:len(ids)].copy_(synth.synth_clip(w, h, ids, fmt, device="cuda"))
+                torch.cuda.synchronize()
+                enc.clip_upload(len(ids))
+                enc.clip_encode(len(ids), g * gop)
+                d2, _ = enc.clip_download(len(ids))
+                spot_ok.append(hashlib.sha256(d2.tobytes()).hexdigest() == allg.get(g))
+            merged = {"gops_total": partition.num_gops(total_frames, gop), "gops_gathered": len(allg),
+                      "spot_gops_reencoded_on_rank0": spots, "merged_equal": bool(spot_ok) and all(spot_ok) and
+                      len(allg) == partition.num_gops(total_frames, gop),
+                      "how": "per-GOP SHA-256 all_gather; rank 0 re-encodes GOPs owned by other ranks with their "
+                             "first_frame_index and compares"}
+            parity_extra_ok = merged["merged_equal"]
+        dist.barrier()
+
+    # -------- the other BASELINE.json configs and strong scaling (same timing rules, fewer steps) --------
+    def sync_all():
+        barrier()
+    others, strong = None, None
+    if not args.no_extras:
+        st_ = max(2, min(args.steps, 3))
+        others = {}
+        if world == 1:
+            plan = [("720p_nv12_300f_gop30_qp25", 300), ("1080p_nv16_300f_gop60_qp25", 300),
+                    ("2160p_nv12_1200f_gop60_qp25_me64", 120)]
+        else:
+            plan = []
+        for name, nfr in plan:
+            spec = WORKLOADS[name]
+            r_ = measure_share(torch, cx, api, synth, spec, list(range(nfr)), local_rank, st_, 1, 2, sync_all, max_over_ranks)
+            W16_, H16_ = ((spec[0] + 15) // 16) * 16, ((spec[1] + 15) // 16) * 16
+            mse_ = r_["sse"] / (nfr * W16_ * H16_)
+            others[name] = {"frames_encoded": nfr, "value": nfr * st_ / (r_["ms_dev"] * 1e-3), "unit": "frames/s",
+                            "e2e": nfr * st_ / (r_["ms_e2e"] * 1e-3), "handles": r_["handles"],
+                            "kbit_per_frame": round(r_["bytes"] * 8 / 1000.0 / nfr, 2),
+                            "y_psnr_db": round(10 * math.log10(255.0 ** 2 / mse_), 3) if mse_ > 0 else None,
+                            "stream_sha256": hashlib.sha256(repr(r_["gop_sha"]).encode()).hexdigest()[:16]}
+        # strong scaling: a FIXED clip split GOP g -> rank g % N (960 frames = 16 GOPs for a clean 8x;
+        # 4800 frames = 80 GOPs so that 8 ranks still hold 10 GOPs each; config 5 = 4K, 1200 frames, +-64)
+        strong = {}
+        dspec = WORKLOADS[DEFAULT_WORKLOAD]
+        for label, spec, clip_frames, max_res_gops in (("1080p_960f", dspec, 960, 16), ("1080p_4800f", dspec, 4800, 10),
+                                                       ("2160p_1200f_me64", WORKLOADS["2160p_nv12_1200f_gop60_qp25_me64"], 1200, 5)):
+            g_ = spec[4]
+            share = partition.frames_for_rank(clip_frames, g_, rank, world)
+            share_gops = len(share) // g_
+            res_gops = min(share_gops, max_res_gops)
+            rep = -(-share_gops // res_gops) if res_gops else 1
+            if world > 1:  # every rank must run the same number of timed passes
+                t_ = torch.tensor([rep], device="cuda")
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                rep = int(t_.item())
+            r_ = measure_share(torch, cx, api, synth, spec, share[:res_gops * g_], local_rank, st_, 1, 2, sync_all, max_over_ranks,
+                               first_frame_index=0, repeat_content=rep)
+            strong[label] = {"clip_frames": clip_frames, "gops": clip_frames // g_, "value": clip_frames * st_ / (r_["ms_dev"] * 1e-3),
+                             "e2e": clip_frames * st_ / (r_["ms_e2e"] * 1e-3), "unit": "frames/s",
+                             "frames_resident_rank0": res_gops * g_, "passes_per_step": rep,
+                             "ceiling_speedup": partition.scaling_ceiling(clip_frames, g_, world)}
     if rank == 0:
         peaks = {}
         try:
@@ -463,6 +635,9 @@ def run_gpu(args, rank, local_rank, world):
             "kernels": kernels,
             "slice_parallel": slice_report,
             "cabac": cabac_stats,
+            "merged": merged,
+            "other_workloads": others,
+            "strong_scaling": strong,
             "quality": {"y_psnr_db": round(10 * math.log10(255.0 ** 2 / mse), 3) if mse > 0 else None,
                         "kbit_per_frame": round(stream_bytes * 8 / 1000.0 / n, 2)},
         }
@@ -483,6 +658,7 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    parity_ok = parity_ok and parity_extra_ok
     if not parity_ok:
         print("bench.py: PARITY FAILURE -- the timed stream differs from the golden model (see \"parity\")", file=sys.stderr)
         return 3
@@ -501,6 +677,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slice-rows", type=int, default=0, help="macroblock rows per slice (0 = one slice per picture)")
     ap.add_argument("--no-slice-report", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other BASELINE configs and the strong-scaling clips")
     ap.add_argument("--clips-in-flight", type=int, default=0,
                     help="encoder handles per GPU, each on its own host thread; steps alternate between them (0 = 2 or 3, by --steps)")
     args = ap.parse_args()

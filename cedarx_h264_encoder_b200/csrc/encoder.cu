@@ -810,9 +810,14 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
         destroy_handle(h);
         return -EINVAL;
     }
+    const auto t_alloc = std::chrono::steady_clock::now();
     r = alloc_buffers(h);
     if (!r)
         r = build_header_table(h);
+    if (getenv("CEDAR_B200_TRACE"))
+        fprintf(stderr, "[trace] open: context + streams %.1f ms, buffers %.1f ms (clip capacity %d frames, %d GOPs in flight)\n",
+                std::chrono::duration<double, std::milli>(t_alloc - h->t_open).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_alloc).count(), h->F, h->L);
     // SPS + PPS, emitted once before the first frame (cedar.c:1058-1061)
     int n1 = r ? 0 : cedar_b200_write_sps(cfg, h->prefix, 40);
     int n2 = r || n1 < 0 ? 0 : cedar_b200_write_pps(cfg, h->prefix + n1, 24);

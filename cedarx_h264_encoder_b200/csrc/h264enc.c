@@ -30,6 +30,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 #include "cedar_b200.h"
@@ -90,17 +91,30 @@ struct reader_ctx {
     int fd_in;
 };
 
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 static void *reader_main(void *arg)
 {
     struct reader_ctx *rc = (struct reader_ctx *)arg;
+    const int trace = getenv("CEDAR_B200_TRACE") != NULL;
     for (;;) {
         size_t frame_bytes = 0;
         int cap = 0, n = 0;
+        double t0 = now_s();
         uint8_t *in = (uint8_t *)cedar_b200_pipe_acquire(rc->pipe, &frame_bytes, &cap);
+        double t1 = now_s();
         if (!in)
             break;
         while (n < cap && read_frame(rc->fd_in, in + (size_t)n * frame_bytes, (int)frame_bytes) == (int)frame_bytes)
             n++;
+        if (trace)
+            fprintf(stderr, "[trace] reader: waited %.1f ms for a staging buffer, read %d frames in %.1f ms\n",
+                    1e3 * (t1 - t0), n, 1e3 * (now_s() - t1));
         if (cedar_b200_pipe_submit(rc->pipe, n) || n < cap)
             break;
     }
@@ -293,7 +307,8 @@ int main(int argc, char **argv)
             emit_frame(fd_out, io.bytestream, ret, stats, sse);
         }
     }
-    printf("\n");
+    /* the reference ends without a newline after the last progress line (userspace/h264enc.c:194-200) */
+    fflush(stdout);
     if (stats && frame_count) {
         double mse = sse_total / ((double)frame_count * config.dst_width * config.dst_height);
         fprintf(stderr, "frames %u, %.2f kbit/frame, Y-PSNR %.2f dB\n", frame_count,

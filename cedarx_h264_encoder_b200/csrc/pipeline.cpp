@@ -12,6 +12,7 @@
 // batches in submission order (next), so reading, encoding and writing overlap.  This file uses only the public C ABI.
 #include "../../include/cedar_b200.h"
 
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
@@ -65,13 +66,20 @@ void worker_main(cedar_b200_pipe *p, int wi)
             if (p->stop)
                 return;
         }
+        static const bool trace = getenv("CEDAR_B200_TRACE") != nullptr;
+        auto t0 = std::chrono::steady_clock::now();
         long long total = cedar_b200_clip_upload(w.h, w.nframes);
         if (total == 0)
             total = cedar_b200_clip_encode(w.h, w.nframes, w.first_frame);
+        auto t1 = std::chrono::steady_clock::now();
         if (total == 0)
             total = cedar_b200_clip_download(w.h, &w.out, w.sizes.data());
         if (total > 0)
             cedar_b200_stats(w.h, w.sse.data(), w.nframes);
+        if (trace)
+            fprintf(stderr, "[trace] worker %d (device %d): %d frames from %d: issue %.1f ms, until downloaded %.1f ms\n", wi,
+                    w.device, w.nframes, w.first_frame, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
         {
             std::lock_guard<std::mutex> lk(p->mu);
             w.total = total;
@@ -97,6 +105,7 @@ int cedar_b200_pipe_open(const struct cedar_b200_config *cfg, const int *devices
         handles_per_device = 2; // two chains per GPU fill the SMs one chain's wavefront kernels leave idle
     if (gops_per_batch == 0)
         gops_per_batch = 4;
+    const auto t_open = std::chrono::steady_clock::now();
     cedar_b200_pipe *p = new cedar_b200_pipe();
     p->K = cfg->keyframe_interval;
     p->cap = gops_per_batch * p->K;
@@ -125,6 +134,9 @@ int cedar_b200_pipe_open(const struct cedar_b200_config *cfg, const int *devices
     }
     for (size_t i = 0; i < p->w.size(); i++)
         p->w[i].thr = std::thread(worker_main, p, (int)i);
+    if (getenv("CEDAR_B200_TRACE"))
+        fprintf(stderr, "[trace] pipe_open: %zu workers x %d frames in %.1f ms\n", p->w.size(), p->cap,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_open).count());
     *out = p;
     return 0;
 }
