@@ -43,7 +43,8 @@ _lib = None
 
 
 def library_path():
-    return os.path.join(PKG_DIR, LIB_NAME)
+    # CEDAR_B200_LIB: development aid (an instrumented build of the same sources, e.g. tools/libcedar_prof.so)
+    return os.environ.get("CEDAR_B200_LIB") or os.path.join(PKG_DIR, LIB_NAME)
 
 
 def build_library(force=False):

@@ -528,7 +528,7 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         // the bins of these frames are final: code them on a side stream while the next frames are reconstructed
         cudaStream_t side = no_overlap ? st : h->stream_cabac[h->side_next];
         CK(cudaStreamWaitEvent(side, h->ev_post[p], 0));
-        LAUNCH_ON(side, K_CRESOLVE, cabac_resolve_kernel, nl * g.nslices, RES_WARPS * 32, 0, g, s, h->K, gop_pos0, h->eb);
+        LAUNCH_ON(side, K_CRESOLVE, cabac_resolve_kernel, nl * g.nslices, RES_THREADS, RES_SMEM_BYTES, g, s, h->K, gop_pos0, h->eb);
         EntropyBufs ebc = h->eb; // the limb scratch of this side stream (its launches are serialised)
         ebc.limbs += (size_t)(no_overlap || !h->clip_mode ? 0 : h->side_next) * h->L * g.nslices * h->eb.limb_cap;
         LAUNCH_ON(side, K_CCODE, cabac_code_kernel, nl * g.nslices, CP_THREADS, CP_SMEM_BYTES, g, s, ebc);
@@ -795,8 +795,9 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
         destroy_handle(h);
         return -ENODEV;
     }
-    if (cudaFuncSetAttribute(cabac_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES) != cudaSuccess) {
-        fprintf(stderr, "cedar_b200: cabac_code_kernel needs %d bytes of shared memory\n", CP_SMEM_BYTES);
+    if (cudaFuncSetAttribute(cabac_code_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(cabac_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RES_SMEM_BYTES) != cudaSuccess) {
+        fprintf(stderr, "cedar_b200: the CABAC kernels need %d / %d bytes of shared memory\n", CP_SMEM_BYTES, RES_SMEM_BYTES);
         cudaGetLastError();
         destroy_handle(h);
         return -ENODEV;

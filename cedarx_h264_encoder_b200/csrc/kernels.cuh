@@ -1830,30 +1830,56 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
 // cedar.c:992-993), in two kernels; entropy.cuh derives the parallel formulation.
 //
 // cabac_resolve_kernel: context-state resolution.  The state a regular bin is coded in depends only on the
-// earlier bins of the same context.  Per tile of RES_TILE bins:
-//   1. histogram of the contexts; the contexts are split over the RES_WARPS warps in contiguous ranges of equal
-//      bin count (prefix sum) -- a fixed split leaves the warp with the hottest contexts at twice the load;
-//   2. stable partition of the tile's regular bins by owning warp (per 32 bins: four ballots give every lane the
-//      mask of lanes of its class, counts per class and group are prefix-summed), so that every warp gets a
-//      dense, ordered queue of its own bins;
-//   3. every warp walks its queue 32 bins at a time: the lowest lane of every context present (its "leader")
-//      advances that context's state over all of its bins with the state in a register -- one table look-up per
-//      bin on the dependent chain -- and leaders of different contexts run side by side.
-// Rewrites the bin stream in place as per-bin records (cabac_meta: isLPS / bypass / terminate + pStateIdx).
-// This is the only stage that is serial along the slice: its critical path is the hottest context's chain.
+// earlier bins of the same context, so the work is a set of independent serial chains, one per context (460 of
+// them; the hottest holds about 6 % of a slice's bins).  One CTA per slice; every context is OWNED by one thread
+// that keeps its state in a register for the whole slice.  Per tile of RES_TILE bins:
+//   A. stable counting sort by context, first half: every warp ranks the bins of its contiguous 256-bin chunk, 32 at a
+//      time -- nine ballots give each lane the lanes holding the same context, the lowest of them bumps the warp's own
+//      counter of that context (no atomics: a counter row belongs to one warp, one leader per context per step);
+//   B. the owner of a context turns its column of the counters into offsets (exclusive prefix over the warps) and the
+//      block scans the per-context totals, rounded up to four, into the start of every context's segment;
+//   C. every bin's VALUE goes to its place in the sorted order (a bit array; one shared atomic OR per 1-bin);
+//   D. the owner walks its segment FOUR bins per dependent table look-up: the 128-state machine composed four times
+//      (2048 entries of 16 bytes: the four records -- cabac_meta: isLPS + pStateIdx -- and the state after them), the
+//      records stored in sorted order with one 8-byte store.  Chain per four bins: OR, shift, LDS.128;
+//   E. every bin fetches its record from its place in the sorted order.
+// The only serial part is D along one context; its length per tile is the hottest context's bin count / 4.
+__device__ __forceinline__ uint4 lds_u128(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t a, uint32_t b)
+{
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
 #define RES_WARPS 16
+#define RES_THREADS (RES_WARPS * 32)
 #define RES_TILE 4096
 #define RES_GROUPS (RES_TILE / 32)
-__global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0,
-                                                                       EntropyBufs eb)
+#define RES_GPW (RES_GROUPS / RES_WARPS)   // 32-bin groups per warp and tile
+#define RES_NCTX 464                       // 460 contexts, padded
+#define RES_SORTED (RES_TILE + 3 * RES_NCTX + 16) // sorted order with every segment padded to a multiple of four
+#define RES_TAB_BYTES (2048 * 16)
+#define RES_SMEM_BYTES (RES_TAB_BYTES + (RES_TILE + 8) * 2 + RES_SORTED * 2 + (RES_SORTED / 32 + 1) * 4)
+__global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0,
+                                                                    EntropyBufs eb)
 {
-    __shared__ __align__(16) uint16_t tile[RES_TILE + 8], mtile[RES_TILE + 8];
-    __shared__ uint32_t queue[RES_TILE];                 // ctx | bit << 9 | index in tile << 10, grouped by owning warp
-    __shared__ uint16_t cnt[RES_WARPS][RES_GROUPS];      // bins of class k in group G -> exclusive prefix over G
-    __shared__ uint32_t coff[RES_WARPS + 1];             // queue range of every class
-    __shared__ uint16_t trans[128];
-    __shared__ uint8_t ctx_state[464], owner[480], pre_s[RES_WARPS][32];
-    __shared__ uint32_t hist[480], cmask[464];
+    extern __shared__ __align__(16) uint8_t res_dyn[];            // RES_SMEM_BYTES
+    uint4 *const step4 = (uint4 *)res_dyn;                        // [state << 4 | four bin values]
+    uint16_t *const tile = (uint16_t *)(res_dyn + RES_TAB_BYTES); // [RES_TILE + 8] bins in, records out
+    uint16_t *const recq = tile + RES_TILE + 8;                   // [RES_SORTED] records in sorted order
+    uint32_t *const bitq = (uint32_t *)(recq + RES_SORTED);       // [RES_SORTED / 32 + 1] bin values in sorted order
+    __shared__ uint16_t wcnt[RES_WARPS][RES_NCTX]; // [w][slot(c)]: bins of context c in warp w's chunk -> exclusive prefix over w
+    __shared__ uint16_t cstart[RES_NCTX];
+    __shared__ uint16_t wsum[RES_WARPS];
     const int f = lane_frame(s, blockIdx.x / g.nslices); // one CTA per slice
     if (f < 0)
         return;
@@ -1867,166 +1893,203 @@ __global__ void __launch_bounds__(RES_WARPS * 32) cabac_resolve_kernel(Geom g, S
     uint16_t *gb = eb.bins + eb.bins_off[u];
     // 16-byte vector loads / stores: tile k starts at the aligned address at or below gb + k * RES_TILE
     const uint32_t mis = (uint32_t)(((uintptr_t)gb >> 1) & 7); // elements between that address and the first bin
-    for (int st = tid; st < 128; st += RES_WARPS * 32) {
-        int ps = st >> 1, mps = st & 1;
-        int after_mps = (h264_next_state_mps[ps] << 1) | mps;
-        int after_lps = (h264_next_state_lps[ps] << 1) | (ps == 0 ? mps ^ 1 : mps);
-        trans[st] = (uint16_t)(after_mps | (after_lps << 8));
+    // step4[(pStateIdx << 1 | valMPS) << 4 | b0 | b1 << 1 | b2 << 2 | b3 << 3]:
+    //   .x = record of bin 0 | record of bin 1 << 16, .y = records of bins 2 and 3, .z = state after the four bins << 4.
+    // The record of a bin coded in state S is (pStateIdx << 3 | valMPS) ^ value: bit 0 = isLPS, bits 3.. = pStateIdx.
+    for (int idx = tid; idx < 2048; idx += RES_THREADS) {
+        uint32_t st7 = idx >> 4, rec[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t ps = st7 >> 1, mps = st7 & 1, bit = (idx >> j) & 1;
+            rec[j] = ((ps << 3) | mps) ^ bit;
+            if (bit == mps)
+                st7 = ((ps < 62 ? ps + 1 : ps) << 1) | mps; // h264_next_state_mps
+            else
+                st7 = (h264_next_state_lps[ps] << 1) | (ps == 0 ? mps ^ 1 : mps);
+        }
+        step4[idx] = make_uint4(rec[0] | (rec[1] << 16), rec[2] | (rec[3] << 16), st7 << 4, 0);
     }
-    for (int i = tid; i < 460; i += RES_WARPS * 32) {
-        ctx_state[i] = (uint8_t)cabac_init_state(i, frame_i, g.qp);
-        cmask[i] = 0;
+    // Thread (warp, lane < 29) owns context lane * 16 + warp: neighbouring contexts -- the hot ones come in runs
+    // (significance flags 105.., levels 227..) -- sit in different warps.  Counters and segment starts are stored at
+    // slot(c) = (c & 15) * 29 + (c >> 4) = warp * 29 + lane of the owner, which pass B reads conflict free.
+    const int myc = lane < 29 ? lane * 16 + warp : 511, myslot = warp * 29 + lane;
+    uint32_t X = myc < 460 ? cabac_init_state(myc, frame_i, g.qp) << 4 : 0; // (pStateIdx << 1 | valMPS) << 4
+    // shared-window addresses for the walk of pass D, made opaque so that they stay in registers (otherwise they are
+    // rebuilt from SR_CgaCtaId, a 20-cycle special-register read, inside the loop)
+    uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(step4), recq_addr = (uint32_t)__cvta_generic_to_shared(recq);
+    uint32_t bitq_addr = (uint32_t)__cvta_generic_to_shared(bitq);
+    asm volatile("mov.u32 %0, %0;" : "+r"(tab_addr));
+    asm volatile("mov.u32 %0, %0;" : "+r"(recq_addr));
+    asm volatile("mov.u32 %0, %0;" : "+r"(bitq_addr));
+#ifdef RES_PROFILE
+    __shared__ unsigned long long prof_acc[8], prof_dmax, prof_dsum, prof_cnt;
+    long long prof_t = clock64();
+    if (tid < 8)
+        prof_acc[tid] = 0;
+    if (tid == 0)
+        prof_dmax = 0, prof_dsum = 0, prof_cnt = 0;
+#define RES_PROF_MARK(i)                                                                                       \
+    {                                                                                                          \
+        const long long now_ = clock64();                                                                      \
+        if (tid == 0) {                                                                                        \
+            prof_acc[i] += (unsigned long long)(now_ - prof_t);                                                \
+            if ((i) == 4) {                                                                                    \
+                prof_dsum += (prof_dmax >> 8) & 0xfff;                                                         \
+                prof_cnt++;                                                                                    \
+                prof_dmax = 0;                                                                                 \
+            }                                                                                                  \
+        }                                                                                                      \
+        prof_t = now_;                                                                                         \
     }
+#else
+#define RES_PROF_MARK(i)
+#endif
     for (uint32_t base = 0; base < nb; base += RES_TILE) {
         const uint32_t n = nb - base < RES_TILE ? nb - base : RES_TILE;
         const uint16_t *src = gb + base - mis; // 16-byte aligned
         const uint32_t nv = (mis + n + 7) >> 3;
-        __syncthreads(); // tables ready / previous tile's records stored
-        for (uint32_t v = tid; v < nv; v += RES_WARPS * 32) {
+        __syncthreads(); // table ready / previous tile's records stored
+        for (uint32_t v = tid; v < nv; v += RES_THREADS) {
             // the first and the last vector may reach into a neighbouring slice's bins (same pool): read-only here
             ((uint4 *)tile)[v] = ((const uint4 *)src)[v];
         }
-        for (int i = tid; i < 480; i += RES_WARPS * 32)
-            hist[i] = 0;
-        for (int i = tid; i < RES_WARPS * RES_GROUPS / 2; i += RES_WARPS * 32)
-            ((uint32_t *)cnt)[i] = 0;
+        for (int i = tid; i < RES_WARPS * RES_NCTX / 2; i += RES_THREADS)
+            ((uint32_t *)wcnt)[i] = 0;
+        if (tid < RES_SORTED / 32 + 1)
+            bitq[tid] = 0;
         __syncthreads();
-        // ---- 1. balance: contexts -> warps in contiguous ranges holding about n / RES_WARPS regular bins each ----
-        for (uint32_t i = tid; i < n; i += RES_WARPS * 32) {
-            const uint32_t b = tile[mis + i];
-            if (!(b & (BIN_BYPASS | BIN_TERM)))
-                atomicAdd(&hist[b & 0x3ff], 1u);
-        }
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t loc[15], sum = 0;
+        RES_PROF_MARK(0);
+        // ---- A. rank inside the warp's chunk ----
+        uint32_t ent[RES_GPW]; // slot | value << 9 | rank in chunk << 10; 0xffffffff = not a regular bin
 #pragma unroll
-            for (int k = 0; k < 15; k++) {
-                loc[k] = sum;
-                sum += hist[lane * 15 + k];
-            }
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o)
-                    incl += y;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31), before = incl - sum;
-#pragma unroll
-            for (int k = 0; k < 15; k++) {
-                uint32_t w = total ? ((before + loc[k]) * RES_WARPS) / total : 0;
-                owner[lane * 15 + k] = (uint8_t)(w < RES_WARPS ? w : RES_WARPS - 1);
-            }
-        }
-        __syncthreads();
-        // ---- 2. stable partition by owner: warp w ranks the bins of groups [w * 8, w * 8 + 8) ----
-        uint32_t ent[RES_GROUPS / RES_WARPS]; // queue entry | rank << 22 | class << 27; 0xffffffff = not a regular bin
-#pragma unroll
-        for (int gi = 0; gi < RES_GROUPS / RES_WARPS; gi++) {
-            const uint32_t G = warp * (RES_GROUPS / RES_WARPS) + gi, i = G * 32 + lane;
+        for (int gi = 0; gi < RES_GPW; gi++) {
+            const uint32_t i = (warp * RES_GPW + gi) * 32 + lane;
             const bool live = i < n;
             const uint32_t b = live ? tile[mis + i] : (uint32_t)BIN_BYPASS;
             const bool reg = !(b & (BIN_BYPASS | BIN_TERM));
-            const uint32_t c = b & 0x3ff, k = reg ? owner[c] : 0;
+            const uint32_t c = b & 0x3ff;
             if (live && !reg)
-                mtile[mis + i] = cabac_meta((uint16_t)b, 0);
-            uint32_t m = __ballot_sync(0xffffffffu, reg);
+                tile[mis + i] = cabac_meta((uint16_t)b, 0);
+            // lanes holding the same context: nine ballots (match.any takes hundreds of cycles per call here)
+            uint32_t peers = __ballot_sync(0xffffffffu, reg);
 #pragma unroll
-            for (int bit = 0; bit < 4; bit++) {
-                const uint32_t bb = __ballot_sync(0xffffffffu, (k >> bit) & 1);
-                m &= ((k >> bit) & 1) ? bb : ~bb;
+            for (int bit = 0; bit < 9; bit++) {
+                const uint32_t bb = __ballot_sync(0xffffffffu, (c >> bit) & 1);
+                peers &= ((c >> bit) & 1) ? bb : ~bb;
             }
-            const uint32_t rank = __popc(m & lt);
-            ent[gi] = 0xffffffffu;
-            if (reg) {
-                if (rank == 0)
-                    cnt[k][G] = (uint16_t)__popc(m);
-                ent[gi] = c | (((b >> 15) & 1) << 9) | (i << 10) | (rank << 22) | (k << 27);
+            if (!reg)
+                peers = 1u << lane;
+            uint32_t cbase = 0;
+            const uint32_t slot = (c & 15) * 29 + (c >> 4);
+            if (reg && !(peers & lt)) { // lowest lane holding context c: this step's only writer of wcnt[warp][slot]
+                cbase = wcnt[warp][slot];
+                wcnt[warp][slot] = (uint16_t)(cbase + __popc(peers));
             }
+            cbase = __shfl_sync(0xffffffffu, cbase, __ffs(peers) - 1);
+            ent[gi] = reg ? (slot | (((b >> 15) & 1) << 9) | ((cbase + __popc(peers & lt)) << 10)) : 0xffffffffu;
+            __syncwarp();
         }
         __syncthreads();
-        { // exclusive prefix of cnt[warp][*] over the groups (4 per lane), class totals
-            uint32_t v[RES_GROUPS / 32], sum = 0;
+        RES_PROF_MARK(1);
+        // ---- B. offsets: over the warps per context, over the contexts (segments padded to multiples of four) ----
+        uint32_t total = 0;
+        if (lane < 29) {
 #pragma unroll
-            for (int k = 0; k < RES_GROUPS / 32; k++) {
-                v[k] = sum;
-                sum += cnt[warp][lane * (RES_GROUPS / 32) + k];
-            }
-            uint32_t incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o)
-                    incl += y;
-            }
-#pragma unroll
-            for (int k = 0; k < RES_GROUPS / 32; k++)
-                cnt[warp][lane * (RES_GROUPS / 32) + k] = (uint16_t)(incl - sum + v[k]);
-            if (lane == 31)
-                coff[warp + 1] = incl; // class total for now
-        }
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t run = 0;
-            coff[0] = 0;
-            for (int k = 1; k <= RES_WARPS; k++) {
-                run += coff[k];
-                coff[k] = run;
+            for (int w = 0; w < RES_WARPS; w++) {
+                const uint32_t v = wcnt[w][myslot];
+                wcnt[w][myslot] = (uint16_t)total;
+                total += v;
             }
         }
-        __syncthreads();
+        const uint32_t padded = (total + 3) & ~3u;
+        uint32_t incl = padded;
 #pragma unroll
-        for (int gi = 0; gi < RES_GROUPS / RES_WARPS; gi++) {
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += y;
+        }
+        if (lane == 31)
+            wsum[warp] = (uint16_t)incl;
+        __syncthreads();
+        uint32_t qs = incl - padded; // start of this thread's context's segment, a multiple of four
+        for (int w = 0; w < warp; w++)
+            qs += wsum[w];
+        if (lane < 29)
+            cstart[myslot] = (uint16_t)qs;
+        __syncthreads();
+        RES_PROF_MARK(2);
+        // ---- C. the bin values in sorted order; ent[] becomes the bin's position there ----
+#pragma unroll
+        for (int gi = 0; gi < RES_GPW; gi++) {
             const uint32_t e = ent[gi];
             if (e != 0xffffffffu) {
-                const uint32_t k = e >> 27, G = warp * (RES_GROUPS / RES_WARPS) + gi;
-                queue[coff[k] + cnt[k][G] + ((e >> 22) & 31)] = e & 0x3fffffu;
+                const uint32_t c = e & 0x1ff, pos = cstart[c] + wcnt[warp][c] + (e >> 10);
+                if (e & 0x200)
+                    atomicOr(&bitq[pos >> 5], 1u << (pos & 31));
+                ent[gi] = pos;
             }
         }
         __syncthreads();
-        // ---- 3. every warp advances the states of its own contexts over its queue ----
-        const uint32_t q0 = coff[warp], q1 = coff[warp + 1];
-        for (uint32_t k0 = q0; k0 < q1; k0 += 32) {
-            const bool live = k0 + lane < q1;
-            const uint32_t e = live ? queue[k0 + lane] : 0;
-            const uint32_t c = e & 0x1ff;
-            const uint32_t bitsmask = __ballot_sync(0xffffffffu, (e >> 9) & 1);
-            if (live)
-                atomicOr(&cmask[c], 1u << lane);
-            __syncwarp();
-            const uint32_t msk = live ? cmask[c] : 0;
-            __syncwarp();
-            if (live && (__ffs(msk) - 1) == lane) { // leader of context c in this batch
-                cmask[c] = 0;
-                uint32_t st = ctx_state[c];
-                for (uint32_t m2 = msk; m2; m2 &= m2 - 1) {
-                    const int j = __ffs(m2) - 1;
-                    const uint32_t tr = trans[st];
-                    pre_s[warp][j] = (uint8_t)st;
-                    st = (((bitsmask >> j) & 1) != (st & 1)) ? (tr >> 8) : (tr & 0xff);
-                }
-                ctx_state[c] = (uint8_t)st;
+        RES_PROF_MARK(3);
+        // ---- D. the owner walks its segment, four bins per look-up ----
+        {
+#ifdef RES_PROFILE
+            const long long d0 = clock64();
+#endif
+            // The four values of a group are one nibble of the bit array; the nibble of the next group is fetched while
+            // this group's look-up is in flight, so the chain per group is OR, shift, LDS.128 (the bit array is padded:
+            // reading one group past a segment's end is harmless).
+            uint32_t k = qs;
+            const uint32_t ke = qs + total;
+            uint32_t nib = lds_u8(bitq_addr + (k >> 3)) >> (k & 4);
+            while (k + 4 <= ke) {
+                const uint32_t kn = k + 4;
+                const uint32_t nn = lds_u8(bitq_addr + (kn >> 3)) >> (kn & 4);
+                const uint4 t = lds_u128(tab_addr + ((X | (nib & 15)) << 4));
+                sts_u64(recq_addr + 2 * k, t.x, t.y);
+                X = t.z;
+                nib = nn;
+                k = kn;
             }
-            __syncwarp();
-            if (live) {
-                const uint32_t st = pre_s[warp][lane];
-                mtile[mis + (e >> 10)] = (uint16_t)((((e >> 9) & 1) ^ (st & 1)) | ((st >> 1) << 3));
+            if (k < ke) { // one to three bins left (padding values are 0): the state after `left` bins is the state the
+                const uint32_t left = ke - k; // next, padding, bin would be coded in, i.e. its record
+                const uint4 t = lds_u128(tab_addr + ((X | (nib & 15)) << 4));
+                sts_u64(recq_addr + 2 * k, t.x, t.y);
+                const uint32_t sr = (left == 1 ? t.x >> 16 : (left == 2 ? t.y : t.y >> 16)) & 0xffff;
+                X = ((sr >> 3) << 5) | ((sr & 1) << 4);
             }
-            __syncwarp();
+#ifdef RES_PROFILE
+            atomicMax(&prof_dmax, ((unsigned long long)(clock64() - d0) << 20) | (total << 8) | (unsigned)warp);
+#endif
         }
+        __syncthreads();
+        RES_PROF_MARK(4);
+        // ---- E. every regular bin fetches its record ----
+#pragma unroll
+        for (int gi = 0; gi < RES_GPW; gi++)
+            if (ent[gi] != 0xffffffffu)
+                tile[mis + (warp * RES_GPW + gi) * 32 + lane] = recq[ent[gi]];
         __syncthreads();
         // records back in place of the bins; the partial vectors at both ends are written element-wise
         uint16_t *dst = gb + base - mis;
-        for (uint32_t v = tid; v < nv; v += RES_WARPS * 32) {
+        for (uint32_t v = tid; v < nv; v += RES_THREADS) {
             const uint32_t e0 = v * 8;
             if (e0 >= mis && e0 + 8 <= mis + n)
-                ((uint4 *)dst)[v] = ((const uint4 *)mtile)[v];
+                ((uint4 *)dst)[v] = ((const uint4 *)tile)[v];
             else
                 for (uint32_t e = e0 > mis ? e0 : mis; e < e0 + 8 && e < mis + n; e++)
-                    dst[e] = mtile[e];
+                    dst[e] = tile[e];
         }
+        RES_PROF_MARK(5);
     }
+#ifdef RES_PROFILE
+    if (tid == 0 && blockIdx.x == 0)
+        printf("resolve profile (CTA 0, %u bins, %llu tiles): load %llu  A %llu  B %llu  C %llu  D %llu  E+store %llu cycles per tile; "
+               "slowest chain avg %llu bins\n", nb, prof_cnt, prof_acc[0] / prof_cnt, prof_acc[1] / prof_cnt, prof_acc[2] / prof_cnt,
+               prof_acc[3] / prof_cnt, prof_acc[4] / prof_cnt, prof_acc[5] / prof_cnt, prof_dsum / prof_cnt);
+#endif
+#undef RES_PROF_MARK
 }
 
 // cabac_code_kernel: the arithmetic coder proper, all bins of the slice in parallel (entropy.cuh, "parallel
