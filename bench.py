@@ -299,6 +299,9 @@ def run_gpu(args, rank, local_rank, world):
     total_frames = nframes * world
     my_frames = partition.frames_for_rank(total_frames, gop, rank, world)
     n = len(my_frames)
+    # Where this rank's share starts in the stream: only the rank that owns stream frame 0 emits SPS + PPS
+    # (kernel/cedar.c:1058-1061), so that the rank streams concatenate GOP by GOP into the single stream.
+    ffi = my_frames[0] if my_frames else 0
 
     cfg = api.make_config(w, h, qp=qp, gop=gop, cabac=cabac, fmt=fmt, me_range=me, device=local_rank,
                           max_clip_frames=n, gops_in_flight=args.lanes, slice_rows=args.slice_rows)
@@ -381,16 +384,16 @@ def run_gpu(args, rank, local_rank, world):
     # -------- device-resident throughput (`value`) --------
     for e in encs:
         e.clip_upload(n)
-    run_steps(encs, max(args.warmup, 0) * len(encs), lambda e: e.clip_encode(n, 0))
+    run_steps(encs, max(args.warmup, 0) * len(encs), lambda e: e.clip_encode(n, ffi))
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = sum(e.launch_count() for e in encs)
-    ms_dev = timed(encs, streams, args.steps, lambda e: e.clip_encode(n, 0))
+    ms_dev = timed(encs, streams, args.steps, lambda e: e.clip_encode(n, ffi))
     clocks = sampler.stop()
     launches = sum(e.launch_count() for e in encs) - launches0
     # the same steps through one handle alone (one clip in flight): the latency-bound figure
-    ms_single = timed(encs[:1], streams[:1], args.steps, lambda e: e.clip_encode(n, 0)) if len(encs) > 1 else ms_dev
+    ms_single = timed(encs[:1], streams[:1], args.steps, lambda e: e.clip_encode(n, ffi)) if len(encs) > 1 else ms_dev
     data, sizes = enc.clip_download(n)
     data = data.copy()  # the view is only valid until the next clip call on this handle
     stream_bytes = int(len(data))
@@ -401,7 +404,7 @@ def run_gpu(args, rank, local_rank, world):
     sse = enc.sse_y(n)
     # CABAC bins of the clip (debug read 6: one count per slice NAL), for the per-bin cost of the two coder kernels
     import numpy as np
-    nbins = 0
+    nbins, nsl = 0, 1
     if cabac:
         mbh_ = (h + 15) // 16
         nsl = 1 if not args.slice_rows or args.slice_rows >= mbh_ else -(-mbh_ // args.slice_rows)
@@ -412,7 +415,7 @@ def run_gpu(args, rank, local_rank, world):
     # -------- end to end through the C ABI with host buffers (`e2e`) --------
     def e2e_step(e):
         e.clip_upload(n)
-        e.clip_encode(n, 0)
+        e.clip_encode(n, ffi)
         e.clip_download(n)
     run_steps(encs, min(args.warmup, 1) * len(encs), e2e_step)
     ms_e2e = timed(encs, streams, args.steps, e2e_step)
@@ -422,13 +425,57 @@ def run_gpu(args, rank, local_rank, world):
     # standalone: the same clip with every kernel issued on one stream (what ncu would see).
     enc.profile_enable(1)
     enc.profile_read(reset=True)
-    enc.clip_encode(n, 0)
+    enc.clip_encode(n, ffi)
     prof_live = enc.profile_read(reset=True)
     enc.profile_enable(2)
-    enc.clip_encode(n, 0)
+    enc.clip_encode(n, ffi)
     prof = enc.profile_read(reset=True)
+    # measurement builds of the kernels (same bytes, work counters): executed VABSDIFF4 lane-instructions of the pruned
+    # search and the CABAC bins per context (for the serial-chain bound of cabac_resolve_kernel)
+    enc.profile_enable(3)
+    enc.profile_read(reset=True)
+    enc.clip_encode(n, ffi)
+    counters = np.zeros(520, np.uint64)
+    enc.L.cedar_b200_debug_read(enc.h, 8, counters.ctypes.data, counters.nbytes)
+    enc.profile_read(reset=True)
     enc.profile_enable(0)
     torch.cuda.synchronize()
+    me_executed = int(counters[0])
+    ctx_bins = counters[8:8 + 460].astype(np.int64)
+    extra_meas = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        # (a) the same clip with the pruning of the motion search switched off (content that defeats it pays this)
+        os.environ["CEDAR_B200_NO_PRUNE"] = "1"
+        e_np = cx.Encoder(cfg)
+        del os.environ["CEDAR_B200_NO_PRUNE"]
+        torch.from_numpy(e_np.clip_input(n)).copy_(staging[:n])
+        e_np.clip_upload(n)
+        e_np.profile_enable(3)
+        e_np.clip_encode(n, ffi)
+        e_np.profile_read(reset=True)
+        e_np.clip_encode(n, ffi)
+        cnt_np = np.zeros(520, np.uint64)
+        e_np.L.cedar_b200_debug_read(e_np.h, 8, cnt_np.ctypes.data, cnt_np.nbytes)
+        p_np = e_np.profile_read(reset=True)
+        d_np, _ = e_np.clip_download(n)
+        extra_meas["no_prune"] = {"me_kernel_ms": p_np.get("me_kernel", (0.0, 0))[0], "executed": int(cnt_np[0]),
+                                  "same_bytes": hashlib.sha256(d_np.tobytes()).hexdigest() == stream_sha}
+        e_np.close()
+        # (b) the dependent chain of ONE macroblock through deblock_kernel: a picture one macroblock row high has no
+        # vertical dependencies, so its launch time / macroblocks = what one warp needs per macroblock with nothing to wait for
+        e_row = cx.Encoder(api.make_config(w, 16, qp=qp, gop=2, cabac=cabac, fmt=fmt, me_range=me, device=local_rank,
+                                           max_clip_frames=2, gops_in_flight=1))
+        torch.from_numpy(e_row.clip_input(2)).copy_(synth.synth_clip(w, 16, [0, 1], fmt, device="cuda").cpu())
+        e_row.clip_upload(2)
+        e_row.clip_encode(2, 0)
+        e_row.profile_enable(2)
+        e_row.profile_read(reset=True)
+        for _ in range(5):
+            e_row.clip_encode(2, 0)
+        p_row = e_row.profile_read(reset=True)
+        e_row.close()
+        if "deblock_kernel" in p_row:
+            extra_meas["deblock_row_ms_per_launch"] = p_row["deblock_kernel"][0] / p_row["deblock_kernel"][1]
 
     value = total_frames * args.steps / (ms_dev * 1e-3)
     e2e = total_frames * args.steps / (ms_e2e * 1e-3)
@@ -569,25 +616,77 @@ def run_gpu(args, rank, local_rank, world):
             if name not in kernels:
                 kernels[name] = {"ms_total": None, "launches": cnt, "share": None, "ms_total_live": round(ms, 4)}
         dominant = max(prof.items(), key=lambda kv: kv[1][0])[0] if prof else None
-        roofline = None
+        clk_hz = (clocks.get("sm_mhz") or 1965) * 1e6
+        my_gops_n = len(partition.gops_for_rank(total_frames, gop, rank, world))
+        p_frames = n - my_gops_n
+        lanes_ = int(enc.cfg.gops_in_flight) or min(16, -(-n // gop))
+        rooflines = {}
         if "me_kernel" in prof:
             ms, cnt = prof["me_kernel"]
-            p_frames = n - len(partition.gops_for_rank(total_frames, gop, rank, world))
             instr = p_frames * nmb * (2 * me + 1) ** 2 * 64.0  # algorithmic VABSDIFF4 lane-instructions
             ach = instr / (ms * 1e-3)
-            roofline = {"kernel": "me_kernel", "bound": "int-simd (VABSDIFF4 issue rate; neither hbm nor tensor)",
-                        "achieved": ach / 1e12, "peak": simd_peak / 1e12, "unit": "T VABSDIFF4 lane-instr/s",
-                        "frac": ach / simd_peak,
-                        "traffic": {"dram_bytes_per_launch": 43.36e6, "algorithmic_bytes_per_launch": 2.0 * W16 * H16 * 10,
-                                    "source": "ncu --set full, profiles/r01_ncu_full_summary.json (1080p, 10 GOPs in flight)"}
-                        if args.workload == DEFAULT_WORKLOAD and world == 1 else None,
-                        "peak_source": "measured on this pool with tools/vabsdiff_bench.cu (63.8 /SM/clk)",
-                        "algorithmic_per_launch": instr / cnt, "avg_launch_ms": ms / cnt,
-                        "frac_live": instr / (prof_live["me_kernel"][0] * 1e-3) / simd_peak if "me_kernel" in prof_live else None,
-                        "timing": "CUDA events per launch; frac = standalone (single stream), frac_live = inside the overlapped step",
-                        "note": "achieved counts the ALGORITHMIC instructions of the exhaustive search; the exact partial-cost pruning "
-                                "executes fewer (ncu: ALU pipe 80 % busy), so frac is an effective fraction",
-                        "dominant_by_time": dominant}
+            npn = extra_meas.get("no_prune")
+            rooflines["me_kernel"] = {
+                "kernel": "me_kernel", "bound": "int-simd (VABSDIFF4 issue rate; neither hbm nor tensor)",
+                "achieved": ach / 1e12, "peak": simd_peak / 1e12, "unit": "T VABSDIFF4 lane-instr/s", "frac": ach / simd_peak,
+                "frac_algorithmic": ach / simd_peak,
+                "frac_executed": (me_executed / (ms * 1e-3)) / simd_peak if me_executed else None,
+                "executed_over_algorithmic": me_executed / instr if me_executed else None,
+                "no_prune": None if not npn else {"ms_per_clip": round(npn["me_kernel_ms"], 3), "frac": (npn["executed"] / (npn["me_kernel_ms"] * 1e-3)) / simd_peak
+                                                  if npn["me_kernel_ms"] else None, "executed_over_algorithmic": npn["executed"] / instr,
+                                                  "same_bytes": npn["same_bytes"],
+                                                  "note": "measurement build (counter + 71 registers): an upper bound of the product kernel's time without pruning"},
+                "traffic": None,
+                "peak_source": "measured on this pool with tools/vabsdiff_bench.cu (63.8 /SM/clk), profiles/vabsdiff4_peak.json",
+                "algorithmic_per_launch": instr / cnt, "avg_launch_ms": ms / cnt,
+                "frac_live": instr / (prof_live["me_kernel"][0] * 1e-3) / simd_peak if "me_kernel" in prof_live else None,
+                "timing": "CUDA events per launch; frac = standalone (single stream), frac_live = inside the overlapped step",
+                "note": "frac / frac_algorithmic count the instructions of the exhaustive search; frac_executed counts what the "
+                        "exactly pruned search really issued (counter in the measurement build of the same kernel)"}
+        if "deblock_kernel" in prof:
+            ms, cnt = prof["deblock_kernel"]
+            mbw_, mbh_ = W16 // 16, H16 // 16
+            steps = mbw_ + 2 * (mbh_ - 1)  # 2:1 wavefront: macroblock (x, y) after (x - 1, y) and (x + 1, y - 1)
+            row = extra_meas.get("deblock_row_ms_per_launch")
+            per_mb = row / mbw_ if row else None
+            floor_ms = per_mb * steps if per_mb else None
+            rooflines["deblock_kernel"] = {
+                "kernel": "deblock_kernel", "bound": "dependency latency (raster-order wavefront)", "unit": "ms per launch",
+                "achieved": ms / cnt, "peak": floor_ms, "floor": floor_ms, "frac": floor_ms / (ms / cnt) if floor_ms else None,
+                "traffic": None,
+                "wavefront_steps": steps, "chain_us_per_macroblock": per_mb * 1e3 if per_mb else None,
+                "cycles_per_step": (ms / cnt) * 1e-3 * clk_hz / steps,
+                "floor_source": "launch time of the same kernel on a picture one macroblock row high (no vertical dependency) / "
+                                "macroblocks, x wavefront steps",
+                "hbm_frac": (2 * W16 * H16 * 1.5 * n / (ms * 1e-3) / 1e9) / hbm_peak}
+        if "cabac_resolve_kernel" in prof and ctx_bins.sum() > 0:
+            ms, cnt = prof["cabac_resolve_kernel"]
+            hot = int(ctx_bins.max())
+            chain = 39.0  # cycles per look-up of four bins: LDS 29 (B300_MICROARCH.md) + two dependent ALU operations
+            floor_ms = (hot / float(lanes_ * nsl)) / 4.0 * chain / clk_hz * 1e3  # the lanes' slices are coded side by side
+            rooflines["cabac_resolve_kernel"] = {
+                "kernel": "cabac_resolve_kernel", "bound": "serial chain along the hottest context", "unit": "ms per clip (sum of launches)",
+                "achieved": ms, "peak": floor_ms, "floor": floor_ms, "frac": floor_ms / ms, "traffic": None,
+                "hottest_context": int(ctx_bins.argmax()), "hottest_context_share": hot / float(ctx_bins.sum()),
+                "chain_cycles_per_4_bins": chain,
+                "floor_source": "bins of the hottest context per slice (counted by the measurement build) / 4 bins per look-up "
+                                "x dependent look-up latency; the sort passes around the chain are the rest",
+                "note": "summed over launches that run on side streams, 10 CTAs each: it is not on the reconstruction chain and "
+                        "may exceed ms_per_step"}
+        if "cabac_code_kernel" in prof and nbins:
+            ms, cnt = prof["cabac_code_kernel"]
+            rooflines["cabac_code_kernel"] = {
+                "kernel": "cabac_code_kernel", "bound": "instruction issue of one SM (one CTA per slice, all bins in parallel)",
+                "unit": "cycles per bin", "achieved": ms * 1e-3 * clk_hz / (nbins / float(lanes_ * nsl)), "peak": None, "floor": None, "frac": None,
+                "traffic": None,
+                "note": "ncu (profiles/): issue slots of its SM; a second CTA per slice would need a split of the range scan"}
+        for k, v in rooflines.items():
+            v["share_of_summed_kernel_time"] = kernels[k]["share"]
+        # the line's `roofline` is the kernel with the largest summed standalone time; `rooflines` has all four
+        roofline = dict(rooflines[max(rooflines, key=lambda k: kernels[k]["ms_total"])]) if rooflines else None
+        if roofline:
+            roofline["dominant_by_time"] = dominant
+            roofline["on_critical_chain"] = roofline["kernel"] in ("me_kernel", "deblock_kernel")
         hbm = {}
         frame_bytes = W16 * H16 * 3 // 2
         alg = {"inter_kernel": 3 * frame_bytes, "deblock_kernel": 2 * frame_bytes, "ingest_kernel": 2 * frame_bytes,
@@ -631,6 +730,7 @@ def run_gpu(args, rank, local_rank, world):
                                    "note": "the same steps through a single handle; `kernels`, `roofline` and `slice_parallel` "
                                            "are measured this way"},
             "roofline": roofline,
+            "rooflines": rooflines,
             "roofline_hbm_kernels": hbm,
             "kernels": kernels,
             "slice_parallel": slice_report,

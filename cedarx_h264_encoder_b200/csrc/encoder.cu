@@ -112,6 +112,8 @@ struct cedar_b200_handle {
     int16_t *d_coef[2];
     int *d_flags; // [3][L][mbh]
     uint32_t *d_me_tabs; // me_kernel's cost / task tables (me_build_tables)
+    unsigned long long *d_counters; // measurement (profiling on): [0] executed VABSDIFF4 lane-instructions, [8 + c] bins of context c
+    bool no_prune;                  // measurement (CEDAR_B200_NO_PRUNE at open): the search accumulates every candidate to the end
     uint8_t *d_bs; // [L][nmb][32] boundary strengths
     unsigned long long *d_sse;
     EntropyBufs eb;
@@ -141,6 +143,7 @@ struct cedar_b200_handle {
     long long launches;
     bool prof;
     bool serialize; // profile mode 2: no stream overlap, so that per-kernel event times are standalone times
+    bool count;     // profile mode 3: mode 2 with the measurement builds of the kernels (work counters, CEDAR_B200_NO_PRUNE)
     std::vector<ProfEntry> prof_pending;
     std::vector<cudaEvent_t> ev_pool;
     float prof_ms[K_COUNT];
@@ -393,6 +396,7 @@ int alloc_buffers(cedar_b200_handle *h)
     }
     r |= dmalloc(&h->d_flags, (size_t)3 * L * g.mbh);
     r |= dmalloc(&h->d_me_tabs, me_table_words(g.R, me_strip(g.R)));
+    r |= dmalloc(&h->d_counters, 8 + 512);
     r |= dmalloc(&h->d_pwant, (size_t)g.nmb * L);
     r |= dmalloc(&h->d_pcount, (size_t)L);
     r |= dmalloc(&h->d_bs, (size_t)g.nmb * L * 32);
@@ -421,6 +425,7 @@ int alloc_buffers(cedar_b200_handle *h)
         me_build_tables(g.R, me_strip(g.R), g.lambda, tabs.data());
         CK(cudaMemcpy(h->d_me_tabs, tabs.data(), tabs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
+    CK(cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * (8 + 512)));
     CK(cudaMemset(h->d_mbi[0], 0, sizeof(MbInfo) * g.nmb * L));
     CK(cudaMemset(h->d_mbi[1], 0, sizeof(MbInfo) * g.nmb * L));
     CK(cudaMemset(h->d_rec[0], 0, g.frame_bytes * L));
@@ -430,7 +435,7 @@ int alloc_buffers(cedar_b200_handle *h)
 
 void free_buffers(cedar_b200_handle *h)
 {
-    void *dev[] = {h->d_raw, h->d_src[0], h->d_src[1], h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi[0], h->d_mbi[1],
+    void *dev[] = {h->d_counters, h->d_raw, h->d_src[0], h->d_src[1], h->d_unf, h->d_rec[0], h->d_rec[1], h->d_mbi[0], h->d_mbi[1],
                    h->d_nnz[0], h->d_nnz[1], h->d_i4[0], h->d_i4[1], h->d_coef[0], h->d_coef[1], h->d_flags, h->d_me_tabs, h->d_pwant, h->d_pcount, h->d_bs,
                    h->d_sse, h->eb.mb_size, h->eb.mb_off, h->d_hdr_bits, h->d_hdr_nbits, h->eb.rbsp_len,
                    h->eb.bins_cursor, h->eb.bins_off, h->eb.bins_len, h->eb.error,
@@ -486,15 +491,28 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         LAUNCH_ON(st, K_INTRA, intra_kernel, dim3((g.mbh + INTRA_ROWS - 1) / INTRA_ROWS, nl), INTRA_ROWS * 32, 0, g, s, src, unf,
                   mbi, nnz, coef, fl_intra, h->d_i4[p], nullptr, nullptr);
     } else {
-        const MeShape ms = me_shape(g.R);
+        MeShape ms = me_shape(g.R);
+        ms.noprune = h->no_prune;
+        ms.exec_count = h->count ? h->d_counters : nullptr;
         const dim3 me_grid((g.mbw + ms.nstrip - 1) / ms.nstrip, (g.mbh + ms.nrow - 1) / ms.nrow, nl);
         const size_t me_smem = me_smem_bytes(g.R, ms.nstrip);
         // the 1080p (R = 16) and 4K (R = 64) geometries have compiled-in row strides
-        switch (ms.RSW) {
-        case 27: LAUNCH_ON(st, K_ME, me_kernel<27>, me_grid, ME_THREADS, me_smem, g, s, ms, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
-        case 43: LAUNCH_ON(st, K_ME, me_kernel<43>, me_grid, ME_THREADS, me_smem, g, s, ms, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
-        default: LAUNCH_ON(st, K_ME, me_kernel<0>, me_grid, ME_THREADS, me_smem, g, s, ms, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs); break;
+#define ME_LAUNCH(RSW_, COUNT_)                                                                                          \
+    LAUNCH_ON(st, K_ME, (me_kernel<RSW_, COUNT_>), me_grid, ME_THREADS, me_smem, g, s, ms, src, ref, mbi, h->d_mbi[p ^ 1], h->d_me_tabs)
+        if (h->count) { // the measurement build (executed-instruction counter, CEDAR_B200_NO_PRUNE)
+            switch (ms.RSW) {
+            case 27: ME_LAUNCH(27, true); break;
+            case 43: ME_LAUNCH(43, true); break;
+            default: ME_LAUNCH(0, true); break;
+            }
+        } else {
+            switch (ms.RSW) {
+            case 27: ME_LAUNCH(27, false); break;
+            case 43: ME_LAUNCH(43, false); break;
+            default: ME_LAUNCH(0, false); break;
+            }
         }
+#undef ME_LAUNCH
         LAUNCH_ON(st, K_INTER, inter_kernel, dim3((g.nmb + 3) / 4, nl), 128, 0, g, s, src, ref, unf, mbi, nnz, coef);
         if (g.p_intra) { // decide (parallel), then re-code the chosen macroblocks as intra in wavefront order
             CK(cudaMemsetAsync(h->d_pcount, 0, sizeof(int) * h->L, st));
@@ -528,7 +546,8 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         // the bins of these frames are final: code them on a side stream while the next frames are reconstructed
         cudaStream_t side = no_overlap ? st : h->stream_cabac[h->side_next];
         CK(cudaStreamWaitEvent(side, h->ev_post[p], 0));
-        LAUNCH_ON(side, K_CRESOLVE, cabac_resolve_kernel, nl * g.nslices, RES_THREADS, RES_SMEM_BYTES, g, s, h->K, gop_pos0, h->eb);
+        LAUNCH_ON(side, K_CRESOLVE, cabac_resolve_kernel, nl * g.nslices, RES_THREADS, RES_SMEM_BYTES, g, s, h->K, gop_pos0, h->eb,
+                  h->count ? h->d_counters + 8 : nullptr);
         EntropyBufs ebc = h->eb; // the limb scratch of this side stream (its launches are serialised)
         ebc.limbs += (size_t)(no_overlap || !h->clip_mode ? 0 : h->side_next) * h->L * g.nslices * h->eb.limb_cap;
         LAUNCH_ON(side, K_CCODE, cabac_code_kernel, nl * g.nslices, CP_THREADS, CP_SMEM_BYTES, g, s, ebc);
@@ -650,6 +669,8 @@ int cedar_b200_slice_header_mb(int frame_i, int frame_p_count, int cabac, int fi
 // (members are zero until they are created: the handle is value-initialised).
 static void destroy_handle(cedar_b200_handle *h)
 {
+    const auto t0 = std::chrono::steady_clock::now();
+    const bool trace = getenv("CEDAR_B200_TRACE") != nullptr && !h->pipe;
     if (h->pipe)
         cedar_b200_pipe_close(h->pipe);
     for (cudaEvent_t e : h->ev_pool)
@@ -674,6 +695,9 @@ static void destroy_handle(cedar_b200_handle *h)
         if (st)
             cudaStreamDestroy(st);
     delete h;
+    if (trace)
+        fprintf(stderr, "[trace] close: buffers, streams and events released in %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 }
 
 // Queued mode (cfg.queue_gops): the handle is a front over a pipeline of worker handles (pipeline.cpp).
@@ -757,6 +781,7 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     h->raw_frame_bytes = (size_t)g.src_w * g.src_h * (g.src_format == CEDAR_B200_FORMAT_NV16 ? 2 : 3) /
                          (g.src_format == CEDAR_B200_FORMAT_NV16 ? 1 : 2);
     h->grow = 1;
+    h->no_prune = getenv("CEDAR_B200_NO_PRUNE") != nullptr;
     if (cfg->queue_gops > 0) {
         r = open_queued(cfg, io, h);
         if (r) {
@@ -805,7 +830,10 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     const int me_smem = (int)me_smem_bytes(g.R, me_strip(g.R));
     if (cudaFuncSetAttribute(me_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess ||
         cudaFuncSetAttribute(me_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess ||
-        cudaFuncSetAttribute(me_kernel<43>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess) {
+        cudaFuncSetAttribute(me_kernel<43>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(me_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(me_kernel<27, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(me_kernel<43, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, me_smem) != cudaSuccess) {
         fprintf(stderr, "cedar_b200: search range %d needs more shared memory than the device offers\n", g.R);
         cudaGetLastError();
         destroy_handle(h);
@@ -1116,7 +1144,8 @@ int cedar_b200_profile_enable(cedar_b200_handle *h, int enable)
     if (!enable && h->prof)
         prof_collect(h);
     h->prof = enable != 0;
-    h->serialize = enable == 2;
+    h->serialize = enable >= 2;
+    h->count = enable == 3;
     return 0;
 }
 
@@ -1141,6 +1170,7 @@ int cedar_b200_profile_read(cedar_b200_handle *h, const char **names, float *ms,
     if (reset) {
         memset(h->prof_ms, 0, sizeof(h->prof_ms));
         memset(h->prof_n, 0, sizeof(h->prof_n));
+        cudaMemset(h->d_counters, 0, sizeof(unsigned long long) * (8 + 512));
     }
     return n;
 }
@@ -1166,6 +1196,7 @@ long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_
     case 5: src = h->d_coef[h->last_par], n = sizeof(int16_t) * COEF_STRIDE * g.nmb; break;
     case 7: src = h->d_i4[h->last_par], n = (size_t)16 * g.nmb; break;
     case 6: src = h->eb.bins_len, n = sizeof(uint32_t) * (h->last_nframes > 0 ? h->last_nframes : 1) * h->S; break;
+    case 8: src = h->d_counters, n = sizeof(unsigned long long) * (8 + 512); break;
     default: return -EINVAL;
     }
     if (n > cap)

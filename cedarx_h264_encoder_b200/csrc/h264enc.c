@@ -39,6 +39,7 @@
 
 static struct cedar_b200_io io;
 static cedar_b200_handle *enc;
+static cedar_b200_pipe *g_pipe;
 
 static int ve_config(struct cedar_b200_config *config) /* userspace/h264enc.c:47-117 */
 {
@@ -70,6 +71,13 @@ static int read_frame(int fd, void *buffer, int size)
     return total;
 }
 
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 static double sse_total, bytes_total;
 static uint32_t frame_count;
 
@@ -90,13 +98,6 @@ struct reader_ctx {
     cedar_b200_pipe *pipe;
     int fd_in;
 };
-
-static double now_s(void)
-{
-    struct timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
-}
 
 static void *reader_main(void *arg)
 {
@@ -123,7 +124,7 @@ static void *reader_main(void *arg)
 }
 
 static int run_pipeline(struct cedar_b200_config *config, const int *devices, int ndevices, int handles, int batch_gops,
-                        int fd_in, int fd_out, int stats)
+                        int fd_in, int fd_out, int stats, double *t_opened)
 {
     cedar_b200_pipe *pipe = NULL;
     struct reader_ctx rc;
@@ -135,6 +136,7 @@ static int run_pipeline(struct cedar_b200_config *config, const int *devices, in
     }
     rc.pipe = pipe;
     rc.fd_in = fd_in;
+    *t_opened = now_s();
     if (pthread_create(&reader, NULL, reader_main, &rc)) {
         cedar_b200_pipe_close(pipe);
         return -EAGAIN;
@@ -157,12 +159,14 @@ static int run_pipeline(struct cedar_b200_config *config, const int *devices, in
         }
     }
     pthread_join(reader, NULL);
-    cedar_b200_pipe_close(pipe);
+    g_pipe = pipe; /* closed by main, after the timing line */
     return 0;
 }
 
 int main(int argc, char **argv)
 {
+    const double t_start = now_s();
+    double t_open = 0, t_stream = 0;
     int width, height, fd_in, fd_out, luma_size, chroma_size, ret, stats = 0, batch_gops = 0, queue_gops = 0;
     int devices[64], ndevices = 0, handles = 0, one_device = -1;
     struct cedar_b200_config config;
@@ -270,14 +274,16 @@ int main(int argc, char **argv)
     if (batch_gops > 0) { /* GOP-parallel: reader thread, pipeline workers (per GPU, per handle), ordered writes */
         if (ndevices == 0 && one_device >= 0)
             devices[ndevices++] = one_device;
-        ret = run_pipeline(&config, ndevices ? devices : NULL, ndevices, handles, batch_gops, fd_in, fd_out, stats);
+        ret = run_pipeline(&config, ndevices ? devices : NULL, ndevices, handles, batch_gops, fd_in, fd_out, stats, &t_open);
         if (ret)
             return ret;
+        t_stream = now_s();
     } else {
         config.queue_gops = queue_gops;
         ret = ve_config(&config);
         if (ret)
             return ret;
+        t_open = now_s();
         while (1) { /* userspace/h264enc.c:181-198, unchanged in shape */
             ret = read_frame(fd_in, io.input_luma, luma_size);
             if (ret != luma_size)
@@ -307,6 +313,8 @@ int main(int argc, char **argv)
             emit_frame(fd_out, io.bytestream, ret, stats, sse);
         }
     }
+    if (!t_stream)
+        t_stream = now_s();
     /* the reference ends without a newline after the last progress line (userspace/h264enc.c:194-200) */
     fflush(stdout);
     if (stats && frame_count) {
@@ -316,5 +324,10 @@ int main(int argc, char **argv)
     }
     if (enc)
         cedar_b200_close(enc);
+    if (g_pipe)
+        cedar_b200_pipe_close(g_pipe);
+    if (stats) /* where the wall time went: CUDA start-up and buffer allocation, the stream itself, teardown */
+        fprintf(stderr, "timing: open %.3f s, stream %.3f s (%.1f frames/s), close %.3f s\n", t_open - t_start,
+                t_stream - t_open, frame_count / (t_stream - t_open > 0 ? t_stream - t_open : 1), now_s() - t_stream);
     return 0;
 }

@@ -213,6 +213,8 @@ __host__ __device__ inline size_t me_smem_bytes(int R, int nstrip)
 // prologue runs once per warp and 200 k warps per launch make every division in it count.
 struct MeShape {
     int nstrip, lstrip, nrow, RSW, CWs, WR, nd, nfull, nleft, ndyg; // lstrip = log2(nstrip)
+    int noprune;                     // measurement only (CEDAR_B200_NO_PRUNE): every candidate is accumulated to the end
+    unsigned long long *exec_count;  // measurement only (profiling on): executed VABSDIFF4 lane-instructions, else null
 };
 inline MeShape me_shape(int R)
 {
@@ -225,13 +227,17 @@ inline MeShape me_shape(int R)
     m.WR = me_window_rows(R);
     m.nd = 2 * R + 1;
     m.nfull = m.nd >> 5, m.nleft = m.nd & 31, m.ndyg = (m.nd + 3) >> 2;
+    m.noprune = 0;
+    m.exec_count = nullptr;
     return m;
 }
 
 // Grid: (strips per macroblock row, macroblock rows / me_rows, lanes).
 // kRSW: words per window row as a compile-time constant (the offsets of the unrolled search loop become immediates:
 // 14 % fewer instructions), 0 = any geometry.
-template <int kRSW>
+// kCount: the measurement build of the same kernel (profiling on): counts the executed VABSDIFF4 lane-instructions and
+// honours MeShape::noprune; the product launches kCount = false, which carries neither.
+template <int kRSW, bool kCount = false>
 __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape ms, const uint8_t *__restrict__ src,
                                                        const uint8_t *__restrict__ ref, MbInfo *__restrict__ mbi,
                                                        const MbInfo *__restrict__ mbi_prev,
@@ -401,6 +407,7 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
                 return pm;
             };
             bool dead = false;
+            int rows_done = 19;
 #pragma unroll
             for (int r = 0; r < 19; r++) {
                 // partial keys (rows 0 .. r - 1 - j of candidate j) against the best complete key.  Measured on the
@@ -408,9 +415,12 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
                 // With a wide range (R = 64, kRSW = 43) most candidates are far from the match and the early check pays;
                 // compile-time, because the extra branch point costs the R = 16 loop 20 % even when it is never taken.
                 if ((r == 5 && kRSW == 43) || r == 9 || r == 13)
-                    dead = min_key() > *(volatile uint32_t *)&mb_best[m];
-                if (dead)
+                    dead = min_key() > *(volatile uint32_t *)&mb_best[m] && !(kCount && ms.noprune);
+                if (dead) {
+                    if (kCount)
+                        rows_done = r;
                     break;
+                }
                 uint32_t w0 = wp[r * RSW], w1 = wp[r * RSW + 1], w2 = wp[r * RSW + 2], w3 = wp[r * RSW + 3];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -425,6 +435,14 @@ __global__ void __launch_bounds__(ME_THREADS) me_kernel(Geom g, Step s, MeShape 
             }
             if (!dead)
                 key = min_key();
+            if (kCount && ms.exec_count) { // window rows 0 .. rows_done - 1: row r feeds min(r + 1, 4, 19 - r) candidates, four words each
+                unsigned n4 = 0;
+                for (int r = 0; r < rows_done; r++)
+                    n4 += 4u * (unsigned)imin_(imin_(r + 1, 4), 19 - r);
+                n4 = __reduce_add_sync(__activemask(), n4);
+                if ((__activemask() & ((1u << lane) - 1)) == 0)
+                    atomicAdd(ms.exec_count, (unsigned long long)n4);
+            }
         }
         // the lanes of a full task share the macroblock; the left-over task mixes macroblocks
         if (task < ntask_full * nmb) {
@@ -1870,7 +1888,7 @@ __device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t a, uint32_t b)
 #define RES_TAB_BYTES (2048 * 16)
 #define RES_SMEM_BYTES (RES_TAB_BYTES + (RES_TILE + 8) * 2 + RES_SORTED * 2 + (RES_SORTED / 32 + 1) * 4)
 __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0,
-                                                                    EntropyBufs eb)
+                                                                    EntropyBufs eb, unsigned long long *ctx_hist)
 {
     extern __shared__ __align__(16) uint8_t res_dyn[];            // RES_SMEM_BYTES
     uint4 *const step4 = (uint4 *)res_dyn;                        // [state << 4 | four bin values]
@@ -1974,8 +1992,9 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
             uint32_t peers = __ballot_sync(0xffffffffu, reg);
 #pragma unroll
             for (int bit = 0; bit < 9; bit++) {
-                const uint32_t bb = __ballot_sync(0xffffffffu, (c >> bit) & 1);
-                peers &= ((c >> bit) & 1) ? bb : ~bb;
+                const int sh = (int)(c << (31 - bit)); // bit `bit` of c in the sign: one shift feeds the vote and the mask
+                const uint32_t bb = __ballot_sync(0xffffffffu, sh < 0);
+                peers &= ~(bb ^ (uint32_t)(sh >> 31));
             }
             if (!reg)
                 peers = 1u << lane;
@@ -2032,6 +2051,8 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
         }
         __syncthreads();
         RES_PROF_MARK(3);
+        if (ctx_hist && total) // measurement only (profiling on): bins per context, for the serial-chain bound
+            atomicAdd(&ctx_hist[myc], (unsigned long long)total);
         // ---- D. the owner walks its segment, four bins per look-up ----
         {
 #ifdef RES_PROFILE

@@ -140,7 +140,9 @@ int cedar_b200_stats(cedar_b200_handle *h, double *sse_y, int nframes);
 
 /* Per-kernel device timing of the work issued since the last call with reset != 0.
  * enable = 1: every launch is bracketed by CUDA events on the stream it is launched on (live, overlapped);
- * enable = 2: additionally all work is issued on one stream, so the event times are standalone kernel times.
+ * enable = 2: additionally all work is issued on one stream, so the event times are standalone kernel times;
+ * enable = 3: as 2, with the measurement builds of the kernels: work counters (debug_read 8) and, if CEDAR_B200_NO_PRUNE was
+ *             set at open(), a motion search without pruning.  Same bytes, slower kernels: never time the product this way.
  * names/ms/launches hold up to `cap` entries; returns the number of kernel classes. */
 int cedar_b200_profile_enable(cedar_b200_handle *h, int enable);
 int cedar_b200_profile_read(cedar_b200_handle *h, const char **names, float *ms, int *launches, int cap, int reset);
@@ -156,7 +158,8 @@ long long cedar_b200_launch_count(cedar_b200_handle *h);
  * what = 0 source planes, 1 unfiltered recon, 2 deblocked recon (Y then U then V, coded size),
  *        3 macroblock info records, 4 nnz records, 5 coefficient levels,
  *        6 CABAC bins per slice NAL of the last call (uint32 each), 7 Intra4x4 prediction modes (16 bytes per
- *        macroblock).  Returns bytes copied. */
+ *        macroblock), 8 measurement counters of the work issued while profiling was on (520 uint64: [0] executed
+ *        VABSDIFF4 lane-instructions of the motion search, [8 + c] CABAC bins of context c).  Returns bytes copied. */
 long long cedar_b200_debug_read(cedar_b200_handle *h, int what, void *dst, size_t cap);
 
 /* Header writer on its own (host C; restates kernel/cedar.c:868-1030) for byte-identity tests. */

@@ -30,16 +30,21 @@ if ngpu > 1:
 res, outs = {}, {}
 for name, extra in modes:
     out = "/tmp/out_%s.264" % name
-    best = None
+    best, timing = None, ""
     for rep in range(2):  # second run: input in the page cache, driver warm
         t = time.time()
-        subprocess.run([cli, raw, str(w), str(h), out, "--qp", "25", "--gop", str(gop)] + extra, check=True,
-                       stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        r = subprocess.run([cli, raw, str(w), str(h), out, "--qp", "25", "--gop", str(gop), "--stats"] + extra, check=True,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
         dt = time.time() - t
-        best = dt if best is None else min(best, dt)
-    res[name] = {"frames_per_s": round(n / best, 1), "wall_s": round(best, 3)}
+        if best is None or dt < best:
+            best = dt
+            timing = [ln for ln in r.stderr.splitlines() if ln.startswith("timing:")][-1]
+    # "timing: open A s, stream B s (C frames/s), close D s": the stream phase is reading, encoding and writing, overlapped
+    parts = timing.replace("(", "").split()
+    res[name] = {"frames_per_s": round(n / best, 1), "wall_s": round(best, 3), "open_s": float(parts[2]),
+                 "stream_s": float(parts[5]), "stream_frames_per_s": float(parts[7]), "close_s": float(parts[10])}
     outs[name] = open(out, "rb").read()
-    print("%-26s %8.1f frames/s (%.2f s wall)" % (name, n / best, best), file=sys.stderr)
+    print("%-26s %8.1f frames/s (%.2f s wall) | %s" % (name, n / best, best, timing), file=sys.stderr)
 same = all(v == outs["frame_at_a_time"] for v in outs.values())
 line = {"tool": "cli_throughput", "clip": "%dx%d nv12, %d frames, GOP %d, QP 25, from a file" % (w, h, n, gop), "gpus": ngpu,
         "modes": res, "outputs_identical": same, "bytes": len(outs["frame_at_a_time"])}
