@@ -710,6 +710,20 @@ def run_gpu(args, rank, local_rank, world):
             for k in ("cabac_resolve_kernel", "cabac_code_kernel"):
                 if k in prof:
                     cabac_stats[k + "_cycles_per_bin"] = round(prof[k][0] * 1e-3 * clocks["sm_mhz"] * 1e6 / per_cta_bins, 2)
+        # host-link ceiling of the end-to-end figure: pinned H2D of every rank's raw clip at once, nothing else running,
+        # measured on this pool's 8-GPU box with tools/h2d_peak.py (profiles/r02_h2d_peak.jsonl)
+        host_link = None
+        try:
+            for ln in open(os.path.join(ROOT, "profiles", "r02_h2d_peak.jsonl")):
+                rec = json.loads(ln)
+                if rec.get("n_gpus") == world:
+                    gbps = max(rec["aggregate_GBps"].values())
+                    ceil_fps = gbps * 1e9 / enc.frame_bytes
+                    host_link = {"aggregate_h2d_GBps": gbps, "frames_per_s_ceiling": round(ceil_fps, 1),
+                                 "e2e_frac_of_ceiling": round(e2e / ceil_fps, 4),
+                                 "source": "profiles/r02_h2d_peak.jsonl (tools/h2d_peak.py, %d ranks, one NUMA node, 32 host cores)" % world}
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -723,7 +737,8 @@ def run_gpu(args, rank, local_rank, world):
                        "scaling_ceiling_strong": partition.scaling_ceiling(nframes, gop, world)},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": int(n * enc.frame_bytes) * world,
-                    "d2h_bytes_per_step": (stream_bytes + 4 * n + 16) * world, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": (stream_bytes + 4 * n + 16) * world, "ms_per_step": ms_e2e / args.steps,
+                    "host_link": host_link},
             "gpu_launches": int(launches),
             "one_clip_in_flight": {"value": total_frames * args.steps / (ms_single * 1e-3), "unit": "frames/s",
                                    "ms_per_step": ms_single / args.steps,

@@ -110,21 +110,39 @@ int cedar_b200_pipe_open(const struct cedar_b200_config *cfg, const int *devices
     p->K = cfg->keyframe_interval;
     p->cap = gops_per_batch * p->K;
     p->w.resize((size_t)ndevices * handles_per_device);
-    int r = 0;
-    // worker order: device fastest, so that consecutive batches land on different GPUs
-    for (size_t i = 0; i < p->w.size() && !r; i++) {
-        Worker &w = p->w[i];
-        cedar_b200_config c = *cfg;
-        c.device = w.device = devices[i % (size_t)ndevices];
-        c.max_clip_frames = p->cap;
-        cedar_b200_io io;
-        r = cedar_b200_open(&c, &io, &w.h);
-        if (r)
-            break;
-        w.staging = (uint8_t *)cedar_b200_clip_input(w.h, &p->frame_bytes);
-        w.sizes.resize((size_t)p->cap);
-        w.sse.resize((size_t)p->cap);
+    // worker order: device fastest, so that consecutive batches land on different GPUs.  Every worker opens its own handle
+    // on its own thread: creating a CUDA context takes a second or two per device, and eight of them in a row is most of
+    // the wall time of a short clip.
+    std::vector<int> rc(p->w.size(), 0);
+    {
+        std::vector<std::thread> openers;
+        for (size_t i = 0; i < p->w.size(); i++) {
+            Worker &w = p->w[i];
+            w.device = devices[i % (size_t)ndevices];
+            openers.emplace_back([&, i] {
+                Worker &wk = p->w[i];
+                cedar_b200_config c = *cfg;
+                c.device = wk.device;
+                c.max_clip_frames = p->cap;
+                cedar_b200_io io;
+                rc[i] = cedar_b200_open(&c, &io, &wk.h);
+                if (rc[i])
+                    return;
+                size_t fb = 0;
+                wk.staging = (uint8_t *)cedar_b200_clip_input(wk.h, &fb);
+                wk.sizes.resize((size_t)p->cap);
+                wk.sse.resize((size_t)p->cap);
+            });
+        }
+        for (auto &t : openers)
+            t.join();
     }
+    int r = 0;
+    for (size_t i = 0; i < p->w.size(); i++)
+        if (rc[i] && !r)
+            r = rc[i];
+    if (!r)
+        cedar_b200_clip_input(p->w[0].h, &p->frame_bytes);
     if (r) {
         for (Worker &w : p->w)
             if (w.h)
