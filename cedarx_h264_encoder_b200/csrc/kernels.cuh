@@ -1412,62 +1412,83 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
         uint8_t *tb = (uint8_t *)me.tile;
         const uint8_t *urow = unf + fo + (size_t)(row * 16 + (lane & 15)) * g.W;
         uint4 nx_px = *(const uint4 *)urow, nx_v = fbs[0], nx_h = fbs[1];
+#ifdef DB_PROFILE
+        long long pt[6] = {0, 0, 0, 0, 0, 0}, pc = clock64();
+#define DB_MARK(i) { long long n_ = clock64(); pt[i] += n_ - pc; pc = n_; }
+#else
+#define DB_MARK(i)
+#endif
         for (int mbx = 0; mbx < g.mbw; mbx++) {
             const bool has_left = mbx > 0;
             const int x0 = mbx * 16, y0 = row * 16;
             const uint4 px = nx_px, bv = nx_v, bh = nx_h;
+            DB_MARK(0);
             if (mbx + 1 < g.mbw) { // prefetch the next macroblock
                 nx_px = *(const uint4 *)(urow + x0 + 16);
                 nx_v = fbs[(mbx + 1) * 2];
                 nx_h = fbs[(mbx + 1) * 2 + 1];
             }
             // ---- vertical edges, lane = row: the row (left MB's last 4 + own 16 pixels) stays in registers ----
+            // A macroblock without a single non-zero strength on its vertical (horizontal) edges -- most macroblocks of a
+            // P picture with coherent motion -- passes through that phase untouched: the strength words are the same in
+            // every lane, so the test is warp uniform and the exact result is unchanged.
+            const bool any_v = (bv.x | bv.y | bv.z | bv.w) != 0, any_h = (bh.x | bh.y | bh.z | bh.w) != 0;
             if (lane < 16) {
                 uint32_t *t = me.tile + lane * 6;
-                uint32_t w[5] = {has_left ? t[4] : 0u, px.x, px.y, px.z, px.w};
-                const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                if (any_v) {
+                    uint32_t w[5] = {has_left ? t[4] : 0u, px.x, px.y, px.z, px.w};
+                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    int bS = (bw[e] >> sh) & 0xff;
-                    if (bS) {
-                        int v[8];
+                    for (int e = 0; e < 4; e++) {
+                        int bS = (bw[e] >> sh) & 0xff;
+                        if (bS) {
+                            int v[8];
 #pragma unroll
-                        for (int i = 0; i < 4; i++)
-                            v[i] = (w[e] >> (8 * i)) & 0xff, v[4 + i] = (w[e + 1] >> (8 * i)) & 0xff;
-                        filter_luma8(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
-                        w[e] = pack4(v);
-                        w[e + 1] = pack4(v + 4);
+                            for (int i = 0; i < 4; i++)
+                                v[i] = (w[e] >> (8 * i)) & 0xff, v[4 + i] = (w[e + 1] >> (8 * i)) & 0xff;
+                            filter_luma8(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
+                            w[e] = pack4(v);
+                            w[e + 1] = pack4(v + 4);
+                        }
                     }
-                }
 #pragma unroll
-                for (int i = 0; i < 5; i++)
-                    t[i] = w[i];
-                // The left edge just changed columns 13..15 of the previous macroblock.  They are final for this row
-                // now: store them before the row below is told it may filter (and store) across them.
-                if (has_left) {
-                    *(uint32_t *)(rec + fo + (size_t)(y0 + lane) * g.W + x0 - 4) = w[0];
-                    if (below_local && lane >= 12)
-                        ((uint32_t *)&me.lb[(mbx - 1) % DB_NB][lane - 12])[3] = w[0];
+                    for (int i = 0; i < 5; i++)
+                        t[i] = w[i];
+                    // The left edge just changed columns 13..15 of the previous macroblock.  They are final for this row
+                    // now: store them before the row below is told it may filter (and store) across them.
+                    if (has_left) {
+                        *(uint32_t *)(rec + fo + (size_t)(y0 + lane) * g.W + x0 - 4) = w[0];
+                        if (below_local && lane >= 12)
+                            ((uint32_t *)&me.lb[(mbx - 1) % DB_NB][lane - 12])[3] = w[0];
+                    }
+                } else { // t[0] <- the left macroblock's last columns (already final and stored), t[1..4] <- this macroblock
+                    t[0] = has_left ? t[4] : 0u;
+                    t[1] = px.x, t[2] = px.y, t[3] = px.z, t[4] = px.w;
                 }
             }
+            DB_MARK(1);
             if (below_local && has_left) {
                 __threadfence_block();
                 __syncwarp();
                 if (lane == 0)
                     me.ready = mbx;
             }
-            // ---- top neighbours ----
+            // ---- top neighbours (the ring of the CTA's first row is consumed in order, so that row always waits) ----
             uint8_t *top = nullptr;
             if (top_local) {
-                spin_until_ge(&rows[j - 1].ready, mbx + 1, lane);
-                top = (uint8_t *)rows[j - 1].lb[mbx % DB_NB];
+                if (any_h) {
+                    spin_until_ge(&rows[j - 1].ready, mbx + 1, lane);
+                    top = (uint8_t *)rows[j - 1].lb[mbx % DB_NB];
+                } else
+                    __syncwarp();
             } else if (has_top) {
                 mail_wait(&mail.top_ready, mbx + 1, lane);
                 top = (uint8_t *)ring[mbx & 1];
             } else
                 __syncwarp();
+            DB_MARK(2);
             // ---- horizontal edges, lane = column: the 20-sample column stays in registers ----
-            if (lane < 16) {
+            if (lane < 16 && any_h) {
                 uint8_t *col = tb + 4 + lane;
                 int cpx[20];
 #pragma unroll
@@ -1493,8 +1514,10 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
                     col[i * 24] = (uint8_t)cpx[4 + i];
             }
             __syncwarp();
+            DB_MARK(3);
             if (below_local) // the slot is free once the row below has consumed macroblock mbx - DB_NB
                 spin_until_ge(&rows[j + 1].consumed, mbx - DB_NB + 1, lane);
+            DB_MARK(4);
             if (lane < 16) {
                 const uint32_t *t = me.tile + lane * 6;
                 uint8_t *o = rec + fo + (size_t)(y0 + lane) * g.W + x0;
@@ -1502,7 +1525,7 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
                 *(uint4 *)o = mine;
                 if (below_local && lane >= 12)
                     me.lb[mbx % DB_NB][lane - 12] = mine;
-            } else if (lane < 19 && has_top) {
+            } else if (lane < 19 && has_top && any_h) {
                 int r = lane - 15; // top rows 1..3 were modified
                 *(uint4 *)(rec + fo + (size_t)(y0 - 4 + r) * g.W + x0) = ((const uint4 *)top)[r];
             }
@@ -1517,7 +1540,14 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
                 if (publish)
                     mail.done = mbx + 1;
             }
+            DB_MARK(5);
         }
+#ifdef DB_PROFILE
+        if (lane == 0 && blockIdx.y == 0 && (row == 20 || row == 24))
+            printf("deblock luma row %d: cycles per MB: prefetch %lld  V-edges %lld  flag+wait-top %lld  H-edges %lld  wait-slot %lld  store+flags %lld\n",
+                   row, pt[0] / g.mbw, pt[1] / g.mbw, pt[2] / g.mbw, pt[3] / g.mbw, pt[4] / g.mbw, pt[5] / g.mbw);
+#endif
+#undef DB_MARK
     } else {
         const int alpha = h264_deblock_alpha[g.qpc], beta = h264_deblock_beta[g.qpc];
         const int tc0_1 = h264_deblock_tc0[g.qpc][0], tc0_2 = h264_deblock_tc0[g.qpc][1], tc0_3 = h264_deblock_tc0[g.qpc][2];
@@ -1539,24 +1569,27 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
                 nx_v = fbs[(mbx + 1) * 2];
                 nx_h = fbs[(mbx + 1) * 2 + 1];
             }
+            const bool any_v = (bv.x | bv.z) != 0, any_h = (bh.x | bh.z) != 0; // warp uniform, as in the luma path
             if (lane < 16) { // vertical edges at chroma x = 0, 4 (luma edges 0, 2): lane = (plane, row)
                 uint32_t *t = tw + r8 * 3;
                 uint32_t w[3] = {has_left ? t[2] : 0u, px.x, px.y};
-                const uint32_t bw[2] = {bv.x, bv.z};
+                if (any_v) {
+                    const uint32_t bw[2] = {bv.x, bv.z};
 #pragma unroll
-                for (int ce = 0; ce < 2; ce++) {
-                    int bS = (bw[ce] >> shc) & 0xff;
-                    if (bS) {
-                        int v[4] = {(int)((w[ce] >> 16) & 0xff), (int)(w[ce] >> 24), (int)(w[ce + 1] & 0xff),
-                                    (int)((w[ce + 1] >> 8) & 0xff)};
-                        filter_chroma4(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
-                        w[ce] = (w[ce] & 0x00ffffffu) | ((uint32_t)v[1] << 24);
-                        w[ce + 1] = (w[ce + 1] & 0xffffff00u) | (uint32_t)v[2];
+                    for (int ce = 0; ce < 2; ce++) {
+                        int bS = (bw[ce] >> shc) & 0xff;
+                        if (bS) {
+                            int v[4] = {(int)((w[ce] >> 16) & 0xff), (int)(w[ce] >> 24), (int)(w[ce + 1] & 0xff),
+                                        (int)((w[ce + 1] >> 8) & 0xff)};
+                            filter_chroma4(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
+                            w[ce] = (w[ce] & 0x00ffffffu) | ((uint32_t)v[1] << 24);
+                            w[ce + 1] = (w[ce + 1] & 0xffffff00u) | (uint32_t)v[2];
+                        }
                     }
                 }
                 t[0] = w[0], t[1] = w[1], t[2] = w[2];
                 // line buffer entry: [plane][row 6, 7] x 8 bytes; the left edge finalises columns 4..7 of the previous MB
-                if (has_left) {
+                if (has_left && any_v) {
                     *(uint32_t *)(rec + po + (size_t)(y0 + r8) * g.CW + x0 - 4) = w[0];
                     if (below_local && r8 >= 6)
                         ((uint32_t *)me.lb[(mbx - 1) % DB_NB])[(pl * 2 + (r8 - 6)) * 2 + 1] = w[0];
@@ -1570,15 +1603,18 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
             }
             uint8_t *topb = nullptr; // [plane][2 rows][8 bytes]
             if (top_local) {
-                spin_until_ge(&rows[j - 1].ready, mbx + 1, lane);
-                topb = (uint8_t *)rows[j - 1].lb[mbx % DB_NB];
+                if (any_h) {
+                    spin_until_ge(&rows[j - 1].ready, mbx + 1, lane);
+                    topb = (uint8_t *)rows[j - 1].lb[mbx % DB_NB];
+                } else
+                    __syncwarp();
             } else if (has_top) {
                 mail_wait(&mail.top_ready, mbx + 1, lane);
                 topb = (uint8_t *)ring[mbx & 1];
             } else
                 __syncwarp();
             uint8_t *top = topb + pl * 16;
-            if (lane < 16) { // horizontal edges at chroma y = 0, 4: lane = (plane, column)
+            if (lane < 16 && any_h) { // horizontal edges at chroma y = 0, 4: lane = (plane, column)
                 uint8_t *col = tb + 4 + r8;
                 int cpx[8];
                 cpx[0] = has_top ? top[r8] : 0;
@@ -1608,7 +1644,7 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
                 *(uint2 *)o = mine;
                 if (below_local && r8 >= 6)
                     ((uint2 *)me.lb[mbx % DB_NB])[pl * 2 + (r8 - 6)] = mine;
-            } else if (lane < 18 && has_top) {
+            } else if (lane < 18 && has_top && any_h) {
                 int p2 = lane - 16;
                 *(uint2 *)(rec + fo + (size_t)g.W * g.H + (size_t)p2 * g.CW * g.CH + (size_t)(y0 - 1) * g.CW + x0) =
                     ((const uint2 *)topb)[p2 * 2 + 1];

@@ -6,16 +6,18 @@
  * bench.py's cpu_baseline / --impl reference legs may build, link or call this code.
  *
  * What is pinned by the reference and what is not:
- *   - Stream framing, SPS, PPS, slice headers, GOP/frame counters follow
- *     /root/reference/kernel/cedar.c:187-223 (bit writer, Exp-Golomb), :868-890 (start code,
- *     trailing-bits quirk), :892-937 (SPS), :939-982 (PPS), :984-1030 (slice header),
- *     :1047-1066 (what is emitted when), :1193-1201 (GOP counter, reference swap), and the
- *     config rules of :744-832 / userspace/h264enc.c:50-66,178-187.  Pinned by the known-answer
- *     vectors in tests/golden/headers.json (derived from those lines; the reference has no tests).
- *   - Slice data (everything per macroblock): the reference has NO source for it -- it is
- *     Allwinner A20 silicon started by kernel/cedar.c:1176.  PARITY UNPINNED by the reference;
- *     pinned instead by (a) an independent conformant decoder (libavcodec) reproducing this
- *     model's reconstruction bit-exactly and (b) committed golden bitstream hashes.
+ *   - Stream framing, SPS, PPS, slice headers, GOP/frame counters, what is emitted when, and the configuration rules
+ *     restate /root/reference/kernel/cedar.c:187-223 (bit writer, Exp-Golomb), :868-890 (start code, trailing-bits
+ *     quirk), :892-937 (SPS), :939-982 (PPS), :984-1030 (slice header), :1047-1066 (what is emitted when), :1193-1201
+ *     (GOP counter, reference swap), :744-832 / userspace/h264enc.c:50-66,178-187 (configuration).  PINNED BY THE
+ *     REFERENCE ITSELF, EXECUTED: oracle/refsim compiles kernel/cedar.c and userspace/h264enc.c unmodified (from where
+ *     they lie) against a software model of the video engine's registers; this model's streams equal what that driver
+ *     returns frame by frame (tests/test_refsim.py), and tests/golden/headers.json + ref_streams.json are generated
+ *     from it (tools/make_ref_headers.py).
+ *   - Slice data (everything per macroblock): the reference has NO source for it -- it is Allwinner A20 silicon
+ *     started by kernel/cedar.c:1176 (in refsim this model IS the engine behind that trigger).  PARITY UNPINNED by
+ *     the reference; pinned instead by (a) an independent conformant decoder (libavcodec) reproducing this model's
+ *     reconstruction bit-exactly and (b) committed golden bitstream hashes.
  */
 #ifndef H264_GOLDEN_H
 #define H264_GOLDEN_H

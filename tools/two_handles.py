@@ -37,7 +37,7 @@ def run(encs, n, iters=4):
     return len(encs) * n * iters / dt
 
 
-for k, n, lanes in [(1, 600, 10), (2, 300, 5), (2, 600, 10), (3, 600, 10), (4, 300, 5)]:
+for k, n, lanes in [(1, 600, 10), (2, 300, 5), (3, 180, 3), (5, 120, 2), (2, 600, 10), (3, 600, 10)]:
     encs = [make(n, lanes) for _ in range(k)]
     print("handles %d x %d frames (lanes %d): %.0f frames/s" % (k, n, lanes, run(encs, n)), flush=True)
     for e in encs:
