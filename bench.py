@@ -404,13 +404,16 @@ def run_gpu(args, rank, local_rank, world):
     sse = enc.sse_y(n)
     # CABAC bins of the clip (debug read 6: one count per slice NAL), for the per-bin cost of the two coder kernels
     import numpy as np
-    nbins, nsl = 0, 1
+    nbins, nsl, bins_p_frame = 0, 1, 0.0
     if cabac:
         mbh_ = (h + 15) // 16
         nsl = 1 if not args.slice_rows or args.slice_rows >= mbh_ else -(-mbh_ // args.slice_rows)
         bins = np.zeros(n * nsl, np.uint32)
         enc.L.cedar_b200_debug_read(enc.h, 6, bins.ctypes.data, bins.nbytes)
         nbins = int(bins.sum())
+        per_frame_bins = bins.reshape(n, nsl).sum(axis=1)
+        p_mask = (np.arange(n) % gop) != 0
+        bins_p_frame = float(per_frame_bins[p_mask].mean()) if p_mask.any() else 0.0
 
     # -------- end to end through the C ABI with host buffers (`e2e`) --------
     def e2e_step(e):
@@ -636,7 +639,9 @@ def run_gpu(args, rank, local_rank, world):
                                                   if npn["me_kernel_ms"] else None, "executed_over_algorithmic": npn["executed"] / instr,
                                                   "same_bytes": npn["same_bytes"],
                                                   "note": "measurement build (counter + 71 registers): an upper bound of the product kernel's time without pruning"},
-                "traffic": None,
+                "traffic": {"dram_bytes_per_launch": 43.36e6, "algorithmic_bytes_per_launch": 2.0 * W16 * H16 * 10,
+                            "source": "ncu --set full of round 1 (profiles/r01_ncu_full_summary.json; 1080p, 10 GOPs in flight; "
+                                      "the product kernel is unchanged since)"} if args.workload == DEFAULT_WORKLOAD and world == 1 else None,
                 "peak_source": "measured on this pool with tools/vabsdiff_bench.cu (63.8 /SM/clk), profiles/vabsdiff4_peak.json",
                 "algorithmic_per_launch": instr / cnt, "avg_launch_ms": ms / cnt,
                 "frac_live": instr / (prof_live["me_kernel"][0] * 1e-3) / simd_peak if "me_kernel" in prof_live else None,
@@ -649,15 +654,18 @@ def run_gpu(args, rank, local_rank, world):
             steps = mbw_ + 2 * (mbh_ - 1)  # 2:1 wavefront: macroblock (x, y) after (x - 1, y) and (x + 1, y - 1)
             row = extra_meas.get("deblock_row_ms_per_launch")
             per_mb = row / mbw_ if row else None
-            floor_ms = per_mb * steps if per_mb else None
+            # lower bound of a wavefront step: the luma warp's instructions for one macroblock at one instruction per
+            # clock (ncu, profiles/r02_ncu_full_summary.json: 81.3 M warp instructions per launch of 81 600 macroblocks
+            # = 1 000 per macroblock for the luma and the chroma warp together, about 600 of them luma)
+            floor_ms = steps * 600.0 / clk_hz * 1e3
             rooflines["deblock_kernel"] = {
                 "kernel": "deblock_kernel", "bound": "dependency latency (raster-order wavefront)", "unit": "ms per launch",
-                "achieved": ms / cnt, "peak": floor_ms, "floor": floor_ms, "frac": floor_ms / (ms / cnt) if floor_ms else None,
-                "traffic": None,
-                "wavefront_steps": steps, "chain_us_per_macroblock": per_mb * 1e3 if per_mb else None,
-                "cycles_per_step": (ms / cnt) * 1e-3 * clk_hz / steps,
-                "floor_source": "launch time of the same kernel on a picture one macroblock row high (no vertical dependency) / "
-                                "macroblocks, x wavefront steps",
+                "achieved": ms / cnt, "peak": floor_ms, "floor": floor_ms, "frac": floor_ms / (ms / cnt), "traffic": None,
+                "wavefront_steps": steps, "cycles_per_step": (ms / cnt) * 1e-3 * clk_hz / steps,
+                "one_warp_alone_cycles_per_macroblock": per_mb * 1e-3 * clk_hz if per_mb else None,
+                "floor_source": "wavefront steps (mbw + 2 (mbh - 1)) x the luma warp's ~600 instructions per macroblock at one per "
+                                "clock; one_warp_alone = the same kernel on a picture one macroblock row high (nothing to wait "
+                                "for, nothing overlapped) / macroblocks",
                 "hbm_frac": (2 * W16 * H16 * 1.5 * n / (ms * 1e-3) / 1e9) / hbm_peak}
         if "cabac_resolve_kernel" in prof and ctx_bins.sum() > 0:
             ms, cnt = prof["cabac_resolve_kernel"]
@@ -675,11 +683,23 @@ def run_gpu(args, rank, local_rank, world):
                         "may exceed ms_per_step"}
         if "cabac_code_kernel" in prof and nbins:
             ms, cnt = prof["cabac_code_kernel"]
+            ach = ms * 1e-3 * clk_hz / (nbins / float(lanes_ * nsl))
+            ipb = None
+            try:  # warp instructions per bin from the ncu capture of an inter step (10 slices in one launch)
+                cap = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_full_summary.json")))
+                for rec in (cap if isinstance(cap, list) else cap.get("launches", [])):
+                    if "cabac_code_kernel" in rec.get("kernel", "") and bins_p_frame:
+                        ipb = float(rec["smsp__inst_executed.sum"]) / (10 * bins_p_frame)
+            except Exception:
+                pass
+            floor = ipb / 4.0 if ipb else None  # four schedulers, one warp instruction per clock each
             rooflines["cabac_code_kernel"] = {
                 "kernel": "cabac_code_kernel", "bound": "instruction issue of one SM (one CTA per slice, all bins in parallel)",
-                "unit": "cycles per bin", "achieved": ms * 1e-3 * clk_hz / (nbins / float(lanes_ * nsl)), "peak": None, "floor": None, "frac": None,
-                "traffic": None,
-                "note": "ncu (profiles/): issue slots of its SM; a second CTA per slice would need a split of the range scan"}
+                "unit": "cycles per bin", "achieved": ach, "peak": floor, "floor": floor, "frac": floor / ach if floor else None,
+                "traffic": None, "warp_instructions_per_bin": ipb,
+                "floor_source": "executed warp instructions per bin (ncu, profiles/r02_ncu_full_summary.json) / 4 issue slots per "
+                                "clock of the one SM a slice's coder runs on",
+                "note": "summed over launches on side streams (10 CTAs each): not on the reconstruction chain, may exceed ms_per_step"}
         for k, v in rooflines.items():
             v["share_of_summed_kernel_time"] = kernels[k]["share"]
         # the line's `roofline` is the kernel with the largest summed standalone time; `rooflines` has all four
