@@ -76,6 +76,7 @@ struct cedar_b200_handle {
     // syntax records are double buffered (index = step parity) so the three can overlap.
     cudaStream_t stream_pre, stream_post;
     cudaEvent_t ev_ingest[2], ev_main[2], ev_post[2], ev_begin, ev_post_done;
+    cudaEvent_t ev_syn[2], ev_ent[2]; // syntax records of step parity p final (after bs_kernel) / its entropy passes done
     bool post_valid[2]; // ev_post[p] has been recorded in this stream of work
     // clip upload: host->device copies run on their own stream in step order; step t waits for ev_upload[t] only
     cudaStream_t stream_copy;
@@ -454,7 +455,8 @@ void free_buffers(cedar_b200_handle *h)
 // One lock-step pass over s.nlanes lanes (one frame per lane).  t = position inside the GOP (0 => IDR).
 //   stream_pre : ingest(t)                                   -> src[p]                 (p = step parity)
 //   stream     : intra | ME, residual, MVP/skip; bS; deblock -> syntax[p], unf, rec[t & 1]
-//   stream_post: SSE, entropy sizes / scan / scatter          -> RBSP (CAVLC) or bins (CABAC)
+//   stream_post: entropy sizes / scan / scatter (as soon as bS / MVP are done, beside the deblocking wavefront), SSE
+//                                                            -> RBSP (CAVLC) or bins (CABAC)
 //   side stream: cabac_resolve_kernel, cabac_code_kernel
 // Buffers with index p are reused two steps later, hence the waits on ev_post[p].
 int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int step_index, bool wait_upload)
@@ -524,13 +526,14 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
     }
     // boundary strengths; on inter steps the same launch runs median MV prediction / the skip decision (K2)
     LAUNCH_ON(st, K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, mbi, nnz, bs, !frame_i);
+    CK(cudaEventRecord(h->ev_syn[p], st)); // the syntax records are final: entropy coding does not wait for deblocking
     LAUNCH_ON(st, K_DEBLOCK, deblock_kernel, dim3((g.mbh + DB_ROWS - 1) / DB_ROWS, nl, 2), (DB_ROWS + 2) * 32, 0, g, s, unf,
               rec, bs, fl_y, fl_c);
     CK(cudaEventRecord(h->ev_main[p], st));
 
-    // ---- one step behind: statistics and the parallel entropy passes ----
-    CK(cudaStreamWaitEvent(post, h->ev_main[p], 0));
-    LAUNCH_ON(post, K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, src, rec, h->d_sse);
+    // ---- beside and behind the chain: the parallel entropy passes (from the syntax records, while the wavefront of
+    // deblock_kernel runs), then the statistics of the deblocked picture ----
+    CK(cudaStreamWaitEvent(post, h->ev_syn[p], 0));
     dim3 egrid((g.nmb + g.nslices + 127) / 128, nl);
     EntropyBufs eb = h->eb;
     eb.i4 = h->d_i4[p];
@@ -540,12 +543,15 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
         LAUNCH_ON(post, K_EZERO, rbsp_zero_kernel, dim3(8, nl, g.nslices), 256, 0, s, h->eb.rbsp, h->eb.rbsp_cap,
                   h->eb.rbsp_len);
     LAUNCH_ON(post, K_EWRITE, entropy_write_kernel, egrid, 128, 0, g, s, frame_i, mbi, nnz, coef, eb);
+    CK(cudaEventRecord(h->ev_ent[p], post));
+    CK(cudaStreamWaitEvent(post, h->ev_main[p], 0));
+    LAUNCH_ON(post, K_SSE, sse_kernel, dim3(32, nl), 256, 0, g, s, src, rec, h->d_sse);
     CK(cudaEventRecord(h->ev_post[p], post));
     h->post_valid[p] = true;
     if (g.cabac) {
         // the bins of these frames are final: code them on a side stream while the next frames are reconstructed
         cudaStream_t side = no_overlap ? st : h->stream_cabac[h->side_next];
-        CK(cudaStreamWaitEvent(side, h->ev_post[p], 0));
+        CK(cudaStreamWaitEvent(side, h->ev_ent[p], 0));
         LAUNCH_ON(side, K_CRESOLVE, cabac_resolve_kernel, nl * g.nslices, RES_THREADS, RES_SMEM_BYTES, g, s, h->K, gop_pos0, h->eb,
                   h->count ? h->d_counters + 8 : nullptr);
         EntropyBufs ebc = h->eb; // the limb scratch of this side stream (its launches are serialised)
@@ -677,7 +683,8 @@ static void destroy_handle(cedar_b200_handle *h)
         cudaEventDestroy(e);
     free_buffers(h);
     cudaEvent_t evs[] = {h->ev_bins, h->ev_begin, h->ev_post_done, h->ev_encode_done, h->ev_ingest[0], h->ev_ingest[1],
-                         h->ev_main[0], h->ev_main[1], h->ev_post[0], h->ev_post[1]};
+                         h->ev_main[0], h->ev_main[1], h->ev_post[0], h->ev_post[1], h->ev_syn[0], h->ev_syn[1], h->ev_ent[0],
+                         h->ev_ent[1]};
     for (cudaEvent_t e : evs)
         if (e)
             cudaEventDestroy(e);
@@ -809,7 +816,8 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     bool ok = mkstream(&h->stream) && mkstream(&h->stream_pre) && mkstream(&h->stream_post) && mkstream(&h->stream_copy) &&
               mkevent(&h->ev_bins) && mkevent(&h->ev_begin) && mkevent(&h->ev_post_done) && mkevent(&h->ev_encode_done);
     for (int i = 0; ok && i < 2; i++)
-        ok = mkevent(&h->ev_ingest[i]) && mkevent(&h->ev_main[i]) && mkevent(&h->ev_post[i]);
+        ok = mkevent(&h->ev_ingest[i]) && mkevent(&h->ev_main[i]) && mkevent(&h->ev_post[i]) && mkevent(&h->ev_syn[i]) &&
+             mkevent(&h->ev_ent[i]);
     h->ev_upload.assign(h->clip_mode ? h->K : 0, nullptr);
     for (auto &e : h->ev_upload)
         ok = ok && mkevent(&e);
