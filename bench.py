@@ -603,9 +603,20 @@ def run_gpu(args, rank, local_rank, world):
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-        simd_peak = 18.54e12  # VABSDIFF4 lane-instr/s measured with tools/vabsdiff_bench.cu (profiles/)
+        # roofline denominator of me_kernel: the issue rate of VABSDIFF4.U8.ACC, measured LIVE on this GPU with the
+        # micro-benchmark tools/vabsdiff_bench (built by __graft_entry__.build()); else the committed measurement
+        simd_peak, simd_src = 18.54e12, "profiles/vabsdiff4_peak.json (round 1 measurement on this pool)"
         try:
             simd_peak = float(json.load(open(os.path.join(ROOT, "profiles", "vabsdiff4_peak.json")))["vabsdiff4_lane_instr_per_s"])
+        except Exception:
+            pass
+        try:
+            import subprocess
+            out = subprocess.run([os.path.join(ROOT, "tools", "vabsdiff_bench")], capture_output=True, text=True, timeout=60,
+                                 env=dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank))))
+            live = json.loads(out.stdout.strip().splitlines()[-1])
+            simd_peak = float(live["vabsdiff4_lane_instr_per_s"])
+            simd_src = "measured live on this GPU by tools/vabsdiff_bench (%.1f lane-instr/SM/clk)" % live["per_sm_per_clk_at_max_clock"]
         except Exception:
             pass
         nmb = (((w + 15) // 16) * ((h + 15) // 16))
@@ -642,7 +653,7 @@ def run_gpu(args, rank, local_rank, world):
                 "traffic": {"dram_bytes_per_launch": 43.36e6, "algorithmic_bytes_per_launch": 2.0 * W16 * H16 * 10,
                             "source": "ncu --set full of round 1 (profiles/r01_ncu_full_summary.json; 1080p, 10 GOPs in flight; "
                                       "the product kernel is unchanged since)"} if args.workload == DEFAULT_WORKLOAD and world == 1 else None,
-                "peak_source": "measured on this pool with tools/vabsdiff_bench.cu (63.8 /SM/clk), profiles/vabsdiff4_peak.json",
+                "peak_source": simd_src,
                 "algorithmic_per_launch": instr / cnt, "avg_launch_ms": ms / cnt,
                 "frac_live": instr / (prof_live["me_kernel"][0] * 1e-3) / simd_peak if "me_kernel" in prof_live else None,
                 "timing": "CUDA events per launch; frac = standalone (single stream), frac_live = inside the overlapped step",
@@ -702,10 +713,26 @@ def run_gpu(args, rank, local_rank, world):
                 "note": "summed over launches on side streams (10 CTAs each): not on the reconstruction chain, may exceed ms_per_step"}
         for k, v in rooflines.items():
             v["share_of_summed_kernel_time"] = kernels[k]["share"]
-        # the line's `roofline` is the kernel with the largest summed standalone time; `rooflines` has all four
-        roofline = dict(rooflines[max(rooflines, key=lambda k: kernels[k]["ms_total"])]) if rooflines else None
+        # Which kernel dominates?  Summed launch durations overstate the CABAC kernels: their launches are 10 CTAs on 10 of
+        # the 148 SMs, on side streams beside the chain.  The resource that binds the headline (three chains sharing the
+        # GPU) is SM time / instruction issue, so dominance is weighed by duration x SMs the launch occupies; `rooflines`
+        # carries the bound of every one of the four either way.
+        mbh__ = H16 // 16
+        sms = {"cabac_resolve_kernel": min(148, lanes_ * nsl), "cabac_code_kernel": min(148, lanes_ * nsl),
+               "deblock_kernel": min(148, -(-mbh__ // 16) * lanes_ * 2), "intra_kernel": min(148, -(-mbh__ // 8) * lanes_)}
+        sm_time = {k: v["ms_total"] * sms.get(k, 148) for k, v in kernels.items() if v["ms_total"]}
+        tot_sm = sum(sm_time.values()) or 1.0
+        for k, v in rooflines.items():
+            v["sms_occupied"] = sms.get(k, 148)
+            v["share_of_sm_time"] = round(sm_time.get(k, 0.0) / tot_sm, 4)
+        by_sm = max(rooflines, key=lambda k: sm_time.get(k, 0.0)) if rooflines else None
+        roofline = dict(rooflines[by_sm]) if by_sm else None
         if roofline:
-            roofline["dominant_by_time"] = dominant
+            roofline["dominance"] = {"by_sm_time": by_sm, "by_summed_launch_duration": dominant,
+                                     "sm_time_share": {k: round(sm_time[k] / tot_sm, 4) for k in sorted(sm_time, key=sm_time.get, reverse=True)[:5]},
+                                     "note": "duration x SMs a launch occupies; the CABAC kernels' launches are 10 CTAs on side "
+                                             "streams, off the reconstruction chain; ncu (profiles/): me_kernel executes 50 % of a "
+                                             "clip's warp instructions"}
             roofline["on_critical_chain"] = roofline["kernel"] in ("me_kernel", "deblock_kernel")
         hbm = {}
         frame_bytes = W16 * H16 * 3 // 2

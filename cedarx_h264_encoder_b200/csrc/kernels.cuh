@@ -1891,7 +1891,7 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
 //      time -- nine ballots give each lane the lanes holding the same context, the lowest of them bumps the warp's own
 //      counter of that context (no atomics: a counter row belongs to one warp, one leader per context per step);
 //   B. the owner of a context turns its column of the counters into offsets (exclusive prefix over the warps) and the
-//      block scans the per-context totals, rounded up to four, into the start of every context's segment;
+//      block scans the per-context totals, rounded up to 32, into the start of every context's segment;
 //   C. every bin's VALUE goes to its place in the sorted order (a bit array; one shared atomic OR per 1-bin);
 //   D. the owner walks its segment FOUR bins per dependent table look-up: the 128-state machine composed four times
 //      (2048 entries of 16 bytes: the four records -- cabac_meta: isLPS + pStateIdx -- and the state after them), the
@@ -1904,10 +1904,10 @@ __device__ __forceinline__ uint4 lds_u128(uint32_t addr)
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
 }
-__device__ __forceinline__ uint32_t lds_u8(uint32_t addr)
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
     uint32_t v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
 __device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t a, uint32_t b)
@@ -1920,9 +1920,9 @@ __device__ __forceinline__ void sts_u64(uint32_t addr, uint32_t a, uint32_t b)
 #define RES_GROUPS (RES_TILE / 32)
 #define RES_GPW (RES_GROUPS / RES_WARPS)   // 32-bin groups per warp and tile
 #define RES_NCTX 464                       // 460 contexts, padded
-#define RES_SORTED (RES_TILE + 3 * RES_NCTX + 16) // sorted order with every segment padded to a multiple of four
+#define RES_SORTED (RES_TILE + 31 * RES_NCTX + 32) // sorted order with every segment padded to a multiple of 32
 #define RES_TAB_BYTES (2048 * 16)
-#define RES_SMEM_BYTES (RES_TAB_BYTES + (RES_TILE + 8) * 2 + RES_SORTED * 2 + (RES_SORTED / 32 + 1) * 4)
+#define RES_SMEM_BYTES (RES_TAB_BYTES + (RES_TILE + 8) * 2 + RES_SORTED * 2 + (RES_SORTED / 32 + 2) * 4)
 __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step s, int gop_len, int gop_pos0,
                                                                     EntropyBufs eb, unsigned long long *ctx_hist)
 {
@@ -1930,7 +1930,7 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
     uint4 *const step4 = (uint4 *)res_dyn;                        // [state << 4 | four bin values]
     uint16_t *const tile = (uint16_t *)(res_dyn + RES_TAB_BYTES); // [RES_TILE + 8] bins in, records out
     uint16_t *const recq = tile + RES_TILE + 8;                   // [RES_SORTED] records in sorted order
-    uint32_t *const bitq = (uint32_t *)(recq + RES_SORTED);       // [RES_SORTED / 32 + 1] bin values in sorted order
+    uint32_t *const bitq = (uint32_t *)(recq + RES_SORTED);       // [RES_SORTED / 32 + 2] bin values in sorted order
     __shared__ uint16_t wcnt[RES_WARPS][RES_NCTX]; // [w][slot(c)]: bins of context c in warp w's chunk -> exclusive prefix over w
     __shared__ uint16_t cstart[RES_NCTX];
     __shared__ uint16_t wsum[RES_WARPS];
@@ -2009,8 +2009,8 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
         }
         for (int i = tid; i < RES_WARPS * RES_NCTX / 2; i += RES_THREADS)
             ((uint32_t *)wcnt)[i] = 0;
-        if (tid < RES_SORTED / 32 + 1)
-            bitq[tid] = 0;
+        for (int i = tid; i < RES_SORTED / 32 + 2; i += RES_THREADS)
+            bitq[i] = 0;
         __syncthreads();
         RES_PROF_MARK(0);
         // ---- A. rank inside the warp's chunk ----
@@ -2056,7 +2056,7 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
                 total += v;
             }
         }
-        const uint32_t padded = (total + 3) & ~3u;
+        const uint32_t padded = (total + 31) & ~31u; // a segment starts on a word of the bit array
         uint32_t incl = padded;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -2067,7 +2067,7 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
         if (lane == 31)
             wsum[warp] = (uint16_t)incl;
         __syncthreads();
-        uint32_t qs = incl - padded; // start of this thread's context's segment, a multiple of four
+        uint32_t qs = incl - padded; // start of this thread's context's segment, a multiple of 32
         for (int w = 0; w < warp; w++)
             qs += wsum[w];
         if (lane < 29)
@@ -2094,25 +2094,30 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
 #ifdef RES_PROFILE
             const long long d0 = clock64();
 #endif
-            // The four values of a group are one nibble of the bit array; the nibble of the next group is fetched while
-            // this group's look-up is in flight, so the chain per group is OR, shift, LDS.128 (the bit array is padded:
-            // reading one group past a segment's end is harmless).
+            // A segment starts on a word of the bit array: one word = the values of eight groups of four bins.  The chain
+            // per group is OR, shift, LDS.128; everything else (the word of the next eight groups, the nibble, the
+            // store of the four records) is off the chain, and the eight groups of a word are unrolled.
             uint32_t k = qs;
-            const uint32_t ke = qs + total;
-            uint32_t nib = lds_u8(bitq_addr + (k >> 3)) >> (k & 4);
-            while (k + 4 <= ke) {
-                const uint32_t kn = k + 4;
-                const uint32_t nn = lds_u8(bitq_addr + (kn >> 3)) >> (kn & 4);
-                const uint4 t = lds_u128(tab_addr + ((X | (nib & 15)) << 4));
-                sts_u64(recq_addr + 2 * k, t.x, t.y);
-                X = t.z;
-                nib = nn;
-                k = kn;
+            const uint32_t kfull = qs + (total & ~3u);
+            uint32_t w = lds_u32(bitq_addr + (k >> 3));
+            while (k < kfull) {
+                const uint32_t wn = lds_u32(bitq_addr + (k >> 3) + 4); // next word (the array is padded)
+                const uint32_t ng = (kfull - k) >> 2;                   // full groups left in this segment
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    if ((uint32_t)j < ng) {
+                        const uint4 t = lds_u128(tab_addr + ((X | ((w >> (4 * j)) & 15)) << 4));
+                        sts_u64(recq_addr + 2 * k + 8 * j, t.x, t.y);
+                        X = t.z;
+                    }
+                w = wn;
+                k += 32;
             }
-            if (k < ke) { // one to three bins left (padding values are 0): the state after `left` bins is the state the
-                const uint32_t left = ke - k; // next, padding, bin would be coded in, i.e. its record
-                const uint4 t = lds_u128(tab_addr + ((X | (nib & 15)) << 4));
-                sts_u64(recq_addr + 2 * k, t.x, t.y);
+            if (total & 3) { // one to three bins left (padding values are 0): the state after `left` bins is the state
+                const uint32_t left = total & 3; // the next, padding, bin would be coded in, i.e. its record
+                const uint32_t nib = (lds_u32(bitq_addr + ((kfull >> 5) << 2)) >> (kfull & 31)) & 15;
+                const uint4 t = lds_u128(tab_addr + ((X | nib) << 4));
+                sts_u64(recq_addr + 2 * kfull, t.x, t.y);
                 const uint32_t sr = (left == 1 ? t.x >> 16 : (left == 2 ? t.y : t.y >> 16)) & 0xffff;
                 X = ((sr >> 3) << 5) | ((sr & 1) << 4);
             }

@@ -33,3 +33,27 @@ def test_gpu_arm_has_no_cpu_fallback():
         pytest.skip("CUDA device present")
     r = run("--steps", "1", "--warmup", "0")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_parity_block_detects_a_single_flipped_byte():
+    """bench.py's parity block: the golden model's GOP hashes against the same frames cut out of the timed stream."""
+    import hashlib
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(1)
+    sizes = rng.integers(50, 400, 12)
+    data = rng.integers(0, 256, int(sizes.sum()), dtype=np.uint8)
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    gops = []
+    for first in (0, 4, 8, 4):  # a repeated GOP (more cores than GOPs) is checked once
+        blob = data[offs[first]:offs[first + 4]].tobytes()
+        gops.append((first, 4, len(blob), hashlib.sha256(blob).hexdigest()))
+    ok = bench.parity_block(gops, data, sizes)
+    assert ok["equal"] and ok["gops_checked"] == 3 and ok["frames_checked"] == 12
+    bad = data.copy()
+    bad[int(offs[5])] ^= 1
+    r = bench.parity_block(gops, bad, sizes)
+    assert not r["equal"] and r["mismatching_gops_first_frame"] == [4]
