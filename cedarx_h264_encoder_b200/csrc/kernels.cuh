@@ -1898,6 +1898,21 @@ __global__ void entropy_write_kernel(Geom g, Step s, int frame_i, const MbInfo *
 //      records stored in sorted order with one 8-byte store.  Chain per four bins: OR, shift, LDS.128;
 //   E. every bin fetches its record from its place in the sorted order.
 // The only serial part is D along one context; its length per tile is the hottest context's bin count / 4.
+// Bounds-check build (-DCEDAR_B200_BOUNDS; compute-sanitizer is closed on the pool): every computed shared-memory index of
+// the resolver is asserted before use; a violation prints where and traps.  tools/san_case.py and the 1080p parity tests
+// run clean under it (profiles/r02_bounds_build.txt).
+#ifdef CEDAR_B200_BOUNDS
+#define RES_ASSERT(cond, what, val)                                                                                  \
+    do {                                                                                                             \
+        if (!(cond)) {                                                                                               \
+            printf("cabac_resolve_kernel: %s out of bounds: %u (block %d thread %d)\n", what, (unsigned)(val), blockIdx.x, \
+                   threadIdx.x);                                                                                     \
+            __trap();                                                                                                \
+        }                                                                                                            \
+    } while (0)
+#else
+#define RES_ASSERT(cond, what, val)
+#endif
 __device__ __forceinline__ uint4 lds_u128(uint32_t addr)
 {
     uint4 v;
@@ -2036,6 +2051,7 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
                 peers = 1u << lane;
             uint32_t cbase = 0;
             const uint32_t slot = (c & 15) * 29 + (c >> 4);
+            RES_ASSERT(!reg || (c < 460 && slot < RES_NCTX), "context / slot", c);
             if (reg && !(peers & lt)) { // lowest lane holding context c: this step's only writer of wcnt[warp][slot]
                 cbase = wcnt[warp][slot];
                 wcnt[warp][slot] = (uint16_t)(cbase + __popc(peers));
@@ -2080,6 +2096,7 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
             const uint32_t e = ent[gi];
             if (e != 0xffffffffu) {
                 const uint32_t c = e & 0x1ff, pos = cstart[c] + wcnt[warp][c] + (e >> 10);
+                RES_ASSERT(c < RES_NCTX && pos < RES_SORTED, "sorted position", pos);
                 if (e & 0x200)
                     atomicOr(&bitq[pos >> 5], 1u << (pos & 31));
                 ent[gi] = pos;
@@ -2099,6 +2116,7 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
             // store of the four records) is off the chain, and the eight groups of a word are unrolled.
             uint32_t k = qs;
             const uint32_t kfull = qs + (total & ~3u);
+            RES_ASSERT((qs & 31) == 0 && qs + ((total + 31) & ~31u) <= RES_SORTED && (X >> 4) < 128, "segment / state", qs);
             uint32_t w = lds_u32(bitq_addr + (k >> 3));
             while (k < kfull) {
                 const uint32_t wn = lds_u32(bitq_addr + (k >> 3) + 4); // next word (the array is padded)
@@ -2106,6 +2124,7 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     if ((uint32_t)j < ng) {
+                        RES_ASSERT((X | 15) < 2048 && k + 4 * j + 3 < RES_SORTED, "table / record index", X);
                         const uint4 t = lds_u128(tab_addr + ((X | ((w >> (4 * j)) & 15)) << 4));
                         sts_u64(recq_addr + 2 * k + 8 * j, t.x, t.y);
                         X = t.z;
@@ -2130,8 +2149,10 @@ __global__ void __launch_bounds__(RES_THREADS) cabac_resolve_kernel(Geom g, Step
         // ---- E. every regular bin fetches its record ----
 #pragma unroll
         for (int gi = 0; gi < RES_GPW; gi++)
-            if (ent[gi] != 0xffffffffu)
+            if (ent[gi] != 0xffffffffu) {
+                RES_ASSERT(ent[gi] < RES_SORTED && mis + (warp * RES_GPW + gi) * 32 + lane < RES_TILE + 8, "record fetch", ent[gi]);
                 tile[mis + (warp * RES_GPW + gi) * 32 + lane] = recq[ent[gi]];
+            }
         __syncthreads();
         // records back in place of the bins; the partial vectors at both ends are written element-wise
         uint16_t *dst = gb + base - mis;
