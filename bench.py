@@ -662,7 +662,7 @@ def run_gpu(args, rank, local_rank, world):
         if "deblock_kernel" in prof:
             ms, cnt = prof["deblock_kernel"]
             mbw_, mbh_ = W16 // 16, H16 // 16
-            steps = mbw_ + 2 * (mbh_ - 1)  # 2:1 wavefront: macroblock (x, y) after (x - 1, y) and (x + 1, y - 1)
+            steps = mbw_ + mbh_ - 1  # 1:1 wavefront: macroblock (x, y) after (x - 1, y) and (x, y - 1)
             row = extra_meas.get("deblock_row_ms_per_launch")
             per_mb = row / mbw_ if row else None
             # lower bound of a wavefront step: the luma warp's instructions for one macroblock at one instruction per
@@ -674,7 +674,7 @@ def run_gpu(args, rank, local_rank, world):
                 "achieved": ms / cnt, "peak": floor_ms, "floor": floor_ms, "frac": floor_ms / (ms / cnt), "traffic": None,
                 "wavefront_steps": steps, "cycles_per_step": (ms / cnt) * 1e-3 * clk_hz / steps,
                 "one_warp_alone_cycles_per_macroblock": per_mb * 1e-3 * clk_hz if per_mb else None,
-                "floor_source": "wavefront steps (mbw + 2 (mbh - 1)) x the luma warp's ~600 instructions per macroblock at one per "
+                "floor_source": "wavefront steps (mbw + mbh - 1) x the luma warp's ~600 instructions per macroblock at one per "
                                 "clock; one_warp_alone = the same kernel on a picture one macroblock row high (nothing to wait "
                                 "for, nothing overlapped) / macroblocks",
                 "hbm_frac": (2 * W16 * H16 * 1.5 * n / (ms * 1e-3) / 1e9) / hbm_peak}

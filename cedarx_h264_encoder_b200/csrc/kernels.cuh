@@ -1213,12 +1213,13 @@ __global__ void __launch_bounds__(INTRA_ROWS * 32) intra_kernel(Geom g, Step s, 
 // bs_kernel: boundary strengths of all 32 edge segments of every macroblock, fully parallel
 // (record = [dir][edge][segment] bytes: dir 0 vertical edges, 1 horizontal).
 //
-// deblock_kernel: standard-exact macroblock raster order realised as a 2:1 wavefront: macroblock
-// (x, y) needs (x-1, y) and (x+1, y-1).  One CTA per macroblock row: warp 0 filters luma, warp 1
-// filters Cb and Cr; they have independent progress flags.  Reads the unfiltered frame `unf`, writes
-// the reference frame `rec`.  The next macroblock's pixels and strengths are prefetched into registers
-// before the current one waits on the row above.
-// Bound: dependency latency (mbw + 2 * mbh steps per frame).
+// deblock_kernel: standard-exact macroblock raster order realised as a 1:1 wavefront: an iteration filters a macroblock's
+// inner vertical edges, its horizontal edges and the LEFT edge of the next macroblock, after which the macroblock is final,
+// so (x, y) only waits for (x, y-1) (the raster order itself would need (x+1, y-1): two steps of lag per row).  Luma and
+// chroma run in separate CTAs with independent progress flags.  Reads the unfiltered frame `unf`, writes the reference
+// frame `rec`.  The next macroblock's pixels and strengths are prefetched into registers before the current one waits on
+// the row above.
+// Bound: dependency latency (mbw + mbh - 1 steps per frame).
 // ================================================================================================
 // with_mvp: the thread of edge (dir 0, e 0) also runs K2 (mvp_skip_mb) for its macroblock, which saves a launch on the
 // critical chain.  K2 only rewrites type P16x16 -> PSKIP and mvd, neither of which a boundary strength depends on.
@@ -1282,7 +1283,7 @@ template <class LoadTop>
 __device__ __forceinline__ void deblock_loader(DeblockMail *mail, const int *fl_above, int mbw, int lane, LoadTop load_top)
 {
     for (int x = 0; x < mbw; x++) {
-        const int need = imin_(x + 2, mbw);
+        const int need = x + 1; // macroblock x of the row above is final once that row has finished its iteration x
         if (lane == 0) {
             while (mail->top_consumed + 2 <= x) // both ring slots still in use
                 __nanosleep(64);
@@ -1412,34 +1413,40 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
         uint8_t *tb = (uint8_t *)me.tile;
         const uint8_t *urow = unf + fo + (size_t)(row * 16 + (lane & 15)) * g.W;
         uint4 nx_px = *(const uint4 *)urow, nx_v = fbs[0], nx_h = fbs[1];
+        uint32_t q0w = nx_px.x; // columns 0..3 of the macroblock about to be processed, its left edge already filtered
 #ifdef DB_PROFILE
         long long pt[6] = {0, 0, 0, 0, 0, 0}, pc = clock64();
 #define DB_MARK(i) { long long n_ = clock64(); pt[i] += n_ - pc; pc = n_; }
 #else
 #define DB_MARK(i)
 #endif
+        // Order inside a row (1:1 wavefront): iteration x = vertical edges 1..3 of macroblock x, its horizontal edges, then
+        // vertical edge 0 of macroblock x + 1.  Every pair of edge filters with overlapping samples keeps the order of the
+        // standard's raster scan (edge 0 of x + 1 touches columns 12..19 of rows of this macroblock row only: after the
+        // horizontal edges of x, before edges 1..3 and the horizontal edges of x + 1), and macroblock x is FINAL when its
+        // iteration ends -- the row below may start on it one iteration later, not two.
         for (int mbx = 0; mbx < g.mbw; mbx++) {
-            const bool has_left = mbx > 0;
+            const bool has_next = mbx + 1 < g.mbw;
             const int x0 = mbx * 16, y0 = row * 16;
             const uint4 px = nx_px, bv = nx_v, bh = nx_h;
             DB_MARK(0);
-            if (mbx + 1 < g.mbw) { // prefetch the next macroblock
+            if (has_next) { // prefetch the next macroblock
                 nx_px = *(const uint4 *)(urow + x0 + 16);
                 nx_v = fbs[(mbx + 1) * 2];
                 nx_h = fbs[(mbx + 1) * 2 + 1];
             }
-            // ---- vertical edges, lane = row: the row (left MB's last 4 + own 16 pixels) stays in registers ----
-            // A macroblock without a single non-zero strength on its vertical (horizontal) edges -- most macroblocks of a
-            // P picture with coherent motion -- passes through that phase untouched: the strength words are the same in
-            // every lane, so the test is warp uniform and the exact result is unchanged.
-            const bool any_v = (bv.x | bv.y | bv.z | bv.w) != 0, any_h = (bh.x | bh.y | bh.z | bh.w) != 0;
+            // A phase without a single non-zero strength -- most macroblocks of a P picture with coherent motion -- is
+            // passed through: the strength words are the same in every lane, so the tests are warp uniform.
+            const bool any_v = (bv.y | bv.z | bv.w) != 0, any_h = (bh.x | bh.y | bh.z | bh.w) != 0;
+            const bool any_vn = has_next && nx_v.x != 0;
+            // ---- vertical edges 1..3, lane = row: the row's 16 pixels stay in registers ----
             if (lane < 16) {
                 uint32_t *t = me.tile + lane * 6;
+                uint32_t w[5] = {0u, q0w, px.y, px.z, px.w};
                 if (any_v) {
-                    uint32_t w[5] = {has_left ? t[4] : 0u, px.x, px.y, px.z, px.w};
-                    const uint32_t bw[4] = {bv.x, bv.y, bv.z, bv.w};
+                    const uint32_t bw[4] = {0u, bv.y, bv.z, bv.w};
 #pragma unroll
-                    for (int e = 0; e < 4; e++) {
+                    for (int e = 1; e < 4; e++) {
                         int bS = (bw[e] >> sh) & 0xff;
                         if (bS) {
                             int v[8];
@@ -1451,28 +1458,10 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
                             w[e + 1] = pack4(v + 4);
                         }
                     }
-#pragma unroll
-                    for (int i = 0; i < 5; i++)
-                        t[i] = w[i];
-                    // The left edge just changed columns 13..15 of the previous macroblock.  They are final for this row
-                    // now: store them before the row below is told it may filter (and store) across them.
-                    if (has_left) {
-                        *(uint32_t *)(rec + fo + (size_t)(y0 + lane) * g.W + x0 - 4) = w[0];
-                        if (below_local && lane >= 12)
-                            ((uint32_t *)&me.lb[(mbx - 1) % DB_NB][lane - 12])[3] = w[0];
-                    }
-                } else { // t[0] <- the left macroblock's last columns (already final and stored), t[1..4] <- this macroblock
-                    t[0] = has_left ? t[4] : 0u;
-                    t[1] = px.x, t[2] = px.y, t[3] = px.z, t[4] = px.w;
                 }
+                t[1] = w[1], t[2] = w[2], t[3] = w[3], t[4] = w[4];
             }
             DB_MARK(1);
-            if (below_local && has_left) {
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0)
-                    me.ready = mbx;
-            }
             // ---- top neighbours (the ring of the CTA's first row is consumed in order, so that row always waits) ----
             uint8_t *top = nullptr;
             if (top_local) {
@@ -1514,9 +1503,29 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
                     col[i * 24] = (uint8_t)cpx[4 + i];
             }
             __syncwarp();
+            // ---- vertical edge 0 of the next macroblock, lane = row: finalises columns 13..15 of this one ----
+            if (lane < 16) {
+                q0w = nx_px.x;
+                if (any_vn) {
+                    int bS = (nx_v.x >> sh) & 0xff;
+                    if (bS) {
+                        uint32_t *t = me.tile + lane * 6;
+                        const uint32_t wp = t[4];
+                        int v[8];
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            v[i] = (wp >> (8 * i)) & 0xff, v[4 + i] = (q0w >> (8 * i)) & 0xff;
+                        filter_luma8(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
+                        t[4] = pack4(v);
+                        q0w = pack4(v + 4);
+                    }
+                }
+            }
             DB_MARK(3);
             if (below_local) // the slot is free once the row below has consumed macroblock mbx - DB_NB
                 spin_until_ge(&rows[j + 1].consumed, mbx - DB_NB + 1, lane);
+            else
+                __syncwarp();
             DB_MARK(4);
             if (lane < 16) {
                 const uint32_t *t = me.tile + lane * 6;
@@ -1529,12 +1538,14 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
                 int r = lane - 15; // top rows 1..3 were modified
                 *(uint4 *)(rec + fo + (size_t)(y0 - 4 + r) * g.W + x0) = ((const uint4 *)top)[r];
             }
+            // the stores to the frame precede the flag: the row below stores this macroblock's rows 13..15 again after its
+            // top edge has filtered them, and that store has to land after this one
             __threadfence_block();
             __syncwarp();
             if (lane == 0) {
                 me.consumed = mbx + 1;
-                if (below_local && mbx == g.mbw - 1)
-                    me.ready = g.mbw;
+                if (below_local)
+                    me.ready = mbx + 1; // macroblock mbx is final: nothing in this row touches it again
                 if (!top_local && has_top)
                     mail.top_consumed = mbx + 1;
                 if (publish)
@@ -1559,47 +1570,33 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
         const uint8_t *urow = unf + po + (size_t)(row * 8 + r8) * g.CW;
         uint2 nx_px = *(const uint2 *)urow;
         uint4 nx_v = fbs[0], nx_h = fbs[1];
+        uint32_t q0w = nx_px.x; // columns 0..3 of the macroblock about to be processed, its left edge already filtered
+        // same order as the luma path: vertical edge at x = 4, horizontal edges, vertical edge at x = 0 of the next macroblock
         for (int mbx = 0; mbx < g.mbw; mbx++) {
-            const bool has_left = mbx > 0;
+            const bool has_next = mbx + 1 < g.mbw;
             const int x0 = mbx * 8, y0 = row * 8;
             const uint2 px = nx_px;
             const uint4 bv = nx_v, bh = nx_h;
-            if (mbx + 1 < g.mbw) {
+            if (has_next) {
                 nx_px = *(const uint2 *)(urow + x0 + 8);
                 nx_v = fbs[(mbx + 1) * 2];
                 nx_h = fbs[(mbx + 1) * 2 + 1];
             }
-            const bool any_v = (bv.x | bv.z) != 0, any_h = (bh.x | bh.z) != 0; // warp uniform, as in the luma path
-            if (lane < 16) { // vertical edges at chroma x = 0, 4 (luma edges 0, 2): lane = (plane, row)
+            const bool any_v = bv.z != 0, any_h = (bh.x | bh.z) != 0; // warp uniform, as in the luma path
+            const bool any_vn = has_next && nx_v.x != 0;
+            if (lane < 16) { // vertical edge at chroma x = 4 (luma edge 2): lane = (plane, row)
                 uint32_t *t = tw + r8 * 3;
-                uint32_t w[3] = {has_left ? t[2] : 0u, px.x, px.y};
+                uint32_t w1 = q0w, w2 = px.y;
                 if (any_v) {
-                    const uint32_t bw[2] = {bv.x, bv.z};
-#pragma unroll
-                    for (int ce = 0; ce < 2; ce++) {
-                        int bS = (bw[ce] >> shc) & 0xff;
-                        if (bS) {
-                            int v[4] = {(int)((w[ce] >> 16) & 0xff), (int)(w[ce] >> 24), (int)(w[ce + 1] & 0xff),
-                                        (int)((w[ce + 1] >> 8) & 0xff)};
-                            filter_chroma4(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
-                            w[ce] = (w[ce] & 0x00ffffffu) | ((uint32_t)v[1] << 24);
-                            w[ce + 1] = (w[ce + 1] & 0xffffff00u) | (uint32_t)v[2];
-                        }
+                    int bS = (bv.z >> shc) & 0xff;
+                    if (bS) {
+                        int v[4] = {(int)((w1 >> 16) & 0xff), (int)(w1 >> 24), (int)(w2 & 0xff), (int)((w2 >> 8) & 0xff)};
+                        filter_chroma4(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
+                        w1 = (w1 & 0x00ffffffu) | ((uint32_t)v[1] << 24);
+                        w2 = (w2 & 0xffffff00u) | (uint32_t)v[2];
                     }
                 }
-                t[0] = w[0], t[1] = w[1], t[2] = w[2];
-                // line buffer entry: [plane][row 6, 7] x 8 bytes; the left edge finalises columns 4..7 of the previous MB
-                if (has_left && any_v) {
-                    *(uint32_t *)(rec + po + (size_t)(y0 + r8) * g.CW + x0 - 4) = w[0];
-                    if (below_local && r8 >= 6)
-                        ((uint32_t *)me.lb[(mbx - 1) % DB_NB])[(pl * 2 + (r8 - 6)) * 2 + 1] = w[0];
-                }
-            }
-            if (below_local && has_left) {
-                __threadfence_block();
-                __syncwarp();
-                if (lane == 0)
-                    me.ready = mbx;
+                t[1] = w1, t[2] = w2;
             }
             uint8_t *topb = nullptr; // [plane][2 rows][8 bytes]
             if (top_local) {
@@ -1636,8 +1633,24 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
                 col[4 * 12] = (uint8_t)cpx[6];
             }
             __syncwarp();
+            if (lane < 16) { // vertical edge at x = 0 of the next macroblock: finalises column 7 of this one
+                q0w = nx_px.x;
+                if (any_vn) {
+                    int bS = (nx_v.x >> shc) & 0xff;
+                    if (bS) {
+                        uint32_t *t = tw + r8 * 3;
+                        const uint32_t wp = t[2];
+                        int v[4] = {(int)((wp >> 16) & 0xff), (int)(wp >> 24), (int)(q0w & 0xff), (int)((q0w >> 8) & 0xff)};
+                        filter_chroma4(v, bS, alpha, beta, bS == 1 ? tc0_1 : (bS == 2 ? tc0_2 : tc0_3));
+                        t[2] = (wp & 0x00ffffffu) | ((uint32_t)v[1] << 24);
+                        q0w = (q0w & 0xffffff00u) | (uint32_t)v[2];
+                    }
+                }
+            }
             if (below_local)
                 spin_until_ge(&rows[j + 1].consumed, mbx - DB_NB + 1, lane);
+            else
+                __syncwarp();
             if (lane < 16) {
                 uint8_t *o = rec + po + (size_t)(y0 + r8) * g.CW + x0;
                 const uint2 mine = make_uint2(tw[r8 * 3 + 1], tw[r8 * 3 + 2]);
@@ -1653,8 +1666,8 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
             __syncwarp();
             if (lane == 0) {
                 me.consumed = mbx + 1;
-                if (below_local && mbx == g.mbw - 1)
-                    me.ready = g.mbw;
+                if (below_local)
+                    me.ready = mbx + 1;
                 if (!top_local && has_top)
                     mail.top_consumed = mbx + 1;
                 if (publish)
