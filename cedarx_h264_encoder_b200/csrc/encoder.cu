@@ -527,8 +527,10 @@ int encode_step(cedar_b200_handle *h, const Step &s, int t, int gop_pos0, int st
     // boundary strengths; on inter steps the same launch runs median MV prediction / the skip decision (K2)
     LAUNCH_ON(st, K_BS, bs_kernel, dim3((g.nmb * 8 + 127) / 128, nl), 128, 0, g, s, mbi, nnz, bs, !frame_i);
     CK(cudaEventRecord(h->ev_syn[p], st)); // the syntax records are final: entropy coding does not wait for deblocking
-    LAUNCH_ON(st, K_DEBLOCK, deblock_kernel, dim3((g.mbh + DB_ROWS - 1) / DB_ROWS, nl, 2), (DB_ROWS + 2) * 32, 0, g, s, unf,
-              rec, bs, fl_y, fl_c);
+    // equally tall CTAs of at most DB_ROWS macroblock rows (1080p: 4 x 17, 720p: 3 x 15, 4K: 8 x 17)
+    const int db_ctas = (g.mbh + DB_ROWS - 1) / DB_ROWS, db_rows = (g.mbh + db_ctas - 1) / db_ctas;
+    LAUNCH_ON(st, K_DEBLOCK, deblock_kernel, dim3((g.mbh + db_rows - 1) / db_rows, nl, 2), (db_rows + 2) * 32, 0, g, s, unf,
+              rec, bs, fl_y, fl_c, db_rows);
     CK(cudaEventRecord(h->ev_main[p], st));
 
     // ---- beside and behind the chain: the parallel entropy passes (from the syntax records, while the wavefront of

@@ -1328,12 +1328,13 @@ __device__ __forceinline__ void mail_wait(volatile int *p, int want, int lane)
     __threadfence_block();
 }
 
-// One CTA filters DB_ROWS consecutive macroblock rows of one plane type (blockIdx.z: 0 luma, 1 Cb+Cr) of one
+// One CTA filters `cta_rows` (<= DB_ROWS, chosen by the host so that the CTAs of a picture are equally tall: 68 rows = 4 x 17)
+// consecutive macroblock rows of one plane type (blockIdx.z: 0 luma, 1 Cb+Cr) of one
 // frame: warp j owns row j and hands the bottom rows of every finished macroblock to warp j+1 through a
 // shared-memory line buffer (a hop of a few hundred cycles); only the first row of a CTA gets its top
 // neighbours from global memory (loader warp, progress flag of the CTA above) and only the last row
 // publishes its progress globally (publisher warp).
-#define DB_ROWS 16
+#define DB_ROWS 17
 #define DB_NB 8 // line-buffer depth in macroblocks
 struct DeblockRow {
     uint32_t tile[16 * 6];   // luma: 16 rows x 24 bytes (cols 0..3 = left MB's last 4 columns);
@@ -1354,7 +1355,7 @@ __device__ __forceinline__ void spin_until_ge(volatile int *p, int want, int lan
 
 __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Step s, const uint8_t *__restrict__ unf,
                                                                       uint8_t *rec, const uint8_t *__restrict__ bs,
-                                                                      int *flags_y, int *flags_c)
+                                                                      int *flags_y, int *flags_c, int cta_rows)
 {
     if (lane_frame(s, blockIdx.y) < 0)
         return;
@@ -1363,7 +1364,7 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
     __shared__ DeblockMail mail;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool chroma = blockIdx.z != 0;
-    const int row0 = blockIdx.x * DB_ROWS, nr = imin_(DB_ROWS, g.mbh - row0);
+    const int row0 = blockIdx.x * cta_rows, nr = imin_(cta_rows, g.mbh - row0);
     const size_t fo = (size_t)blockIdx.y * g.frame_bytes;
     int *fl = (chroma ? flags_c : flags_y) + (size_t)blockIdx.y * g.mbh;
     if (threadIdx.x < DB_ROWS) {
@@ -1374,7 +1375,7 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
         mail.top_ready = mail.top_consumed = mail.done = 0;
     __syncthreads();
 
-    if (warp == DB_ROWS) { // loader: top neighbours of row0 from the CTA above
+    if (warp == cta_rows) { // loader: top neighbours of row0 from the CTA above
         if (row0 > 0) {
             if (!chroma)
                 deblock_loader(&mail, fl + row0 - 1, g.mbw, lane, [&](int slot, int mbx) {
@@ -1393,7 +1394,7 @@ __global__ void __launch_bounds__((DB_ROWS + 2) * 32) deblock_kernel(Geom g, Ste
         }
         return;
     }
-    if (warp == DB_ROWS + 1) { // publisher: progress of the CTA's last row, for the CTA below
+    if (warp == cta_rows + 1) { // publisher: progress of the CTA's last row, for the CTA below
         if (row0 + nr < g.mbh)
             deblock_publisher(&mail, fl + row0 + nr - 1, g.mbw, lane);
         return;
