@@ -549,3 +549,20 @@ def test_clip_mode_with_a_capacity_of_one_frame(oracle):
     with cx.Encoder(api.make_config(w, h, qp=24, gop=1, me_range=8, max_clip_frames=1)) as enc:
         got, gsz = enc.encode_clip(clip)
     assert got == want
+
+
+@pytest.mark.parametrize("mbh", [1, 2, 17, 18, 34, 35, 52, 69])
+@pytest.mark.parametrize("kind,qp", [("noise", 38), ("synth", 24)])
+def test_deblocking_wavefront_across_cta_boundaries(oracle, mbh, kind, qp):
+    """deblock_kernel cuts a picture into equally tall CTAs of at most 17 macroblock rows that hand rows over through
+    global flags: every height around those cuts, strong (intra) and normal filtering, deblocked planes == golden model."""
+    w, h = 80, 16 * mbh
+    gold = oracle.Encoder(oracle.make_config(w, h, qp=qp, gop=2, cabac=0, me_range=4))
+    with cx.Encoder(api.make_config(w, h, qp=qp, gop=2, cabac=0, me_range=4)) as enc:
+        for t in range(3):
+            y, c = content(kind, w, h, t)
+            want, got = gold.encode(y, c), enc.encode(y, c)
+            for p, (a, b) in enumerate(zip(gold.recon(), enc.debug_planes(2))):
+                assert np.array_equal(a, b), "deblocked plane %d frame %d" % (p, t)
+            assert got == want
+    gold.close()
