@@ -83,7 +83,7 @@ struct cedar_b200_handle {
     std::vector<cudaEvent_t> ev_upload;
     cudaEvent_t ev_encode_done;
     bool upload_pending;
-    cudaEvent_t ev_bins, ev_cabac[NSIDE];
+    cudaEvent_t ev_cabac[NSIDE];
     unsigned side_used; // bit i: side stream i has work the main stream has not joined yet
     int side_next;
     int grow;             // multiplier on the heuristic entropy-buffer bounds; clip mode raises it and re-encodes on overflow
@@ -684,7 +684,7 @@ static void destroy_handle(cedar_b200_handle *h)
     for (cudaEvent_t e : h->ev_pool)
         cudaEventDestroy(e);
     free_buffers(h);
-    cudaEvent_t evs[] = {h->ev_bins, h->ev_begin, h->ev_post_done, h->ev_encode_done, h->ev_ingest[0], h->ev_ingest[1],
+    cudaEvent_t evs[] = {h->ev_begin, h->ev_post_done, h->ev_encode_done, h->ev_ingest[0], h->ev_ingest[1],
                          h->ev_main[0], h->ev_main[1], h->ev_post[0], h->ev_post[1], h->ev_syn[0], h->ev_syn[1], h->ev_ent[0],
                          h->ev_ent[1]};
     for (cudaEvent_t e : evs)
@@ -816,7 +816,7 @@ int cedar_b200_open(const struct cedar_b200_config *cfg, struct cedar_b200_io *i
     auto mkstream = [](cudaStream_t *st) { return cudaStreamCreateWithFlags(st, cudaStreamNonBlocking) == cudaSuccess; };
     auto mkevent = [](cudaEvent_t *e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
     bool ok = mkstream(&h->stream) && mkstream(&h->stream_pre) && mkstream(&h->stream_post) && mkstream(&h->stream_copy) &&
-              mkevent(&h->ev_bins) && mkevent(&h->ev_begin) && mkevent(&h->ev_post_done) && mkevent(&h->ev_encode_done);
+              mkevent(&h->ev_begin) && mkevent(&h->ev_post_done) && mkevent(&h->ev_encode_done);
     for (int i = 0; ok && i < 2; i++)
         ok = mkevent(&h->ev_ingest[i]) && mkevent(&h->ev_main[i]) && mkevent(&h->ev_post[i]) && mkevent(&h->ev_syn[i]) &&
              mkevent(&h->ev_ent[i]);
