@@ -166,8 +166,8 @@ void *cedar_b200_pipe_acquire(cedar_b200_pipe *p, size_t *frame_bytes, int *capa
     if (!p)
         return nullptr;
     std::unique_lock<std::mutex> lk(p->mu);
-    if (p->acquired != p->submitted || p->finished)
-        return nullptr; // one batch is filled at a time, in order
+    if (p->acquired != p->submitted || p->finished || p->partial_seen)
+        return nullptr; // one batch is filled at a time, in order; a short batch was the last one of the stream
     Worker &w = p->w[(size_t)(p->acquired % (long long)p->w.size())];
     p->cv.wait(lk, [&] { return w.state == FREE; });
     w.state = FILLING;

@@ -188,7 +188,8 @@ int cedar_b200_pipe_open(const struct cedar_b200_config *cfg, const int *devices
 int cedar_b200_pipe_workers(cedar_b200_pipe *p);
 /* Pinned host staging of the next batch: capacity_frames packed frames of frame_bytes each (luma then chroma, as the
  * reference's read loop consumes them, userspace/h264enc.c:181-187).  Blocks until the worker that will encode the
- * batch is free (its previous batch consumed).  NULL when a batch is already being filled or after finish. */
+ * batch is free (its previous batch consumed).  NULL when a batch is already being filled, after a short batch (it ends
+ * the stream) or after finish. */
 void *cedar_b200_pipe_acquire(cedar_b200_pipe *p, size_t *frame_bytes, int *capacity_frames);
 /* Hands the acquired batch, holding nframes frames, to its worker (asynchronous).  Only the last batch of a stream may
  * hold fewer than capacity_frames; nframes == 0 gives the buffer back and ends the stream. */

@@ -566,3 +566,39 @@ def test_deblocking_wavefront_across_cta_boundaries(oracle, mbh, kind, qp):
                 assert np.array_equal(a, b), "deblocked plane %d frame %d" % (p, t)
             assert got == want
     gold.close()
+
+
+def test_queue_and_pipeline_edge_cases(oracle):
+    """flush with nothing queued, close with frames still queued, a pipeline closed with unconsumed batches, an invalid
+    configuration through the pipeline, a batch longer than the capacity: errors, never hangs."""
+    import ctypes as C
+    w, h, gop = 64, 48, 2
+    cfg = api.make_config(w, h, qp=24, gop=gop, me_range=4, queue_gops=1)
+    with cx.Encoder(cfg) as enc:
+        assert enc.flush() == b""
+    clip = make_clip("synth", w, h, 5)
+    enc = cx.Encoder(cfg)
+    for t in range(3):
+        assert enc.encode(*split_frame(clip[t], w, h, 0)) == b""
+    enc.close()  # frames still queued: dropped, no hang
+    with pytest.raises(OSError):
+        cx.Pipe(api.make_config(w, h, qp=99, gop=gop), None, 1, 1)
+    with pytest.raises(OSError):
+        cx.Pipe(api.make_config(w, h, qp=24, gop=gop, device=99), None, 1, 1)
+    pipe = cx.Pipe(api.make_config(w, h, qp=24, gop=gop, me_range=4), None, 2, 1)
+    buf = pipe.acquire()
+    assert buf.shape[0] == gop
+    with pytest.raises(OSError):
+        pipe.submit(gop + 1)
+    buf[:] = clip[:gop]
+    pipe.submit(gop)
+    buf = pipe.acquire()
+    buf[:1] = clip[gop:gop + 1]
+    pipe.submit(1)  # a short batch ends the stream: nothing may follow it
+    with pytest.raises(RuntimeError):
+        pipe.acquire()
+    pipe.close()  # two batches never consumed
+    want, _, _ = oracle_encode_clip(clip[:3], w, h, qp=24, gop=gop, cabac=1, me_range=4)
+    with cx.Pipe(api.make_config(w, h, qp=24, gop=gop, me_range=4), None, 2, 1) as pipe:
+        got, _ = pipe.encode(clip[:3])
+    assert got == want
