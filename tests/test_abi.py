@@ -81,3 +81,20 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(api, "PKG_DIR", str(tmp_path))
     with pytest.raises(api.LibraryMissing):
         api.load_library()
+
+
+def test_pipeline_fails_loudly_without_gpu_and_rejects_bad_arguments(product_lib):
+    """cedar_b200_pipe_open: argument errors are -EINVAL anywhere; on a box without a CUDA device every worker's open fails
+    with -ENODEV and the call returns it (no hang, nothing left behind)."""
+    import torch
+    from cedarx_h264_encoder_b200 import api
+    cfg = api.make_config(64, 48)
+    p = C.c_void_p()
+    assert product_lib.cedar_b200_pipe_open(C.byref(cfg), None, -1, 0, 0, C.byref(p)) == -22
+    assert product_lib.cedar_b200_pipe_open(None, None, 0, 0, 0, C.byref(p)) == -22
+    bad = api.make_config(64, 48, qp=0)
+    assert product_lib.cedar_b200_pipe_open(C.byref(bad), None, 0, 2, 1, C.byref(p)) == -22
+    if not torch.cuda.is_available():
+        assert product_lib.cedar_b200_pipe_open(C.byref(cfg), None, 0, 2, 1, C.byref(p)) == -19
+    assert product_lib.cedar_b200_flush(None) == -22
+    assert product_lib.cedar_b200_pipe_next(None, None, None, None, None, 0) == -22

@@ -23,6 +23,14 @@ def test_usage_matches_reference(product_lib):
         assert q.stdout.replace(REF_CLI, "X") == r.stdout.replace(CLI, "X")
 
 
+def test_cli_rejects_bad_extension_flags(product_lib, tmp_path):
+    """unknown flags and impossible combinations end with a message and a non-zero status before anything is opened"""
+    out = str(tmp_path / "o.264")
+    for flags in (["--bogus"], ["--gpus", "0"], ["--gpus", "65"], ["--batch-gops", "2", "--queue-gops", "1"], ["--handles", "-1"]):
+        r = subprocess.run([CLI, "-", "64", "48", out] + flags, input=b"", capture_output=True)
+        assert r.returncode != 0 and r.stderr, flags
+
+
 def test_cli_fails_loudly_without_gpu(product_lib, tmp_path):
     if torch.cuda.is_available():
         pytest.skip("GPU present")
