@@ -58,7 +58,7 @@ static void bw_put(bitw *b, uint32_t data, int size)
     }
 }
 
-static int ue_len(uint32_t v)
+static __attribute__((unused)) int ue_len(uint32_t v)
 {
     v++;
     return (32 - __builtin_clz(v)) * 2 - 1;

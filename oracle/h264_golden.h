@@ -13,7 +13,7 @@
  *     REFERENCE ITSELF, EXECUTED: oracle/refsim compiles kernel/cedar.c and userspace/h264enc.c unmodified (from where
  *     they lie) against a software model of the video engine's registers; this model's streams equal what that driver
  *     returns frame by frame (tests/test_refsim.py), and tests/golden/headers.json + ref_streams.json are generated
- *     from it (tools/make_ref_headers.py).
+ *     from it (tests/golden/make_ref_headers.py).
  *   - Slice data (everything per macroblock): the reference has NO source for it -- it is Allwinner A20 silicon
  *     started by kernel/cedar.c:1176 (in refsim this model IS the engine behind that trigger).  PARITY UNPINNED by
  *     the reference; pinned instead by (a) an independent conformant decoder (libavcodec) reproducing this model's

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Stage-by-stage comparison of the CUDA encoder with the CPU golden model (development aid;
 the pytest version of these checks lives in tests/test_gpu_parity.py).  Run on a GPU box:
-    python tools/gpu_check.py [quick|full]
+    python tests/gpu_check.py [quick|full]
 """
 import os
 import sys

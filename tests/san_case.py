@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Small cases that run every kernel (both entropy coders, I + P, slices, Intra4x4, intra in P, NV16, ragged size, clip and
-frame mode, the pipeline) for `compute-sanitizer --tool memcheck python tools/san_case.py`; checks the bytes against the
+frame mode, the pipeline) for `compute-sanitizer --tool memcheck python tests/san_case.py`; checks the bytes against the
 golden model as it goes."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

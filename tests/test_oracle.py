@@ -1,6 +1,6 @@
 """Pins the oracle: (1) an independent conformant decoder (FFmpeg's h264 in the bundled libavcodec)
 must reproduce the golden model's reconstruction bit-exactly -- north star correctness part 3;
-(2) committed bitstream hashes (tests/golden/stream_hashes.json, made by tools/make_golden.py)."""
+(2) committed bitstream hashes (tests/golden/stream_hashes.json, made by tests/golden/make_golden.py)."""
 import hashlib
 import json
 import os

@@ -48,7 +48,7 @@ def test_sps_pps_equal_the_reference_writer(oracle, product_lib, w, h):
 
 
 def test_committed_header_vectors_are_what_the_reference_writes_today():
-    """tests/golden/headers.json is generated (tools/make_ref_headers.py); spot-check it against a live run."""
+    """tests/golden/headers.json is generated (tests/golden/make_ref_headers.py); spot-check it against a live run."""
     gold = json.load(open(os.path.join(HERE, "golden", "headers.json")))
     nals = R.split_nals(_run("flat", 1920, 1088, 1, qp=25)[0])
     assert (b"\x00\x00\x00\x01" + nals[0]).hex(" ") == gold["sps"]["1920x1088"]
