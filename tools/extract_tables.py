@@ -8,8 +8,8 @@ opencv-python-headless, sanity-checked against a few valu
 from the standard, and written out as plain C arrays.  The generated headers are committed,
 so nothing at build, test or run time depends on this script or on libavcodec.
 
-Usage: python tools/extract_tables.py   (rewrites oracle/h264_tables.h and
-       cedarx_h264_encoder_b200/csrc/h264_tables.h with identical content)
+Usage: python tools/extract_tables.py   (rewrites cedarx_h264_encoder_b200/csrc/h264_tables.h, the one copy in the
+       tree; oracle/h264_tables.h only includes it)
 """
 import glob
 import os
@@ -163,7 +163,7 @@ def main():
         body.append(emit(k, v))
     body.append("#endif /* H264_TABLES_H */\n")
     text = "\n".join(body)
-    for rel in ("oracle/h264_tables.h", "cedarx_h264_encoder_b200/csrc/h264_tables.h"):
+    for rel in ("cedarx_h264_encoder_b200/csrc/h264_tables.h",):
         with open(os.path.join(ROOT, rel), "w") as f:
             f.write(text)
         print("wrote", rel, len(text), "bytes")
