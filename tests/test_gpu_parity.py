@@ -95,6 +95,30 @@ def test_clip_mode_matches_oracle(oracle, cabac, lanes):
         assert got2 == want
 
 
+@pytest.mark.parametrize("ahead", ["0", "1", "3", "100"])
+@pytest.mark.parametrize("lanes", [0, 2])
+def test_paced_upload_matches_oracle(oracle, monkeypatch, ahead, lanes):
+    """CEDAR_B200_UPLOAD_AHEAD = D: the copies of pass j + D are issued behind the ingest of pass j (encoder.cu
+    upload_pass).  Different clips back to back through one handle (a stale frame would show), several waves of GOPs,
+    a short last GOP, a clip shorter than the one before, and an upload that covers more frames than the encode."""
+    monkeypatch.setenv("CEDAR_B200_UPLOAD_AHEAD", ahead)
+    w, h, n, gop = 96, 80, 14, 4
+    clips = [make_clip(kind, w, h, m) for kind, m in (("synth", n), ("noise", n), ("shift", 9), ("static", n))]
+    want = [oracle_encode_clip(c, w, h, qp=27, gop=gop, cabac=1, me_range=8)[0] for c in clips]
+    with cx.Encoder(api.make_config(w, h, qp=27, gop=gop, cabac=1, me_range=8, max_clip_frames=n,
+                                    gops_in_flight=lanes)) as enc:
+        for _ in range(2):
+            for c, wnt in zip(clips, want):
+                assert enc.encode_clip(c)[0] == wnt
+        # upload 14 frames, encode the first 8 and then all 14 without another upload
+        enc.clip_input(n)[:] = clips[1].reshape(n, -1)
+        enc.clip_upload(n)
+        enc.clip_encode(8, 0)
+        enc.clip_download(8)
+        enc.clip_encode(n, 0)
+        assert enc.clip_download(n)[0].tobytes() == want[1]
+
+
 def test_handles_on_their_own_threads_do_not_interfere(oracle):
     """bench.py and INTEGRATION.md section 4 drive two or three handles per GPU, each from its own host thread: handles
     share nothing, so every one of them must still produce the oracle's bytes (different content, entropy coder and
