@@ -18,6 +18,8 @@
  *   --batch-gops N   a reader thread fills batches of N GOPs while earlier batches are encoded and written
  *                    (cedar_b200_pipe_*); --handles M encoder handles per GPU (default 2)
  *   --gpus N         the same across GPUs 0..N-1 of this box (batch b -> worker b mod (N*M)); --devices a,b,c picks them
+ *   --reader-threads N  a batch of a regular input file is read by N threads with pread() (default 4; a pipe is read by
+ *                    one thread, as is N = 1): one thread copies 7.7 GB/s out of the page cache, 2 500 frames/s of 1080p
  */
 #define _GNU_SOURCE
 #define _FILE_OFFSET_BITS 64
@@ -30,6 +32,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -93,10 +96,99 @@ static void emit_frame(int fd_out, const void *data, int bytes, int stats, doubl
     frame_count++;
 }
 
+/* ---- a batch of a regular file, read by several threads ---- */
+struct pread_job {
+    int fd;
+    uint8_t *dst;
+    off_t off;
+    size_t frame_bytes;
+    int nframes, done; /* done: whole frames read, from the first one of the job */
+};
+
+static void *pread_main(void *arg)
+{
+    struct pread_job *j = (struct pread_job *)arg;
+    for (j->done = 0; j->done < j->nframes; j->done++) {
+        size_t got = 0;
+        while (got < j->frame_bytes) {
+            ssize_t len = pread(j->fd, j->dst + (size_t)j->done * j->frame_bytes + got, j->frame_bytes - got,
+                                j->off + (off_t)((size_t)j->done * j->frame_bytes + got));
+            if (len <= 0)
+                return NULL; /* end of file inside a frame, or an error: the stream ends before this frame */
+            got += (size_t)len;
+        }
+    }
+    return NULL;
+}
+
+/* Reads up to `cap` whole frames from the current position of the regular file `fd` into `dst` with `threads` threads
+ * and moves the position behind them.  Returns the number of frames read: fewer than `cap` at the end of the file (a
+ * trailing partial frame is dropped, like the read loop of userspace/h264enc.c:181-187 does). */
+static int read_batch_parallel(int fd, uint8_t *dst, size_t frame_bytes, int cap, int threads)
+{
+    struct pread_job job[16];
+    pthread_t th[16];
+    int started[16], n = 0, nt, per, stop = 0;
+    struct stat sb;
+    off_t pos = lseek(fd, 0, SEEK_CUR);
+    if (pos < 0 || fstat(fd, &sb) || cap <= 0)
+        return 0;
+    if (sb.st_size > pos && (off_t)((sb.st_size - pos) / (off_t)frame_bytes) < (off_t)cap)
+        cap = (int)((sb.st_size - pos) / (off_t)frame_bytes);
+    else if (sb.st_size <= pos)
+        cap = 0;
+    if (cap == 0)
+        return 0;
+    nt = threads > 16 ? 16 : threads;
+    if (nt > cap)
+        nt = cap;
+    per = (cap + nt - 1) / nt;
+    for (int i = 0; i < nt; i++) {
+        int first = i * per, cnt = cap - first < per ? cap - first : per;
+        job[i].fd = fd, job[i].dst = dst + (size_t)first * frame_bytes, job[i].off = pos + (off_t)((size_t)first * frame_bytes);
+        job[i].frame_bytes = frame_bytes, job[i].nframes = cnt > 0 ? cnt : 0, job[i].done = 0;
+        started[i] = job[i].nframes > 0 && i > 0 && !pthread_create(&th[i], NULL, pread_main, &job[i]);
+    }
+    pread_main(&job[0]); /* this thread takes the first share */
+    for (int i = 1; i < nt; i++) {
+        if (started[i])
+            pthread_join(th[i], NULL);
+        else if (job[i].nframes > 0)
+            pread_main(&job[i]); /* no thread to be had: read the share here */
+    }
+    for (int i = 0; i < nt && !stop; i++) { /* the frames that are there without a gap (a file truncated meanwhile) */
+        n += job[i].done;
+        stop = job[i].done < job[i].nframes;
+    }
+    lseek(fd, pos + (off_t)((size_t)n * frame_bytes), SEEK_SET);
+    return n;
+}
+
+#ifdef H264ENC_READER_SELFTEST
+/* tests/test_cli.py: h264enc_reader_selftest <file> <frame_bytes> <cap> <threads> -> the batches' bytes on stdout */
+int main(int argc, char **argv)
+{
+    if (argc != 5)
+        return 2;
+    size_t fb = (size_t)atol(argv[2]);
+    int cap = atoi(argv[3]), threads = atoi(argv[4]), fd = open(argv[1], O_RDONLY), n;
+    uint8_t *buf = malloc(fb * (size_t)cap);
+    if (fd < 0 || !buf)
+        return 3;
+    do {
+        n = read_batch_parallel(fd, buf, fb, cap, threads);
+        if (n > 0 && fwrite(buf, fb, (size_t)n, stdout) != (size_t)n)
+            return 4;
+        fprintf(stderr, "%d\n", n);
+    } while (n == cap);
+    return 0;
+}
+#else
+
 /* ---- --batch-gops / --gpus: reader thread -> pipeline workers -> writer (this thread) ---- */
 struct reader_ctx {
     cedar_b200_pipe *pipe;
-    int fd_in;
+    int fd_in, threads; /* threads > 1: fd_in is a regular file and a batch is read with pread() by that many threads */
 };
 
 static void *reader_main(void *arg)
@@ -111,8 +203,11 @@ static void *reader_main(void *arg)
         double t1 = now_s();
         if (!in)
             break;
-        while (n < cap && read_frame(rc->fd_in, in + (size_t)n * frame_bytes, (int)frame_bytes) == (int)frame_bytes)
-            n++;
+        if (rc->threads > 1)
+            n = read_batch_parallel(rc->fd_in, in, frame_bytes, cap, rc->threads);
+        else
+            while (n < cap && read_frame(rc->fd_in, in + (size_t)n * frame_bytes, (int)frame_bytes) == (int)frame_bytes)
+                n++;
         if (trace)
             fprintf(stderr, "[trace] reader: waited %.1f ms for a staging buffer, read %d frames in %.1f ms\n",
                     1e3 * (t1 - t0), n, 1e3 * (now_s() - t1));
@@ -124,7 +219,7 @@ static void *reader_main(void *arg)
 }
 
 static int run_pipeline(struct cedar_b200_config *config, const int *devices, int ndevices, int handles, int batch_gops,
-                        int fd_in, int fd_out, int stats, double *t_opened)
+                        int fd_in, int fd_out, int stats, double *t_opened, int reader_threads)
 {
     cedar_b200_pipe *pipe = NULL;
     struct reader_ctx rc;
@@ -136,6 +231,10 @@ static int run_pipeline(struct cedar_b200_config *config, const int *devices, in
     }
     rc.pipe = pipe;
     rc.fd_in = fd_in;
+    {
+        struct stat sb;
+        rc.threads = (reader_threads > 1 && !fstat(fd_in, &sb) && S_ISREG(sb.st_mode)) ? reader_threads : 1;
+    }
     *t_opened = now_s();
     if (pthread_create(&reader, NULL, reader_main, &rc)) {
         cedar_b200_pipe_close(pipe);
@@ -168,7 +267,7 @@ int main(int argc, char **argv)
     const double t_start = now_s();
     double t_open = 0, t_stream = 0;
     int width, height, fd_in, fd_out, luma_size, chroma_size, ret, stats = 0, batch_gops = 0, queue_gops = 0;
-    int devices[64], ndevices = 0, handles = 0, one_device = -1;
+    int devices[64], ndevices = 0, handles = 0, one_device = -1, reader_threads = 4;
     struct cedar_b200_config config;
 
     if (argc < 5 || (argc > 5 && strncmp(argv[5], "--", 2))) {
@@ -236,6 +335,8 @@ int main(int argc, char **argv)
             batch_gops = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--queue-gops") && i + 1 < argc)
             queue_gops = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--reader-threads") && i + 1 < argc)
+            reader_threads = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--stats"))
             stats = 1;
         else {
@@ -243,8 +344,8 @@ int main(int argc, char **argv)
             return -1;
         }
     }
-    if (batch_gops < 0 || queue_gops < 0 || handles < 0 || (batch_gops && queue_gops)) {
-        fprintf(stderr, "%s: invalid --batch-gops / --queue-gops / --handles\n", argv[0]);
+    if (batch_gops < 0 || queue_gops < 0 || handles < 0 || (batch_gops && queue_gops) || reader_threads < 1 || reader_threads > 16) {
+        fprintf(stderr, "%s: invalid --batch-gops / --queue-gops / --handles / --reader-threads\n", argv[0]);
         return -1;
     }
     if (ndevices > 0 && !batch_gops)
@@ -274,7 +375,8 @@ int main(int argc, char **argv)
     if (batch_gops > 0) { /* GOP-parallel: reader thread, pipeline workers (per GPU, per handle), ordered writes */
         if (ndevices == 0 && one_device >= 0)
             devices[ndevices++] = one_device;
-        ret = run_pipeline(&config, ndevices ? devices : NULL, ndevices, handles, batch_gops, fd_in, fd_out, stats, &t_open);
+        ret = run_pipeline(&config, ndevices ? devices : NULL, ndevices, handles, batch_gops, fd_in, fd_out, stats, &t_open,
+                           reader_threads);
         if (ret)
             return ret;
         t_stream = now_s();
@@ -331,3 +433,4 @@ int main(int argc, char **argv)
                 t_stream - t_open, frame_count / (t_stream - t_open > 0 ? t_stream - t_open : 1), now_s() - t_stream);
     return 0;
 }
+#endif /* H264ENC_READER_SELFTEST */

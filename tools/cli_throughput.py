@@ -4,7 +4,7 @@ frame at a time (the reference's synchronous flow), --queue-gops (the same loop 
 thread + pipeline workers + ordered writer) and --gpus N when the box has several GPUs.  Prints one JSON line with
 frames/s of each (process start, pinned allocations and file I/O included) and checks that all outputs are identical.
 
-    python tools/cli_throughput.py [frames] [out.json]"""
+    python tools/cli_throughput.py [frames] [out.json] [modes, comma separated]"""
 import json
 import os
 import subprocess
@@ -24,9 +24,13 @@ with open(raw, "wb") as f:
 cli = os.path.join(ROOT, "cedarx_h264_encoder_b200", "h264enc")
 modes = [("frame_at_a_time", []), ("queue_gops_2", ["--queue-gops", "2"]), ("batch_gops_2_handles_2", ["--batch-gops", "2"]),
          ("batch_gops_5_handles_2", ["--batch-gops", "5"]), ("batch_gops_2_handles_3", ["--batch-gops", "2", "--handles", "3"])]
+modes += [("batch_gops_2_reader_1", ["--batch-gops", "2", "--reader-threads", "1"]),
+          ("batch_gops_2_handles_3_reader_8", ["--batch-gops", "2", "--handles", "3", "--reader-threads", "8"])]
 ngpu = torch.cuda.device_count()
 if ngpu > 1:
     modes.append(("gpus_%d_batch_gops_2" % ngpu, ["--gpus", str(ngpu), "--batch-gops", "2"]))
+if len(sys.argv) > 3:
+    modes = [m for m in modes if m[0] in sys.argv[3].split(",")]
 res, outs = {}, {}
 for name, extra in modes:
     out = "/tmp/out_%s.264" % name
@@ -45,9 +49,10 @@ for name, extra in modes:
                  "stream_s": float(parts[5]), "stream_frames_per_s": float(parts[7]), "close_s": float(parts[10])}
     outs[name] = open(out, "rb").read()
     print("%-26s %8.1f frames/s (%.2f s wall) | %s" % (name, n / best, best, timing), file=sys.stderr)
-same = all(v == outs["frame_at_a_time"] for v in outs.values())
+first = next(iter(outs.values()))
+same = all(v == first for v in outs.values())
 line = {"tool": "cli_throughput", "clip": "%dx%d nv12, %d frames, GOP %d, QP 25, from a file" % (w, h, n, gop), "gpus": ngpu,
-        "modes": res, "outputs_identical": same, "bytes": len(outs["frame_at_a_time"])}
+        "modes": res, "outputs_identical": same, "bytes": len(first)}
 print(json.dumps(line))
 if len(sys.argv) > 2:
     json.dump(line, open(sys.argv[2], "w"), indent=1)
