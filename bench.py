@@ -667,9 +667,10 @@ def run_gpu(args, rank, local_rank, world):
                                                   if npn["me_kernel_ms"] else None, "executed_over_algorithmic": npn["executed"] / instr,
                                                   "same_bytes": npn["same_bytes"],
                                                   "note": "measurement build (counter + 71 registers): an upper bound of the product kernel's time without pruning"},
-                "traffic": {"dram_bytes_per_launch": 43.36e6, "algorithmic_bytes_per_launch": 2.0 * W16 * H16 * 10,
-                            "source": "ncu --set full of round 1 (profiles/r01_ncu_full_summary.json; 1080p, 10 GOPs in flight; "
-                                      "the product kernel is unchanged since)"} if args.workload == DEFAULT_WORKLOAD and world == 1 else None,
+                "traffic": {"dram_bytes_per_launch": 43.54e6, "algorithmic_bytes_per_launch": 2.0 * W16 * H16 * 10,
+                            "source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel "
+                                      "with the final code (profiles/r02_ncu_me_inter_full_summary.json; 1080p, 10 GOPs in "
+                                      "flight, second inter step)"} if args.workload == DEFAULT_WORKLOAD and world == 1 else None,
                 "peak_source": simd_src,
                 "algorithmic_per_launch": instr / cnt, "avg_launch_ms": ms / cnt,
                 "frac_live": instr / (prof_live["me_kernel"][0] * 1e-3) / simd_peak if "me_kernel" in prof_live else None,
