@@ -147,6 +147,63 @@ def test_config_validation_equals_the_reference_ioctl(oracle, product_lib, kw):
     assert r == want or (want == 0 and r == -19), "product %d, reference %d" % (r, want)  # -ENODEV: no GPU here
 
 
+def _open_rc(make, base):
+    try:
+        make(base).close()
+        return 0
+    except OSError as e:
+        return -e.errno
+
+
+def test_config_validation_fuzz_equals_the_reference_ioctl(oracle, product_lib):
+    """The same three-way comparison over seeded random configurations around every limit of cedar.c:749-789 (most
+    of them invalid: only the return value is compared, nothing is encoded).  Zero-sized pictures are left out: the
+    reference's rules let them through and its allocator fails afterwards."""
+    from cedarx_h264_encoder_b200 import api
+    rng = np.random.default_rng(20261018)
+    def pick(good, bad):  # mostly a valid value, now and then one from beyond a limit
+        v = bad if rng.random() < 0.12 else good
+        return int(v[rng.integers(len(v))])
+    seen = {0: 0, -22: 0}
+    for _ in range(300):
+        w, h = pick((16, 62, 64, 100, 854, 1920, 4096), (1, 15, 17, 4097)), pick((16, 46, 48, 50, 480, 1088, 2304), (1, 15, 47, 4097))
+        aw, ah = (w + 15) & ~15, (h + 15) & ~15
+        base = dict(width=w, height=h, qp=pick((1, 24, 47), (-1, 0, 48, 51, 100)), gop=pick((1, 2, 25, 31), (-1, 0, 32, 100)),
+                    fmt=pick((0, 1), (-1, 2)), cabac=pick((0, 1), (0, 1)),
+                    dst_width=pick((aw, aw, aw + 16, 4112), (w | 1, aw - 16, 0, aw + 8)),
+                    dst_height=pick((ah, ah, ah + 16, 4112), (h | 1, ah - 16, 0, ah + 8)))
+        want = _ref_config_rc(**base)
+        assert want in (0, -22), base
+        seen[want] += 1
+        assert _open_rc(lambda b: oracle.Encoder(oracle.make_config(relax_gop=0, **b)), base) == want, base
+        cfg, io, hd = api.make_config(relax_gop=0, **base), api.CedarIO(), C.c_void_p()
+        r = product_lib.cedar_b200_open(C.byref(cfg), C.byref(io), C.byref(hd))
+        if r == 0:
+            product_lib.cedar_b200_close(hd)
+        assert r == want or (want == 0 and r in (-19, -12)), "%r: product %d, reference %d" % (base, r, want)
+    assert seen[0] >= 60 and seen[-22] >= 60, seen  # the sweep reaches both sides
+
+
+def test_header_fuzz_equals_the_reference_writer(oracle, product_lib):
+    """SPS / PPS / first slice header for seeded random valid configurations (size, QP, profile_idc and level_idc as the
+    caller passes them, entropy coder): reference driver (executed) == golden model == product writer."""
+    from cedarx_h264_encoder_b200 import api
+    rng = np.random.default_rng(7)
+    for _ in range(40):
+        w, h = int(rng.integers(8, 41)) * 2, int(rng.integers(8, 31)) * 2
+        kw = dict(qp=int(rng.integers(1, 48)), cabac=int(rng.integers(2)), profile=int(rng.choice([66, 77, 88, 100])),
+                  level=int(rng.choice([10, 13, 30, 31, 40, 41, 42, 51])))
+        gop = int(rng.integers(1, 32))
+        with R.Device() as d:
+            assert d.config(R.make_config(w, h, gop=gop, **kw)) == 0
+            nals = R.split_nals(d.encode(*content("flat", w, h, 0)))
+        sps, pps = b"\x00\x00\x00\x01" + nals[0], b"\x00\x00\x00\x01" + nals[1]
+        for mod in (oracle, api):
+            c = mod.make_config(w, h, gop=gop, **kw)
+            assert mod.write_sps(c) == sps and mod.write_pps(c) == pps, (w, h, kw)
+            assert mod.slice_header_bits(1, 0, kw["cabac"]) == R.rbsp_bits(nals[2], 16)
+
+
 def test_second_config_is_rejected_and_encode_needs_config():
     with R.Device() as d:
         assert d.L.refsim_ioctl(R.IOCTL_ENCODE, None) == -22  # cedar.c:1039-1043
