@@ -1327,7 +1327,7 @@ static void filter_line(uint8_t *pix, int xs, int bS, int alpha, int beta, int t
     if (chroma) {
         if (bS < 4) {
             int tc = tc0 + 1;
-            int delta = CLIP3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+            int delta = CLIP3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
             pix[-xs] = (uint8_t)clip255(p0 + delta);
             pix[0] = (uint8_t)clip255(q0 - delta);
         } else {
@@ -1340,7 +1340,7 @@ static void filter_line(uint8_t *pix, int xs, int bS, int alpha, int beta, int t
     int ap = iabs(p2 - p0), aq = iabs(q2 - q0);
     if (bS < 4) {
         int tc = tc0 + (ap < beta) + (aq < beta);
-        int delta = CLIP3(-tc, tc, (((q0 - p0) << 2) + (p1 - q1) + 4) >> 3);
+        int delta = CLIP3(-tc, tc, (((q0 - p0) * 4) + (p1 - q1) + 4) >> 3);
         pix[-xs] = (uint8_t)clip255(p0 + delta);
         pix[0] = (uint8_t)clip255(q0 - delta);
         if (ap < beta)
