@@ -14,6 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIB = os.path.join(ORACLE_DIR, "_ref", "librefsim.so")
 CLI = os.path.join(ORACLE_DIR, "_ref", "h264enc_sim")
+CLI_B200 = os.path.join(ORACLE_DIR, "_ref", "h264enc_b200")  # the same program bound to the product (refsim/b200_shim.c)
 REF = os.environ.get("CEDAR_REFERENCE", "/root/reference")
 
 IOCTL_ENCODE, IOCTL_CONFIG = 0x600, 0x601  # enum cedar_ioctl_cmd, kernel/cedar_ioctl.h:7-10

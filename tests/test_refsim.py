@@ -262,6 +262,24 @@ def test_reference_cli_end_to_end_equals_golden_cli(oracle, tmp_path):
     assert r.returncode == 255 and r.stdout.startswith("Usage: ")
 
 
+def test_reference_cli_bound_to_the_product_has_no_cpu_path(tmp_path):
+    """oracle/_ref/h264enc_b200 = userspace/h264enc.c, unmodified, with its /dev/cedar_dev calls bound to libcedar_b200.so
+    (oracle/refsim/b200_shim.c).  Without a GPU the CONFIG ioctl fails with ENODEV and the program ends the way the
+    reference does when its ioctl fails (userspace/h264enc.c:68-73,151-153); the usage line is the reference's."""
+    import torch
+    if not os.path.exists(R.CLI_B200):
+        pytest.skip("oracle/_ref/h264enc_b200 is built where the reference sources are")
+    r = subprocess.run([R.CLI_B200, "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 255 and r.stdout.startswith("Usage: ")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: see test_unmodified_reference_cli_on_the_product_library")
+    src = tmp_path / "in.nv12"
+    src.write_bytes(bytes(96 * 80 * 3 // 2))
+    r = subprocess.run([R.CLI_B200, str(src), "96", "80", str(tmp_path / "o.264")], capture_output=True, text=True)
+    assert r.returncode == 255
+    assert "CEDAR_IOCTL_CONFIG failed: No such device" in r.stderr and "no CPU fallback" in r.stderr
+
+
 def _umask():
     m = os.umask(0)
     os.umask(m)
@@ -307,3 +325,23 @@ def test_product_cli_equals_reference_cli(tmp_path):
     assert open(a, "rb").read() == open(b, "rb").read()
     prog = lambda s: [x for x in s.split(b"\r") if x.startswith(b"Frame")]  # noqa: E731
     assert prog(r1.stdout) == prog(r2.stdout)
+
+
+@pytest.mark.gpu
+def test_unmodified_reference_cli_on_the_product_library(tmp_path):
+    """The drop-in boundary, executed: the reference's own userspace/h264enc.c -- not a line changed, compiled from
+    /root/reference by oracle/Makefile -- with open / ioctl / mmap on /dev/cedar_dev bound to the product's C ABI
+    (oracle/refsim/b200_shim.c, the binding of INTEGRATION.md section 2) writes the same file and prints the same
+    progress lines as the same program on the reference's own driver in simulation."""
+    if not os.path.exists(R.CLI_B200):
+        pytest.fail("oracle/_ref/h264enc_b200 missing: it is built next to h264enc_sim and travels with it")
+    w, h, n = 176, 144, 28
+    src, a, b = str(tmp_path / "in.nv12"), str(tmp_path / "ref.264"), str(tmp_path / "b200.264")
+    _write_clip(src, w, h, n)
+    r1 = subprocess.run([R.CLI, src, str(w), str(h), a], capture_output=True, timeout=300)
+    r2 = subprocess.run([R.CLI_B200, src, str(w), str(h), b], capture_output=True, timeout=300)
+    assert r1.returncode == 0 and r2.returncode == 0, r2.stderr
+    assert open(a, "rb").read() == open(b, "rb").read()
+    prog = lambda s: [x for x in s.split(b"\r") if x.startswith(b"Frame")]  # noqa: E731
+    assert prog(r1.stdout) == prog(r2.stdout) and len(prog(r2.stdout)) == n
+    assert b"Time spent" in r2.stderr  # cedar_b200_close at exit, like the driver's release (kernel/cedar.c:706-730)
