@@ -96,6 +96,26 @@ def test_golden_model_stream_equals_reference_driver_stream(oracle, kind, w, h, 
     gold.close()
 
 
+def test_golden_model_stream_fuzz_equals_reference_driver_stream(oracle):
+    """The same comparison over seeded random small configurations: sizes that are not multiples of 16 (the driver pads
+    to dst = ALIGN16, cedar.c:756-761), every QP, GOP lengths 1..31, both entropy coders, all content kinds.  NV12 only:
+    the driver stores src_format and never programs it anywhere (cedar.c:793 is its last use), so a refsim run reads
+    NV16 input as NV12 -- the NV16 path is the golden model's and the product's own (north star: "raw NV12/NV16")."""
+    rng = np.random.default_rng(42)
+    kinds = ["synth", "noise", "static", "shift", "flat"]
+    for _ in range(24):
+        w, h = int(rng.integers(8, 49)) * 2, int(rng.integers(8, 41)) * 2
+        kw = dict(qp=int(rng.integers(1, 48)), gop=int(rng.integers(1, 32)), cabac=int(rng.integers(2)), fmt=0)
+        kind, n, me = kinds[int(rng.integers(len(kinds)))], int(rng.integers(2, 6)), int(rng.choice([4, 8, 16]))
+        with R.Device(me_range=me) as d:
+            assert d.config(R.make_config(w, h, **kw)) == 0
+            ref = [d.encode(*content(kind, w, h, t, kw["fmt"])) for t in range(n)]
+        gold = oracle.Encoder(oracle.make_config(w, h, relax_gop=0, me_range=me, **kw))
+        for t in range(n):
+            assert gold.encode(*content(kind, w, h, t, kw["fmt"])) == ref[t], (w, h, kw, kind, me, t)
+        gold.close()
+
+
 def test_committed_reference_stream_hashes(oracle):
     """The same comparison against committed hashes of the reference-driver streams (tests/golden/ref_streams.json), so it
     also holds where only the golden model can run."""
